@@ -1,0 +1,185 @@
+"""ctypes binding of oracle_ops.c + CPU autograd wrappers (TEST INFRASTRUCTURE ONLY).
+
+Mirrors the Python surface of the reference op module
+(/root/reference/src/e2eflow/ops.py:69-107): ``correlation`` returns the cost
+volume only; gradients: BackwardWarp -> [None, dflow], ForwardWarp -> [dflow],
+Correlation -> [g0, g1], Downsample -> not differentiable.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "liboracle_ops.so")
+_lib = None
+
+_f32p = ctypes.POINTER(ctypes.c_float)
+_i32 = ctypes.c_int
+
+
+def build(force=False):
+    """Compile oracle_ops.c with the Makefile beside it (gcc only)."""
+    src = os.path.join(_HERE, "oracle_ops.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-B", "liboracle_ops.so"],
+                              stdout=subprocess.DEVNULL)
+    return _SO
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = ctypes.CDLL(_SO)
+        _lib.oracle_correlation_shape.restype = _i32
+        _lib.oracle_correlation_fwd.restype = _i32
+        _lib.oracle_correlation_bwd.restype = _i32
+        _lib.oracle_downsample.restype = _i32
+        _lib.oracle_num_threads.restype = _i32
+    return _lib
+
+
+def num_threads():
+    return int(lib().oracle_num_threads())
+
+
+def _p(t):
+    assert t.dtype == torch.float32 and t.is_contiguous() and t.device.type == "cpu"
+    return ctypes.cast(t.data_ptr(), _f32p)
+
+
+def _f32c(t):
+    return torch.as_tensor(np.asarray(t) if not torch.is_tensor(t) else t).to(torch.float32).contiguous()
+
+
+_CORR_DEFAULTS = dict(kernel_size=1, max_displacement=20, pad=20, stride_1=1, stride_2=2)
+
+
+def _corr_attrs(kwargs):
+    a = dict(_CORR_DEFAULTS)
+    for k, v in kwargs.items():
+        if k not in a:
+            raise TypeError("correlation() got an unexpected attribute %r" % k)
+        a[k] = int(v)
+    return a
+
+
+class _Correlation(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, in0, in1, attrs):
+        in0 = in0.contiguous()
+        in1 = in1.contiguous()
+        if in0.shape != in1.shape:
+            raise ValueError("Input shapes have to be the same")
+        B, C, H, W = in0.shape
+        a = attrs
+        if a["kernel_size"] % 2 == 0:
+            raise ValueError("kernel_size must be odd")
+        oc, oh, ow = _i32(), _i32(), _i32()
+        rc = lib().oracle_correlation_shape(H, W, a["kernel_size"], a["max_displacement"], a["pad"],
+                                            a["stride_1"], a["stride_2"],
+                                            ctypes.byref(oc), ctypes.byref(oh), ctypes.byref(ow))
+        if rc != 0:
+            raise ValueError("Invalid correlation settings")
+        out = torch.empty(B, oc.value, oh.value, ow.value, dtype=torch.float32)
+        ph, pw = H + 2 * a["pad"], W + 2 * a["pad"]
+        pad0 = torch.empty(B, ph, pw, C, dtype=torch.float32)
+        pad1 = torch.empty(B, ph, pw, C, dtype=torch.float32)
+        rc = lib().oracle_correlation_fwd(_p(in0), _p(in1), _p(out), _p(pad0), _p(pad1),
+                                          B, C, H, W, a["kernel_size"], a["max_displacement"],
+                                          a["pad"], a["stride_1"], a["stride_2"])
+        assert rc == 0
+        ctx.save_for_backward(pad0, pad1)
+        ctx.attrs = a
+        ctx.shape = (B, C, H, W)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        pad0, pad1 = ctx.saved_tensors
+        a = ctx.attrs
+        B, C, H, W = ctx.shape
+        gout = gout.contiguous()
+        g0 = torch.empty(B, C, H, W, dtype=torch.float32)
+        g1 = torch.empty(B, C, H, W, dtype=torch.float32)
+        rc = lib().oracle_correlation_bwd(_p(gout), _p(pad0), _p(pad1), _p(g0), _p(g1),
+                                          B, C, H, W, a["kernel_size"], a["max_displacement"],
+                                          a["pad"], a["stride_1"], a["stride_2"])
+        assert rc == 0
+        return g0, g1, None
+
+
+def correlation(first, second, **kwargs):
+    """NCHW x NCHW -> NCHW cost volume (reference ops.py:69-70)."""
+    return _Correlation.apply(_f32c(first), _f32c(second), _corr_attrs(kwargs))
+
+
+class _BackwardWarp(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, images, flows):
+        images = images.contiguous()
+        flows = flows.contiguous()
+        B, H, W, C = images.shape
+        assert flows.shape == (B, H, W, 2)
+        out = torch.empty_like(images)
+        if out.numel():
+            lib().oracle_backward_warp_fwd(_p(images), _p(flows), _p(out), B, H, W, C)
+        ctx.save_for_backward(images, flows)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad):
+        images, flows = ctx.saved_tensors
+        B, H, W, C = images.shape
+        out = torch.zeros_like(flows)
+        if out.numel():
+            lib().oracle_backward_warp_bwd(_p(grad.contiguous()), _p(images), _p(flows), _p(out),
+                                           B, H, W, C)
+        return None, out  # reference ops.py:80-84: [None, grad0]
+
+
+def backward_warp(images, flows):
+    return _BackwardWarp.apply(_f32c(images), _f32c(flows))
+
+
+class _ForwardWarp(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, flows):
+        flows = flows.contiguous()
+        B, H, W, two = flows.shape
+        assert two == 2
+        out = torch.zeros(B, H, W, 1, dtype=torch.float32)
+        if out.numel():
+            lib().oracle_forward_warp_fwd(_p(flows), _p(out), B, H, W)
+        ctx.save_for_backward(flows)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad):
+        (flows,) = ctx.saved_tensors
+        B, H, W, _ = flows.shape
+        out = torch.zeros_like(flows)
+        if out.numel():
+            lib().oracle_forward_warp_bwd(_p(grad.contiguous()), _p(flows), _p(out), B, H, W)
+        return out
+
+
+def forward_warp(flows):
+    return _ForwardWarp.apply(_f32c(flows))
+
+
+def downsample(images, scale=2):
+    """Box mean; not differentiable (reference ops.py:107)."""
+    images = _f32c(images).detach()
+    B, H, W, C = images.shape
+    scale = int(scale)
+    if H % scale != 0 or W % scale != 0:
+        raise ValueError("Input height and width must be divisible by scale")
+    out = torch.empty(B, H // scale, W // scale, C, dtype=torch.float32)
+    if out.numel():
+        rc = lib().oracle_downsample(_p(images), _p(out), B, H, W, C, scale)
+        assert rc == 0
+    return out
