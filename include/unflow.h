@@ -1,0 +1,116 @@
+/*
+ * unflow.h -- C ABI of libunflow.so, the sm_100a kernels behind the UnFlow hot path.
+ *
+ * This is the drop-in boundary: the reference binds its ops through
+ * TensorFlow's C++ OpKernel interface (tf.load_op_library, reference
+ * src/e2eflow/ops.py:56-63); a maintainer replacing those four .so files binds
+ * the entry points below instead (INTEGRATION.md shows the ctypes stub).  Each
+ * entry point cites the reference interface it replaces (file:line under
+ * /root/reference).
+ *
+ * Conventions:
+ *   - every pointer is a DEVICE pointer to float32 data, densely packed, in the
+ *     layout the reference op uses (NCHW for correlation, NHWC elsewhere);
+ *   - the caller allocates and owns every buffer, including outputs;
+ *   - `stream` is a cudaStream_t (CUstream) passed as void*; kernels are only
+ *     enqueued on it; nothing here synchronises or allocates device memory;
+ *   - return value: UNFLOW_OK, UNFLOW_EINVAL (argument check failed -- mirrors
+ *     the reference's OP_REQUIRES -> InvalidArgument), UNFLOW_ECUDA (launch
+ *     failed); unflow_last_error() returns a thread-local message;
+ *   - re-entrant: no global mutable state apart from the launch counter and
+ *     the thread-local error string; safe to call from several host threads on
+ *     distinct streams.
+ */
+#ifndef UNFLOW_H_
+#define UNFLOW_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UNFLOW_OK 0
+#define UNFLOW_EINVAL 1
+#define UNFLOW_ECUDA 2
+
+#define UNFLOW_BORDER_ZERO 0  /* BackwardWarp op: taps outside the image contribute 0 */
+#define UNFLOW_BORDER_CLAMP 1 /* image_warp: tap indices clamped to the image       */
+
+/* Library / diagnostics. */
+int unflow_abi_version(void);
+const char *unflow_last_error(void);
+/* Number of kernels this library has launched since load (or since the last
+ * reset); bench.py reports it as gpu_launches. */
+unsigned long long unflow_launch_count(void);
+void unflow_reset_launch_count(void);
+
+/* ------------------------------------------------------------------------
+ * Correlation   (reference: REGISTER_OP("Correlation") ops/correlation_op.cc:133-168,
+ * CorrelationOp::Compute ops/correlation_op.cc:38-85, geometry ops/correlation_op.h:28-52,
+ * kernels ops/correlation_op.cu.cc:31-117,250-315)
+ *   in0,in1 : [B,C,H,W]    out : [B, D*D, out_h, out_w],  D = 2*(max_displacement/stride_2)+1
+ * The reference's padded_0/padded_1 outputs are an implementation detail of
+ * its kernels (consumed only by its own gradient) and are not produced.
+ * EINVAL: even kernel_size (correlation_op.h:16-17), out_h<=0 or out_w<=0
+ * (correlation_op.cc:60-61), non-positive strides/sizes.
+ * ---------------------------------------------------------------------- */
+int unflow_correlation_out_shape(int H, int W, int kernel_size, int max_displacement, int pad,
+                                 int stride_1, int stride_2, int *out_c, int *out_h, int *out_w);
+size_t unflow_correlation_workspace_bytes(int B, int C, int H, int W, int kernel_size,
+                                          int max_displacement, int pad, int stride_1,
+                                          int stride_2);
+int unflow_correlation_fwd(const float *in0, const float *in1, float *out, int B, int C, int H,
+                           int W, int kernel_size, int max_displacement, int pad, int stride_1,
+                           int stride_2, void *stream);
+/* CorrelationGrad (REGISTER_OP ops/correlation_op.cc:170-187, Compute :87-129, kernels
+ * ops/correlation_op.cu.cc:120-248,317-390): gout [B,D*D,out_h,out_w] -> g0,g1 [B,C,H,W].
+ * Reads the original inputs directly (no padded copies). */
+int unflow_correlation_bwd(const float *gout, const float *in0, const float *in1, float *g0,
+                           float *g1, int B, int C, int H, int W, int kernel_size,
+                           int max_displacement, int pad, int stride_1, int stride_2,
+                           void *stream);
+/* Which implementation the dispatcher picks for these attributes:
+ * 0 = generic kernel, 1 = tiled TMA kernel (the FlowNetC path). */
+int unflow_correlation_fwd_path(int C, int H, int W, int kernel_size, int max_displacement,
+                                int pad, int stride_1, int stride_2);
+
+/* ------------------------------------------------------------------------
+ * BackwardWarp / image_warp
+ *   reference op: REGISTER_OP("BackwardWarp") ops/backward_warp_op.cc:77-91, kernel
+ *   ops/backward_warp_op.cu.cc:14-68 (border_mode = UNFLOW_BORDER_ZERO);
+ *   reference training path: image_warp, src/e2eflow/core/image_warp.py:4-76
+ *   (border_mode = UNFLOW_BORDER_CLAMP).
+ *   images [B,H,W,C], flows [B,H,W,2] -> out [B,H,W,C]
+ * ---------------------------------------------------------------------- */
+int unflow_backward_warp_fwd(const float *images, const float *flows, float *out, int B, int H,
+                             int W, int C, int border_mode, void *stream);
+/* BackwardWarpGrad (ops/backward_warp_op.cu.cc:70-138) -> dflow [B,H,W,2].
+ * dimage may be NULL (the op returns no image gradient, src/e2eflow/ops.py:80-84);
+ * when non-NULL it must be zero-initialised by the caller and receives the
+ * scatter-add gradient TF autodiff produces for image_warp (tf.gather -> scatter). */
+int unflow_backward_warp_bwd(const float *grad, const float *images, const float *flows,
+                             float *dflow, float *dimage, int B, int H, int W, int C,
+                             int border_mode, void *stream);
+
+/* ------------------------------------------------------------------------
+ * ForwardWarp  (REGISTER_OP ops/forward_warp_op.cc:81-100; kernels
+ * ops/forward_warp_op.cu.cc:16-125).  flows [B,H,W,2] -> out [B,H,W,1].
+ * The launcher zeroes `out` itself (the reference runs SetZero first, :139-143).
+ * ---------------------------------------------------------------------- */
+int unflow_forward_warp_fwd(const float *flows, float *out, int B, int H, int W, void *stream);
+int unflow_forward_warp_bwd(const float *grad, const float *flows, float *dflow, int B, int H,
+                            int W, void *stream);
+
+/* ------------------------------------------------------------------------
+ * Downsample  (REGISTER_OP ops/downsample_op.cc:63-81, Compute :30-57, kernel
+ * ops/downsample_op.cu.cc:15-72).  images [B,H,W,C] -> out [B,H/scale,W/scale,C].
+ * EINVAL when H or W is not divisible by scale (downsample_op.cc:37-40).
+ * ---------------------------------------------------------------------- */
+int unflow_downsample(const float *images, float *out, int B, int H, int W, int C, int scale,
+                      void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UNFLOW_H_ */

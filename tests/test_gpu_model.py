@@ -1,0 +1,94 @@
+"""GPU parity of the model and the loss assembly against the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import flownet as oflownet
+from oracle import losses as olosses
+from oracle import unsupervised as ounsup
+import synth
+
+TERMS = ['sym', 'occ', 'photo', 'grad', 'smooth_1st', 'smooth_2nd', 'fb', 'ternary']
+
+
+def close(got, want, rtol=1e-4, atol_rel=1e-5, msg=""):
+    want = want.detach().cpu()
+    got = got.detach().cpu()
+    atol = atol_rel * max(float(want.abs().max()), 1e-12)
+    np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=rtol, atol=atol, err_msg=msg)
+
+
+@pytest.mark.parametrize("mask_occlusion,use_border,dist", [('fb', True, 3), ('', False, 1),
+                                                            ('disocc', True, 2), ('fb', False, 2)])
+def test_compute_losses_unfused_vs_oracle(mask_occlusion, use_border, dist):
+    from unflow_b200.e2eflow.core import losses as L
+    im1, im2, ffw, fbw = synth.level_inputs(2, 24, 40)
+    border = olosses.create_border_mask(im1, 0.1) if use_border else None
+    fo, bo = ffw.clone().requires_grad_(True), fbw.clone().requires_grad_(True)
+    fg, bg = ffw.cuda().requires_grad_(True), fbw.cuda().requires_grad_(True)
+    want = olosses.compute_losses(im1, im2, fo, bo, border_mask=border, mask_occlusion=mask_occlusion,
+                                  data_max_distance=dist)
+    got = L.compute_losses(im1.cuda(), im2.cuda(), fg, bg,
+                           border_mask=border.cuda() if use_border else None,
+                           mask_occlusion=mask_occlusion, data_max_distance=dist, _fused=False)
+    assert set(got) == set(TERMS)
+    for k in TERMS:
+        close(got[k], want[k], rtol=2e-4, msg=k)
+    wsum = lambda d: (d['ternary'] + 3.0 * d['smooth_2nd'] + 0.2 * d['fb'] + 12.4 * d['occ'] +
+                      d['photo'] + d['grad'] + d['smooth_1st'] + d['sym'])
+    wsum(want).backward()
+    wsum(got).backward()
+    close(fg.grad, fo.grad, rtol=1e-3, atol_rel=1e-4, msg="dflow_fw")
+    close(bg.grad, bo.grad, rtol=1e-3, atol_rel=1e-4, msg="dflow_bw")
+
+
+@pytest.mark.parametrize("spec,hw", [("C", (64, 128)), ("CS", (64, 128)), ("c", (64, 64))])
+def test_flownet_vs_oracle(spec, hw):
+    from unflow_b200.e2eflow.core.flownet import FlowNetVariables, flownet
+    tfv = oflownet.init_variables(spec, False, seed=5)
+    v = FlowNetVariables(spec, False, seed=0).load_tf_dict(tfv).cuda()
+    im1, im2, _ = synth.image_pair(1, hw[0], hw[1], seed=3)
+    im1, im2 = im1 / 255.0 - 0.4, im2 / 255.0 - 0.4
+    want_fw, want_bw = oflownet.flownet(tfv, im1, im2, spec, backward_flow=True)
+    with torch.no_grad():
+        got_fw, got_bw = flownet(im1.cuda(), im2.cuda(), spec, backward_flow=True, variables=v)
+    assert len(got_fw) == len(spec)
+    for net in range(len(spec)):
+        for w, g in zip(want_fw[net] + want_bw[net], got_fw[net] + got_bw[net]):
+            close(g, w, rtol=1e-3, atol_rel=1e-4, msg="%s net %d" % (spec, net))
+    # forward-only call returns the same forward flows (flownet.py:79-81)
+    with torch.no_grad():
+        only_fw = flownet(im1.cuda(), im2.cuda(), spec, variables=v)
+    for w, g in zip(got_fw[-1], only_fw[-1]):
+        close(g, w, rtol=1e-4, atol_rel=1e-5)
+
+
+@pytest.mark.parametrize("spec,hw", [("C", (128, 256)), ("S", (128, 192))])
+def test_unsupervised_loss_vs_oracle(spec, hw):
+    """configs[0]/[2] graph at reduced size: loss value, final flows (1e-4 relative) and the
+    gradient of the loss w.r.t. a set of variables."""
+    from unflow_b200.e2eflow.core.flownet import FlowNetVariables
+    from unflow_b200.e2eflow.core.unsupervised import unsupervised_loss
+    params = dict(synth.KITTI_PARAMS, flownet=spec)
+    tfv = oflownet.init_variables(spec, False, seed=11)
+    for k in tfv:  # leaves for the oracle's autograd
+        tfv[k] = tfv[k].clone().requires_grad_(True)
+    v = FlowNetVariables(spec, False, seed=0).load_tf_dict({k: t.detach() for k, t in tfv.items()}).cuda()
+    im1, im2, _ = synth.image_pair(1, hw[0], hw[1], seed=21)
+    want_loss, want_fw, want_bw = ounsup.unsupervised_loss(tfv, (im1, im2), params, synth.KITTI_NORMALIZATION,
+                                                           augment=False, return_flow=True)
+    got_loss, got_fw, got_bw = unsupervised_loss((im1.cuda(), im2.cuda()), params, synth.KITTI_NORMALIZATION,
+                                                 augment=False, return_flow=True, variables=v)
+    close(got_loss, want_loss, rtol=2e-4)
+    # north_star tolerance: flow within 1e-4 relative (to the flow magnitude) of the reference
+    close(got_fw, want_fw, rtol=1e-4, atol_rel=1e-4)
+    close(got_bw, want_bw, rtol=1e-4, atol_rel=1e-4)
+    want_loss.backward()
+    got_loss.backward()
+    for scope in v.kinds:
+        w, b = v.weights(scope)
+        gw = tfv[scope + '/weights'].grad.permute(3, 2, 0, 1)
+        close(w.grad, gw, rtol=5e-3, atol_rel=2e-3, msg=scope + '/weights')
+        close(b.grad, tfv[scope + '/biases'].grad, rtol=5e-3, atol_rel=2e-3, msg=scope + '/biases')

@@ -1,0 +1,348 @@
+// correlation_tiled.cu -- the FlowNetC cost volume on sm_100a: TMA-staged, register-tiled fp32.
+//
+// Serves kernel_size=1, stride_1=1, stride_2=2, pad == max_displacement <= 20, H even, W % 4 == 0
+// (reference call site src/e2eflow/core/flownet.py:221-222; math of CorrelateData,
+// ops/correlation_op.cu.cc:52-117):
+//
+//   out[b,(p,o),y,x] = (1/C) * sum_c in0[b,c,y,x] * in1[b,c,y+2p,x+2o]     (0 outside the image)
+//
+// This is a banded batched contraction, FMA-bound on CUDA cores in exact fp32 (59 FLOP/B,
+// SURVEY.md R5), so the design goal is to keep the FMA pipe busy with few shared-memory
+// wavefronts per FMA and to touch HBM exactly once:
+//
+//  * work item = (image b, 4 consecutive in1 rows y2, 16-pixel column tile).  All (y, y2) row
+//    pairs with y2 in the group and |y2-y| <= 2r, y2-y even, are compacted into a pair list
+//    (<= 84 pairs); row pairs whose in1 row is outside the image are never computed -- their
+//    outputs are exact zeros and are written by a zero-fill pass of the same kernel
+//    (22% of the nominal FLOPs at H=48 are such zeros).
+//  * a warp owns 8 row pairs; lane = (pair 0..7, pixel group 0..1, displacement half 0..1).
+//    Each thread keeps an 8-pixel x 11-displacement register tile: per channel it loads
+//    8 in0 values and a 28-float in1 window (the Toeplitz structure x2 = x + 2o makes 88 FMAs
+//    need only 36 operands), all as 128-bit shared loads.  Lanes that share an in1 row read the
+//    same window addresses (shared-memory broadcast).
+//  * in0 is staged as two row-parity planes (TMA 5-D view [B][C][H/2][2][W]) with a 20-float
+//    row pitch so the 8 row pairs of a quarter warp hit 8 different bank groups;
+//    in1 is staged as a dense [c][4][56] box.  Out-of-image rows/columns are TMA zero fill --
+//    there is no padded copy of the inputs (the reference writes 2 x 144 MB of them).
+//  * one producer warp feeds a 4-stage mbarrier ring of 8-channel slices; 11 consumer warps.
+//  * every output element is written exactly once, as float4, by the thread that owns it.
+//
+// Algorithmic bytes: 4*B*H*W*(2C + D^2); FLOPs: 2*B*H*W*C*D^2.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "correlation.cuh"
+
+namespace unflow {
+
+namespace ct {
+constexpr int S2 = 2;
+constexpr int RMAX = 10;                   // max neighbourhood radius (md/stride_2)
+constexpr int NY2 = 4;                     // in1 rows per work item
+constexpr int TX = 16;                     // output columns per work item
+constexpr int WIN = TX + 2 * S2 * RMAX;    // 56 staged in1 columns
+constexpr int P0 = 20;                     // in0 row pitch in floats (TX used)
+constexpr int ROWS0 = NY2 + 2 * S2 * RMAX; // 44 in0 rows reachable from the in1 group
+constexpr int R0H = ROWS0 / 2;             // 22 rows per parity plane
+constexpr int CC = 8;                      // channels per pipeline stage
+constexpr int STAGES = 4;
+constexpr int NCW = 11;                    // consumer warps (11*8 = 88 >= 84 pair slots)
+constexpr int NTHREADS = (NCW + 1) * 32;   // + 1 producer warp
+constexpr int DO = 11;                     // displacements per thread (two halves overlap at o=0)
+constexpr int PX = 8;                      // pixels per thread
+constexpr int MAXPAIRS = NY2 * (2 * RMAX + 1);
+
+constexpr int IN0_PLANE_FLOATS = CC * R0H * P0;     // 3520
+constexpr int IN1_FLOATS = CC * NY2 * WIN;          // 1792
+constexpr int STAGE_FLOATS = 2 * IN0_PLANE_FLOATS + IN1_FLOATS;
+constexpr int STAGE_BYTES = STAGE_FLOATS * 4;       // 35328
+static_assert((IN0_PLANE_FLOATS * 4) % 128 == 0 && (IN1_FLOATS * 4) % 128 == 0, "TMA dst alignment");
+
+struct Smem {
+  float stage[STAGES][STAGE_FLOATS];
+  unsigned long long full[STAGES];
+  unsigned long long empty[STAGES];
+  int npairs, nzero;
+  short pair_y[MAXPAIRS], pair_y2r[MAXPAIRS], pair_p[MAXPAIRS];
+  short zero_y[MAXPAIRS], zero_p[MAXPAIRS];
+};
+}  // namespace ct
+
+// ------------------------------------------------------------------------------------------
+// PTX helpers (mbarrier + TMA), sm_100a
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void *p) {
+  return (unsigned)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+  const unsigned addr = smem_u32(bar);
+  unsigned done;
+  do {
+    asm volatile(
+        "{\n"
+        " .reg .pred p;\n"
+        " mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        " selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *map, unsigned long long *bar,
+                                            int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(void *dst, const CUtensorMap *map, unsigned long long *bar,
+                                            int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+
+// ------------------------------------------------------------------------------------------
+// Forward kernel
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(ct::NTHREADS, 1)
+corr_fwd_tiled_kernel(const __grid_constant__ CUtensorMap map0,  // in0 as [B][C][H/2][2][W]
+                      const __grid_constant__ CUtensorMap map1,  // in1 as [B][C][H][W]
+                      float *__restrict__ out, int C, int H, int W, int r, int y2_first) {
+  using namespace ct;
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int x0 = blockIdx.x * TX;
+  const int Y2 = y2_first + blockIdx.y * NY2;  // first in1 row of this group (multiple of 4)
+  const int b = blockIdx.z;
+  const int D = 2 * r + 1;
+  const int ybase = Y2 - S2 * RMAX;  // first staged in0 row (even)
+
+  if (tid == 0) {
+    int np = 0, nz = 0;
+    for (int y2r = 0; y2r < NY2; ++y2r) {
+      const int y2 = Y2 + y2r;
+      const bool inside = y2 >= 0 && y2 < H;
+      for (int p = -r; p <= r; ++p) {
+        const int y = y2 - S2 * p;
+        if (y < 0 || y >= H) continue;
+        if (inside) { sm.pair_y[np] = (short)y; sm.pair_y2r[np] = (short)y2r; sm.pair_p[np] = (short)(p + r); ++np; }
+        else { sm.zero_y[nz] = (short)y; sm.zero_p[nz] = (short)(p + r); ++nz; }
+      }
+    }
+    sm.npairs = np; sm.nzero = nz;
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], NCW); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int npairs = sm.npairs, nzero = sm.nzero;
+  const size_t plane_out = (size_t)H * W;        // out_h == H, out_w == W on this path
+  float *outb = out + (size_t)b * D * D * plane_out;
+
+  // ---- exact zeros: row pairs whose in1 row lies outside the image -------------------------
+  if (nzero > 0) {
+    const int per_pair = D * (TX / 4);
+    for (int i = tid; i < nzero * per_pair; i += NTHREADS) {
+      const int zp = i / per_pair, rem = i - zp * per_pair;
+      const int o = rem / (TX / 4), q = rem - o * (TX / 4);
+      const int x = x0 + 4 * q;
+      if (x < W) {
+        float *dst = outb + ((size_t)(sm.zero_p[zp] * D + o)) * plane_out + (size_t)sm.zero_y[zp] * W + x;
+        *reinterpret_cast<float4 *>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+  }
+  if (npairs == 0) return;
+
+  const int nchunks = (C + CC - 1) / CC;
+
+  if (warp == NCW) {
+    // ---------------- producer warp: one lane drives TMA -----------------------------------
+    if (lane == 0) {
+      for (int it = 0; it < nchunks; ++it) {
+        const int s = it % STAGES;
+        const unsigned ph = (unsigned)(it / STAGES) & 1u;
+        mbar_wait(&sm.empty[s], ph ^ 1u);
+        mbar_arrive_expect_tx(&sm.full[s], STAGE_BYTES);
+        float *st = sm.stage[s];
+        const int c0 = it * CC;
+        // in0 parity planes: coords (x, parity, hh, c, b)
+        tma_load_5d(st, &map0, &sm.full[s], x0, 0, ybase >> 1, c0, b);
+        tma_load_5d(st + IN0_PLANE_FLOATS, &map0, &sm.full[s], x0, 1, ybase >> 1, c0, b);
+        // in1 window: coords (x, y, c, b)
+        tma_load_4d(st + 2 * IN0_PLANE_FLOATS, &map1, &sm.full[s], x0 - S2 * RMAX, Y2, c0, b);
+      }
+    }
+    return;
+  }
+
+  // ---------------- consumer warps ----------------------------------------------------------
+  const int slot = warp * 8 + (lane & 7);
+  const bool active = slot < npairs;
+  const int pslot = active ? slot : 0;
+  const int pxg = (lane >> 3) & 1, og = lane >> 4;
+  const int y = sm.pair_y[pslot], y2r = sm.pair_y2r[pslot], pidx = sm.pair_p[pslot];
+  const int yrel = y - ybase;
+  // float offsets inside a stage (channel 0)
+  const int off0 = (yrel & 1) * IN0_PLANE_FLOATS + (yrel >> 1) * P0 + pxg * PX;
+  const int off1 = 2 * IN0_PLANE_FLOATS + y2r * WIN + pxg * PX + og * (S2 * RMAX);
+
+  float acc[DO][PX];
+#pragma unroll
+  for (int t = 0; t < DO; ++t)
+#pragma unroll
+    for (int i = 0; i < PX; ++i) acc[t][i] = 0.0f;
+
+  const bool warp_active = warp * 8 < npairs;
+  for (int it = 0; it < nchunks; ++it) {
+    const int s = it % STAGES;
+    const unsigned ph = (unsigned)(it / STAGES) & 1u;
+    mbar_wait(&sm.full[s], ph);
+    if (warp_active) {
+      const float *p0 = sm.stage[s] + off0;
+      const float *p1 = sm.stage[s] + off1;
+#pragma unroll 2
+      for (int cc = 0; cc < CC; ++cc) {
+        float a[PX], w[PX + S2 * (DO - 1)];
+        {
+          const float4 v0 = *reinterpret_cast<const float4 *>(p0 + cc * (R0H * P0));
+          const float4 v1 = *reinterpret_cast<const float4 *>(p0 + cc * (R0H * P0) + 4);
+          a[0] = v0.x; a[1] = v0.y; a[2] = v0.z; a[3] = v0.w;
+          a[4] = v1.x; a[5] = v1.y; a[6] = v1.z; a[7] = v1.w;
+        }
+#pragma unroll
+        for (int k = 0; k < (PX + S2 * (DO - 1)) / 4; ++k) {
+          const float4 v = *reinterpret_cast<const float4 *>(p1 + cc * (NY2 * WIN) + 4 * k);
+          w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w;
+        }
+#pragma unroll
+        for (int t = 0; t < DO; ++t)
+#pragma unroll
+          for (int i = 0; i < PX; ++i) acc[t][i] = fmaf(a[i], w[i + S2 * t], acc[t][i]);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&sm.empty[s]);
+  }
+
+  // ---------------- epilogue: each thread stores its 8 x 11 tile ----------------------------
+  if (active) {
+    const float denom = (float)C;  // sumelems = K*K*C with K = 1; true division as the reference
+    const int x = x0 + pxg * PX;
+#pragma unroll
+    for (int t = 0; t < DO; ++t) {
+      const int o = og == 0 ? t - RMAX : t;
+      if (o < -r || o > r || (og == 1 && t == 0)) continue;
+      float *dst = outb + ((size_t)(pidx * D + (o + r))) * plane_out + (size_t)y * W + x;
+      if (x < W)
+        *reinterpret_cast<float4 *>(dst) =
+            make_float4(acc[t][0] / denom, acc[t][1] / denom, acc[t][2] / denom, acc[t][3] / denom);
+      if (x + 4 < W)
+        *reinterpret_cast<float4 *>(dst + 4) =
+            make_float4(acc[t][4] / denom, acc[t][5] / denom, acc[t][6] / denom, acc[t][7] / denom);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Host side
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
+                                  const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+static int encode_map(CUtensorMap *m, const float *base, int rank, const cuuint64_t *dims,
+                      const cuuint64_t *strides_bytes, const cuuint32_t *box) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return UNFLOW_ECUDA; }
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, (void *)base, dims,
+                  strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return UNFLOW_ECUDA; }
+  return UNFLOW_OK;
+}
+
+bool corr_tiled_supported(const CorrGeom &g) {
+  return g.ks == 1 && g.s1 == 1 && g.s2 == ct::S2 && g.pad == g.md && g.ngr <= ct::RMAX &&
+         g.H % 2 == 0 && g.W % 4 == 0 && g.W >= ct::TX && g.H >= 2 && g.B <= 65535;
+}
+
+int corr_fwd_tiled(const float *in0, const float *in1, float *out, const CorrGeom &g, cudaStream_t s) {
+  using namespace ct;
+  if (((uintptr_t)in0 | (uintptr_t)in1 | (uintptr_t)out) & 15) {
+    set_error("correlation: pointers must be 16-byte aligned");
+    return UNFLOW_EINVAL;
+  }
+  const cuuint64_t B = g.B, C = g.C, H = g.H, W = g.W;
+  CUtensorMap map0, map1;
+  {
+    // in0 viewed as [B][C][H/2][2][W]; strides (bytes) of dims 1..4
+    cuuint64_t dims[5] = {W, 2, H / 2, C, B};
+    cuuint64_t str[4] = {W * 4, 2 * W * 4, H * W * 4, C * H * W * 4};
+    cuuint32_t box[5] = {P0, 1, R0H, CC, 1};
+    int rc = encode_map(&map0, in0, 5, dims, str, box);
+    if (rc) return rc;
+  }
+  {
+    cuuint64_t dims[4] = {W, H, C, B};
+    cuuint64_t str[3] = {W * 4, H * W * 4, C * H * W * 4};
+    cuuint32_t box[4] = {WIN, NY2, CC, 1};
+    int rc = encode_map(&map1, in1, 4, dims, str, box);
+    if (rc) return rc;
+  }
+  static bool attr_set = false;
+  const int smem_bytes = (int)sizeof(Smem);
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(corr_fwd_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         smem_bytes);
+    if (e != cudaSuccess) { set_error("correlation smem attribute: %s", cudaGetErrorString(e)); return UNFLOW_ECUDA; }
+    attr_set = true;
+  }
+  const int r = g.ngr;
+  const int y2_first = -((S2 * r + NY2 - 1) / NY2) * NY2;
+  const int y2_end = g.H + S2 * r;  // exclusive
+  dim3 grid(ceil_div(g.W, TX), ceil_div(y2_end - y2_first, NY2), g.B);
+  corr_fwd_tiled_kernel<<<grid, NTHREADS, smem_bytes, s>>>(map0, map1, out, g.C, g.H, g.W, r, y2_first);
+  count_launch();
+  return check_launch("correlation_fwd(tiled)");
+}
+
+int corr_bwd_tiled(const float *gout, const float *in0, const float *in1, float *g0, float *g1,
+                   const CorrGeom &g, cudaStream_t s) {
+  // TODO(round 1): tiled backward; the generic kernel is correct for every configuration.
+  return corr_bwd_generic(gout, in0, in1, g0, g1, g, s);
+}
+
+}  // namespace unflow

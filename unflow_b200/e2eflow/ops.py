@@ -1,0 +1,191 @@
+"""The four custom ops, same Python surface as the reference op module
+(/root/reference/src/e2eflow/ops.py:69-107), backed by libunflow.so through the C ABI.
+
+  correlation(first, second, **kwargs)   NCHW x NCHW -> NCHW cost volume (output 0 only)
+  backward_warp(images, flows)           NHWC bilinear gather, zero outside
+  forward_warp(flows)                    NHWC Gaussian splat count map [B,H,W,1]
+  downsample(images, scale)              NHWC box mean
+
+Gradient table (reference ops.py:80-107): BackwardWarp -> [None, dflow]; ForwardWarp ->
+[dflow]; Correlation -> [g0, g1]; Downsample -> not differentiable.
+
+Inputs must be float32 CUDA tensors; anything else raises -- there is no CPU fallback.
+``python -m unflow_b200.e2eflow.ops`` rebuilds the library (the reference's compile entry,
+ops.py:51-52).
+"""
+import torch
+
+from .. import _native
+from .._native import BORDER_CLAMP, BORDER_ZERO, check
+
+# Register ops for compilation here (reference ops.py:11)
+OP_NAMES = ['backward_warp', 'downsample', 'correlation', 'forward_warp']
+
+
+def compile(op=None):
+    """Reference ops.py:21-48 compiled one .so per op; here all ops live in libunflow.so."""
+    from .. import build
+    return build.build(force=True)
+
+
+def _prep(t, name, ndim=4):
+    if not torch.is_tensor(t):
+        raise TypeError("%s must be a torch tensor" % name)
+    if t.device.type != "cuda":
+        raise RuntimeError("%s must be a CUDA tensor: the UnFlow ops have GPU kernels only "
+                           "(as in the reference, which registers DEVICE_GPU kernels only)" % name)
+    if t.dtype != torch.float32:
+        raise TypeError("%s must be float32" % name)
+    if t.dim() != ndim:
+        raise ValueError("%s must have rank %d" % (name, ndim))
+    return t.contiguous()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+_CORR_DEFAULTS = dict(kernel_size=1, max_displacement=20, pad=20, stride_1=1, stride_2=2)
+
+
+def _corr_attrs(kwargs):
+    a = dict(_CORR_DEFAULTS)
+    for k, v in kwargs.items():
+        if k not in a:
+            raise TypeError("correlation() got an unexpected attribute %r" % k)
+        a[k] = int(v)
+    return (a['kernel_size'], a['max_displacement'], a['pad'], a['stride_1'], a['stride_2'])
+
+
+class _Correlation(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, in0, in1, attrs):
+        in0 = _prep(in0, "input_0")
+        in1 = _prep(in1, "input_1")
+        if in0.shape != in1.shape:
+            raise ValueError("Input shapes have to be the same")
+        B, C, H, W = in0.shape
+        import ctypes
+        oc, oh, ow = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        lib = _native.lib()
+        check(lib.unflow_correlation_out_shape(H, W, *attrs, ctypes.byref(oc), ctypes.byref(oh),
+                                               ctypes.byref(ow)), "correlation")
+        out = torch.empty(B, oc.value, oh.value, ow.value, device=in0.device, dtype=torch.float32)
+        with torch.cuda.device(in0.device):
+            check(lib.unflow_correlation_fwd(in0.data_ptr(), in1.data_ptr(), out.data_ptr(),
+                                             B, C, H, W, *attrs, _stream()), "correlation")
+        ctx.save_for_backward(in0, in1)
+        ctx.attrs = attrs
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        in0, in1 = ctx.saved_tensors
+        B, C, H, W = in0.shape
+        gout = gout.contiguous()
+        g0 = torch.empty_like(in0)
+        g1 = torch.empty_like(in1)
+        with torch.cuda.device(in0.device):
+            check(_native.lib().unflow_correlation_bwd(gout.data_ptr(), in0.data_ptr(), in1.data_ptr(),
+                                                       g0.data_ptr(), g1.data_ptr(), B, C, H, W,
+                                                       *ctx.attrs, _stream()), "correlation_grad")
+        return g0, g1, None
+
+
+def correlation(first, second, **kwargs):
+    return _Correlation.apply(first, second, _corr_attrs(kwargs))
+
+
+class _Warp(torch.autograd.Function):
+    """Bilinear gather; ``mode`` selects the op semantics (zero) or image_warp (clamp)."""
+
+    @staticmethod
+    def forward(ctx, images, flows, mode, image_grad):
+        images = _prep(images, "images")
+        flows = _prep(flows, "flows")
+        B, H, W, C = images.shape
+        if tuple(flows.shape) != (B, H, W, 2):
+            raise ValueError("flows must have shape [B,H,W,2] matching images")
+        out = torch.empty_like(images)
+        with torch.cuda.device(images.device):
+            check(_native.lib().unflow_backward_warp_fwd(images.data_ptr(), flows.data_ptr(),
+                                                         out.data_ptr(), B, H, W, C, mode, _stream()),
+                  "backward_warp")
+        ctx.save_for_backward(images, flows)
+        ctx.mode = mode
+        ctx.image_grad = image_grad
+        return out
+
+    @staticmethod
+    def backward(ctx, grad):
+        images, flows = ctx.saved_tensors
+        B, H, W, C = images.shape
+        grad = grad.contiguous()
+        dflow = torch.empty_like(flows)
+        want_dimg = ctx.image_grad and ctx.needs_input_grad[0]
+        dimg = torch.zeros_like(images) if want_dimg else None
+        with torch.cuda.device(images.device):
+            check(_native.lib().unflow_backward_warp_bwd(
+                grad.data_ptr(), images.data_ptr(), flows.data_ptr(), dflow.data_ptr(),
+                dimg.data_ptr() if want_dimg else None, B, H, W, C, ctx.mode, _stream()),
+                "backward_warp_grad")
+        return dimg, dflow, None, None
+
+
+def backward_warp(images, flows):
+    # reference ops.py:80-84: gradient for the flow only
+    return _Warp.apply(images, flows, BORDER_ZERO, False)
+
+
+def _image_warp(im, flow):
+    """core.image_warp.image_warp: clamped taps, gradients for image and flow."""
+    return _Warp.apply(im, flow, BORDER_CLAMP, True)
+
+
+class _ForwardWarp(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, flows):
+        flows = _prep(flows, "flows")
+        B, H, W, two = flows.shape
+        if two != 2:
+            raise ValueError("flows must have shape [B,H,W,2]")
+        out = torch.empty(B, H, W, 1, device=flows.device, dtype=torch.float32)
+        with torch.cuda.device(flows.device):
+            check(_native.lib().unflow_forward_warp_fwd(flows.data_ptr(), out.data_ptr(), B, H, W,
+                                                        _stream()), "forward_warp")
+        ctx.save_for_backward(flows)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad):
+        (flows,) = ctx.saved_tensors
+        B, H, W, _ = flows.shape
+        grad = grad.contiguous()
+        dflow = torch.empty_like(flows)
+        with torch.cuda.device(flows.device):
+            check(_native.lib().unflow_forward_warp_bwd(grad.data_ptr(), flows.data_ptr(),
+                                                        dflow.data_ptr(), B, H, W, _stream()),
+                  "forward_warp_grad")
+        return dflow
+
+
+def forward_warp(flows):
+    return _ForwardWarp.apply(flows)
+
+
+def downsample(images, scale=2):
+    """Not differentiable (reference ops.py:107)."""
+    images = _prep(images.detach() if torch.is_tensor(images) else images, "images")
+    B, H, W, C = images.shape
+    scale = int(scale)
+    if scale < 1 or H % scale != 0 or W % scale != 0:
+        raise ValueError("Input height and width must be divisible by scale")
+    out = torch.empty(B, H // scale, W // scale, C, device=images.device, dtype=torch.float32)
+    with torch.cuda.device(images.device):
+        check(_native.lib().unflow_downsample(images.data_ptr(), out.data_ptr(), B, H, W, C, scale,
+                                              _stream()), "downsample")
+    return out
+
+
+if __name__ == "__main__":
+    print(compile())
