@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""bench.py -- the UnFlow hot path on N B200s (one process per GPU).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # CPU restatement of the reference
+
+Workload ("step" = one pass of the hot path over one batch of synthetic input): the full
+unsupervised FlowNetC training step of BASELINE.json configs[2]/[3] -- bidirectional FlowNetC
+forward (correlation d=20), 5-level census / fb-occlusion / 2nd-order-smoothness loss, backward,
+gradient all-reduce (N>1) and Adam update -- on 4 synthetic KITTI-shaped 384x1280 pairs PER GPU
+(weak scaling: global batch 4*N; configs[3] is N=8 -> batch 32).  configs[1] (forward only) is a
+subset of this step and is covered by the parity tests.
+
+One JSON line on rank 0:
+  value   frame-pairs/s, whole job, inputs already resident in HBM when the timed region starts
+  e2e     the same metric through the public API (e2eflow ... Trainer.step) with the inputs in
+          pinned HOST memory: H2D copy of both frames and D2H read of the loss inside every step
+  roofline  correlation forward kernel: algorithmic bytes / CUDA-event time measured live inside
+          the timed region, against the measured HBM peak (MEASURED_PEAKS.json); extra fields give
+          the fp32-FMA fraction and the same figures for the other hand-written kernels
+  cpu_baseline  (N=1) the CPU oracle (a restatement of the reference -- the reference itself has
+          no CPU path for this graph) on a bounded sample, timed on the host cores
+  clocks  nvidia-smi SM clock / throttle reasons sampled during the timed region
+Timing: CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks.
+L2: one step streams several GB of activations (>> 126 MB L2), so no explicit flush is needed.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+import synth  # noqa: E402
+
+H, W, PER_GPU_BATCH = 384, 1280, 4
+METRIC = "frame-pairs/s at 384x1280 FlowNetC"
+
+
+def load_peaks():
+    peaks = {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0, "_source": "fallback (B200_PROFILING.md)"}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            peaks.update(json.load(fh))
+            peaks["_source"] = "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        pass
+    return peaks
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons, sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(smax) if smax else None, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def make_batch(rank, pinned):
+    im1, im2, _ = synth.image_pair(PER_GPU_BATCH, H, W, seed=1234 + rank)
+    if pinned:
+        im1, im2 = im1.pin_memory(), im2.pin_memory()
+    return im1, im2
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+def run_ours(args):
+    from unflow_b200 import _native
+    from unflow_b200.e2eflow import ops
+    from unflow_b200.e2eflow.core.train import Trainer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node %d" % args.gpus)
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _native.lib()  # fail loudly if libunflow.so is missing
+
+    params = dict(synth.KITTI_PARAMS, learning_rate=1.0e-5)
+    trainer = Trainer(params, synth.KITTI_NORMALIZATION, dev, seed=1234)
+    trainer.broadcast_variables(0)
+    h_im1, h_im2 = make_batch(rank, pinned=True)
+    d_im1, d_im2 = h_im1.to(dev), h_im2.to(dev)
+    loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def resident_step():
+        return trainer.step(d_im1, d_im2)
+
+    def e2e_step():
+        a = h_im1.to(dev, non_blocking=True)
+        b = h_im2.to(dev, non_blocking=True)
+        loss = trainer.step(a, b)
+        loss_host.copy_(loss, non_blocking=True)
+        return loss
+
+    def timed(fn, steps, hook=False):
+        barrier()
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        _native.reset_launch_count()
+        if hook:
+            ops.kernel_timer.enable()
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record()
+        for _ in range(steps):
+            fn()
+        end.record()
+        barrier()
+        launches = _native.launch_count()
+        ktimes = ops.kernel_timer.collect() if hook else {}
+        clocks = sampler.stop() if rank == 0 else None
+        ms = torch.tensor([start.elapsed_time(end)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), launches, ktimes, clocks
+
+    for _ in range(args.warmup):
+        resident_step()
+    ms, launches, ktimes, clocks = timed(resident_step, args.steps, hook=True)
+    for _ in range(min(args.warmup, 2)):
+        e2e_step()
+    ms_e2e, _, _, _ = timed(e2e_step, args.steps)
+    torch.cuda.synchronize()
+    final_loss = float(loss_host.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = load_peaks()
+    pairs = PER_GPU_BATCH * world * args.steps
+    value = pairs / (ms * 1e-3)
+    e2e = pairs / (ms_e2e * 1e-3)
+    fma_peak = 148 * 128 * 2 * peaks["sm_max_mhz"] * 1e6 / 1e12
+
+    def roof(name, nbytes, flops=None):
+        t = ktimes.get(name)
+        if not t:
+            return None
+        avg = sum(t) / len(t) * 1e-3
+        r = {"kernel": name, "bound": "hbm", "launches_timed": len(t), "avg_us": round(avg * 1e6, 2),
+             "achieved": round(nbytes / avg / 1e9, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
+             "frac": round(nbytes / avg / 1e9 / peaks["hbm_gbs"], 4), "peak_source": peaks["_source"],
+             "algorithmic_bytes": nbytes, "traffic": TRAFFIC.get(name)}
+        if flops:
+            r["fp32_tflops"] = round(flops / avg / 1e12, 2)
+            r["fma_frac"] = round(flops / avg / 1e12 / fma_peak, 4)
+        return r
+
+    Bc, C, hc, wc, D2 = PER_GPU_BATCH, 256, H // 8, W // 8, 441
+    corr_bytes = 4 * Bc * hc * wc * (2 * C + D2)
+    corr_flops = 2 * Bc * hc * wc * C * D2
+    npx0 = PER_GPU_BATCH * (H // 4) * (W // 4)
+    roofs = [roof("correlation_fwd", corr_bytes, corr_flops),
+             roof("correlation_bwd", 4 * Bc * hc * wc * (D2 + 4 * C), 2 * corr_flops),
+             roof("level_loss_fwd_%dx%d" % (H // 4, W // 4), (44 + 16) * npx0),
+             roof("level_loss_bwd_%dx%d" % (H // 4, W // 4), (60 + 16) * npx0)]
+    roofs = [r for r in roofs if r]
+    line = {
+        "metric": METRIC, "value": round(value, 3), "unit": "frame-pairs/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic (seeded smooth images + smooth <=8px flow + noise; random-init weights)",
+        "config": {"workload": "BASELINE configs[2]/[3]: FlowNetC full unsupervised training step "
+                               "(bidir forward, corr d=20, 5-level census/fb/2nd-order loss, backward, "
+                               "grad all-reduce, Adam), 384x1280, batch 4 per GPU",
+                   "global_batch": PER_GPU_BATCH * world, "parallelism": "dp%d" % world,
+                   "l2": "inputs+activations per step >> 126 MB L2 (no flush needed)",
+                   "conv_precision": "fp32 (cuDNN, TF32 disabled)"},
+        "e2e": {"value": round(e2e, 3), "unit": "frame-pairs/s", "ms_per_step": round(ms_e2e / args.steps, 3),
+                "h2d_bytes_per_step": 2 * h_im1.numel() * 4, "d2h_bytes_per_step": 4},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "final_loss": final_loss,
+    }
+    if roofs:
+        line["roofline"] = roofs[0]
+        line["rooflines_other"] = roofs[1:]
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(steps=1, warmup=0)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# measured once with `ncu --set full` (profiles/): dram__bytes_read.sum + dram__bytes_write.sum per launch
+TRAFFIC = {}
+try:
+    with open(os.path.join(ROOT, "profiles", "dram_traffic.json")) as _fh:
+        TRAFFIC = json.load(_fh)
+except Exception:
+    pass
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the oracle (CPU restatement of the reference) on the host cores
+# ---------------------------------------------------------------------------------------------
+def cpu_step_fn():
+    from oracle import flownet as ofl, unsupervised as oun, ops as oops
+    torch.set_num_threads(os.cpu_count() or 1)
+    tfv = ofl.init_variables('C', False, seed=1234)
+    for k in tfv:
+        tfv[k].requires_grad_(True)
+    im1, im2, _ = synth.image_pair(1, H, W, seed=1234)
+
+    def step():
+        for v in tfv.values():
+            v.grad = None
+        loss = oun.unsupervised_loss(tfv, (im1, im2), synth.KITTI_PARAMS, synth.KITTI_NORMALIZATION,
+                                     augment=False)
+        loss.backward()
+        return float(loss)
+
+    return step, oops.num_threads()
+
+
+def cpu_baseline(steps=1, warmup=0):
+    step, nthreads = cpu_step_fn()
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": round(1.0 / dt, 4), "unit": "frame-pairs/s", "cores": int(os.cpu_count() or 1),
+            "threads": int(max(nthreads, torch.get_num_threads())), "kind": "port",
+            "sample": "%d step(s) of 1 pair 384x1280: FlowNetC fwd + 5-level loss + backward "
+                      "(no optimiser), CPU restatement of the reference in oracle/ (the reference "
+                      "has no CPU kernels for this graph)" % steps,
+            "seconds_per_pair": round(dt, 3)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    step, nthreads = cpu_step_fn()
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    total = time.perf_counter() - t0
+    value = args.steps / total
+    cb = {"value": round(value, 4), "unit": "frame-pairs/s", "cores": int(os.cpu_count() or 1),
+          "threads": int(max(nthreads, torch.get_num_threads())), "kind": "port",
+          "sample": "each step = 1 pair 384x1280 (FlowNetC fwd + 5-level loss + backward) on the host "
+                    "cores; CPU restatement of the reference (oracle/), the reference itself has no "
+                    "CPU path (SURVEY.md R1)"}
+    line = {"impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": "frame-pairs/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(total / args.steps * 1e3, 2), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "BASELINE configs[2]/[3] step graph, bounded sample: 1 pair per step "
+                                   "on the host CPU", "global_batch": 1, "parallelism": "cpu"},
+            "cpu_baseline": cb,
+            "e2e": {"value": round(value, 4), "unit": "frame-pairs/s", "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if args.warmup < 3:
+            args.warmup = 3
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -110,6 +110,59 @@ int unflow_forward_warp_bwd(const float *grad, const float *flows, float *dflow,
 int unflow_downsample(const float *images, float *out, int B, int H, int W, int C, int scale,
                       void *stream);
 
+/* ------------------------------------------------------------------------
+ * Fused per-level loss  (reference: compute_losses, src/e2eflow/core/losses.py:16-87, with
+ * image_warp image_warp.py:4-76, ternary_loss :90-122, fb occlusion :38-56, second_order_loss
+ * :258-295, smoothness_loss :206-255, charbonnier_loss :298-322, masks :325-366).
+ * The reference has no native entry point here (it is a graph of TF ops); this is the fused
+ * replacement the Python mirror (e2eflow.core.losses.compute_losses) calls.
+ *   im1, im2            [B,h,w,3] in [0,1]
+ *   flow_fw, flow_bw    [B,h,w,2] in pixels (already scaled)
+ *   border_mask         [B,h,w,1] or NULL (NULL -> create_outgoing_mask of each flow)
+ *   fwarp_fw, fwarp_bw  [B,h,w,1] outputs of unflow_forward_warp_fwd for the two flows; only
+ *                       needed when mask_occlusion == 2 ('disocc') or the sym term is requested
+ *   losses              [8] out: sym, occ, photo, grad, smooth_1st, smooth_2nd, fb, ternary
+ *                       (UNFLOW_TERM_* order; terms not requested are written as 0)
+ *   saved               [4*B*h*w] out, consumed by the backward pass (needed for ternary)
+ *   masks_out           optional [2*B*h*w] out: mask_fw, mask_bw (binary; for parity tests)
+ *   workspace           unflow_level_loss_workspace_bytes(B,h,w) bytes of scratch
+ *   mask_occlusion      0 '' / 1 'fb' / 2 'disocc';  max_distance 1..3 (census patch 3/5/7)
+ *   terms               bit k set = compute term k.  The 'grad' term (bit 3) is not fused: EINVAL.
+ * Backward: grad_losses [8] (device) = dL/dloss_k -> dflow_fw, dflow_bw [B,h,w,2] (zeroed by the
+ * launcher, accumulated with atomics).  Masks / occlusion maps carry no gradient (tf.cast).
+ * ---------------------------------------------------------------------- */
+#define UNFLOW_TERM_SYM 0
+#define UNFLOW_TERM_OCC 1
+#define UNFLOW_TERM_PHOTO 2
+#define UNFLOW_TERM_GRAD 3
+#define UNFLOW_TERM_SMOOTH_1ST 4
+#define UNFLOW_TERM_SMOOTH_2ND 5
+#define UNFLOW_TERM_FB 6
+#define UNFLOW_TERM_TERNARY 7
+size_t unflow_level_loss_workspace_bytes(int B, int h, int w);
+int unflow_level_loss_fwd(const float *im1, const float *im2, const float *flow_fw,
+                          const float *flow_bw, const float *border_mask, const float *fwarp_fw,
+                          const float *fwarp_bw, float *losses, float *saved, float *masks_out,
+                          void *workspace, int B, int h, int w, int mask_occlusion,
+                          int max_distance, unsigned terms, void *stream);
+int unflow_level_loss_bwd(const float *grad_losses, const float *im1, const float *im2,
+                          const float *flow_fw, const float *flow_bw, const float *border_mask,
+                          const float *fwarp_fw, const float *fwarp_bw, const float *saved,
+                          float *dflow_fw, float *dflow_bw, int B, int h, int w,
+                          int mask_occlusion, int max_distance, unsigned terms, void *stream);
+
+/* ------------------------------------------------------------------------
+ * Fused Adam update on the flat parameter buffer (reference: tf.train.AdamOptimizer(beta1=0.9,
+ * beta2=0.999), src/e2eflow/core/train.py:151-152; gradient averaging train.py:388-422 becomes
+ * one NCCL all-reduce on `grads` before this call).  TF update rule:
+ *   lr_t = lr*sqrt(1-beta2^step)/(1-beta1^step);  p -= lr_t * m / (sqrt(v) + eps).
+ * grads are multiplied by grad_scale first (1/world_size when the all-reduce summed); when
+ * zero_grad != 0 the gradient buffer is cleared in the same pass.  n must be a multiple of 4.
+ * ---------------------------------------------------------------------- */
+int unflow_adam_step(float *params, float *grads, float *m, float *v, long long n, float lr,
+                     float beta1, float beta2, float eps, long long step, float grad_scale,
+                     int zero_grad, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -87,8 +87,50 @@ def test_unsupervised_loss_vs_oracle(spec, hw):
     close(got_bw, want_bw, rtol=1e-4, atol_rel=1e-4)
     want_loss.backward()
     got_loss.backward()
+    # Gradients: the loss contains hard masks (fb occlusion `>`), so a 1e-7 difference in a flow
+    # value can flip a mask pixel and move every gradient by O(1/pixels): compare in
+    # the L2 norm per variable instead of element by element.
     for scope in v.kinds:
         w, b = v.weights(scope)
-        gw = tfv[scope + '/weights'].grad.permute(3, 2, 0, 1)
-        close(w.grad, gw, rtol=5e-3, atol_rel=2e-3, msg=scope + '/weights')
-        close(b.grad, tfv[scope + '/biases'].grad, rtol=5e-3, atol_rel=2e-3, msg=scope + '/biases')
+        for got, want, name in ((w.grad.cpu(), tfv[scope + '/weights'].grad.permute(3, 2, 0, 1), '/weights'),
+                                (b.grad.cpu(), tfv[scope + '/biases'].grad, '/biases')):
+            err = float((got - want).norm() / want.norm().clamp_min(1e-20))
+            assert err < 5e-3, "%s%s: relative L2 gradient error %.3e" % (scope, name, err)
+
+
+def test_adam_kernel_matches_tf_rule():
+    """csrc/adam.cu against the TF AdamOptimizer update written out in float64."""
+    from unflow_b200 import _native
+    n = 4096 + 4
+    g = torch.Generator().manual_seed(0)
+    p = torch.randn(n, generator=g)
+    grads = [torch.randn(n, generator=g) for _ in range(3)]
+    pd, m, v = p.double(), torch.zeros(n, dtype=torch.float64), torch.zeros(n, dtype=torch.float64)
+    pc, gc = p.cuda(), torch.zeros(n, device="cuda")
+    mc, vc = torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    lr, b1, b2, eps = 1e-3, 0.9, 0.999, 1e-8
+    for t, gr in enumerate(grads, 1):
+        gc.copy_(gr * 2.0)                                   # "sum over 2 ranks", scale 0.5
+        _native.check(_native.lib().unflow_adam_step(pc.data_ptr(), gc.data_ptr(), mc.data_ptr(), vc.data_ptr(),
+                                                     n, lr, b1, b2, eps, t, 0.5, 1,
+                                                     torch.cuda.current_stream().cuda_stream), "adam")
+        assert float(gc.abs().max()) == 0.0                  # gradient cleared in the same pass
+        gd = gr.double()
+        m = b1 * m + (1 - b1) * gd
+        v = b2 * v + (1 - b2) * gd * gd
+        lr_t = lr * (1 - b2 ** t) ** 0.5 / (1 - b1 ** t)
+        pd = pd - lr_t * m / (v.sqrt() + eps)
+    np.testing.assert_allclose(pc.cpu().numpy(), pd.float().numpy(), rtol=1e-5, atol=1e-6)
+
+
+def test_trainer_step_decreases_loss_and_counts_launches():
+    from unflow_b200 import _native
+    from unflow_b200.e2eflow.core.train import Trainer
+    params = dict(synth.KITTI_PARAMS, learning_rate=1e-4)
+    tr = Trainer(params, synth.KITTI_NORMALIZATION, "cuda", seed=3)
+    im1, im2, _ = synth.image_pair(2, 128, 256, seed=8)
+    im1, im2 = im1.cuda(), im2.cuda()
+    _native.reset_launch_count()
+    losses = [float(tr.step(im1, im2)) for _ in range(6)]
+    assert _native.launch_count() > 6 * 10
+    assert all(np.isfinite(losses)) and losses[-1] < losses[0]

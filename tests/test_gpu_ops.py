@@ -69,6 +69,9 @@ CORR_CASES = [
     dict(shape=(2, 32, 12, 40), kernel_size=1, max_displacement=20, pad=20, stride_1=1, stride_2=2),
     dict(shape=(1, 64, 48, 64), kernel_size=1, max_displacement=20, pad=20, stride_1=1, stride_2=2),
     dict(shape=(1, 8, 6, 36), kernel_size=1, max_displacement=7, pad=7, stride_1=1, stride_2=2),
+    # tiled backward: two channel slabs (one partial), H % 4 != 0, partial column tile
+    dict(shape=(1, 130, 6, 24), kernel_size=1, max_displacement=20, pad=20, stride_1=1, stride_2=2),
+    dict(shape=(2, 40, 14, 72), kernel_size=1, max_displacement=8, pad=8, stride_1=1, stride_2=2),
 ]
 
 

@@ -169,3 +169,10 @@ def test_unsupervised_loss_rejects_augment():
     from unflow_b200.e2eflow.core.unsupervised import unsupervised_loss
     with pytest.raises(NotImplementedError):
         unsupervised_loss((torch.zeros(1, 64, 64, 3),) * 2, {}, normalization=([0, 0, 0], 1.0))
+
+
+def test_every_product_module_imports_without_gpu():
+    import importlib
+    for m in ("ops", "core.image_warp", "core.losses", "core.fused_loss", "core.flownet",
+              "core.unsupervised", "core.util", "core.tf_image"):
+        importlib.import_module("unflow_b200.e2eflow." + m)

@@ -339,10 +339,254 @@ int corr_fwd_tiled(const float *in0, const float *in1, float *out, const CorrGeo
   return check_launch("correlation_fwd(tiled)");
 }
 
+// ------------------------------------------------------------------------------------------
+// Backward kernels.  Both gradients have the form
+//
+//   OUT[c,y,x] = (1/C) * sum_{p,o} G(p,o;y,x) * SRC[c, y+2p, x+2o]
+//
+//   g0 (CorrelateDataBackward0, reference :120-181): SRC = in1, G = gout[(p,o)][y][x]
+//   g1 (CorrelateDataBackward1, reference :184-248): SRC = in0, G = gout[(-p,-o)][y+2p][x+2o]
+//
+// i.e. 441 taps per output element, the tap weight shared by all C channels.  Tiling:
+//   * CTA = (image b, 128-channel slab, row pair {y, y+2}, 64 columns); 8 consumer warps, one per
+//     8-pixel group, + 1 TMA producer warp.  lane <-> 4 channels {lane, lane+32, lane+64, lane+96},
+//     so every tap weight is a shared-memory BROADCAST and every SRC load is a conflict-free
+//     128-bit load (channel pitch 108 floats == 12 mod 32).
+//   * register tile = 2 rows x 4 channels x 8 pixels (64 accumulators).  The SRC window of a
+//     channel slides by 2 columns per displacement o: it is kept in a 12-float rotating register
+//     window refilled with ONE 128-bit load per channel per two displacements.
+//   * pipeline stage = one SRC row y2 (box 108 x 128 channels) + the two tap-weight tiles that
+//     use it (row y with p=(y2-y)/2, row y+2 with p-1): each SRC row is staged once per row pair.
+// ------------------------------------------------------------------------------------------
+namespace cb {
+constexpr int RMAX = 10, S2 = 2;
+constexpr int NPXG = 8, PXW = 8, TXB = NPXG * PXW;     // 64 output columns per CTA
+constexpr int CCH = 128;                               // channels per CTA
+constexpr int SW = TXB + 2 * S2 * RMAX;                // 104 SRC columns needed
+constexpr int PITCH = 108;                             // SRC channel pitch (floats)
+constexpr int STAGES = 3;
+constexpr int NTHREADS = (NPXG + 1) * 32;
+constexpr int DMAX = 2 * RMAX + 1;
+constexpr int S_FLOATS = CCH * PITCH;                  // 13824
+constexpr int G0_FLOATS = DMAX * TXB;                  // 1344  (g0: [o][64])
+constexpr int G1_FLOATS = 2208;                        // >= DMAX*SW = 2184 (g1: [o][104]), 128 B multiple
+template <bool G1> struct Cfg {
+  static constexpr int GW = G1 ? SW : TXB;
+  static constexpr int G_FLOATS = G1 ? G1_FLOATS : G0_FLOATS;
+  static constexpr int STAGE_FLOATS = S_FLOATS + 2 * G_FLOATS;
+};
+template <bool G1> struct Smem {
+  float stage[STAGES][Cfg<G1>::STAGE_FLOATS];
+  unsigned long long full[STAGES];
+  unsigned long long empty[STAGES];
+};
+static_assert((S_FLOATS * 4) % 128 == 0 && (G0_FLOATS * 4) % 128 == 0 && (G1_FLOATS * 4) % 128 == 0, "");
+}  // namespace cb
+
+template <bool G1>
+__global__ void __launch_bounds__(cb::NTHREADS, 1)
+corr_bwd_tiled_kernel(const __grid_constant__ CUtensorMap map_src,   // SRC [B][C][H][W], box (108,1,128,1)
+                      const __grid_constant__ CUtensorMap map_g,     // gout [B][D*D][H][W], box (GW,1,D,1)
+                      float *__restrict__ outp, int C, int H, int W, int r, int slabs) {
+  using namespace cb;
+  using CF = Cfg<G1>;
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  Smem<G1> &sm = *reinterpret_cast<Smem<G1> *>(smem_raw);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int x0 = blockIdx.x * TXB;
+  const int ya = (blockIdx.y >> 1) * 4 + (blockIdx.y & 1), yb = ya + 2;   // row pair
+  const int b = blockIdx.z / slabs, c0 = (blockIdx.z % slabs) * CCH;
+  const int D = 2 * r + 1;
+  const int joff = S2 * (RMAX - r);        // column offset of displacement o=-r inside the staged window
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], NPXG); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  // stages: SRC rows y2 = ya - 2r + 2k, k = 0 .. 2r+1, inside the image
+  const int nk = 2 * r + 2;
+
+  if (warp == NPXG) {
+    if (lane == 0) {
+      int it = 0;
+      for (int k = 0; k < nk; ++k) {
+        const int y2 = ya - S2 * r + S2 * k;
+        if (y2 < 0 || y2 >= H) continue;
+        const int pa = k - r, pb = pa - 1;                 // displacement rows used by ya / yb
+        const bool va = pa <= r && ya < H, vb = pb >= -r && yb < H;
+        const int s = it % STAGES;
+        const unsigned ph = (unsigned)(it / STAGES) & 1u;
+        mbar_wait(&sm.empty[s], ph ^ 1u);
+        const unsigned bytes = (unsigned)(S_FLOATS + (va ? D * CF::GW : 0) + (vb ? D * CF::GW : 0)) * 4u;
+        mbar_arrive_expect_tx(&sm.full[s], bytes);
+        float *st = sm.stage[s];
+        tma_load_4d(st, &map_src, &sm.full[s], x0 - S2 * RMAX, y2, c0, b);
+        if (!G1) {
+          if (va) tma_load_4d(st + S_FLOATS, &map_g, &sm.full[s], x0, ya, (pa + r) * D, b);
+          if (vb) tma_load_4d(st + S_FLOATS + CF::G_FLOATS, &map_g, &sm.full[s], x0, yb, (pb + r) * D, b);
+        } else {
+          if (va) tma_load_4d(st + S_FLOATS, &map_g, &sm.full[s], x0 - S2 * RMAX, y2, (r - pa) * D, b);
+          if (vb) tma_load_4d(st + S_FLOATS + CF::G_FLOATS, &map_g, &sm.full[s], x0 - S2 * RMAX, y2, (r - pb) * D, b);
+        }
+        ++it;
+      }
+    }
+    return;
+  }
+
+  const int pxg = warp;
+  const bool warp_active = x0 + pxg * PXW < W;
+  float acc[2][4][PXW];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc)
+#pragma unroll
+      for (int i = 0; i < PXW; ++i) acc[a][cc][i] = 0.0f;
+
+  int it = 0;
+  for (int k = 0; k < nk; ++k) {
+    const int y2 = ya - S2 * r + S2 * k;
+    if (y2 < 0 || y2 >= H) continue;
+    const int pa = k - r, pb = pa - 1;
+    const bool va = pa <= r && ya < H, vb = pb >= -r && yb < H;
+    const int s = it % STAGES;
+    const unsigned ph = (unsigned)(it / STAGES) & 1u;
+    mbar_wait(&sm.full[s], ph);
+    if (warp_active) {
+      const float *S = sm.stage[s] + lane * PITCH + pxg * PXW + joff;
+      const float *Ga = sm.stage[s] + S_FLOATS;
+      const float *Gb = Ga + CF::G_FLOATS;
+      // rotating 12-float window per channel: column col (relative to S) lives in slot col % 12
+      float win[4][12];
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        const float4 v0 = *reinterpret_cast<const float4 *>(S + cc * 32 * PITCH);
+        const float4 v1 = *reinterpret_cast<const float4 *>(S + cc * 32 * PITCH + 4);
+        win[cc][0] = v0.x; win[cc][1] = v0.y; win[cc][2] = v0.z; win[cc][3] = v0.w;
+        win[cc][4] = v1.x; win[cc][5] = v1.y; win[cc][6] = v1.z; win[cc][7] = v1.w;
+      }
+#pragma unroll
+      for (int tp = 0; tp <= RMAX; ++tp) {       // displacement pairs t = 2tp, 2tp+1
+        if (2 * tp < D) {
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) {
+            const float4 v = *reinterpret_cast<const float4 *>(S + cc * 32 * PITCH + 4 * tp + 8);
+            win[cc][(4 * tp + 8) % 12] = v.x; win[cc][(4 * tp + 9) % 12] = v.y;
+            win[cc][(4 * tp + 10) % 12] = v.z; win[cc][(4 * tp + 11) % 12] = v.w;
+          }
+#pragma unroll
+          for (int tt = 0; tt < 2; ++tt) {
+            const int t = 2 * tp + tt;
+            if (t < D) {
+#pragma unroll
+              for (int a = 0; a < 2; ++a) {
+                if (a == 0 ? va : vb) {
+                  const float *G = a == 0 ? Ga : Gb;
+                  float g[PXW];
+                  if (!G1) {
+                    const float4 g0 = *reinterpret_cast<const float4 *>(G + t * TXB + pxg * PXW);
+                    const float4 g1 = *reinterpret_cast<const float4 *>(G + t * TXB + pxg * PXW + 4);
+                    g[0] = g0.x; g[1] = g0.y; g[2] = g0.z; g[3] = g0.w;
+                    g[4] = g1.x; g[5] = g1.y; g[6] = g1.z; g[7] = g1.w;
+                  } else {
+                    const float *gp = G + (D - 1 - t) * SW + pxg * PXW + joff + 2 * t;
+#pragma unroll
+                    for (int h2 = 0; h2 < 4; ++h2) {
+                      const float2 gv = *reinterpret_cast<const float2 *>(gp + 2 * h2);
+                      g[2 * h2] = gv.x; g[2 * h2 + 1] = gv.y;
+                    }
+                  }
+#pragma unroll
+                  for (int cc = 0; cc < 4; ++cc)
+#pragma unroll
+                    for (int i = 0; i < PXW; ++i)
+                      acc[a][cc][i] = fmaf(g[i], win[cc][(2 * t + i) % 12], acc[a][cc][i]);
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&sm.empty[s]);
+    ++it;
+  }
+
+  if (warp_active) {
+    const float denom = (float)C;
+    const int x = x0 + pxg * PXW;
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      const int y = a == 0 ? ya : yb;
+      if (y >= H) continue;
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        const int c = c0 + lane + 32 * cc;
+        if (c >= C) continue;
+        float *dst = outp + (((size_t)b * C + c) * H + y) * W + x;
+        *reinterpret_cast<float4 *>(dst) = make_float4(acc[a][cc][0] / denom, acc[a][cc][1] / denom,
+                                                       acc[a][cc][2] / denom, acc[a][cc][3] / denom);
+        if (x + 4 < W)
+          *reinterpret_cast<float4 *>(dst + 4) = make_float4(acc[a][cc][4] / denom, acc[a][cc][5] / denom,
+                                                             acc[a][cc][6] / denom, acc[a][cc][7] / denom);
+      }
+    }
+  }
+}
+
+bool corr_bwd_tiled_supported(const CorrGeom &g) {
+  return corr_tiled_supported(g) && g.ngr % 2 == 0 && g.ngr >= 2 && (long long)g.B * ceil_div(g.C, cb::CCH) <= 65535;
+}
+
+template <bool G1>
+static int launch_bwd(const float *src, const float *gout, float *outp, const CorrGeom &g, cudaStream_t s) {
+  using namespace cb;
+  const cuuint64_t B = g.B, C = g.C, H = g.H, W = g.W, D = g.ngw;
+  CUtensorMap map_src, map_g;
+  {
+    cuuint64_t dims[4] = {W, H, C, B};
+    cuuint64_t str[3] = {W * 4, H * W * 4, C * H * W * 4};
+    cuuint32_t box[4] = {PITCH, 1, CCH, 1};
+    int rc = encode_map(&map_src, src, 4, dims, str, box);
+    if (rc) return rc;
+  }
+  {
+    cuuint64_t dims[4] = {W, H, D * D, B};
+    cuuint64_t str[3] = {W * 4, H * W * 4, D * D * H * W * 4};
+    cuuint32_t box[4] = {(cuuint32_t)Cfg<G1>::GW, 1, (cuuint32_t)D, 1};
+    int rc = encode_map(&map_g, gout, 4, dims, str, box);
+    if (rc) return rc;
+  }
+  static bool attr_set = false;
+  const int smem_bytes = (int)sizeof(Smem<G1>);
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(corr_bwd_tiled_kernel<G1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         smem_bytes);
+    if (e != cudaSuccess) { set_error("correlation_grad smem attribute: %s", cudaGetErrorString(e)); return UNFLOW_ECUDA; }
+    attr_set = true;
+  }
+  const int slabs = ceil_div(g.C, CCH);
+  dim3 grid(ceil_div(g.W, TXB), ceil_div(g.H, 4) * 2, g.B * slabs);
+  corr_bwd_tiled_kernel<G1><<<grid, NTHREADS, smem_bytes, s>>>(map_src, map_g, outp, g.C, g.H, g.W, g.ngr, slabs);
+  count_launch();
+  return check_launch(G1 ? "correlation_bwd1(tiled)" : "correlation_bwd0(tiled)");
+}
+
 int corr_bwd_tiled(const float *gout, const float *in0, const float *in1, float *g0, float *g1,
                    const CorrGeom &g, cudaStream_t s) {
-  // TODO(round 1): tiled backward; the generic kernel is correct for every configuration.
-  return corr_bwd_generic(gout, in0, in1, g0, g1, g, s);
+  if (!corr_bwd_tiled_supported(g)) return corr_bwd_generic(gout, in0, in1, g0, g1, g, s);
+  if (((uintptr_t)in0 | (uintptr_t)in1 | (uintptr_t)gout | (uintptr_t)g0 | (uintptr_t)g1) & 15) {
+    set_error("correlation_grad: pointers must be 16-byte aligned");
+    return UNFLOW_EINVAL;
+  }
+  int rc = launch_bwd<false>(in1, gout, g0, g, s);
+  if (rc) return rc;
+  return launch_bwd<true>(in0, gout, g1, g, s);
 }
 
 }  // namespace unflow

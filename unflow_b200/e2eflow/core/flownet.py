@@ -27,6 +27,25 @@ from . import tf_image
 FLOW_SCALE = 5.0
 
 
+def set_conv_precision(mode='fp32'):
+    """Arithmetic of the cuDNN conv / deconv stacks.
+
+    'fp32' (default): exact float32 multiply-accumulate, what the reference's TF1 graph computes
+    (torch enables TF32 tensor-core convolutions by default, which costs ~1e-3 relative on the
+    flow fields and breaks the 1e-4 parity bar -- so it is switched off here).
+    'tf32': let cuDNN round conv inputs to TF32 (10-bit mantissa); an explicitly reduced
+    precision mode, never used for parity or for the headline benchmark.
+    The flag is process-global because autograd runs the backward convolutions later."""
+    if mode not in ('fp32', 'tf32'):
+        raise ValueError("conv precision must be 'fp32' or 'tf32'")
+    torch.backends.cudnn.allow_tf32 = (mode == 'tf32')
+    torch.backends.cuda.matmul.allow_tf32 = (mode == 'tf32')
+    return mode
+
+
+set_conv_precision(__import__('os').environ.get('UNFLOW_CONV_PRECISION', 'fp32'))
+
+
 # ---------------------------------------------------------------------------------------------
 # Variables
 # ---------------------------------------------------------------------------------------------
@@ -176,9 +195,25 @@ class FlowNetVariables(nn.Module):
         """slim.l2_regularizer(0.0004) on every ``weights`` variable (flownet.py:176,200,218):
         sum_v scale * sum(v^2) / 2  ==  tf.losses.get_regularization_loss()."""
         ws = [self.params[_key(n + '/weights')] for n in self.kinds]
-        sq = torch._foreach_norm(ws, 2)
-        total = torch.stack(sq).square().sum()
-        return (0.5 * scale) * total
+        return _L2Reg.apply(float(scale), *ws)
+
+
+class _L2Reg(torch.autograd.Function):
+    """0.5 * scale * sum_k ||w_k||^2 with multi-tensor kernels (a handful of launches instead of
+    three per variable)."""
+
+    @staticmethod
+    def forward(ctx, scale, *ws):
+        ctx.scale = scale
+        ctx.save_for_backward(*ws)
+        norms = torch._foreach_norm([w.detach() for w in ws], 2)
+        return ((0.5 * scale) * torch.stack(norms).double().square().sum()).float()
+
+    @staticmethod
+    def backward(ctx, gout):
+        ws = ctx.saved_tensors
+        grads = torch._foreach_mul([w.detach() for w in ws], gout * ctx.scale)
+        return (None,) + tuple(g if w.requires_grad else None for g, w in zip(grads, ws))
 
 
 _default_store = {}

@@ -40,13 +40,24 @@ def compute_losses(im1, im2, flow_fw, flow_bw,
     ``_fused`` (private): force (True) / forbid (False) the fused CUDA path; None = auto.
     """
     from . import fused_loss
+    terms = list(fused_loss.TERM_ORDER) if _terms is None else list(_terms)
     use_fused = fused_loss.available(im1, flow_fw, mask_occlusion, data_max_distance) \
         if _fused is None else _fused
-    if use_fused:
+    if not use_fused:
+        return _compute_losses_unfused(im1, im2, flow_fw, flow_bw, border_mask, mask_occlusion,
+                                       data_max_distance, _terms)
+    fused_terms = [t for t in terms if t != 'grad']
+    if 'grad' not in terms:
         return fused_loss.compute_losses_fused(im1, im2, flow_fw, flow_bw, border_mask,
-                                               mask_occlusion, data_max_distance, _terms)
-    return _compute_losses_unfused(im1, im2, flow_fw, flow_bw, border_mask, mask_occlusion,
-                                   data_max_distance, _terms)
+                                               mask_occlusion, data_max_distance, fused_terms)
+    # the Sobel 'grad' term ("NOT TESTED" in the reference config) is not fused: evaluate it
+    # with the stand-alone functions on the masks the fused kernel produced
+    losses, mask_fw, mask_bw = fused_loss.compute_losses_fused(
+        im1, im2, flow_fw, flow_bw, border_mask, mask_occlusion, data_max_distance, fused_terms,
+        return_masks=True)
+    losses['grad'] = (gradient_loss(im1, image_warp(im2, flow_fw), mask_fw) +
+                      gradient_loss(im2, image_warp(im1, flow_bw), mask_bw))
+    return losses
 
 
 def _compute_losses_unfused(im1, im2, flow_fw, flow_bw, border_mask, mask_occlusion,

@@ -45,6 +45,51 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+class _KernelTimer:
+    """Optional CUDA-event timing of individual launches on the launching stream (bench.py uses it
+    to measure the per-launch duration of the hand-written kernels inside the timed region)."""
+
+    def __init__(self):
+        self.enabled = False
+        self.records = []
+
+    def enable(self):
+        self.enabled = True
+        self.records = []
+
+    def collect(self):
+        """-> {name: [ms, ...]}; call after a device synchronize."""
+        self.enabled = False
+        out = {}
+        for name, s, e in self.records:
+            out.setdefault(name, []).append(s.elapsed_time(e))
+        self.records = []
+        return out
+
+    class _Span:
+        def __init__(self, timer, name):
+            self.t, self.name = timer, name
+
+        def __enter__(self):
+            if self.t.enabled:
+                self.s = torch.cuda.Event(enable_timing=True)
+                self.e = torch.cuda.Event(enable_timing=True)
+                self.s.record()
+            return self
+
+        def __exit__(self, *exc):
+            if self.t.enabled:
+                self.e.record()
+                self.t.records.append((self.name, self.s, self.e))
+            return False
+
+    def span(self, name):
+        return self._Span(self, name)
+
+
+kernel_timer = _KernelTimer()
+
+
 _CORR_DEFAULTS = dict(kernel_size=1, max_displacement=20, pad=20, stride_1=1, stride_2=2)
 
 
@@ -71,7 +116,7 @@ class _Correlation(torch.autograd.Function):
         check(lib.unflow_correlation_out_shape(H, W, *attrs, ctypes.byref(oc), ctypes.byref(oh),
                                                ctypes.byref(ow)), "correlation")
         out = torch.empty(B, oc.value, oh.value, ow.value, device=in0.device, dtype=torch.float32)
-        with torch.cuda.device(in0.device):
+        with torch.cuda.device(in0.device), kernel_timer.span("correlation_fwd"):
             check(lib.unflow_correlation_fwd(in0.data_ptr(), in1.data_ptr(), out.data_ptr(),
                                              B, C, H, W, *attrs, _stream()), "correlation")
         ctx.save_for_backward(in0, in1)
@@ -85,7 +130,7 @@ class _Correlation(torch.autograd.Function):
         gout = gout.contiguous()
         g0 = torch.empty_like(in0)
         g1 = torch.empty_like(in1)
-        with torch.cuda.device(in0.device):
+        with torch.cuda.device(in0.device), kernel_timer.span("correlation_bwd"):
             check(_native.lib().unflow_correlation_bwd(gout.data_ptr(), in0.data_ptr(), in1.data_ptr(),
                                                        g0.data_ptr(), g1.data_ptr(), B, C, H, W,
                                                        *ctx.attrs, _stream()), "correlation_grad")
