@@ -134,6 +134,8 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     _native.lib()  # fail loudly if libunflow.so is missing
+    from unflow_b200.e2eflow.core import conv_ops
+    conv_ops.set_mode(args.conv)
 
     params = dict(synth.KITTI_PARAMS, learning_rate=1.0e-5)
     trainer = Trainer(params, synth.KITTI_NORMALIZATION, dev, seed=1234)
@@ -231,7 +233,8 @@ def run_ours(args):
                                "grad all-reduce, Adam), 384x1280, batch 4 per GPU",
                    "global_batch": PER_GPU_BATCH * world, "parallelism": "dp%d" % world,
                    "l2": "inputs+activations per step >> 126 MB L2 (no flush needed)",
-                   "conv_precision": "fp32 (cuDNN, TF32 disabled)"},
+                   "conv_precision": ("fp32 (cuDNN, TF32 disabled)" if args.conv == "fp32" else
+                                      "3xTF32 split on tensor cores (fp32-level accuracy, parity-tested)")},
         "e2e": {"value": round(e2e, 3), "unit": "frame-pairs/s", "ms_per_step": round(ms_e2e / args.steps, 3),
                 "h2d_bytes_per_step": 2 * h_im1.numel() * 4, "d2h_bytes_per_step": 4},
         "gpu_launches": int(launches),
@@ -262,7 +265,12 @@ except Exception:
 # ---------------------------------------------------------------------------------------------
 def cpu_step_fn():
     from oracle import flownet as ofl, unsupervised as oun, ops as oops
-    torch.set_num_threads(os.cpu_count() or 1)
+    # all the host threads this process can really use (affinity / cgroup quota aware; capped:
+    # the conv sizes of one image pair stop scaling beyond a few dozen threads)
+    if os.environ.get("UNFLOW_CPU_THREADS"):
+        oops.set_num_threads(int(os.environ["UNFLOW_CPU_THREADS"]))
+    else:
+        oops.calibrate_threads()
     tfv = ofl.init_variables('C', False, seed=1234)
     for k in tfv:
         tfv[k].requires_grad_(True)
@@ -274,7 +282,7 @@ def cpu_step_fn():
         loss = oun.unsupervised_loss(tfv, (im1, im2), synth.KITTI_PARAMS, synth.KITTI_NORMALIZATION,
                                      augment=False)
         loss.backward()
-        return float(loss)
+        return float(loss.detach())
 
     return step, oops.num_threads()
 
@@ -287,8 +295,8 @@ def cpu_baseline(steps=1, warmup=0):
     for _ in range(steps):
         step()
     dt = (time.perf_counter() - t0) / steps
-    return {"value": round(1.0 / dt, 4), "unit": "frame-pairs/s", "cores": int(os.cpu_count() or 1),
-            "threads": int(max(nthreads, torch.get_num_threads())), "kind": "port",
+    return {"value": round(1.0 / dt, 4), "unit": "frame-pairs/s", "cores": int(nthreads), "host_cpus": int(os.cpu_count() or 1),
+            "kind": "port",
             "sample": "%d step(s) of 1 pair 384x1280: FlowNetC fwd + 5-level loss + backward "
                       "(no optimiser), CPU restatement of the reference in oracle/ (the reference "
                       "has no CPU kernels for this graph)" % steps,
@@ -307,8 +315,7 @@ def run_reference(args):
         step()
     total = time.perf_counter() - t0
     value = args.steps / total
-    cb = {"value": round(value, 4), "unit": "frame-pairs/s", "cores": int(os.cpu_count() or 1),
-          "threads": int(max(nthreads, torch.get_num_threads())), "kind": "port",
+    cb = {"value": round(value, 4), "unit": "frame-pairs/s", "cores": int(nthreads), "host_cpus": int(os.cpu_count() or 1), "kind": "port",
           "sample": "each step = 1 pair 384x1280 (FlowNetC fwd + 5-level loss + backward) on the host "
                     "cores; CPU restatement of the reference (oracle/), the reference itself has no "
                     "CPU path (SURVEY.md R1)"}
@@ -332,6 +339,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--conv", default=os.environ.get("UNFLOW_CONV_PRECISION", "fp32"),
+                    choices=["fp32", "3xtf32"], help="arithmetic of the cuDNN conv stacks")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -163,6 +163,15 @@ int unflow_adam_step(float *params, float *grads, float *m, float *v, long long 
                      float beta1, float beta2, float eps, long long step, float grad_scale,
                      int zero_grad, void *stream);
 
+/* ------------------------------------------------------------------------
+ * 3xTF32 operand split for the conv / deconv stacks (no reference counterpart: the reference
+ * runs its slim.conv2d layers in plain fp32 on cuDNN, src/e2eflow/core/flownet.py:174-233).
+ * For each of `items` slabs of `inner` floats writes three slabs: order 0 -> (hi, hi, lo),
+ * order 1 -> (hi, lo, hi), hi = round-to-nearest TF32(x), lo = x - hi.  out holds 3*items*inner.
+ * ---------------------------------------------------------------------- */
+int unflow_split3_tf32(const float *x, float *out, long long items, long long inner, int order,
+                       void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -46,6 +46,62 @@ def num_threads():
     return int(lib().oracle_num_threads())
 
 
+def usable_cpus():
+    """CPUs this process may really use: affinity mask and cgroup quota, not the host's count."""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as fh:                       # cgroup v2
+            quota, period = fh.read().split()[:2]
+            if quota != "max":
+                n = min(n, max(1, int(float(quota) / float(period))))
+    except Exception:
+        pass
+    try:
+        with open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us") as fh:         # cgroup v1
+            quota = int(fh.read())
+        with open("/sys/fs/cgroup/cpu/cpu.cfs_period_us") as fh:
+            period = int(fh.read())
+        if quota > 0 and period > 0:
+            n = min(n, max(1, quota // period))
+    except Exception:
+        pass
+    return max(1, n)
+
+
+def calibrate_threads(cap=None):
+    """Pick the thread count that actually runs fastest on this host (visible cores can exceed what
+    the container may use; oversubscription makes the CPU baseline collapse).  ~1 s."""
+    import time
+    import torch.nn.functional as F
+    limit = usable_cpus() if cap is None else min(usable_cpus(), cap)
+    cands = sorted({c for c in (4, 8, 16, 32, 64, 96, 128, limit) if c <= limit})
+    x = torch.randn(2, 256, 48, 160)
+    w = torch.randn(256, 256, 3, 3)
+    a = torch.randn(1, 64, 24, 40)
+    best, best_t = cands[0], float("inf")
+    for c in cands:
+        set_num_threads(c)
+        F.conv2d(x, w, padding=1)
+        t0 = time.perf_counter()
+        F.conv2d(x, w, padding=1)
+        correlation(a, a, max_displacement=8, pad=8)
+        dt = time.perf_counter() - t0
+        if dt < best_t * 0.95:
+            best, best_t = c, dt
+    set_num_threads(best)
+    return best
+
+
+def set_num_threads(n):
+    lib().oracle_set_num_threads(int(n))
+    torch.set_num_threads(int(n))
+    return int(n)
+
+
 def _p(t):
     assert t.dtype == torch.float32 and t.is_contiguous() and t.device.type == "cpu"
     return ctypes.cast(t.data_ptr(), _f32p)

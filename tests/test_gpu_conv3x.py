@@ -1,0 +1,105 @@
+"""The 3xTF32 tensor-core conv path (core/conv_ops.py + csrc/split.cu): accuracy against float64
+and end-to-end parity of the model against the fp32 oracle at the same tolerances as plain fp32."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from oracle import flownet as oflownet
+from oracle import unsupervised as ounsup
+import synth
+
+
+@pytest.fixture
+def mode3x():
+    from unflow_b200.e2eflow.core import conv_ops
+    old = conv_ops.get_mode()
+    conv_ops.set_mode('3xtf32')
+    yield
+    conv_ops.set_mode(old)
+
+
+def rel(a, b):
+    return float((a.double() - b).norm() / b.norm())
+
+
+def test_split_kernel_exact():
+    from unflow_b200.e2eflow.core.conv_ops import _cat_channels, _cat_batch
+    x = torch.randn(3, 5, 7, 9, device="cuda") * 100
+    s = _cat_channels(x, 0)
+    hi, hi2, lo = s[:, :5], s[:, 5:10], s[:, 10:]
+    assert torch.equal(hi, hi2)
+    assert torch.equal(hi + lo, x)                              # exact decomposition
+    assert int((hi.view(torch.int32) & 0x1FFF).abs().max()) == 0   # hi is a TF32 number
+    assert float((lo.abs() / x.abs()).max()) <= 2.0 ** -11
+    s1 = _cat_batch(x, 1)
+    assert torch.equal(s1[:3], hi) and torch.equal(s1[3:6], lo) and torch.equal(s1[6:], hi)
+
+
+@pytest.mark.parametrize("stride,k,pads", [(1, 3, (1, 1, 1, 1)), (2, 5, (1, 2, 1, 2)), (2, 7, (2, 3, 2, 3))])
+def test_conv3x_matches_float64(mode3x, stride, k, pads):
+    from unflow_b200.e2eflow.core import conv_ops
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 24, 20, 28, generator=g)
+    w = torch.randn(16, 24, k, k, generator=g) * 0.1
+    b = torch.randn(16, generator=g)
+    xd = F.pad(x.double(), (pads[2], pads[3], pads[0], pads[1])).requires_grad_(True)
+    wd, bd = w.double().requires_grad_(True), b.double().requires_grad_(True)
+    yd = F.conv2d(xd, wd, bd, stride=stride)
+    go = torch.randn(yd.shape, generator=g)
+    yd.backward(go.double())
+    xc, wc, bc = x.cuda().requires_grad_(True), w.cuda().requires_grad_(True), b.cuda().requires_grad_(True)
+    y = conv_ops.conv2d(xc, wc, bc, stride, pads)
+    y.backward(go.cuda())
+    H, W = x.shape[2], x.shape[3]
+    gx_ref = xd.grad[:, :, pads[0]:pads[0] + H, pads[2]:pads[2] + W]
+    for got, want, name in ((y, yd, "y"), (xc.grad, gx_ref, "dx"), (wc.grad, wd.grad, "dw"), (bc.grad, bd.grad, "db")):
+        e = rel(got.detach().cpu(), want.detach())
+        assert e < 2e-6, "%s: rel err %.2e" % (name, e)       # fp32-level, ~1000x better than 1xTF32
+
+
+def test_deconv3x_matches_float64(mode3x):
+    from unflow_b200.e2eflow.core import conv_ops
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(2, 20, 9, 11, generator=g)
+    w = torch.randn(20, 12, 4, 4, generator=g) * 0.1
+    b = torch.randn(12, generator=g)
+    xd, wd, bd = (t.double().requires_grad_(True) for t in (x, w, b))
+    yd = F.conv_transpose2d(xd, wd, bd, stride=2, padding=1)
+    go = torch.randn(yd.shape, generator=g)
+    yd.backward(go.double())
+    xc, wc, bc = x.cuda().requires_grad_(True), w.cuda().requires_grad_(True), b.cuda().requires_grad_(True)
+    y = conv_ops.conv_transpose2d(xc, wc, bc)
+    y.backward(go.cuda())
+    for got, want, name in ((y, yd, "y"), (xc.grad, xd.grad, "dx"), (wc.grad, wd.grad, "dw"), (bc.grad, bd.grad, "db")):
+        e = rel(got.detach().cpu(), want.detach())
+        assert e < 2e-6, "%s: rel err %.2e" % (name, e)
+
+
+def test_unsupervised_loss_3xtf32_vs_oracle(mode3x):
+    """Same bar as the fp32 path: loss 2e-4, final flows 1e-4 relative, gradients in L2."""
+    from unflow_b200.e2eflow.core.flownet import FlowNetVariables
+    from unflow_b200.e2eflow.core.unsupervised import unsupervised_loss
+    params = dict(synth.KITTI_PARAMS)
+    tfv = oflownet.init_variables('C', False, seed=11)
+    for k in tfv:
+        tfv[k] = tfv[k].clone().requires_grad_(True)
+    v = FlowNetVariables('C', False, seed=0).load_tf_dict({k: t.detach() for k, t in tfv.items()}).cuda()
+    im1, im2, _ = synth.image_pair(1, 128, 256, seed=21)
+    want_loss, want_fw, want_bw = ounsup.unsupervised_loss(tfv, (im1, im2), params, synth.KITTI_NORMALIZATION,
+                                                           augment=False, return_flow=True)
+    got_loss, got_fw, got_bw = unsupervised_loss((im1.cuda(), im2.cuda()), params, synth.KITTI_NORMALIZATION,
+                                                 augment=False, return_flow=True, variables=v)
+    assert abs(float(got_loss) - float(want_loss)) / abs(float(want_loss)) < 2e-4
+    for g_, w_ in ((got_fw, want_fw), (got_bw, want_bw)):
+        np.testing.assert_allclose(g_.detach().cpu().numpy(), w_.detach().numpy(), rtol=1e-4,
+                                   atol=1e-4 * float(w_.abs().max()))
+    want_loss.backward()
+    got_loss.backward()
+    for scope in v.kinds:
+        w, _ = v.weights(scope)
+        want = tfv[scope + '/weights'].grad.permute(3, 2, 0, 1)
+        err = float((w.grad.cpu() - want).norm() / want.norm().clamp_min(1e-20))
+        assert err < 5e-3, "%s: relative L2 gradient error %.3e" % (scope, err)

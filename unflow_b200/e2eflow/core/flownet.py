@@ -23,24 +23,20 @@ import torch.nn.functional as F
 from ..ops import correlation
 from .image_warp import image_warp
 from . import tf_image
+from . import conv_ops
 
 FLOW_SCALE = 5.0
 
 
 def set_conv_precision(mode='fp32'):
-    """Arithmetic of the cuDNN conv / deconv stacks.
+    """Arithmetic of the conv / deconv stacks (see core/conv_ops.py).
 
-    'fp32' (default): exact float32 multiply-accumulate, what the reference's TF1 graph computes
-    (torch enables TF32 tensor-core convolutions by default, which costs ~1e-3 relative on the
-    flow fields and breaks the 1e-4 parity bar -- so it is switched off here).
-    'tf32': let cuDNN round conv inputs to TF32 (10-bit mantissa); an explicitly reduced
-    precision mode, never used for parity or for the headline benchmark.
-    The flag is process-global because autograd runs the backward convolutions later."""
-    if mode not in ('fp32', 'tf32'):
-        raise ValueError("conv precision must be 'fp32' or 'tf32'")
-    torch.backends.cudnn.allow_tf32 = (mode == 'tf32')
-    torch.backends.cuda.matmul.allow_tf32 = (mode == 'tf32')
-    return mode
+    'fp32' (default): exact float32 cuDNN convolutions, what the reference's TF1 graph computes.
+    torch enables single-pass TF32 convolutions by default, which costs ~1e-3 relative on the flow
+    fields and breaks the 1e-4 parity bar (measured) -- so it is switched off on import.
+    '3xtf32': tensor-core convolutions at fp32-level accuracy (operand split, one fused conv).
+    'tf32': single-pass TF32, an explicitly reduced-precision mode."""
+    return conv_ops.set_mode(mode)
 
 
 set_conv_precision(__import__('os').environ.get('UNFLOW_CONV_PRECISION', 'fp32'))
@@ -254,17 +250,14 @@ class _Scope:
     def conv(self, x, name, stride=1, act=True):
         w, b = self.v.weights(self.p + name)
         k = w.shape[2]
-        pt, pb = _same_pad(x.shape[2], k, stride)
-        pl, pr = _same_pad(x.shape[3], k, stride)
-        if pt == pb and pl == pr:
-            y = F.conv2d(x, w, b, stride=stride, padding=(pt, pl))
-        else:  # TF SAME is asymmetric for the stride-2 layers at even sizes
-            y = F.conv2d(F.pad(x, (pl, pr, pt, pb)), w, b, stride=stride)
+        # TF SAME padding: asymmetric for the stride-2 layers at even sizes
+        pads = _same_pad(x.shape[2], k, stride) + _same_pad(x.shape[3], k, stride)
+        y = conv_ops.conv2d(x, w, b, stride, pads)
         return _leaky_relu(y) if act else y
 
     def deconv(self, x, name, act=True):
         w, b = self.v.weights(self.p + name)
-        y = F.conv_transpose2d(x, w, b, stride=2, padding=1)  # slim.conv2d_transpose(k=4, s=2, SAME)
+        y = conv_ops.conv_transpose2d(x, w, b)  # slim.conv2d_transpose(k=4, s=2, SAME)
         return _leaky_relu(y) if act else y
 
 
