@@ -40,7 +40,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
-import synth  # noqa: E402
+from unflow_b200 import synthetic as synth  # noqa: E402
 
 H, W, PER_GPU_BATCH = 384, 1280, 4
 METRIC = "frame-pairs/s at 384x1280 FlowNetC"

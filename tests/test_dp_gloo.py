@@ -76,5 +76,8 @@ def test_flat_views_alias_parameters():
     assert float(w.abs().sum()) == 0.0
     tr.flat_grad.fill_(2.0)
     assert float(w.grad.mean()) == 2.0
-    p = dict(learning_rate=1e-4, decay_after=10, decay_interval=5)
-    assert learning_rate_at(10, p) == 1e-4 and learning_rate_at(15, p) == 5e-5 and learning_rate_at(21, p) == 2.5e-5
+    p = dict(learning_rate=1e-4, decay_after=10, decay_interval=5)   # train.py:237-244
+    assert learning_rate_at(9, p) == 1e-4 and learning_rate_at(10, p) == 1e-4
+    assert learning_rate_at(15, p) == 5e-5 and learning_rate_at(21, p) == 2.5e-5
+    m = dict(manual_decay_iters=[3, 2], manual_decay_lrs=[1e-5, 5e-6])  # train.py:228-236
+    assert [learning_rate_at(i, m) for i in range(6)] == [1e-5, 1e-5, 1e-5, 1e-5, 5e-6, 5e-6]

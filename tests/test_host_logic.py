@@ -176,3 +176,42 @@ def test_every_product_module_imports_without_gpu():
     for m in ("ops", "core.image_warp", "core.losses", "core.fused_loss", "core.flownet",
               "core.unsupervised", "core.util", "core.tf_image"):
         importlib.import_module("unflow_b200.e2eflow." + m)
+
+
+def test_run_config_semantics(tmp_path):
+    """config.ini parsing as the reference does it (util.py:37-73, run.py:90-92)."""
+    from unflow_b200 import run as R
+    ini = tmp_path / "config.ini"
+    ini.write_text("""
+[dirs]
+log = ../log
+[run]
+batch_size = 4
+gpu_list = 0
+dataset = kitti_ft
+development = False
+[train]
+decay_interval = 100000
+save_interval = 5000
+flownet = C
+pyramid_loss = True
+ternary_weight = 1.0
+smooth_2nd_weight = 3.0
+[train_kitti_ft]
+height = 320
+width = 768
+manual_decay_iters = 45000,20000
+manual_decay_lrs = 0.5e-5,0.25e-5
+""")
+    cfg = R.config_dict(str(ini))
+    assert cfg['run']['batch_size'] == 4 and cfg['run']['development'] is False
+    assert cfg['train']['ternary_weight'] == 1.0 and cfg['train']['pyramid_loss'] is True
+    assert cfg['train']['flownet'] == 'C' and isinstance(cfg['train']['decay_interval'], int)
+    p = dict(cfg['train'])
+    p.update(cfg['train_kitti_ft'])
+    R.convert_input_strings(p)
+    assert p['manual_decay_iters'] == [45000, 20000] and p['manual_decay_lrs'] == [0.5e-5, 0.25e-5]
+    assert p['num_iters'] == 65000 and p['height'] == 320
+    (tmp_path / "model.ckpt-5000.pt").write_bytes(b"")
+    (tmp_path / "model.ckpt-15000.pt").write_bytes(b"")
+    assert R.latest_checkpoint(str(tmp_path))[0] == 15000

@@ -25,14 +25,30 @@ from .flownet import FlowNetVariables
 from .unsupervised import unsupervised_loss
 
 
-def learning_rate_at(i, params):
-    """Host-side LR schedule of the reference training loop (train.py:225-244)."""
+def learning_rate_at(decay_iters, params):
+    """Host-side LR schedule of the reference training loop (train.py:225-244).
+
+    ``decay_iters`` = number of iterations already done (the reference's
+    ``local_i + iter_offset``, 0 for the first step)."""
+    if 'manual_decay_lrs' in params and 'manual_decay_iters' in params:
+        decay_index = 0
+        iter_counter = 0
+        for decay_i, manual_decay_iter in enumerate(params['manual_decay_iters']):
+            iter_counter += manual_decay_iter
+            if decay_iters <= iter_counter:
+                decay_index = decay_i
+                break
+        return params['manual_decay_lrs'][decay_index]
     lr = params.get('learning_rate', 1.0e-4)
-    decay_after = params.get('decay_after')
     decay_interval = params.get('decay_interval')
-    if decay_after is None or decay_interval is None or i <= decay_after:
+    if not decay_interval:
         return lr
-    return lr / (2 ** int((i - decay_after) / decay_interval))
+    decay_after = params.get('decay_after', 0)
+    if decay_iters >= decay_after:
+        decay_minimum = decay_after / decay_interval
+        decay = (decay_iters // decay_interval) - decay_minimum
+        return lr / (2 ** decay)
+    return lr
 
 
 class Trainer:
@@ -115,6 +131,6 @@ class Trainer:
         loss.backward()   # accumulates into the flat gradient views
         scale = self.reduce_gradients()
         if lr is None:
-            lr = learning_rate_at(self.iteration, self.params)
+            lr = learning_rate_at(self.iteration - 1, self.params)
         self.apply_update(lr, scale)
         return loss.detach()
