@@ -312,7 +312,7 @@ def nchw_to_nhwc(tensors):
 def flownet_s(inputs, channel_mult=1, full_res=False, _scope=None):
     """Given stacked inputs, returns flow predictions in decreasing resolution (FlowNetSimple)."""
     s = _scope
-    x = nhwc_to_nchw([inputs])[0].contiguous()
+    x = conv_ops.network_input(inputs)
     conv1 = s.conv(x, 'conv1', 2)
     conv2 = s.conv(conv1, 'conv2', 2)
     conv3 = s.conv(conv2, 'conv3', 2)
@@ -330,7 +330,7 @@ def flownet_s(inputs, channel_mult=1, full_res=False, _scope=None):
 
 def flownet_c_features(im, channel_mult=1, reuse=None, _scope=None):
     s = _scope
-    x = nhwc_to_nchw([im])[0].contiguous()
+    x = conv_ops.network_input(im)
     conv1 = s.conv(x, 'conv1', 2)
     conv2 = s.conv(conv1, 'conv2', 2)
     conv3 = s.conv(conv2, 'conv3', 2)
@@ -350,13 +350,37 @@ def _flownet_c_trunk(s, conv_redir_and_corr, conv2_a, channel_mult, full_res):
     return nchw_to_nhwc(res)
 
 
+def _concat_channels_last(first, second_batch_parts):
+    """concat([first..., cat(second_batch_parts, 0)], 1) written straight into ONE channels_last
+    buffer (each source is read once; no intermediate NCHW concat + layout transform)."""
+    n = first[0].shape[0]
+    c_first = sum(t.shape[1] for t in first)
+    c = c_first + second_batch_parts[0].shape[1]
+    h, w = first[0].shape[2], first[0].shape[3]
+    out = torch.empty((n, c, h, w), device=first[0].device, dtype=first[0].dtype,
+                      memory_format=torch.channels_last)
+    off = 0
+    for t in first:
+        out[:, off:off + t.shape[1]] = t
+        off += t.shape[1]
+    b0 = 0
+    for t in second_batch_parts:
+        out[b0:b0 + t.shape[0], off:] = t
+        b0 += t.shape[0]
+    return out
+
+
 def flownet_c(conv3_a, conv3_b, conv2_a, channel_mult=1, full_res=False, _scope=None):
     """Given two feature maps, returns flow predictions in decreasing resolution (FlowNetCorr)."""
     s = _scope
     corr = correlation(conv3_a, conv3_b,
                        pad=20, kernel_size=1, max_displacement=20, stride_1=1, stride_2=2)
     conv_redir = s.conv(conv3_a, 'conv_redir')
-    return _flownet_c_trunk(s, torch.cat([conv_redir, corr], 1), conv2_a, channel_mult, full_res)
+    if conv_ops.channels_last_active(conv_redir):
+        trunk_in = _concat_channels_last([conv_redir], [corr])
+    else:
+        trunk_in = torch.cat([conv_redir, corr], 1)
+    return _flownet_c_trunk(s, trunk_in, conv2_a, channel_mult, full_res)
 
 
 def flownet(im1, im2, flownet_spec='S', full_resolution=False, train_all=False,
@@ -392,7 +416,10 @@ def flownet(im1, im2, flownet_spec='S', full_resolution=False, train_all=False,
                 corr_ab = correlation(conv3_a, conv3_b, **kw)
                 corr_ba = correlation(conv3_b, conv3_a, **kw)
                 conv_redir = cs.conv(conv3_ab, 'conv_redir')
-                trunk_in = torch.cat([conv_redir, torch.cat([corr_ab, corr_ba], 0)], 1)
+                if conv_ops.channels_last_active(conv_redir):
+                    trunk_in = _concat_channels_last([conv_redir], [corr_ab, corr_ba])
+                else:
+                    trunk_in = torch.cat([conv_redir, torch.cat([corr_ab, corr_ba], 0)], 1)
                 flows = _flownet_c_trunk(cs, trunk_in, conv2_ab, channel_mult, full_res)
                 flows_fw.append([f[:B] for f in flows])
                 flows_bw.append([f[B:] for f in flows])
