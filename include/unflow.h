@@ -44,6 +44,9 @@ const char *unflow_last_error(void);
  * reset); bench.py reports it as gpu_launches. */
 unsigned long long unflow_launch_count(void);
 void unflow_reset_launch_count(void);
+/* Tuning knobs for tests / benchmarks.  "corr_fwd_variant": 1 (one row pair per thread) or
+ * 3 (three row pairs per thread); default 1 (faster on B200); results are bit-identical. */
+int unflow_set_int_option(const char *name, int value);
 
 /* ------------------------------------------------------------------------
  * Correlation   (reference: REGISTER_OP("Correlation") ops/correlation_op.cc:133-168,

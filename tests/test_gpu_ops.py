@@ -139,6 +139,21 @@ def test_correlation_full_size_properties():
     assert torch.equal(single[0], out[3])
 
 
+def test_correlation_forward_variants_bit_identical():
+    from unflow_b200 import _native
+    lib = _native.lib()
+    a, b = rnd((2, 48, 20, 56), 31).cuda(), rnd((2, 48, 20, 56), 32).cuda()
+    try:
+        assert lib.unflow_set_int_option(b"corr_fwd_variant", 1) == 0
+        o1 = _ops().correlation(a, b)
+        assert lib.unflow_set_int_option(b"corr_fwd_variant", 3) == 0
+        o3 = _ops().correlation(a, b)
+    finally:
+        lib.unflow_set_int_option(b"corr_fwd_variant", 3)
+    assert torch.equal(o1, o3)
+    assert lib.unflow_set_int_option(b"corr_fwd_variant", 2) == 1
+
+
 def test_correlation_errors():
     ops = _ops()
     a = rnd((1, 2, 4, 4), 1).cuda()

@@ -59,8 +59,11 @@ def main():
     D2 = 441
     nbytes = 4 * B * H * W * (2 * C + D2)
     flops = 2 * B * H * W * C * D2
-    t = timeit(lambda: ops.correlation(a, b))
-    report("correlation_fwd B8 256x48x160 d20", *t, nbytes, flops)
+    from unflow_b200 import _native
+    for variant in (1, 3):
+        _native.lib().unflow_set_int_option(b"corr_fwd_variant", variant)
+        t = timeit(lambda: ops.correlation(a, b))
+        report("correlation_fwd(v%d) B8 256x48x160 d20" % variant, *t, nbytes, flops)
 
     ar, br = a.clone().requires_grad_(True), b.clone().requires_grad_(True)
     out = ops.correlation(ar, br)

@@ -29,6 +29,7 @@ SIGNATURES = {
     "unflow_last_error": (ctypes.c_char_p, []),
     "unflow_launch_count": (ctypes.c_ulonglong, []),
     "unflow_reset_launch_count": (None, []),
+    "unflow_set_int_option": (_i, [ctypes.c_char_p, _i]),
     "unflow_correlation_out_shape": (_i, [_i] * 7 + [ctypes.POINTER(_i)] * 3),
     "unflow_correlation_workspace_bytes": (ctypes.c_size_t, [_i] * 9),
     "unflow_correlation_fwd": (_i, [_vp, _vp, _vp] + [_i] * 9 + [_vp]),

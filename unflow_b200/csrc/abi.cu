@@ -3,6 +3,7 @@
 #include <cstring>
 
 #include "common.cuh"
+#include "correlation.cuh"
 
 namespace unflow {
 static thread_local char g_err[512] = "";
@@ -22,4 +23,12 @@ int unflow_abi_version(void) { return 1; }
 const char *unflow_last_error(void) { return unflow::g_err; }
 unsigned long long unflow_launch_count(void) { return unflow::g_launches.load(); }
 void unflow_reset_launch_count(void) { unflow::g_launches.store(0); }
+int unflow_set_int_option(const char *name, int value) {
+  if (name && !strcmp(name, "corr_fwd_variant") && (value == 1 || value == 3)) {
+    unflow::g_corr_fwd_variant = value;
+    return UNFLOW_OK;
+  }
+  unflow::set_error("unknown option or value: %s=%d", name ? name : "(null)", value);
+  return UNFLOW_EINVAL;
+}
 }

@@ -134,21 +134,39 @@ corr_fwd_tiled_kernel(const __grid_constant__ CUtensorMap map0,  // in0 as [B][C
   const int D = 2 * r + 1;
   const int ybase = Y2 - S2 * RMAX;  // first staged in0 row (even)
 
-  if (tid == 0) {
-    int np = 0, nz = 0;
-    for (int y2r = 0; y2r < NY2; ++y2r) {
-      const int y2 = Y2 + y2r;
-      const bool inside = y2 >= 0 && y2 < H;
-      for (int p = -r; p <= r; ++p) {
-        const int y = y2 - S2 * p;
-        if (y < 0 || y >= H) continue;
-        if (inside) { sm.pair_y[np] = (short)y; sm.pair_y2r[np] = (short)y2r; sm.pair_p[np] = (short)(p + r); ++np; }
-        else { sm.zero_y[nz] = (short)y; sm.zero_p[nz] = (short)(p + r); ++nz; }
-      }
-    }
-    sm.npairs = np; sm.nzero = nz;
+  // Work lists, built in parallel: warp y2r scans the 2r+1 displacement rows of in1 row Y2+y2r
+  // (lane <-> p), ballots the valid ones and ranks them; the producer warp initialises the barriers.
+  // (A serial build by thread 0 cost 4.5 % of the kernel in the first ncu profile.)
+  __shared__ int s_cnt[NY2], s_zcnt[NY2];
+  unsigned vmask = 0, zmask = 0;
+  int my_y = 0;
+  if (warp < NY2) {
+    const int y2 = Y2 + warp;
+    const bool inside = y2 >= 0 && y2 < H;
+    my_y = y2 - S2 * (lane - r);
+    const bool ok = lane < D && my_y >= 0 && my_y < H;
+    vmask = __ballot_sync(0xffffffffu, ok && inside);
+    zmask = __ballot_sync(0xffffffffu, ok && !inside);
+    if (lane == 0) { s_cnt[warp] = __popc(vmask); s_zcnt[warp] = __popc(zmask); }
+  }
+  if (warp == NCW && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], NCW); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp < NY2) {
+    int pbase = 0, zbase = 0;
+    for (int k = 0; k < warp; ++k) { pbase += s_cnt[k]; zbase += s_zcnt[k]; }
+    const unsigned lt = (1u << lane) - 1u;
+    if ((vmask >> lane) & 1u) {
+      const int pi = pbase + __popc(vmask & lt);
+      sm.pair_y[pi] = (short)my_y; sm.pair_y2r[pi] = (short)warp; sm.pair_p[pi] = (short)lane;
+    }
+    if ((zmask >> lane) & 1u) {
+      const int zi = zbase + __popc(zmask & lt);
+      sm.zero_y[zi] = (short)my_y; sm.zero_p[zi] = (short)lane;
+    }
+    if (warp == NY2 - 1 && lane == 0) { sm.npairs = pbase + s_cnt[warp]; sm.nzero = zbase + s_zcnt[warp]; }
   }
   __syncthreads();
   const int npairs = sm.npairs, nzero = sm.nzero;
@@ -217,19 +235,29 @@ corr_fwd_tiled_kernel(const __grid_constant__ CUtensorMap map0,  // in0 as [B][C
     if (warp_active) {
       const float *p0 = sm.stage[s] + off0;
       const float *p1 = sm.stage[s] + off1;
-#pragma unroll 2
+      // explicit register double buffering: the operands of channel cc+1 are loaded before the
+      // 88 FMAs of channel cc are issued, so the shared-memory latency hides behind the math even
+      // with only ~3 warps per scheduler
+      float4 an[2], wn[(PX + S2 * (DO - 1)) / 4];
+      an[0] = *reinterpret_cast<const float4 *>(p0);
+      an[1] = *reinterpret_cast<const float4 *>(p0 + 4);
+#pragma unroll
+      for (int k = 0; k < (PX + S2 * (DO - 1)) / 4; ++k) wn[k] = *reinterpret_cast<const float4 *>(p1 + 4 * k);
+#pragma unroll
       for (int cc = 0; cc < CC; ++cc) {
         float a[PX], w[PX + S2 * (DO - 1)];
-        {
-          const float4 v0 = *reinterpret_cast<const float4 *>(p0 + cc * (R0H * P0));
-          const float4 v1 = *reinterpret_cast<const float4 *>(p0 + cc * (R0H * P0) + 4);
-          a[0] = v0.x; a[1] = v0.y; a[2] = v0.z; a[3] = v0.w;
-          a[4] = v1.x; a[5] = v1.y; a[6] = v1.z; a[7] = v1.w;
-        }
+        a[0] = an[0].x; a[1] = an[0].y; a[2] = an[0].z; a[3] = an[0].w;
+        a[4] = an[1].x; a[5] = an[1].y; a[6] = an[1].z; a[7] = an[1].w;
 #pragma unroll
         for (int k = 0; k < (PX + S2 * (DO - 1)) / 4; ++k) {
-          const float4 v = *reinterpret_cast<const float4 *>(p1 + cc * (NY2 * WIN) + 4 * k);
-          w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w;
+          w[4 * k] = wn[k].x; w[4 * k + 1] = wn[k].y; w[4 * k + 2] = wn[k].z; w[4 * k + 3] = wn[k].w;
+        }
+        if (cc + 1 < CC) {
+          an[0] = *reinterpret_cast<const float4 *>(p0 + (cc + 1) * (R0H * P0));
+          an[1] = *reinterpret_cast<const float4 *>(p0 + (cc + 1) * (R0H * P0) + 4);
+#pragma unroll
+          for (int k = 0; k < (PX + S2 * (DO - 1)) / 4; ++k)
+            wn[k] = *reinterpret_cast<const float4 *>(p1 + (cc + 1) * (NY2 * WIN) + 4 * k);
         }
 #pragma unroll
         for (int t = 0; t < DO; ++t)
@@ -256,6 +284,209 @@ corr_fwd_tiled_kernel(const __grid_constant__ CUtensorMap map0,  // in0 as [B][C
       if (x + 4 < W)
         *reinterpret_cast<float4 *>(dst + 4) =
             make_float4(acc[t][4] / denom, acc[t][5] / denom, acc[t][6] / denom, acc[t][7] / denom);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Forward kernel, variant 2: three row pairs per thread.
+//
+// Variant 1 issues 9 LDS.128 per 88 FMAs (9.8 FMA per 128-bit shared load); measured on B200 it
+// sits at ~43 % of the fp32 peak with the shared-memory pipe as the limiter (a 128-bit warp load
+// costs 4 wavefronts even when lanes share addresses, so >= 16 FMA per LDS.128 are needed to be
+// FMA-bound).  Here a thread owns THREE row pairs that share the in1 row (y, y-2, y-4 against the
+// same y2, i.e. p, p+1, p+2), 4 pixels and 11 displacements: the 24-float in1 window is loaded once
+// for 3 x 4 x 11 = 132 FMAs -> 9 LDS.128 per 132 FMAs (14.7).  21 displacement rows = 7 trios per
+// in1 row, 28 trios per work item = 7 consumer warps (lane = trio 0..3, pixel group 0..3,
+// displacement half 0..1).  Same staging, same pipeline, same zero-fill pass as variant 1; every
+// output is still produced by one thread summing channels in ascending order, so v1 and v2 are
+// bit-identical.
+// ------------------------------------------------------------------------------------------
+namespace ct2 {
+using namespace ct;
+constexpr int NTR = 3;                     // row pairs per thread
+constexpr int PX2 = 4;                     // pixels per thread
+constexpr int NCW2 = 7;                    // consumer warps (7*4 = 28 trio slots)
+constexpr int NTHREADS2 = (NCW2 + 1) * 32;
+constexpr int MAXTRIOS = NY2 * ((2 * RMAX + 1 + NTR - 1) / NTR);   // 28
+constexpr int WLEN = PX2 + S2 * (DO - 1);  // 24-float in1 window
+struct Smem2 {
+  float stage[STAGES][STAGE_FLOATS];
+  unsigned long long full[STAGES];
+  unsigned long long empty[STAGES];
+  int ntrios, nzero;
+  short trio_y[MAXTRIOS], trio_y2r[MAXTRIOS], trio_p[MAXTRIOS], trio_n[MAXTRIOS];
+  short zero_y[MAXPAIRS], zero_p[MAXPAIRS];
+};
+}  // namespace ct2
+
+__global__ void __launch_bounds__(ct2::NTHREADS2, 1)
+corr_fwd_tiled3_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1,
+                       float *__restrict__ out, int C, int H, int W, int r, int y2_first) {
+  using namespace ct2;
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  Smem2 &sm = *reinterpret_cast<Smem2 *>(smem_raw);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int x0 = blockIdx.x * TX;
+  const int Y2 = y2_first + blockIdx.y * NY2;
+  const int b = blockIdx.z;
+  const int D = 2 * r + 1;
+  const int ybase = Y2 - S2 * RMAX;
+
+  // Work lists, built in parallel: warp y2r scans the 2r+1 displacement rows of in1 row Y2+y2r
+  // (lane <-> p), ballots the valid ones and ranks them; the producer warp meanwhile initialises the
+  // barriers.  (A serial build by one thread cost 4.5 % of the kernel in the first profile.)
+  __shared__ int s_cnt[NY2], s_zcnt[NY2];
+  unsigned vmask = 0, zmask = 0;
+  int my_y = 0;
+  if (warp < NY2) {
+    const int y2 = Y2 + warp;
+    const bool inside = y2 >= 0 && y2 < H;
+    const int p = lane - r;
+    my_y = y2 - S2 * p;
+    const bool ok = lane < D && my_y >= 0 && my_y < H;
+    vmask = __ballot_sync(0xffffffffu, ok && inside);
+    zmask = __ballot_sync(0xffffffffu, ok && !inside);
+    if (lane == 0) { s_cnt[warp] = __popc(vmask); s_zcnt[warp] = __popc(zmask); }
+  }
+  if (warp == NCW2 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], NCW2); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp < NY2) {
+    int tbase = 0, zbase = 0;
+    for (int k = 0; k < warp; ++k) { tbase += (s_cnt[k] + NTR - 1) / NTR; zbase += s_zcnt[k]; }
+    const unsigned lt = (1u << lane) - 1u;
+    if ((vmask >> lane) & 1u) {
+      const int rank = __popc(vmask & lt), cnt = __popc(vmask);
+      if (rank % NTR == 0) {
+        const int ti = tbase + rank / NTR;
+        sm.trio_y[ti] = (short)my_y; sm.trio_y2r[ti] = (short)warp; sm.trio_p[ti] = (short)lane;
+        sm.trio_n[ti] = (short)min(NTR, cnt - rank);
+      }
+    }
+    if ((zmask >> lane) & 1u) {
+      const int zi = zbase + __popc(zmask & lt);
+      sm.zero_y[zi] = (short)my_y; sm.zero_p[zi] = (short)lane;
+    }
+    if (warp == NY2 - 1 && lane == 0) {
+      sm.ntrios = tbase + (s_cnt[warp] + NTR - 1) / NTR;
+      sm.nzero = zbase + s_zcnt[warp];
+    }
+  }
+  __syncthreads();
+  const int ntrios = sm.ntrios, nzero = sm.nzero;
+  const size_t plane_out = (size_t)H * W;
+  float *outb = out + (size_t)b * D * D * plane_out;
+
+  if (nzero > 0) {
+    const int per_pair = D * (TX / 4);
+    for (int i = tid; i < nzero * per_pair; i += NTHREADS2) {
+      const int zp = i / per_pair, rem = i - zp * per_pair;
+      const int o = rem / (TX / 4), q = rem - o * (TX / 4);
+      const int x = x0 + 4 * q;
+      if (x < W) {
+        float *dst = outb + ((size_t)(sm.zero_p[zp] * D + o)) * plane_out + (size_t)sm.zero_y[zp] * W + x;
+        *reinterpret_cast<float4 *>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+  }
+  if (ntrios == 0) return;
+
+  const int nchunks = (C + CC - 1) / CC;
+
+  if (warp == NCW2) {
+    if (lane == 0) {
+      for (int it = 0; it < nchunks; ++it) {
+        const int s = it % STAGES;
+        const unsigned ph = (unsigned)(it / STAGES) & 1u;
+        mbar_wait(&sm.empty[s], ph ^ 1u);
+        mbar_arrive_expect_tx(&sm.full[s], STAGE_BYTES);
+        float *st = sm.stage[s];
+        const int c0 = it * CC;
+        tma_load_5d(st, &map0, &sm.full[s], x0, 0, ybase >> 1, c0, b);
+        tma_load_5d(st + IN0_PLANE_FLOATS, &map0, &sm.full[s], x0, 1, ybase >> 1, c0, b);
+        tma_load_4d(st + 2 * IN0_PLANE_FLOATS, &map1, &sm.full[s], x0 - S2 * RMAX, Y2, c0, b);
+      }
+    }
+    return;
+  }
+
+  const int slot = warp * 4 + (lane & 3);
+  const bool active = slot < ntrios;
+  const int ts = active ? slot : 0;
+  const int pxg = (lane >> 2) & 3, og = lane >> 4;
+  const int y = sm.trio_y[ts], y2r = sm.trio_y2r[ts], pidx = sm.trio_p[ts], nrows = active ? sm.trio_n[ts] : 0;
+  const int yrel = y - ybase;
+  // rows of the trio: y, y-2, y-4 -> same parity plane, consecutive (descending) plane rows
+  int off0[NTR];
+#pragma unroll
+  for (int k = 0; k < NTR; ++k) {
+    const int kk = k < nrows ? k : 0;   // unused slots alias row 0 (stay inside the staged tile)
+    off0[k] = (yrel & 1) * IN0_PLANE_FLOATS + ((yrel >> 1) - kk) * P0 + pxg * PX2;
+  }
+  const int off1 = 2 * IN0_PLANE_FLOATS + y2r * WIN + pxg * PX2 + og * (S2 * RMAX);
+
+  float acc[NTR][DO][PX2];
+#pragma unroll
+  for (int k = 0; k < NTR; ++k)
+#pragma unroll
+    for (int t = 0; t < DO; ++t)
+#pragma unroll
+      for (int i = 0; i < PX2; ++i) acc[k][t][i] = 0.0f;
+
+  const bool warp_active = warp * 4 < ntrios;
+  for (int it = 0; it < nchunks; ++it) {
+    const int s = it % STAGES;
+    const unsigned ph = (unsigned)(it / STAGES) & 1u;
+    mbar_wait(&sm.full[s], ph);
+    if (warp_active) {
+      const float *st = sm.stage[s];
+      const float *p1 = st + off1;
+#pragma unroll 2
+      for (int cc = 0; cc < CC; ++cc) {
+        float a[NTR][PX2], w[WLEN];
+#pragma unroll
+        for (int k = 0; k < NTR; ++k) {
+          const float4 v = *reinterpret_cast<const float4 *>(st + off0[k] + cc * (R0H * P0));
+          a[k][0] = v.x; a[k][1] = v.y; a[k][2] = v.z; a[k][3] = v.w;
+        }
+#pragma unroll
+        for (int q = 0; q < WLEN / 4; ++q) {
+          const float4 v = *reinterpret_cast<const float4 *>(p1 + cc * (NY2 * WIN) + 4 * q);
+          w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
+        }
+#pragma unroll
+        for (int k = 0; k < NTR; ++k)
+#pragma unroll
+          for (int t = 0; t < DO; ++t)
+#pragma unroll
+            for (int i = 0; i < PX2; ++i) acc[k][t][i] = fmaf(a[k][i], w[i + S2 * t], acc[k][t][i]);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&sm.empty[s]);
+  }
+
+  if (active) {
+    const float denom = (float)C;
+    const int x = x0 + pxg * PX2;
+    if (x < W) {
+#pragma unroll
+      for (int k = 0; k < NTR; ++k) {
+        if (k >= nrows) continue;
+        const int yk = y - S2 * k;          // p + k  <->  row y - 2k
+#pragma unroll
+        for (int t = 0; t < DO; ++t) {
+          const int o = og == 0 ? t - RMAX : t;
+          if (o < -r || o > r || (og == 1 && t == 0)) continue;
+          float *dst = outb + ((size_t)((pidx + k) * D + (o + r))) * plane_out + (size_t)yk * W + x;
+          *reinterpret_cast<float4 *>(dst) = make_float4(acc[k][t][0] / denom, acc[k][t][1] / denom,
+                                                         acc[k][t][2] / denom, acc[k][t][3] / denom);
+        }
+      }
     }
   }
 }
@@ -294,6 +525,8 @@ static int encode_map(CUtensorMap *m, const float *base, int rank, const cuuint6
   return UNFLOW_OK;
 }
 
+int g_corr_fwd_variant = 1;   // measured: v1 0.429 ms, v3 0.486 ms at B=8 (fewer warps hide less latency)
+
 bool corr_tiled_supported(const CorrGeom &g) {
   return g.ks == 1 && g.s1 == 1 && g.s2 == ct::S2 && g.pad == g.md && g.ngr <= ct::RMAX &&
          g.H % 2 == 0 && g.W % 4 == 0 && g.W >= ct::TX && g.H >= 2 && g.B <= 65535;
@@ -323,10 +556,13 @@ int corr_fwd_tiled(const float *in0, const float *in1, float *out, const CorrGeo
     if (rc) return rc;
   }
   static bool attr_set = false;
-  const int smem_bytes = (int)sizeof(Smem);
+  const int smem_bytes = (int)sizeof(Smem), smem_bytes2 = (int)sizeof(ct2::Smem2);
+  const int variant = g_corr_fwd_variant;   // 1: pair per thread, 3: trio per thread (default)
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(corr_fwd_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          smem_bytes);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(corr_fwd_tiled3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes2);
     if (e != cudaSuccess) { set_error("correlation smem attribute: %s", cudaGetErrorString(e)); return UNFLOW_ECUDA; }
     attr_set = true;
   }
@@ -334,7 +570,10 @@ int corr_fwd_tiled(const float *in0, const float *in1, float *out, const CorrGeo
   const int y2_first = -((S2 * r + NY2 - 1) / NY2) * NY2;
   const int y2_end = g.H + S2 * r;  // exclusive
   dim3 grid(ceil_div(g.W, TX), ceil_div(y2_end - y2_first, NY2), g.B);
-  corr_fwd_tiled_kernel<<<grid, NTHREADS, smem_bytes, s>>>(map0, map1, out, g.C, g.H, g.W, r, y2_first);
+  if (variant == 1)
+    corr_fwd_tiled_kernel<<<grid, NTHREADS, smem_bytes, s>>>(map0, map1, out, g.C, g.H, g.W, r, y2_first);
+  else
+    corr_fwd_tiled3_kernel<<<grid, ct2::NTHREADS2, smem_bytes2, s>>>(map0, map1, out, g.C, g.H, g.W, r, y2_first);
   count_launch();
   return check_launch("correlation_fwd(tiled)");
 }
@@ -377,13 +616,17 @@ template <bool G1> struct Cfg {
 };
 template <bool G1> struct Smem {
   float stage[STAGES][Cfg<G1>::STAGE_FLOATS];
+  float zero_tile[Cfg<G1>::G_FLOATS];     // tap weights of a row that does not use this SRC row
   unsigned long long full[STAGES];
   unsigned long long empty[STAGES];
 };
 static_assert((S_FLOATS * 4) % 128 == 0 && (G0_FLOATS * 4) % 128 == 0 && (G1_FLOATS * 4) % 128 == 0, "");
 }  // namespace cb
 
-template <bool G1>
+// RT > 0: neighbourhood radius known at compile time (RT = 10 is FlowNetC): the displacement loop
+// is branch-free, so the compiler can hoist the shared loads of the next displacement pair above
+// the FMAs of the current one.  RT = 0: radius read at run time (any even r <= 10).
+template <bool G1, int RT>
 __global__ void __launch_bounds__(cb::NTHREADS, 1)
 corr_bwd_tiled_kernel(const __grid_constant__ CUtensorMap map_src,   // SRC [B][C][H][W], box (108,1,128,1)
                       const __grid_constant__ CUtensorMap map_g,     // gout [B][D*D][H][W], box (GW,1,D,1)
@@ -397,6 +640,7 @@ corr_bwd_tiled_kernel(const __grid_constant__ CUtensorMap map_src,   // SRC [B][
   const int x0 = blockIdx.x * TXB;
   const int ya = (blockIdx.y >> 1) * 4 + (blockIdx.y & 1), yb = ya + 2;   // row pair
   const int b = blockIdx.z / slabs, c0 = (blockIdx.z % slabs) * CCH;
+  if (RT > 0) r = RT;
   const int D = 2 * r + 1;
   const int joff = S2 * (RMAX - r);        // column offset of displacement o=-r inside the staged window
 
@@ -404,6 +648,7 @@ corr_bwd_tiled_kernel(const __grid_constant__ CUtensorMap map_src,   // SRC [B][
     for (int s = 0; s < STAGES; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], NPXG); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  for (int i = tid; i < CF::G_FLOATS; i += NTHREADS) sm.zero_tile[i] = 0.0f;
   __syncthreads();
 
   // stages: SRC rows y2 = ya - 2r + 2k, k = 0 .. 2r+1, inside the image
@@ -458,8 +703,9 @@ corr_bwd_tiled_kernel(const __grid_constant__ CUtensorMap map_src,   // SRC [B][
     mbar_wait(&sm.full[s], ph);
     if (warp_active) {
       const float *S = sm.stage[s] + lane * PITCH + pxg * PXW + joff;
-      const float *Ga = sm.stage[s] + S_FLOATS;
-      const float *Gb = Ga + CF::G_FLOATS;
+      // a row that does not use this SRC row reads an all-zero tap tile: no branch in the hot loop
+      const float *Ga = va ? sm.stage[s] + S_FLOATS : sm.zero_tile;
+      const float *Gb = vb ? sm.stage[s] + S_FLOATS + CF::G_FLOATS : sm.zero_tile;
       // rotating 12-float window per channel: column col (relative to S) lives in slot col % 12
       float win[4][12];
 #pragma unroll
@@ -471,7 +717,7 @@ corr_bwd_tiled_kernel(const __grid_constant__ CUtensorMap map_src,   // SRC [B][
       }
 #pragma unroll
       for (int tp = 0; tp <= RMAX; ++tp) {       // displacement pairs t = 2tp, 2tp+1
-        if (2 * tp < D) {
+        if (RT > 0 || 2 * tp < D) {
 #pragma unroll
           for (int cc = 0; cc < 4; ++cc) {
             const float4 v = *reinterpret_cast<const float4 *>(S + cc * 32 * PITCH + 4 * tp + 8);
@@ -481,31 +727,29 @@ corr_bwd_tiled_kernel(const __grid_constant__ CUtensorMap map_src,   // SRC [B][
 #pragma unroll
           for (int tt = 0; tt < 2; ++tt) {
             const int t = 2 * tp + tt;
-            if (t < D) {
+            if (RT > 0 ? t < 2 * RT + 1 : t < D) {
 #pragma unroll
               for (int a = 0; a < 2; ++a) {
-                if (a == 0 ? va : vb) {
-                  const float *G = a == 0 ? Ga : Gb;
-                  float g[PXW];
-                  if (!G1) {
-                    const float4 g0 = *reinterpret_cast<const float4 *>(G + t * TXB + pxg * PXW);
-                    const float4 g1 = *reinterpret_cast<const float4 *>(G + t * TXB + pxg * PXW + 4);
-                    g[0] = g0.x; g[1] = g0.y; g[2] = g0.z; g[3] = g0.w;
-                    g[4] = g1.x; g[5] = g1.y; g[6] = g1.z; g[7] = g1.w;
-                  } else {
-                    const float *gp = G + (D - 1 - t) * SW + pxg * PXW + joff + 2 * t;
+                const float *G = a == 0 ? Ga : Gb;
+                float g[PXW];
+                if (!G1) {
+                  const float4 g0 = *reinterpret_cast<const float4 *>(G + t * TXB + pxg * PXW);
+                  const float4 g1 = *reinterpret_cast<const float4 *>(G + t * TXB + pxg * PXW + 4);
+                  g[0] = g0.x; g[1] = g0.y; g[2] = g0.z; g[3] = g0.w;
+                  g[4] = g1.x; g[5] = g1.y; g[6] = g1.z; g[7] = g1.w;
+                } else {
+                  const float *gp = G + (D - 1 - t) * SW + pxg * PXW + joff + 2 * t;
 #pragma unroll
-                    for (int h2 = 0; h2 < 4; ++h2) {
-                      const float2 gv = *reinterpret_cast<const float2 *>(gp + 2 * h2);
-                      g[2 * h2] = gv.x; g[2 * h2 + 1] = gv.y;
-                    }
+                  for (int h2 = 0; h2 < 4; ++h2) {
+                    const float2 gv = *reinterpret_cast<const float2 *>(gp + 2 * h2);
+                    g[2 * h2] = gv.x; g[2 * h2 + 1] = gv.y;
                   }
-#pragma unroll
-                  for (int cc = 0; cc < 4; ++cc)
-#pragma unroll
-                    for (int i = 0; i < PXW; ++i)
-                      acc[a][cc][i] = fmaf(g[i], win[cc][(2 * t + i) % 12], acc[a][cc][i]);
                 }
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc)
+#pragma unroll
+                  for (int i = 0; i < PXW; ++i)
+                    acc[a][cc][i] = fmaf(g[i], win[cc][(2 * t + i) % 12], acc[a][cc][i]);
               }
             }
           }
@@ -565,14 +809,19 @@ static int launch_bwd(const float *src, const float *gout, float *outp, const Co
   static bool attr_set = false;
   const int smem_bytes = (int)sizeof(Smem<G1>);
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(corr_bwd_tiled_kernel<G1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(corr_bwd_tiled_kernel<G1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          smem_bytes);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(corr_bwd_tiled_kernel<G1, RMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) { set_error("correlation_grad smem attribute: %s", cudaGetErrorString(e)); return UNFLOW_ECUDA; }
     attr_set = true;
   }
   const int slabs = ceil_div(g.C, CCH);
   dim3 grid(ceil_div(g.W, TXB), ceil_div(g.H, 4) * 2, g.B * slabs);
-  corr_bwd_tiled_kernel<G1><<<grid, NTHREADS, smem_bytes, s>>>(map_src, map_g, outp, g.C, g.H, g.W, g.ngr, slabs);
+  if (g.ngr == RMAX)
+    corr_bwd_tiled_kernel<G1, RMAX><<<grid, NTHREADS, smem_bytes, s>>>(map_src, map_g, outp, g.C, g.H, g.W, g.ngr, slabs);
+  else
+    corr_bwd_tiled_kernel<G1, 0><<<grid, NTHREADS, smem_bytes, s>>>(map_src, map_g, outp, g.C, g.H, g.W, g.ngr, slabs);
   count_launch();
   return check_launch(G1 ? "correlation_bwd1(tiled)" : "correlation_bwd0(tiled)");
 }

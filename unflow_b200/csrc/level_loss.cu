@@ -406,18 +406,18 @@ level_loss_bwd_kernel(Params p) {
       const float(*gB)[RW] = sg[dir == 0 ? 2 : 3];
       const float(*Wq)[RW] = sg[dir == 0 ? 4 : 5];
       const float cA = gA[ly][lx], cB = gB[ly][lx], wc = Wq[ly][lx];
-      float s_in = 0.f, s_self = 0.f;
+      // dL/dgB(q) = sum_k E_k(q-k) - sum_k E_k(q),  E_k(c) = W(c) * phi(gA(c+k)-gA(c), gB(c+k)-gB(c)).
+      // phi is odd (phi(-s1,-s2) = -phi(s1,s2)), so pixel q as a neighbour of centre n and n as a
+      // neighbour of centre q share one evaluation:  dL/dgB(q) = sum_n (W(n) + W(q)) * phi(cA-gA(n), cB-gB(n)).
+      float ssum = 0.f;
 #pragma unroll
       for (int dy = -R; dy <= R; ++dy)
 #pragma unroll
         for (int dx = -R; dx <= R; ++dx) {
-          // pixel q as the neighbour (q = c + k) of centre c = q - k
-          const float wn = Wq[ly - dy][lx - dx];
-          if (wn != 0.f) s_in += wn * tern_phi(cA - gA[ly - dy][lx - dx], cB - gB[ly - dy][lx - dx]);
-          // pixel q as the centre
-          if (wc != 0.f) s_self += tern_phi(gA[ly + dy][lx + dx] - cA, gB[ly + dy][lx + dx] - cB);
+          const float wsum = Wq[ly + dy][lx + dx] + wc;
+          if (wsum != 0.f) ssum += wsum * tern_phi(cA - gA[ly + dy][lx + dx], cB - gB[ly + dy][lx + dx]);
         }
-      dG = u_tern * (s_in - wc * s_self);
+      dG = u_tern * ssum;
     }
     if (dG != 0.f || (u_photo != 0.f && m != 0.f)) {
 #pragma unroll
