@@ -189,6 +189,16 @@ def run_ours(args):
     ms_e2e, _, _, _ = timed(e2e_step, args.steps)
     torch.cuda.synchronize()
     final_loss = float(loss_host.item())
+    fp32_exact = None
+    if args.also_fp32 and args.conv != "fp32":
+        conv_ops.set_mode("fp32")
+        for _ in range(3):
+            resident_step()
+        ms32, _, _, _ = timed(resident_step, max(3, args.steps // 2))
+        fp32_exact = {"ms_per_step": round(ms32 / max(3, args.steps // 2), 3),
+                      "value": round(PER_GPU_BATCH * world / (ms32 / max(3, args.steps // 2) * 1e-3), 3),
+                      "unit": "frame-pairs/s", "conv_precision": "fp32 (cuDNN, no tensor cores)"}
+        conv_ops.set_mode(args.conv)
 
     if rank != 0:
         if world > 1:
@@ -241,6 +251,8 @@ def run_ours(args):
         "clocks": clocks,
         "final_loss": final_loss,
     }
+    if fp32_exact:
+        line["fp32_exact"] = fp32_exact
     if roofs:
         line["roofline"] = roofs[0]
         line["rooflines_other"] = roofs[1:]
@@ -335,12 +347,16 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--conv", default=os.environ.get("UNFLOW_CONV_PRECISION", "fp32"),
-                    choices=["fp32", "3xtf32"], help="arithmetic of the cuDNN conv stacks")
+    ap.add_argument("--conv", default=os.environ.get("UNFLOW_CONV_PRECISION", "3xtf32"),
+                    choices=["fp32", "3xtf32"],
+                    help="arithmetic of the conv stacks: 3xtf32 = tensor cores at fp32-level accuracy "
+                         "(parity-tested at the same 1e-4 flow tolerance), fp32 = plain cuDNN float32")
+    ap.add_argument("--also-fp32", action="store_true",
+                    help="additionally time the plain-fp32 conv mode and report it as fp32_exact")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -167,13 +167,19 @@ int unflow_adam_step(float *params, float *grads, float *m, float *v, long long 
                      int zero_grad, void *stream);
 
 /* ------------------------------------------------------------------------
- * 3xTF32 operand split for the conv / deconv stacks (no reference counterpart: the reference
- * runs its slim.conv2d layers in plain fp32 on cuDNN, src/e2eflow/core/flownet.py:174-233).
- * For each of `items` slabs of `inner` floats writes three slabs: order 0 -> (hi, hi, lo),
- * order 1 -> (hi, lo, hi), hi = round-to-nearest TF32(x), lo = x - hi.  out holds 3*items*inner.
+ * 3xTF32 operand preparation for the conv / deconv stacks (no reference counterpart: the
+ * reference runs its slim.conv2d layers in plain fp32 on cuDNN, src/e2eflow/core/flownet.py:174-233).
+ * Reads a logical [N,C,H,W] fp32 tensor through arbitrary strides (in floats) and writes the dense
+ * NHWC operand of one TF32 library convolution: x = hi + lo (hi = round-to-nearest TF32), three
+ * slabs (order 0: hi,hi,lo; order 1: hi,lo,hi) side by side along C (concat_batch = 0, output
+ * [N_out, Hp, Wp, 3*C_pad]) or along N (concat_batch = 1, output [3*N_out, Hp, Wp, C_pad]); channels
+ * C..C_pad-1, items N..N_out-1 and the spatial border (TF SAME padding, Hp = H+pad_top+pad_bottom)
+ * are written as zeros.  C_pad % 4 == 0.
  * ---------------------------------------------------------------------- */
-int unflow_split3_tf32(const float *x, float *out, long long items, long long inner, int order,
-                       void *stream);
+int unflow_conv_operand_tf32(const float *x, float *out, int N, int C, int H, int W, long long sN,
+                             long long sC, long long sH, long long sW, int N_out, int C_pad,
+                             int pad_top, int pad_bottom, int pad_left, int pad_right,
+                             int concat_batch, int order, void *stream);
 
 #ifdef __cplusplus
 }

@@ -25,17 +25,31 @@ def rel(a, b):
     return float((a.double() - b).norm() / b.norm())
 
 
-def test_split_kernel_exact():
-    from unflow_b200.e2eflow.core.conv_ops import _cat_channels, _cat_batch
-    x = torch.randn(3, 5, 7, 9, device="cuda") * 100
-    s = _cat_channels(x, 0)
-    hi, hi2, lo = s[:, :5], s[:, 5:10], s[:, 10:]
+def test_operand_kernel_exact():
+    """csrc/split.cu: exact hi/lo decomposition, channel / batch concatenation, zero padding of
+    channels, items and the TF-SAME border, arbitrary source strides."""
+    from unflow_b200.e2eflow.core.conv_ops import _operand
+    base = torch.randn(3, 7, 9, 6, device="cuda") * 100          # NHWC memory
+    x = base.permute(0, 3, 1, 2)[:, :5]                           # [3,5,7,9] channel-sliced channels_last view
+    s = _operand(x, 0, c_pad=8, pads=(1, 2, 0, 1))               # -> [3, 24, 10, 10]
+    assert s.shape == (3, 24, 10, 10) and s.is_contiguous(memory_format=torch.channels_last)
+    hi, hi2, lo = s[:, 0:8], s[:, 8:16], s[:, 16:24]
     assert torch.equal(hi, hi2)
-    assert torch.equal(hi + lo, x)                              # exact decomposition
-    assert int((hi.view(torch.int32) & 0x1FFF).abs().max()) == 0   # hi is a TF32 number
-    assert float((lo.abs() / x.abs()).max()) <= 2.0 ** -11
-    s1 = _cat_batch(x, 1)
-    assert torch.equal(s1[:3], hi) and torch.equal(s1[3:6], lo) and torch.equal(s1[6:], hi)
+    inner = (slice(None), slice(0, 5), slice(1, 8), slice(0, 9))
+    assert torch.equal((hi + lo)[inner], x)                       # exact decomposition
+    assert int((hi.contiguous().view(torch.int32) & 0x1FFF).abs().max()) == 0   # hi is a TF32 number
+    total = (hi + lo)
+    mask = torch.zeros_like(total, dtype=torch.bool)
+    mask[inner] = True
+    assert float(total[~mask].abs().max()) == 0.0                 # channel pad + spatial border are zeros
+    assert float((lo[inner].abs() / x.abs()).max()) <= 2.0 ** -11
+    # batch concat, order (hi;lo;hi), extra zero items, NCHW-contiguous source (weights)
+    w = torch.randn(5, 3, 4, 4, device="cuda")
+    b = _operand(w, 1, concat_batch=True, c_pad=4, n_out=8)      # -> [24, 4, 4, 4]
+    assert b.shape == (24, 4, 4, 4)
+    h0, l0, h1 = b[0:8], b[8:16], b[16:24]
+    assert torch.equal(h0, h1) and torch.equal((h0 + l0)[:5, :3], w)
+    assert float(h0[5:].abs().max()) == 0.0 and float(h0[:, 3:].abs().max()) == 0.0
 
 
 @pytest.mark.parametrize("stride,k,pads", [(1, 3, (1, 1, 1, 1)), (2, 5, (1, 2, 1, 2)), (2, 7, (2, 3, 2, 3))])

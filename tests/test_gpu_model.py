@@ -61,8 +61,10 @@ def test_flownet_vs_oracle(spec, hw):
     # forward-only call returns the same forward flows (flownet.py:79-81)
     with torch.no_grad():
         only_fw = flownet(im1.cuda(), im2.cuda(), spec, variables=v)
+    # (not bit-identical: the bidirectional pass runs 2B samples through cuDNN, which may pick other
+    # algorithms than for B samples)
     for w, g in zip(got_fw[-1], only_fw[-1]):
-        close(g, w, rtol=1e-4, atol_rel=1e-5)
+        close(g, w, rtol=1e-3, atol_rel=1e-4)
 
 
 @pytest.mark.parametrize("spec,hw", [("C", (128, 256)), ("S", (128, 192))])

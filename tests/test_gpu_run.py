@@ -1,0 +1,65 @@
+"""python -m unflow_b200.run: config.ini semantics, checkpoint cadence and resume-by-iteration
+(reference src/run.py, src/e2eflow/core/train.py:116-145,258-259) on a short synthetic run."""
+import glob
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+CFG = """
+[dirs]
+log = {d}/log
+checkpoints = {d}/log/checkpoints
+data = {d}/nodata
+[run]
+batch_size = 2
+gpu_list = 0
+dataset = kitti
+development = False
+[train]
+decay_interval = 100000
+save_interval = 2
+display_interval = 1
+flownet = C
+pyramid_loss = True
+border_mask = True
+ternary_weight = 1.0
+smooth_2nd_weight = 3.0
+[train_kitti]
+height = 128
+width = 256
+num_iters = 6
+learning_rate = 1.0e-5
+decay_after = 100000
+fb_weight = 0.2
+mask_occlusion = fb
+occ_weight = 12.4
+"""
+
+
+def test_run_trains_checkpoints_and_resumes(tmp_path, capsys):
+    from unflow_b200 import run as R
+    ini = tmp_path / "config.ini"
+    ini.write_text(CFG.format(d=str(tmp_path)))
+    R.main(["--ex", "t1", "--config", str(ini), "--synthetic", "--max-iters", "4"])
+    out = capsys.readouterr().out
+    assert "-- training from i = 1 to 4" in out and "-- train: i = 4, loss" in out
+    ck = sorted(glob.glob(str(tmp_path / "log" / "checkpoints" / "t1" / "model.ckpt-*.pt")))
+    assert [os.path.basename(c) for c in ck] == ["model.ckpt-2.pt", "model.ckpt-4.pt"]
+    state = torch.load(ck[-1])
+    assert "flownet_c/conv3_1/weights" in state["variables"]
+    assert tuple(state["variables"]["flownet_c_features/conv1/weights"].shape) == (7, 7, 3, 64)  # HWIO
+    # resume: parses the iteration from the file name and continues at 5
+    R.main(["--ex", "t1", "--config", str(ini), "--synthetic"])
+    out = capsys.readouterr().out
+    assert "-- training from i = 5 to 6" in out
+    assert os.path.exists(str(tmp_path / "log" / "checkpoints" / "t1" / "model.ckpt-6.pt"))
+    # finished experiment: nothing left to do
+    R.main(["--ex", "t1", "--config", str(ini), "--synthetic"])
+    assert "max_iter reached" in capsys.readouterr().out
+    # --ow starts over, --debug writes no checkpoints
+    R.main(["--ex", "t1", "--config", str(ini), "--synthetic", "--ow", "--debug", "--max-iters", "2"])
+    assert "-- training from i = 1 to 2" in capsys.readouterr().out
+    assert not glob.glob(str(tmp_path / "log" / "checkpoints" / "t1" / "model.ckpt-*.pt"))

@@ -36,93 +36,105 @@ def get_mode():
     return _MODE
 
 
-CL = torch.channels_last
+def _round4(c):
+    return (c + 3) // 4 * 4
 
 
-def _cl(x):
-    """Dense NHWC memory (channels_last) -- the layout cuDNN's tensor-core kernels compute in; with
-    NCHW tensors cuDNN wraps every conv in nchwToNhwc / nhwcToNchw transform kernels (24 % of the
-    step when measured)."""
-    return x.contiguous(memory_format=CL)
-
-
-def _split3(x, items, inner, order):
-    """x: dense tensor viewed as [items][inner] -> 3 slabs per item (csrc/split.cu), flat output."""
-    out = torch.empty((3 * items * inner,), device=x.device, dtype=torch.float32)
+def _operand(x, order, concat_batch=False, c_pad=None, n_out=None, pads=(0, 0, 0, 0)):
+    """One pass of csrc/split.cu: logical [N,C,H,W] (any strides) -> the dense channels_last TF32
+    operand [N_out, 3*C_pad, Hp, Wp] (channel concat) or [3*N_out, C_pad, Hp, Wp] (batch concat)."""
+    N, C, H, W = x.shape
+    c_pad = _round4(C) if c_pad is None else c_pad
+    n_out = N if n_out is None else n_out
+    pt, pb, pl, pr = pads
+    Hp, Wp = H + pt + pb, W + pl + pr
+    out = torch.empty((3 * n_out * Hp * Wp * c_pad,), device=x.device, dtype=torch.float32)
+    sN, sC, sH, sW = x.stride()
     with torch.cuda.device(x.device):
-        check(_native.lib().unflow_split3_tf32(x.data_ptr(), out.data_ptr(), items, inner, order,
-                                               torch.cuda.current_stream().cuda_stream), "split3_tf32")
-    return out
+        check(_native.lib().unflow_conv_operand_tf32(
+            x.data_ptr(), out.data_ptr(), N, C, H, W, sN, sC, sH, sW, n_out, c_pad, pt, pb, pl, pr,
+            1 if concat_batch else 0, order, torch.cuda.current_stream().cuda_stream), "conv_operand_tf32")
+    if concat_batch:
+        return out.view(3 * n_out, Hp, Wp, c_pad).permute(0, 3, 1, 2)
+    return out.view(n_out, Hp, Wp, 3 * c_pad).permute(0, 3, 1, 2)
 
 
-def _cat_channels(x, order):
-    """[N,C,H,W] -> [N,3C,H,W] (channels_last): per pixel (hi,hi,lo) or (hi,lo,hi) along C."""
-    x = _cl(x)
-    N, C, H, W = x.shape
-    return _split3(x, N * H * W, C, order).view(N, H, W, 3 * C).permute(0, 3, 1, 2)
-
-
-def _cat_batch(x, order):
-    """[N,C,H,W] -> [3N,C,H,W] (channels_last) = (hi;hi;lo) or (hi;lo;hi) along the batch."""
-    x = _cl(x)
-    N, C, H, W = x.shape
-    return _split3(x, 1, x.numel(), order).view(3 * N, H, W, C).permute(0, 3, 1, 2)
+def _pad_bias(b, co_p):
+    if b is None or b.shape[0] == co_p:
+        return b
+    return F.pad(b, (0, co_p - b.shape[0]))
 
 
 class _Conv3x(torch.autograd.Function):
+    """conv2d(pad_same(x), w) + b at fp32-level accuracy on the tensor cores (one TF32 cuDNN conv
+    over the channel-concatenated hi/lo operands).  ``pads`` = TF SAME (top, bottom, left, right)."""
+
     @staticmethod
-    def forward(ctx, x, w, b, stride, padding):
+    def forward(ctx, x, w, b, stride, pads):
+        Co, Ci = w.shape[0], w.shape[1]
+        ci_p, co_p = _round4(Ci), _round4(Co)
         ctx.save_for_backward(x, w)
-        ctx.cfg = (stride, padding, b is not None)
-        xs = _cat_channels(x, 0)                       # [N,3Ci,H,W]   hi,hi,lo
-        ws = _cat_channels(w, 1)                       # [Co,3Ci,k,k]  hi,lo,hi
-        return F.conv2d(xs, ws, b, stride=stride, padding=padding)
+        ctx.cfg = (stride, pads, b is not None, ci_p, co_p)
+        xs = _operand(x, 0, c_pad=ci_p, pads=pads)               # [N, 3Ci_p, Hp, Wp]  hi,hi,lo
+        ws = _operand(w, 1, c_pad=ci_p, n_out=co_p)              # [Co_p, 3Ci_p, k, k] hi,lo,hi
+        y = F.conv2d(xs, ws, _pad_bias(b, co_p), stride=stride, padding=0)
+        return y if co_p == Co else y[:, :Co]
 
     @staticmethod
     def backward(ctx, g):
         x, w = ctx.saved_tensors
-        stride, padding, has_b = ctx.cfg
-        g = _cl(g)
+        stride, pads, has_b, ci_p, co_p = ctx.cfg
+        Co, Ci, k = w.shape[0], w.shape[1], w.shape[2]
+        N, _, H, W = x.shape
+        pt, pb, pl, pr = pads
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
-            gs = _cat_channels(g, 0)                   # [N,3Co,..]   hi,hi,lo
-            wt = _cat_batch(w, 1)                      # [3Co,Ci,k,k] hi;lo;hi
-            gx = nngrad.conv2d_input(x.shape, wt, gs, stride=stride, padding=padding)
+            gs = _operand(g, 0, c_pad=co_p)                                        # [N, 3Co_p, ..]
+            wt = _operand(w, 1, concat_batch=True, c_pad=ci_p, n_out=co_p)        # [3Co_p, Ci_p, k, k]
+            gxp = nngrad.conv2d_input((N, ci_p, H + pt + pb, W + pl + pr), wt, gs, stride=stride, padding=0)
+            gx = gxp[:, :Ci, pt:pt + H, pl:pl + W]
         if ctx.needs_input_grad[1]:
-            xb = _cat_batch(x, 0)                      # [3N,Ci,..]   hi;hi;lo
-            gb3 = _cat_batch(g, 1)                     # [3N,Co,..]   hi;lo;hi
-            gw = nngrad.conv2d_weight(xb, w.shape, gb3, stride=stride, padding=padding)
+            xb = _operand(x, 0, concat_batch=True, c_pad=ci_p, pads=pads)          # [3N, Ci_p, Hp, Wp]
+            gb3 = _operand(g, 1, concat_batch=True, c_pad=co_p)                    # [3N, Co_p, ..]
+            gwp = nngrad.conv2d_weight(xb, (co_p, ci_p, k, k), gb3, stride=stride, padding=0)
+            gw = gwp[:Co, :Ci]
         if has_b and ctx.needs_input_grad[2]:
             gb = g.sum((0, 2, 3))
         return gx, gw, gb, None, None
 
 
 class _Deconv3x(torch.autograd.Function):
-    """conv_transpose2d(x, w[in,out,4,4], stride=2, padding=1)"""
+    """conv_transpose2d(x, w[in,out,4,4], stride=2, padding=1) + b, same scheme."""
 
     @staticmethod
     def forward(ctx, x, w, b):
+        Ci, Co = w.shape[0], w.shape[1]
+        ci_p, co_p = _round4(Ci), _round4(Co)
         ctx.save_for_backward(x, w)
-        ctx.has_b = b is not None
-        xs = _cat_channels(x, 0)                       # [N,3Ci,h,w]
-        ws = _cat_batch(w, 1)                          # [3Ci,Co,4,4]
-        return F.conv_transpose2d(xs, ws, b, stride=2, padding=1)
+        ctx.cfg = (b is not None, ci_p, co_p)
+        xs = _operand(x, 0, c_pad=ci_p)                                           # [N, 3Ci_p, h, w]
+        ws = _operand(w, 1, concat_batch=True, c_pad=co_p, n_out=ci_p)            # [3Ci_p, Co_p, 4, 4]
+        y = F.conv_transpose2d(xs, ws, _pad_bias(b, co_p), stride=2, padding=1)
+        return y if co_p == Co else y[:, :Co]
 
     @staticmethod
     def backward(ctx, g):
         x, w = ctx.saved_tensors
-        g = _cl(g)
+        has_b, ci_p, co_p = ctx.cfg
+        Ci, Co = w.shape[0], w.shape[1]
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
-            gs = _cat_channels(g, 0)                   # [N,3Co,2h,2w]
-            wc = _cat_channels(w, 1)                   # [Ci,3Co,4,4]
-            gx = F.conv2d(gs, wc, None, stride=2, padding=1)
+            gs = _operand(g, 0, c_pad=co_p)                                       # [N, 3Co_p, 2h, 2w]
+            wc = _operand(w, 1, c_pad=co_p, n_out=ci_p)                           # [Ci_p, 3Co_p, 4, 4]
+            gxp = F.conv2d(gs, wc, None, stride=2, padding=1)
+            gx = gxp if ci_p == Ci else gxp[:, :Ci]
         if ctx.needs_input_grad[1]:
             # d/dw of conv_transpose == weight gradient of the conv whose input is g and output x
-            gb3 = _cat_batch(g, 0)
-            xb = _cat_batch(x, 1)
-            gw = nngrad.conv2d_weight(gb3, w.shape, xb, stride=2, padding=1)
-        if ctx.has_b and ctx.needs_input_grad[2]:
+            gb3 = _operand(g, 0, concat_batch=True, c_pad=co_p)
+            xb = _operand(x, 1, concat_batch=True, c_pad=ci_p)
+            gwp = nngrad.conv2d_weight(gb3, (ci_p, co_p, 4, 4), xb, stride=2, padding=1)
+            gw = gwp[:Ci, :Co]
+        if has_b and ctx.needs_input_grad[2]:
             gb = g.sum((0, 2, 3))
         return gx, gw, gb
 
@@ -143,14 +155,14 @@ def network_input(x_nhwc):
 
 def conv2d(x, w, b, stride, pads):
     """pads = (top, bottom, left, right) TF-SAME padding."""
+    if _MODE == '3xtf32' and x.is_cuda:
+        return _Conv3x.apply(x, w, b, stride, tuple(pads))
     pt, pb, pl, pr = pads
     if pt == pb and pl == pr:
         padding = (pt, pl)
     else:
         x = F.pad(x, (pl, pr, pt, pb))
         padding = (0, 0)
-    if _MODE == '3xtf32' and x.is_cuda:
-        return _Conv3x.apply(x, w, b, stride, padding)
     return F.conv2d(x, w, b, stride=stride, padding=padding)
 
 

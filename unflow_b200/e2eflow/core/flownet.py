@@ -266,22 +266,22 @@ def _flownet_upconv(s, conv6_1, conv5_1, conv4_1, conv3_1, conv2, conv1=None, in
     flow6 = s.conv(conv6_1, 'flow6', act=False)
     deconv5 = s.deconv(conv6_1, 'deconv5')
     flow6_up5 = s.deconv(flow6, 'flow6_up5', act=False)
-    concat5 = torch.cat([conv5_1, deconv5, flow6_up5], 1)
+    concat5 = _cat_c([conv5_1, deconv5, flow6_up5])
     flow5 = s.conv(concat5, 'flow5', act=False)
 
     deconv4 = s.deconv(concat5, 'deconv4')
     flow5_up4 = s.deconv(flow5, 'flow5_up4', act=False)
-    concat4 = torch.cat([conv4_1, deconv4, flow5_up4], 1)
+    concat4 = _cat_c([conv4_1, deconv4, flow5_up4])
     flow4 = s.conv(concat4, 'flow4', act=False)
 
     deconv3 = s.deconv(concat4, 'deconv3')
     flow4_up3 = s.deconv(flow4, 'flow4_up3', act=False)
-    concat3 = torch.cat([conv3_1, deconv3, flow4_up3], 1)
+    concat3 = _cat_c([conv3_1, deconv3, flow4_up3])
     flow3 = s.conv(concat3, 'flow3', act=False)
 
     deconv2 = s.deconv(concat3, 'deconv2')
     flow3_up2 = s.deconv(flow3, 'flow3_up2', act=False)
-    concat2 = torch.cat([conv2, deconv2, flow3_up2], 1)
+    concat2 = _cat_c([conv2, deconv2, flow3_up2])
     flow2 = s.conv(concat2, 'flow2', act=False)
 
     flows = [flow2, flow3, flow4, flow5, flow6]
@@ -290,12 +290,12 @@ def _flownet_upconv(s, conv6_1, conv5_1, conv4_1, conv3_1, conv2, conv1=None, in
         f = s.sub('full_res')
         deconv1 = f.deconv(concat2, 'deconv1')
         flow2_up1 = f.deconv(flow2, 'flow2_up1', act=False)
-        concat1 = torch.cat([conv1, deconv1, flow2_up1], 1)
+        concat1 = _cat_c([conv1, deconv1, flow2_up1])
         flow1 = f.conv(concat1, 'flow1', act=False)
 
         deconv0 = f.deconv(concat1, 'deconv0')
         flow1_up0 = f.deconv(flow1, 'flow1_up0', act=False)
-        concat0 = torch.cat([inputs, deconv0, flow1_up0], 1)
+        concat0 = _cat_c([inputs, deconv0, flow1_up0])
         flow0 = f.conv(concat0, 'flow0', act=False)
         flows = [flow0, flow1] + flows
     return flows
@@ -350,12 +350,12 @@ def _flownet_c_trunk(s, conv_redir_and_corr, conv2_a, channel_mult, full_res):
     return nchw_to_nhwc(res)
 
 
-def _concat_channels_last(first, second_batch_parts):
-    """concat([first..., cat(second_batch_parts, 0)], 1) written straight into ONE channels_last
-    buffer (each source is read once; no intermediate NCHW concat + layout transform)."""
+def _concat_channels_last(first, second_batch_parts=None):
+    """concat(first + [cat(second_batch_parts, 0)], 1) written straight into ONE channels_last
+    buffer: each source (dense, NCHW or a channel-sliced view) is read once; no intermediate concat
+    in a different layout followed by a layout transform."""
     n = first[0].shape[0]
-    c_first = sum(t.shape[1] for t in first)
-    c = c_first + second_batch_parts[0].shape[1]
+    c = sum(t.shape[1] for t in first) + (second_batch_parts[0].shape[1] if second_batch_parts else 0)
     h, w = first[0].shape[2], first[0].shape[3]
     out = torch.empty((n, c, h, w), device=first[0].device, dtype=first[0].dtype,
                       memory_format=torch.channels_last)
@@ -364,10 +364,17 @@ def _concat_channels_last(first, second_batch_parts):
         out[:, off:off + t.shape[1]] = t
         off += t.shape[1]
     b0 = 0
-    for t in second_batch_parts:
+    for t in (second_batch_parts or []):
         out[b0:b0 + t.shape[0], off:] = t
         b0 += t.shape[0]
     return out
+
+
+def _cat_c(tensors):
+    """tf.concat(tensors, 1) of NCHW-shaped tensors."""
+    if conv_ops.channels_last_active(tensors[0]):
+        return _concat_channels_last(list(tensors))
+    return torch.cat(tensors, 1)
 
 
 def flownet_c(conv3_a, conv3_b, conv2_a, channel_mult=1, full_res=False, _scope=None):
