@@ -136,6 +136,7 @@ def run_ours(args):
     _native.lib()  # fail loudly if libunflow.so is missing
     from unflow_b200.e2eflow.core import conv_ops
     conv_ops.set_mode(args.conv)
+    torch.backends.cudnn.benchmark = bool(args.cudnn_benchmark)
 
     params = dict(synth.KITTI_PARAMS, learning_rate=1.0e-5)
     trainer = Trainer(params, synth.KITTI_NORMALIZATION, dev, seed=1234)
@@ -210,10 +211,12 @@ def run_ours(args):
     e2e = pairs / (ms_e2e * 1e-3)
     fma_peak = 148 * 128 * 2 * peaks["sm_max_mhz"] * 1e6 / 1e12
 
-    def roof(name, nbytes, flops=None):
+    def roof(name, nbytes=None, flops=None):
         t = ktimes.get(name)
         if not t:
             return None
+        if nbytes is None:   # spans that declared their bytes: average over all launches
+            nbytes = ops.kernel_timer.bytes.get(name, 0) / len(t)
         avg = sum(t) / len(t) * 1e-3
         r = {"kernel": name, "bound": "hbm", "launches_timed": len(t), "avg_us": round(avg * 1e6, 2),
              "achieved": round(nbytes / avg / 1e9, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
@@ -231,7 +234,8 @@ def run_ours(args):
     roofs = [roof("correlation_fwd", corr_bytes, corr_flops),
              roof("correlation_bwd", 4 * Bc * hc * wc * (D2 + 4 * C), 2 * corr_flops),
              roof("level_loss_fwd_%dx%d" % (H // 4, W // 4), (44 + 16) * npx0),
-             roof("level_loss_bwd_%dx%d" % (H // 4, W // 4), (60 + 16) * npx0)]
+             roof("level_loss_bwd_%dx%d" % (H // 4, W // 4), (60 + 16) * npx0),
+             roof("conv_operand"), roof("adam")]
     roofs = [r for r in roofs if r]
     line = {
         "metric": METRIC, "value": round(value, 3), "unit": "frame-pairs/s", "n_gpus": world,
@@ -244,7 +248,8 @@ def run_ours(args):
                    "global_batch": PER_GPU_BATCH * world, "parallelism": "dp%d" % world,
                    "l2": "inputs+activations per step >> 126 MB L2 (no flush needed)",
                    "conv_precision": ("fp32 (cuDNN, TF32 disabled)" if args.conv == "fp32" else
-                                      "3xTF32 split on tensor cores (fp32-level accuracy, parity-tested)")},
+                                      "3xTF32 split on tensor cores (fp32-level accuracy, parity-tested)"),
+                   "cudnn_benchmark": bool(args.cudnn_benchmark)},
         "e2e": {"value": round(e2e, 3), "unit": "frame-pairs/s", "ms_per_step": round(ms_e2e / args.steps, 3),
                 "h2d_bytes_per_step": 2 * h_im1.numel() * 4, "d2h_bytes_per_step": 4},
         "gpu_launches": int(launches),
@@ -355,6 +360,8 @@ def main():
                     choices=["fp32", "3xtf32"],
                     help="arithmetic of the conv stacks: 3xtf32 = tensor cores at fp32-level accuracy "
                          "(parity-tested at the same 1e-4 flow tolerance), fp32 = plain cuDNN float32")
+    ap.add_argument("--cudnn-benchmark", type=int, default=int(os.environ.get("UNFLOW_CUDNN_BENCHMARK", "1")),
+                    help="1: let cuDNN autotune its algorithm per conv shape during warm-up")
     ap.add_argument("--also-fp32", action="store_true",
                     help="additionally time the plain-fp32 conv mode and report it as fp32_exact")
     args = ap.parse_args()

@@ -50,7 +50,8 @@ def _operand(x, order, concat_batch=False, c_pad=None, n_out=None, pads=(0, 0, 0
     Hp, Wp = H + pt + pb, W + pl + pr
     out = torch.empty((3 * n_out * Hp * Wp * c_pad,), device=x.device, dtype=torch.float32)
     sN, sC, sH, sW = x.stride()
-    with torch.cuda.device(x.device):
+    from ..ops import kernel_timer
+    with torch.cuda.device(x.device), kernel_timer.span("conv_operand", 4 * x.numel() + 4 * out.numel()):
         check(_native.lib().unflow_conv_operand_tf32(
             x.data_ptr(), out.data_ptr(), N, C, H, W, sN, sC, sH, sW, n_out, c_pad, pt, pb, pl, pr,
             1 if concat_batch else 0, order, torch.cuda.current_stream().cuda_stream), "conv_operand_tf32")

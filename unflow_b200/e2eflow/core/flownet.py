@@ -350,24 +350,46 @@ def _flownet_c_trunk(s, conv_redir_and_corr, conv2_a, channel_mult, full_res):
     return nchw_to_nhwc(res)
 
 
+class _ConcatCL(torch.autograd.Function):
+    """Channel concat written straight into ONE channels_last buffer.
+
+    forward: each source (dense, NCHW or a channel-sliced view) is read once -- no intermediate
+    concat in another layout followed by a layout transform.  backward: the gradients are channel
+    (and batch) slices of the incoming gradient, returned as VIEWS.  (Building the buffer with
+    ``out[:, a:b] = t`` costs one full-size clone of the gradient per assignment in autograd's
+    CopySlices backward -- 14 % of the step when profiled.)
+
+    Inputs: ``n_first`` tensors concatenated along C, then optionally tensors that are first
+    concatenated along N and appended along C (the two correlation directions of FlowNetC)."""
+
+    @staticmethod
+    def forward(ctx, n_first, *tensors):
+        first, second = tensors[:n_first], tensors[n_first:]
+        n = first[0].shape[0]
+        c = sum(t.shape[1] for t in first) + (second[0].shape[1] if second else 0)
+        h, w = first[0].shape[2], first[0].shape[3]
+        out = torch.empty((n, c, h, w), device=first[0].device, dtype=first[0].dtype,
+                          memory_format=torch.channels_last)
+        spans, off = [], 0
+        for t in first:
+            out[:, off:off + t.shape[1]].copy_(t)
+            spans.append((0, n, off, off + t.shape[1]))
+            off += t.shape[1]
+        b0 = 0
+        for t in second:
+            out[b0:b0 + t.shape[0], off:].copy_(t)
+            spans.append((b0, b0 + t.shape[0], off, c))
+            b0 += t.shape[0]
+        ctx.spans = spans
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return (None,) + tuple(g[b0:b1, c0:c1] for (b0, b1, c0, c1) in ctx.spans)
+
+
 def _concat_channels_last(first, second_batch_parts=None):
-    """concat(first + [cat(second_batch_parts, 0)], 1) written straight into ONE channels_last
-    buffer: each source (dense, NCHW or a channel-sliced view) is read once; no intermediate concat
-    in a different layout followed by a layout transform."""
-    n = first[0].shape[0]
-    c = sum(t.shape[1] for t in first) + (second_batch_parts[0].shape[1] if second_batch_parts else 0)
-    h, w = first[0].shape[2], first[0].shape[3]
-    out = torch.empty((n, c, h, w), device=first[0].device, dtype=first[0].dtype,
-                      memory_format=torch.channels_last)
-    off = 0
-    for t in first:
-        out[:, off:off + t.shape[1]] = t
-        off += t.shape[1]
-    b0 = 0
-    for t in (second_batch_parts or []):
-        out[b0:b0 + t.shape[0], off:] = t
-        b0 += t.shape[0]
-    return out
+    return _ConcatCL.apply(len(first), *(list(first) + list(second_batch_parts or [])))
 
 
 def _cat_c(tensors):

@@ -117,7 +117,8 @@ class Trainer:
     def apply_update(self, lr, grad_scale=1.0):
         if self.flat_param.device.type != "cuda":
             raise RuntimeError("the Adam update is a CUDA kernel (csrc/adam.cu); no CPU fallback")
-        with torch.cuda.device(self.device):
+        from ..ops import kernel_timer
+        with torch.cuda.device(self.device), kernel_timer.span("adam", 32 * self.flat_param.numel()):
             check(_native.lib().unflow_adam_step(
                 self.flat_param.data_ptr(), self.flat_grad.data_ptr(), self.adam_m.data_ptr(),
                 self.adam_v.data_ptr(), self.flat_param.numel(), float(lr), 0.9, 0.999, 1e-8,

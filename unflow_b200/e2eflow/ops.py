@@ -52,23 +52,26 @@ class _KernelTimer:
     def __init__(self):
         self.enabled = False
         self.records = []
+        self.bytes = {}
 
     def enable(self):
         self.enabled = True
         self.records = []
 
     def collect(self):
-        """-> {name: [ms, ...]}; call after a device synchronize."""
+        """-> {name: [ms, ...]}; call after a device synchronize.  ``self.bytes[name]`` holds the
+        algorithmic bytes summed over the same launches (for spans that declared them)."""
         self.enabled = False
-        out = {}
-        for name, s, e in self.records:
+        out, self.bytes = {}, {}
+        for name, s, e, nbytes in self.records:
             out.setdefault(name, []).append(s.elapsed_time(e))
+            self.bytes[name] = self.bytes.get(name, 0) + nbytes
         self.records = []
         return out
 
     class _Span:
-        def __init__(self, timer, name):
-            self.t, self.name = timer, name
+        def __init__(self, timer, name, nbytes=0):
+            self.t, self.name, self.nbytes = timer, name, nbytes
 
         def __enter__(self):
             if self.t.enabled:
@@ -80,11 +83,11 @@ class _KernelTimer:
         def __exit__(self, *exc):
             if self.t.enabled:
                 self.e.record()
-                self.t.records.append((self.name, self.s, self.e))
+                self.t.records.append((self.name, self.s, self.e, self.nbytes))
             return False
 
-    def span(self, name):
-        return self._Span(self, name)
+    def span(self, name, nbytes=0):
+        return self._Span(self, name, nbytes)
 
 
 kernel_timer = _KernelTimer()
