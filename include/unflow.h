@@ -36,6 +36,8 @@ extern "C" {
 
 #define UNFLOW_BORDER_ZERO 0  /* BackwardWarp op: taps outside the image contribute 0 */
 #define UNFLOW_BORDER_CLAMP 1 /* image_warp: tap indices clamped to the image       */
+#define UNFLOW_BORDER_STN 2   /* spatial_transformer sampler (augmentation): `flows` holds ABSOLUTE
+                                 sample coordinates; forward only (the reference stops gradients) */
 
 /* Library / diagnostics. */
 int unflow_abi_version(void);
@@ -165,6 +167,12 @@ int unflow_level_loss_bwd(const float *grad_losses, const float *im1, const floa
 int unflow_adam_step(float *params, float *grads, float *m, float *v, long long n, float lr,
                      float beta1, float beta2, float eps, long long step, float grad_scale,
                      int zero_grad, void *stream);
+/* Same update with the hyper-parameters read from DEVICE memory at run time:
+ * hyper = [lr, beta1, beta2, eps, grad_scale, step]; lr_t is computed on the device from `step`
+ * (1 for the first update), which a one-thread kernel advances after the update.  Lets a CUDA graph
+ * of the whole training step be replayed without per-step host writes. */
+int unflow_adam_step_dev(float *params, float *grads, float *m, float *v, long long n,
+                         float *hyper, int zero_grad, void *stream);
 
 /* ------------------------------------------------------------------------
  * 3xTF32 operand preparation for the conv / deconv stacks (no reference counterpart: the

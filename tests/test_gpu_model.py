@@ -149,3 +149,27 @@ def test_trainer_step_applies_adam_to_the_flat_buffer():
     np.testing.assert_allclose(got[nz].cpu().numpy(), want[nz].cpu().numpy(), rtol=2e-3, atol=2e-6)
     losses = [float(tr.step(im1, im2)) for _ in range(3)]
     assert all(np.isfinite(losses)) and tr.iteration == 4
+
+
+def test_cuda_graph_step_matches_eager_step():
+    """Trainer.capture(): replaying the captured step must do what the eager step does."""
+    from unflow_b200.e2eflow.core.train import Trainer
+    params = dict(synth.KITTI_PARAMS, learning_rate=1e-4)
+    im1, im2, _ = synth.image_pair(1, 128, 256, seed=4)
+    im1, im2 = im1.cuda(), im2.cuda()
+    jm1, jm2, _ = synth.image_pair(1, 128, 256, seed=5)
+    jm1, jm2 = jm1.cuda(), jm2.cuda()
+    a = Trainer(params, synth.KITTI_NORMALIZATION, "cuda", seed=9)
+    b = Trainer(params, synth.KITTI_NORMALIZATION, "cuda", seed=9)
+    p0 = b.flat_param.clone()
+    b.capture(im1, im2)
+    assert torch.equal(b.flat_param, p0) and b.iteration == 0      # capture leaves the state untouched
+    assert float(b.adam_m.abs().max()) == 0.0
+    la = [float(a.step(im1, im2)), float(a.step(jm1, jm2)), float(a.step(im1, im2))]
+    lb = [float(b.step(im1, im2)), float(b.step(jm1, jm2)), float(b.step(im1, im2))]
+    np.testing.assert_allclose(lb, la, rtol=2e-4)
+    # Adam normalises every gradient to ~lr*sign(g): elements whose gradient is summation noise may
+    # step the other way (|diff| up to 2*lr per step); everything else must agree closely
+    diff = (a.flat_param - b.flat_param).abs()
+    assert float((diff > 2e-5).float().mean()) < 0.02, float((diff > 2e-5).float().mean())
+    assert b.graph_replays == 3 and b._graph_launches > 20

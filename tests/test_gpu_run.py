@@ -63,3 +63,24 @@ def test_run_trains_checkpoints_and_resumes(tmp_path, capsys):
     R.main(["--ex", "t1", "--config", str(ini), "--synthetic", "--ow", "--debug", "--max-iters", "2"])
     assert "-- training from i = 1 to 2" in capsys.readouterr().out
     assert not glob.glob(str(tmp_path / "log" / "checkpoints" / "t1" / "model.ckpt-*.pt"))
+
+
+def test_evaluate_loop_on_synthetic_ground_truth():
+    """Row N1: Trainer.eval counterpart -- AEE / outlier averages against a known flow."""
+    from unflow_b200 import synthetic
+    from unflow_b200.e2eflow.core.flownet import FlowNetVariables
+    from unflow_b200.e2eflow.core.train import evaluate
+    v = FlowNetVariables('C', seed=2).cuda()
+    ex = []
+    for s in (1, 2):
+        im1, im2, flow = synthetic.image_pair(1, 96, 320, seed=s, max_flow=4.0)
+        mask = torch.ones(1, 96, 320, 1)
+        noc = (torch.rand(1, 96, 320, 1, generator=torch.Generator().manual_seed(s)) > 0.2).float()
+        ex.append(tuple(t.cuda() for t in (im1, im2, flow, mask, flow, noc)))
+    res, images = evaluate(v, dict(synthetic.KITTI_PARAMS), synthetic.KITTI_NORMALIZATION, ex, eval_size=(128, 384))
+    assert res['num_examples'] == 2
+    # an untrained network predicts ~zero flow: the AEE is about the mean magnitude of the truth
+    mean_mag = sum(float(e[2].norm(dim=3).mean()) for e in ex) / 2
+    assert 0.5 * mean_mag < res['AEE/occluded'] < 1.5 * mean_mag
+    assert 0 <= res['outliers/non-occluded'] <= 100
+    assert images['flow'].shape == (1, 96, 320, 3) and images['reverse disocc'].dtype == torch.bool

@@ -165,10 +165,11 @@ def test_install_as_e2eflow_alias():
     assert LOSSES == ['occ', 'sym', 'fb', 'grad', 'ternary', 'photo', 'smooth_1st', 'smooth_2nd']
 
 
-def test_unsupervised_loss_rejects_augment():
+def test_unsupervised_loss_needs_cuda_inputs():
     from unflow_b200.e2eflow.core.unsupervised import unsupervised_loss
-    with pytest.raises(NotImplementedError):
-        unsupervised_loss((torch.zeros(1, 64, 64, 3),) * 2, {}, normalization=([0, 0, 0], 1.0))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        unsupervised_loss((torch.zeros(1, 64, 64, 3),) * 2, {'flownet': 'S', 'ternary_weight': 1.0},
+                          normalization=([0, 0, 0], 1.0), augment=False)
 
 
 def test_every_product_module_imports_without_gpu():

@@ -12,10 +12,20 @@
 
 namespace unflow {
 
+// hyper (device, optional): [lr, beta1, beta2, eps, grad_scale, step] -- read at run time so that a
+// CUDA graph of the whole training step can be replayed: the step counter lives on the device and
+// is advanced by a one-thread kernel after the update, the host only rewrites `lr` when the
+// schedule changes it.
 __global__ void __launch_bounds__(256)
 adam_kernel(float4 *__restrict__ p, float4 *__restrict__ g, float4 *__restrict__ m,
             float4 *__restrict__ v, long long n4, float lr_t, float b1, float b2, float eps,
-            float grad_scale, int zero_grad) {
+            float grad_scale, int zero_grad, const float *__restrict__ hyper) {
+  if (hyper) {
+    b1 = __ldg(hyper + 1); b2 = __ldg(hyper + 2); eps = __ldg(hyper + 3);
+    grad_scale = __ldg(hyper + 4);
+    const float t = __ldg(hyper + 5);
+    lr_t = __ldg(hyper) * sqrtf(1.0f - powf(b2, t)) / (1.0f - powf(b1, t));
+  }
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
        i += (long long)gridDim.x * blockDim.x) {
     float4 pp = p[i], gg = g[i], mm = m[i], vv = v[i];
@@ -32,6 +42,8 @@ adam_kernel(float4 *__restrict__ p, float4 *__restrict__ g, float4 *__restrict__
     if (zero_grad) g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
+
+__global__ void adam_advance_kernel(float *step) { *step += 1.0f; }
 
 }  // namespace unflow
 
@@ -50,7 +62,23 @@ extern "C" int unflow_adam_step(float *params, float *grads, float *m, float *v,
   const long long n4 = n / 4;
   adam_kernel<<<grid_for(n4, 256, 8), 256, 0, (cudaStream_t)stream>>>(
       (float4 *)params, (float4 *)grads, (float4 *)m, (float4 *)v, n4, (float)lr_t, beta1, beta2, eps,
-      grad_scale, zero_grad);
+      grad_scale, zero_grad, nullptr);
   count_launch();
   return check_launch("adam_step");
+}
+
+extern "C" int unflow_adam_step_dev(float *params, float *grads, float *m, float *v, long long n,
+                                    float *hyper, int zero_grad, void *stream) {
+  using namespace unflow;
+  UNFLOW_REQUIRE(n >= 0 && n % 4 == 0, "adam: the flat buffer length must be a multiple of 4");
+  if (n == 0) return UNFLOW_OK;
+  UNFLOW_REQUIRE(params && grads && m && v && hyper, "adam: null pointer");
+  UNFLOW_REQUIRE((((uintptr_t)params | (uintptr_t)grads | (uintptr_t)m | (uintptr_t)v) & 15) == 0,
+                 "adam: buffers must be 16-byte aligned");
+  const long long n4 = n / 4;
+  adam_kernel<<<grid_for(n4, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+      (float4 *)params, (float4 *)grads, (float4 *)m, (float4 *)v, n4, 0.f, 0.f, 0.f, 0.f, 0.f, zero_grad, hyper);
+  adam_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(hyper + 5);
+  count_launch(2);
+  return check_launch("adam_step_dev");
 }

@@ -43,6 +43,21 @@ __device__ __forceinline__ Taps make_taps(int sx, int sy, float u, float v, int 
     t.wc = t.xw * t.w_top;      // (y0,x1)
     t.wb = t.w_left * t.yw;     // (y1,x0)
     t.wd = t.xw * t.yw;         // (y1,x1)
+  } else if (MODE == UNFLOW_BORDER_STN) {
+    // spatial_transformer._interpolate (reference core/spatial_transformer.py:57-114): (u,v) are
+    // ABSOLUTE sample coordinates; indices are clamped and the weights are formed from the CLAMPED
+    // indices, so samples outside [0,W-1]x[0,H-1] cancel to exactly zero.
+    const float x = u, y = v;
+    const int x0 = (int)floorf(x), y0 = (int)floorf(y);
+    t.x0 = min(max(x0, 0), W - 1); t.x1 = min(max(x0 + 1, 0), W - 1);
+    t.y0 = min(max(y0, 0), H - 1); t.y1 = min(max(y0 + 1, 0), H - 1);
+    t.vx0 = t.vx1 = t.vy0 = t.vy1 = true;
+    t.w_left = (float)t.x1 - x; t.xw = x - (float)t.x0;
+    t.w_top = (float)t.y1 - y;  t.yw = y - (float)t.y0;
+    t.wa = t.w_left * t.w_top;
+    t.wb = t.w_left * t.yw;
+    t.wc = t.xw * t.w_top;
+    t.wd = t.xw * t.yw;
   } else {
     const float fu = floorf(u), fv = floorf(v);
     t.xw = u - fu; t.yw = v - fv;
@@ -178,13 +193,15 @@ extern "C" int unflow_backward_warp_fwd(const float *images, const float *flows,
                                         int H, int W, int C, int border_mode, void *stream) {
   using namespace unflow;
   UNFLOW_REQUIRE(B >= 0 && H >= 0 && W >= 0 && C >= 0, "backward_warp: negative dimension");
-  UNFLOW_REQUIRE(border_mode == UNFLOW_BORDER_ZERO || border_mode == UNFLOW_BORDER_CLAMP,
+  UNFLOW_REQUIRE(border_mode == UNFLOW_BORDER_ZERO || border_mode == UNFLOW_BORDER_CLAMP ||
+                     border_mode == UNFLOW_BORDER_STN,
                  "backward_warp: unknown border_mode %d", border_mode);
   const long long npix = (long long)B * H * W;
   if (npix == 0 || C == 0) return UNFLOW_OK;
   UNFLOW_REQUIRE(images && flows && out, "backward_warp: null pointer");
   cudaStream_t s = (cudaStream_t)stream;
   if (border_mode == UNFLOW_BORDER_ZERO) launch_fwd<UNFLOW_BORDER_ZERO>(images, flows, out, B, H, W, C, npix, s);
+  else if (border_mode == UNFLOW_BORDER_STN) launch_fwd<UNFLOW_BORDER_STN>(images, flows, out, B, H, W, C, npix, s);
   else launch_fwd<UNFLOW_BORDER_CLAMP>(images, flows, out, B, H, W, C, npix, s);
   count_launch();
   return check_launch("backward_warp_fwd");

@@ -80,6 +80,7 @@ class Trainer:
         self.trainable = trainable
         self._flatten()
         self.iteration = 0
+        self._graph = None
 
     def _flatten(self):
         n = sum(p.numel() for p in self.trainable)
@@ -125,13 +126,113 @@ class Trainer:
                 self.iteration, float(grad_scale), 1, torch.cuda.current_stream().cuda_stream),
                 "adam_step")
 
+    def _set_hyper(self, lr, step):
+        """(rare, synchronous) host -> device update of [lr, beta1, beta2, eps, grad_scale, step]."""
+        vals = torch.tensor([lr, 0.9, 0.999, 1e-8, 1.0 / self.world_size, float(step), 0.0, 0.0])
+        self._hyper_dev.copy_(vals.to(self.device))
+        torch.cuda.synchronize(self.device)
+        self._hyper_lr = lr
+
+    def _step_impl(self, im1, im2):
+        """forward + loss + backward + gradient mean + Adam, hyper-parameters from device memory."""
+        loss = self.loss(im1, im2)
+        loss.backward()
+        self.reduce_gradients()
+        from ..ops import kernel_timer
+        with torch.cuda.device(self.device), kernel_timer.span("adam", 32 * self.flat_param.numel()):
+            check(_native.lib().unflow_adam_step_dev(
+                self.flat_param.data_ptr(), self.flat_grad.data_ptr(), self.adam_m.data_ptr(),
+                self.adam_v.data_ptr(), self.flat_param.numel(), self._hyper_dev.data_ptr(), 1,
+                torch.cuda.current_stream().cuda_stream), "adam_step")
+        return loss.detach()
+
+    def capture(self, im1, im2, warmup=3):
+        """Capture the whole training step (several hundred kernels: cuDNN convs, the hand-written
+        kernels, the NCCL all-reduce, Adam) into ONE CUDA graph.  Later ``step`` calls copy the batch
+        into the static input buffers, refresh the hyper-parameter vector and replay the graph, so
+        the host launches one graph instead of ~800 kernels per step."""
+        assert self.flat_param.is_cuda
+        self._hyper_dev = torch.zeros(8, device=self.device, dtype=torch.float32)
+        self._static_im1 = im1.to(self.device).clone()
+        self._static_im2 = im2.to(self.device).clone()
+        self._set_hyper(0.0, 1.0)                         # lr = 0 while warming up / capturing
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):                       # eager warm-up (cuDNN autotune, caches)
+                self._step_impl(self._static_im1, self._static_im2)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        n0 = _native.launch_count()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self._static_loss = self._step_impl(self._static_im1, self._static_im2)
+        self._graph_launches = _native.launch_count() - n0
+        torch.cuda.synchronize(self.device)
+        # lr = 0 left the parameters alone but fed the moments: reset them and the step counter
+        self.adam_m.zero_(); self.adam_v.zero_(); self.flat_grad.zero_()
+        self._set_hyper(learning_rate_at(self.iteration, self.params), self.iteration + 1)
+        self._graph = graph
+        self.graph_replays = 0
+        return self
+
     def step(self, im1, im2, lr=None):
         """One optimisation step on this rank's shard; returns the (local) loss tensor."""
         self.iteration += 1
+        if lr is None:
+            lr = learning_rate_at(self.iteration - 1, self.params)
+        if self._graph is not None:
+            if lr != self._hyper_lr:                      # the schedule moved: rewrite lr (rare)
+                self._set_hyper(lr, self.iteration)
+            self._static_im1.copy_(im1, non_blocking=True)
+            self._static_im2.copy_(im2, non_blocking=True)
+            self._graph.replay()
+            self.graph_replays += 1
+            return self._static_loss
         loss = self.loss(im1, im2)
         loss.backward()   # accumulates into the flat gradient views
         scale = self.reduce_gradients()
-        if lr is None:
-            lr = learning_rate_at(self.iteration - 1, self.params)
         self.apply_update(lr, scale)
         return loss.detach()
+
+
+def evaluate(variables, params, normalization, examples, eval_size=(384, 1280)):
+    """The checkpoint-evaluation loop of the reference Trainer (train.py:265-385) without the TF
+    session / summary scaffolding.
+
+    ``examples``: iterable of ``(im1, im2, flow_occ, mask_occ, flow_noc, mask_noc)`` with float
+    tensors ``[1,h,w,C]`` on the device (the layout ``einput.input_train_2012()`` yields).
+    Each pair is resized to ``eval_size`` (384x1280, train.py:274-275) with the TF1 bilinear kernel,
+    run through ``unsupervised_loss(augment=False, return_flow=True)``, the flow is resized back and
+    rescaled (``resize_output_flow``), and AEE / outlier-% are averaged over the examples for the
+    'occluded' (all valid) and 'non-occluded' masks (train.py:314-321).  Returns the dict of
+    averages plus the last example's visualisation tensors (train.py:290-293)."""
+    from . import flow_util, tf_image
+    from .flow_io import resize_output_flow
+    from .image_warp import image_warp
+    from .losses import DISOCC_THRESH, create_outgoing_mask, occlusion
+    from ..ops import forward_warp
+    sums, n, images = {}, 0, None
+    rh, rw = eval_size
+    with torch.no_grad():
+        for (im1, im2, flow_occ, mask_occ, flow_noc, mask_noc) in examples:
+            h, w = im1.shape[1], im1.shape[2]
+            a = tf_image.resize_bilinear(im1, [rh, rw])
+            b = tf_image.resize_bilinear(im2, [rh, rw])
+            _, flow, flow_bw = unsupervised_loss((a, b), params, normalization, augment=False,
+                                                 return_flow=True, variables=variables)
+            flow = resize_output_flow(flow, h, w).contiguous()
+            flow_bw = resize_output_flow(flow_bw, h, w).contiguous()
+            for name, gt, mask in (('occluded', flow_occ, mask_occ), ('non-occluded', flow_noc, mask_noc)):
+                sums['AEE/' + name] = sums.get('AEE/' + name, 0.0) + float(flow_util.flow_error_avg(gt, flow, mask))
+                sums['outliers/' + name] = sums.get('outliers/' + name, 0.0) + float(
+                    flow_util.outlier_pct(gt, flow, mask))
+            n += 1
+            images = {'warped image': image_warp(im1.contiguous(), flow) / 255,
+                      'flow': flow_util.flow_to_color(flow),
+                      'occ': 1 - (1 - occlusion(flow, flow_bw)[0]) * create_outgoing_mask(flow),
+                      'reverse disocc': forward_warp(flow_bw) < DISOCC_THRESH,
+                      'flow error': flow_util.flow_error_image(flow, flow_occ, mask_occ, mask_noc)}
+    out = {k: v / max(n, 1) for k, v in sums.items()}
+    out['num_examples'] = n
+    return out, images

@@ -5,8 +5,8 @@
 
 ``params`` holds the keys of config.ini [train] (+ the dataset section), exactly as the
 reference reads them (flownet, full_res, train_all, pyramid_loss, mask_occlusion, border_mask,
-<loss>_weight).  ``augment=True`` (random affine / photometric augmentation, augment.py) is
-outside the hot path and raises NotImplementedError.
+<loss>_weight).  ``augment=True`` applies the reference's random affine / photometric augmentation
+(core/augment.py) with torch's random stream in place of TF's.
 
 Extra keyword ``variables`` (FlowNetVariables) replaces TF's implicit graph variable store; the
 default is the module-level store of core.flownet.
@@ -25,6 +25,17 @@ LOSSES = ['occ', 'sym', 'fb', 'grad', 'ternary', 'photo', 'smooth_1st', 'smooth_
 # equivalent is a dict refreshed on every call.
 tracked = {}
 
+_const_cache = {}
+
+
+def _device_constant(values, device):
+    """Small host constants as cached device tensors (no host->device copy inside the step: the
+    step must be capturable in a CUDA graph)."""
+    key = (tuple(float(v) for v in values), str(device))
+    if key not in _const_cache:
+        _const_cache[key] = torch.tensor(list(values), device=device, dtype=torch.float32)
+    return _const_cache[key]
+
 
 def _track_loss(op, name):
     tracked[name] = op.detach() if torch.is_tensor(op) else op
@@ -32,12 +43,8 @@ def _track_loss(op, name):
 
 def unsupervised_loss(batch, params, normalization=None, augment=True,
                       return_flow=False, variables=None):
-    if augment:
-        raise NotImplementedError(
-            "augment=True (random_affine / random_photometric) is not part of the accelerated "
-            "hot path; call with augment=False")
     im1, im2 = batch
-    channel_mean = torch.tensor(normalization[0], device=im1.device, dtype=torch.float32) / 255.0
+    channel_mean = _device_constant([v / 255.0 for v in normalization[0]], im1.device)
     im1 = im1 / 255.0
     im2 = im2 / 255.0
     im_shape = im1.shape[1:3]
@@ -45,8 +52,30 @@ def unsupervised_loss(batch, params, normalization=None, augment=True,
     # -------------------------------------------------------------------------
     # Data & mask augmentation
     border_mask = create_border_mask(im1, 0.1)
-    im1_geo, im2_geo = im1, im2
-    im1_photo, im2_photo = im1, im2
+
+    if augment:
+        from .augment import random_affine, random_photometric
+        im1_geo, im2_geo, border_mask_global = random_affine(
+            [im1, im2, border_mask.contiguous()],
+            horizontal_flipping=True,
+            min_scale=0.9, max_scale=1.1
+            )
+
+        # augment locally
+        im2_geo, border_mask_local = random_affine(
+            [im2_geo, border_mask.contiguous()],
+            min_scale=0.9, max_scale=1.1
+            )
+        border_mask = border_mask_local * border_mask_global
+
+        im1_photo, im2_photo = random_photometric(
+            [im1_geo, im2_geo],
+            noise_stddev=0.04, min_contrast=-0.3, max_contrast=0.3,
+            brightness_stddev=0.02, min_colour=0.9, max_colour=1.1,
+            min_gamma=0.7, max_gamma=1.5)
+    else:
+        im1_geo, im2_geo = im1, im2
+        im1_photo, im2_photo = im1, im2
 
     # Images for loss comparisons with values in [0, 1] (scale to original using * 255)
     im1_norm = im1_geo
