@@ -132,7 +132,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=300))
     _native.lib()  # fail loudly if libunflow.so is missing
     from unflow_b200.e2eflow.core import conv_ops
     conv_ops.set_mode(args.conv)
@@ -216,8 +217,7 @@ def run_ours(args):
         conv_ops.set_mode(args.conv)
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        _finish(world)
         return
     peaks = load_peaks()
     pairs = PER_GPU_BATCH * world * args.steps
@@ -279,8 +279,19 @@ def run_ours(args):
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(steps=1, warmup=0)
     print(json.dumps(line), flush=True)
+    _finish(world)
+
+
+def _finish(world):
+    """Leave without ncclCommDestroy: destroy_process_group() was observed to hang for minutes after
+    the timed work was done (communicators that were used inside a captured CUDA graph), which would
+    burn the GPU lease; all results are already printed and flushed."""
     if world > 1:
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 # measured once with `ncu --set full` (profiles/): dram__bytes_read.sum + dram__bytes_write.sum per launch
@@ -364,7 +375,16 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def _watchdog():
+    """A hung collective must not burn the GPU lease: dump every thread's Python stack and exit."""
+    import faulthandler
+    secs = int(os.environ.get("UNFLOW_BENCH_WATCHDOG", "1500"))
+    if secs > 0:
+        faulthandler.dump_traceback_later(secs, exit=True)
+
+
 def main():
+    _watchdog()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

@@ -187,7 +187,19 @@ int unflow_adam_step_dev(float *params, float *grads, float *m, float *v, long l
 int unflow_conv_operand_tf32(const float *x, float *out, int N, int C, int H, int W, long long sN,
                              long long sC, long long sH, long long sW, int N_out, int C_pad,
                              int pad_top, int pad_bottom, int pad_left, int pad_right,
-                             int concat_batch, int order, void *stream);
+                             int concat_batch, int order, const float *act, float slope,
+                             void *stream);
+/* `act` (optional, dense NHWC [N,H,W,C]): the leaky-ReLU OUTPUT of the layer whose gradient `x`
+ * is; the source is multiplied by lrelu'(act) = (act > 0 ? 1 : slope) on the fly (fused
+ * leaky_relu backward, reference activation flownet.py:84-86).
+ *
+ * unflow_bias_lrelu: y = leaky_relu(y + bias[c]) in place on dense NHWC [pixels][C] (C % 4 == 0).
+ * unflow_bias_grad_lrelu: gb[c] = sum_pixels g * lrelu'(act)  (act NULL: plain bias gradient);
+ * g is read through strides, gb is zeroed by the launcher. */
+int unflow_bias_lrelu(float *y, const float *bias, long long pixels, int C, float slope, void *stream);
+int unflow_bias_grad_lrelu(const float *g, long long sN, long long sC, long long sH, long long sW,
+                           const float *act, float *gb, int N, int C, int H, int W, float slope,
+                           void *stream);
 
 #ifdef __cplusplus
 }

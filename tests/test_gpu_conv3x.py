@@ -117,3 +117,33 @@ def test_unsupervised_loss_3xtf32_vs_oracle(mode3x):
         want = tfv[scope + '/weights'].grad.permute(3, 2, 0, 1)
         err = float((w.grad.cpu() - want).norm() / want.norm().clamp_min(1e-20))
         assert err < 5e-3, "%s: relative L2 gradient error %.3e" % (scope, err)
+
+
+@pytest.mark.parametrize("deconv", [False, True])
+def test_fused_bias_leaky_relu_layer_matches_float64(mode3x, deconv):
+    """conv (+bias +leaky ReLU fused in one pass) and its backward (activation derivative folded into
+    the operand kernel, masked bias gradient) against float64."""
+    from unflow_b200.e2eflow.core import conv_ops
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 12, 10, 14, generator=g)
+    w = torch.randn(12, 8, 4, 4, generator=g) * 0.2 if deconv else torch.randn(8, 12, 3, 3, generator=g) * 0.2
+    b = torch.randn(8, generator=g) * 0.5
+    xd, wd, bd = (t.double().requires_grad_(True) for t in (x, w, b))
+    yd = F.conv_transpose2d(xd, wd, bd, stride=2, padding=1) if deconv else F.conv2d(xd, wd, bd, padding=1)
+    ad = F.leaky_relu(yd, 0.1)
+    go = torch.randn(ad.shape, generator=g)
+    ad.backward(go.double())
+    xc, wc = x.cuda().requires_grad_(True), w.cuda().requires_grad_(True)
+    # parameters are views into the flat buffer: only 4-byte aligned
+    bc = torch.cat([torch.zeros(1), b]).cuda()[1:].detach().requires_grad_(True)
+    assert bc.data_ptr() % 16 != 0
+    a = (conv_ops.conv_transpose2d(xc, wc, bc, act=True) if deconv
+         else conv_ops.conv2d(xc, wc, bc, 1, (1, 1, 1, 1), act=True))
+    # feed the gradient through a channel-sliced, strided view like the concat backward does
+    gbuf = torch.zeros(a.shape[0], a.shape[2], a.shape[3], a.shape[1] + 3, device="cuda")
+    gview = gbuf.permute(0, 3, 1, 2)[:, 2:2 + a.shape[1]]
+    gview.copy_(go.cuda())
+    a.backward(gview)
+    for got, want, name in ((a, ad, "a"), (xc.grad, xd.grad, "dx"), (wc.grad, wd.grad, "dw"), (bc.grad, bd.grad, "db")):
+        e = rel(got.detach().cpu(), want.detach())
+        assert e < 3e-5, "%s: rel err %.2e" % (name, e)

@@ -39,6 +39,8 @@ struct OperandArgs {
   long long item_stride;          // floats between consecutive output pixels (3*Cp or Cp)
   long long slab_stride;          // floats between the three slabs (Cp or No*Hp*Wp*Cp)
   long long total;                // No*Hp*Wp*(Cp/4) work items
+  const float *act;               // optional: leaky-ReLU OUTPUT of the layer (dense NHWC [N,H,W,C]);
+  float slope;                    //   the source is a gradient and is multiplied by lrelu'(act)
 };
 
 template <int ORDER, bool VEC>
@@ -64,6 +66,12 @@ conv_operand_kernel(OperandArgs a) {
         for (int k = 0; k < 4; ++k)
           if (c + k < a.C) v[k] = __ldg(src + k * a.sC);
       }
+      if (a.act) {  // fused leaky_relu backward: d/dy = g * (out > 0 ? 1 : slope)
+        const float *ap = a.act + (((long long)n * a.H + y) * a.W + x) * a.C + c;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (c + k < a.C && __ldg(ap + k) <= 0.0f) v[k] *= a.slope;
+      }
     }
     float hi[4], lo[4];
 #pragma unroll
@@ -78,13 +86,100 @@ conv_operand_kernel(OperandArgs a) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fused bias + leaky ReLU (in place, dense NHWC) and its bias gradient.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+bias_lrelu_kernel(float4 *__restrict__ y, const float *__restrict__ bias, long long n4, int c4n, float slope) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % c4n) * 4;
+    float4 v = y[i];
+    // the bias is a view into the flat parameter buffer: only 4-byte aligned
+    v.x += __ldg(bias + c); v.y += __ldg(bias + c + 1); v.z += __ldg(bias + c + 2); v.w += __ldg(bias + c + 3);
+    v.x = v.x > 0.f ? v.x : v.x * slope; v.y = v.y > 0.f ? v.y : v.y * slope;
+    v.z = v.z > 0.f ? v.z : v.z * slope; v.w = v.w > 0.f ? v.w : v.w * slope;
+    y[i] = v;
+  }
+}
+
+// gb[c] += sum over pixels of g * lrelu'(act); one CTA = 32 channels x a strip of pixels
+__global__ void __launch_bounds__(256)
+bias_grad_lrelu_kernel(const float *__restrict__ g, long long sN, long long sC, long long sH, long long sW,
+                       const float *__restrict__ act, float *__restrict__ gb, int N, int C, int H, int W,
+                       float slope, int pix_per_cta) {
+  __shared__ float red[8][32];
+  const int lane = threadIdx.x & 31, row = threadIdx.x >> 5;
+  const int c = blockIdx.y * 32 + lane;
+  const long long npix = (long long)N * H * W;
+  const long long p0 = (long long)blockIdx.x * pix_per_cta;
+  const long long p1 = p0 + pix_per_cta < npix ? p0 + pix_per_cta : npix;
+  float s = 0.f;
+  if (c < C) {
+    for (long long p = p0 + row; p < p1; p += 8) {
+      const int x = (int)(p % W);
+      const int y = (int)((p / W) % H);
+      const long long n = p / ((long long)W * H);
+      float v = __ldg(g + n * sN + y * sH + x * sW + c * sC);
+      if (act && __ldg(act + p * C + c) <= 0.0f) v *= slope;
+      s += v;
+    }
+  }
+  red[row][lane] = s;
+  __syncthreads();
+  if (row == 0 && c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k][lane];
+    atomicAdd(gb + c, t);
+  }
+}
+
 }  // namespace unflow
+
+extern "C" int unflow_bias_lrelu(float *y, const float *bias, long long pixels, int C, float slope,
+                                 void *stream) {
+  using namespace unflow;
+  UNFLOW_REQUIRE(pixels >= 0 && C >= 4 && C % 4 == 0, "bias_lrelu: C must be a positive multiple of 4");
+  if (pixels == 0) return UNFLOW_OK;
+  UNFLOW_REQUIRE(y && bias, "bias_lrelu: null pointer");
+  UNFLOW_REQUIRE(((uintptr_t)y & 15) == 0, "bias_lrelu: y must be 16-byte aligned");
+  const long long n4 = pixels * (C / 4);
+  bias_lrelu_kernel<<<grid_for(n4, 256, 16), 256, 0, (cudaStream_t)stream>>>((float4 *)y, bias, n4, C / 4, slope);
+  count_launch();
+  return check_launch("bias_lrelu");
+}
+
+extern "C" int unflow_bias_grad_lrelu(const float *g, long long sN, long long sC, long long sH,
+                                      long long sW, const float *act, float *gb, int N, int C, int H,
+                                      int W, float slope, void *stream) {
+  using namespace unflow;
+  UNFLOW_REQUIRE(N >= 0 && C >= 1 && H >= 1 && W >= 1, "bias_grad: bad shape");
+  UNFLOW_REQUIRE(g && gb, "bias_grad: null pointer");
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(gb, 0, sizeof(float) * C, s);
+  if (e != cudaSuccess) { set_error("bias_grad memset: %s", cudaGetErrorString(e)); return UNFLOW_ECUDA; }
+  const long long npix = (long long)N * H * W;
+  if (npix == 0) return UNFLOW_OK;
+  const int cblocks = ceil_div(C, 32);
+  long long strips = (long long)kNumSMs * 8 / cblocks;
+  if (strips < 1) strips = 1;
+  int pix_per_cta = (int)((npix + strips - 1) / strips);
+  if (pix_per_cta < 64) pix_per_cta = 64;
+  dim3 grid(ceil_div(npix, pix_per_cta), cblocks);
+  bias_grad_lrelu_kernel<<<grid, 256, 0, s>>>(g, sN, sC, sH, sW, act, gb, N, C, H, W, slope, pix_per_cta);
+  count_launch();
+  return check_launch("bias_grad_lrelu");
+}
+
+namespace unflow {
+}
 
 extern "C" int unflow_conv_operand_tf32(const float *x, float *out, int N, int C, int H, int W,
                                         long long sN, long long sC, long long sH, long long sW,
                                         int N_out, int C_pad, int pad_top, int pad_bottom,
                                         int pad_left, int pad_right, int concat_batch, int order,
-                                        void *stream) {
+                                        const float *act, float slope, void *stream) {
   using namespace unflow;
   UNFLOW_REQUIRE(N >= 0 && C >= 1 && H >= 1 && W >= 1, "conv_operand: bad source shape");
   UNFLOW_REQUIRE(N_out >= N && C_pad >= C && C_pad % 4 == 0, "conv_operand: bad padded shape");
@@ -102,6 +197,7 @@ extern "C" int unflow_conv_operand_tf32(const float *x, float *out, int N, int C
   a.item_stride = concat_batch ? C_pad : 3ll * C_pad;
   a.slab_stride = concat_batch ? pixels * C_pad : C_pad;
   a.total = pixels * (C_pad / 4);
+  a.act = act; a.slope = slope;
   const bool vec = sC == 1 && C % 4 == 0 && ((uintptr_t)x & 15) == 0 && sN % 4 == 0 && sH % 4 == 0 && sW % 4 == 0;
   const int grid = grid_for(a.total, 256, 16);
   cudaStream_t s = (cudaStream_t)stream;

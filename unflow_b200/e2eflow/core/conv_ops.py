@@ -36,11 +36,37 @@ def get_mode():
     return _MODE
 
 
+LRELU_SLOPE = 0.1   # _leaky_relu: tf.maximum(0.1 * x, x)  (reference flownet.py:84-86)
+
+
+def _bias_act_(y, b):
+    """y = leaky_relu(y + b) in place (one pass instead of bias add + activation)."""
+    N, C, H, W = y.shape
+    assert y.is_contiguous(memory_format=torch.channels_last) and C % 4 == 0
+    with torch.cuda.device(y.device):
+        check(_native.lib().unflow_bias_lrelu(y.data_ptr(), b.data_ptr(), N * H * W, C, LRELU_SLOPE,
+                                              torch.cuda.current_stream().cuda_stream), "bias_lrelu")
+    return y
+
+
+def _bias_grad(g, act):
+    """sum over pixels of g * lrelu'(act) (act None: plain sum) -> [C]."""
+    N, C, H, W = g.shape
+    gb = torch.empty(C, device=g.device, dtype=torch.float32)
+    sN, sC, sH, sW = g.stride()
+    with torch.cuda.device(g.device):
+        check(_native.lib().unflow_bias_grad_lrelu(g.data_ptr(), sN, sC, sH, sW,
+                                                   act.data_ptr() if act is not None else None, gb.data_ptr(),
+                                                   N, C, H, W, LRELU_SLOPE,
+                                                   torch.cuda.current_stream().cuda_stream), "bias_grad_lrelu")
+    return gb
+
+
 def _round4(c):
     return (c + 3) // 4 * 4
 
 
-def _operand(x, order, concat_batch=False, c_pad=None, n_out=None, pads=(0, 0, 0, 0)):
+def _operand(x, order, concat_batch=False, c_pad=None, n_out=None, pads=(0, 0, 0, 0), act=None):
     """One pass of csrc/split.cu: logical [N,C,H,W] (any strides) -> the dense channels_last TF32
     operand [N_out, 3*C_pad, Hp, Wp] (channel concat) or [3*N_out, C_pad, Hp, Wp] (batch concat)."""
     N, C, H, W = x.shape
@@ -54,7 +80,8 @@ def _operand(x, order, concat_batch=False, c_pad=None, n_out=None, pads=(0, 0, 0
     with torch.cuda.device(x.device), kernel_timer.span("conv_operand", 4 * x.numel() + 4 * out.numel()):
         check(_native.lib().unflow_conv_operand_tf32(
             x.data_ptr(), out.data_ptr(), N, C, H, W, sN, sC, sH, sW, n_out, c_pad, pt, pb, pl, pr,
-            1 if concat_batch else 0, order, torch.cuda.current_stream().cuda_stream), "conv_operand_tf32")
+            1 if concat_batch else 0, order, act.data_ptr() if act is not None else None, LRELU_SLOPE,
+            torch.cuda.current_stream().cuda_stream), "conv_operand_tf32")
     if concat_batch:
         return out.view(3 * n_out, Hp, Wp, c_pad).permute(0, 3, 1, 2)
     return out.view(n_out, Hp, Wp, 3 * c_pad).permute(0, 3, 1, 2)
@@ -71,73 +98,93 @@ class _Conv3x(torch.autograd.Function):
     over the channel-concatenated hi/lo operands).  ``pads`` = TF SAME (top, bottom, left, right)."""
 
     @staticmethod
-    def forward(ctx, x, w, b, stride, pads):
+    def forward(ctx, x, w, b, stride, pads, act):
         Co, Ci = w.shape[0], w.shape[1]
         ci_p, co_p = _round4(Ci), _round4(Co)
-        ctx.save_for_backward(x, w)
-        ctx.cfg = (stride, pads, b is not None, ci_p, co_p)
+        fuse = bool(act) and b is not None and co_p == Co
         xs = _operand(x, 0, c_pad=ci_p, pads=pads)               # [N, 3Ci_p, Hp, Wp]  hi,hi,lo
         ws = _operand(w, 1, c_pad=ci_p, n_out=co_p)              # [Co_p, 3Ci_p, k, k] hi,lo,hi
-        y = F.conv2d(xs, ws, _pad_bias(b, co_p), stride=stride, padding=0)
+        if fuse:     # conv -> (bias + leaky ReLU) in one in-place pass
+            y = _bias_act_(F.conv2d(xs, ws, None, stride=stride, padding=0), b)
+            ctx.save_for_backward(x, w, y)
+        else:
+            assert not act, "fused activation needs a bias and C_out % 4 == 0"
+            y = F.conv2d(xs, ws, _pad_bias(b, co_p), stride=stride, padding=0)
+            ctx.save_for_backward(x, w)
+        ctx.cfg = (stride, pads, b is not None, ci_p, co_p)
+        ctx.fuse = fuse
         return y if co_p == Co else y[:, :Co]
 
     @staticmethod
     def backward(ctx, g):
-        x, w = ctx.saved_tensors
+        if ctx.fuse:
+            x, w, a = ctx.saved_tensors
+        else:
+            (x, w), a = ctx.saved_tensors, None
         stride, pads, has_b, ci_p, co_p = ctx.cfg
         Co, Ci, k = w.shape[0], w.shape[1], w.shape[2]
         N, _, H, W = x.shape
         pt, pb, pl, pr = pads
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
-            gs = _operand(g, 0, c_pad=co_p)                                        # [N, 3Co_p, ..]
+            gs = _operand(g, 0, c_pad=co_p, act=a)                                 # [N, 3Co_p, ..]
             wt = _operand(w, 1, concat_batch=True, c_pad=ci_p, n_out=co_p)        # [3Co_p, Ci_p, k, k]
             gxp = nngrad.conv2d_input((N, ci_p, H + pt + pb, W + pl + pr), wt, gs, stride=stride, padding=0)
             gx = gxp[:, :Ci, pt:pt + H, pl:pl + W]
         if ctx.needs_input_grad[1]:
             xb = _operand(x, 0, concat_batch=True, c_pad=ci_p, pads=pads)          # [3N, Ci_p, Hp, Wp]
-            gb3 = _operand(g, 1, concat_batch=True, c_pad=co_p)                    # [3N, Co_p, ..]
+            gb3 = _operand(g, 1, concat_batch=True, c_pad=co_p, act=a)             # [3N, Co_p, ..]
             gwp = nngrad.conv2d_weight(xb, (co_p, ci_p, k, k), gb3, stride=stride, padding=0)
             gw = gwp[:Co, :Ci]
         if has_b and ctx.needs_input_grad[2]:
-            gb = g.sum((0, 2, 3))
-        return gx, gw, gb, None, None
+            gb = _bias_grad(g, a)
+        return gx, gw, gb, None, None, None
 
 
 class _Deconv3x(torch.autograd.Function):
     """conv_transpose2d(x, w[in,out,4,4], stride=2, padding=1) + b, same scheme."""
 
     @staticmethod
-    def forward(ctx, x, w, b):
+    def forward(ctx, x, w, b, act):
         Ci, Co = w.shape[0], w.shape[1]
         ci_p, co_p = _round4(Ci), _round4(Co)
-        ctx.save_for_backward(x, w)
-        ctx.cfg = (b is not None, ci_p, co_p)
+        fuse = bool(act) and b is not None and co_p == Co
         xs = _operand(x, 0, c_pad=ci_p)                                           # [N, 3Ci_p, h, w]
         ws = _operand(w, 1, concat_batch=True, c_pad=co_p, n_out=ci_p)            # [3Ci_p, Co_p, 4, 4]
-        y = F.conv_transpose2d(xs, ws, _pad_bias(b, co_p), stride=2, padding=1)
+        if fuse:
+            y = _bias_act_(F.conv_transpose2d(xs, ws, None, stride=2, padding=1), b)
+            ctx.save_for_backward(x, w, y)
+        else:
+            assert not act, "fused activation needs a bias and C_out % 4 == 0"
+            y = F.conv_transpose2d(xs, ws, _pad_bias(b, co_p), stride=2, padding=1)
+            ctx.save_for_backward(x, w)
+        ctx.cfg = (b is not None, ci_p, co_p)
+        ctx.fuse = fuse
         return y if co_p == Co else y[:, :Co]
 
     @staticmethod
     def backward(ctx, g):
-        x, w = ctx.saved_tensors
+        if ctx.fuse:
+            x, w, a = ctx.saved_tensors
+        else:
+            (x, w), a = ctx.saved_tensors, None
         has_b, ci_p, co_p = ctx.cfg
         Ci, Co = w.shape[0], w.shape[1]
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
-            gs = _operand(g, 0, c_pad=co_p)                                       # [N, 3Co_p, 2h, 2w]
+            gs = _operand(g, 0, c_pad=co_p, act=a)                                # [N, 3Co_p, 2h, 2w]
             wc = _operand(w, 1, c_pad=co_p, n_out=ci_p)                           # [Ci_p, 3Co_p, 4, 4]
             gxp = F.conv2d(gs, wc, None, stride=2, padding=1)
             gx = gxp if ci_p == Ci else gxp[:, :Ci]
         if ctx.needs_input_grad[1]:
             # d/dw of conv_transpose == weight gradient of the conv whose input is g and output x
-            gb3 = _operand(g, 0, concat_batch=True, c_pad=co_p)
+            gb3 = _operand(g, 0, concat_batch=True, c_pad=co_p, act=a)
             xb = _operand(x, 1, concat_batch=True, c_pad=ci_p)
             gwp = nngrad.conv2d_weight(gb3, (ci_p, co_p, 4, 4), xb, stride=2, padding=1)
             gw = gwp[:Ci, :Co]
         if has_b and ctx.needs_input_grad[2]:
-            gb = g.sum((0, 2, 3))
-        return gx, gw, gb
+            gb = _bias_grad(g, a)
+        return gx, gw, gb, None
 
 
 def channels_last_active(x):
@@ -154,20 +201,26 @@ def network_input(x_nhwc):
     return x if channels_last_active(x_nhwc) else x.contiguous()
 
 
-def conv2d(x, w, b, stride, pads):
-    """pads = (top, bottom, left, right) TF-SAME padding."""
+def conv2d(x, w, b, stride, pads, act=False):
+    """pads = (top, bottom, left, right) TF-SAME padding; act: apply the leaky ReLU."""
     if _MODE == '3xtf32' and x.is_cuda:
-        return _Conv3x.apply(x, w, b, stride, tuple(pads))
+        fuse = act and b is not None and w.shape[0] % 4 == 0
+        y = _Conv3x.apply(x, w, b, stride, tuple(pads), fuse)
+        return F.leaky_relu(y, LRELU_SLOPE) if (act and not fuse) else y
     pt, pb, pl, pr = pads
     if pt == pb and pl == pr:
         padding = (pt, pl)
     else:
         x = F.pad(x, (pl, pr, pt, pb))
         padding = (0, 0)
-    return F.conv2d(x, w, b, stride=stride, padding=padding)
+    y = F.conv2d(x, w, b, stride=stride, padding=padding)
+    return F.leaky_relu(y, LRELU_SLOPE) if act else y
 
 
-def conv_transpose2d(x, w, b):
+def conv_transpose2d(x, w, b, act=False):
     if _MODE == '3xtf32' and x.is_cuda:
-        return _Deconv3x.apply(x, w, b)
-    return F.conv_transpose2d(x, w, b, stride=2, padding=1)
+        fuse = act and b is not None and w.shape[1] % 4 == 0
+        y = _Deconv3x.apply(x, w, b, fuse)
+        return F.leaky_relu(y, LRELU_SLOPE) if (act and not fuse) else y
+    y = F.conv_transpose2d(x, w, b, stride=2, padding=1)
+    return F.leaky_relu(y, LRELU_SLOPE) if act else y

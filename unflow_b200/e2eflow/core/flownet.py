@@ -252,13 +252,11 @@ class _Scope:
         k = w.shape[2]
         # TF SAME padding: asymmetric for the stride-2 layers at even sizes
         pads = _same_pad(x.shape[2], k, stride) + _same_pad(x.shape[3], k, stride)
-        y = conv_ops.conv2d(x, w, b, stride, pads)
-        return _leaky_relu(y) if act else y
+        return conv_ops.conv2d(x, w, b, stride, pads, act=act)
 
     def deconv(self, x, name, act=True):
         w, b = self.v.weights(self.p + name)
-        y = conv_ops.conv_transpose2d(x, w, b)  # slim.conv2d_transpose(k=4, s=2, SAME)
-        return _leaky_relu(y) if act else y
+        return conv_ops.conv_transpose2d(x, w, b, act=act)  # slim.conv2d_transpose(k=4, s=2, SAME)
 
 
 def _flownet_upconv(s, conv6_1, conv5_1, conv4_1, conv3_1, conv2, conv1=None, inputs=None,
