@@ -133,6 +133,8 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         import datetime
+        # keep stdout to the single JSON line: NCCL's own banner ("NCCL version ...") goes to a file
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/unflow_nccl.%h.%p.log")
         dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=300))
     _native.lib()  # fail loudly if libunflow.so is missing
     from unflow_b200.e2eflow.core import conv_ops
@@ -378,7 +380,7 @@ def run_reference(args):
 def _watchdog():
     """A hung collective must not burn the GPU lease: dump every thread's Python stack and exit."""
     import faulthandler
-    secs = int(os.environ.get("UNFLOW_BENCH_WATCHDOG", "1500"))
+    secs = int(os.environ.get("UNFLOW_BENCH_WATCHDOG", "900"))
     if secs > 0:
         faulthandler.dump_traceback_later(secs, exit=True)
 

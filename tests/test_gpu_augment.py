@@ -27,7 +27,8 @@ def test_transformer_vs_oracle():
     # neighbours, the output stays inside the input range, samples beyond W-1 are exactly zero
     ident = oaug.affine_matrices(torch.zeros(1), torch.zeros(1), torch.zeros(1), torch.ones(1))
     out = A.transformer(U[:1].cuda(), ident.cuda(), (20, 28)).cpu()
-    assert float(out.max()) <= float(U[:1].max()) + 1e-6 and float(out[0, :, -1].abs().max()) == 0.0
+    assert float(out.max()) <= float(U[:1].max()) + 1e-5
+    assert float(out[0, :, -1].abs().max()) < 1e-6     # weights from clamped indices cancel (to rounding)
 
 
 def test_photometric_vs_oracle_and_random_wrappers():

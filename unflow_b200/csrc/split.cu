@@ -103,7 +103,10 @@ bias_lrelu_kernel(float4 *__restrict__ y, const float *__restrict__ bias, long l
   }
 }
 
-// gb[c] += sum over pixels of g * lrelu'(act); one CTA = 32 channels x a strip of pixels
+// gb[c] += sum over pixels of g * lrelu'(act); one CTA = 32 channels x a strip of pixels.
+// LINEAR: the gradient is NHWC-like (possibly a channel slice of a wider buffer), so pixel p lives
+// at p*pix_stride -- no per-element div/mod (the first version spent most of its time on them).
+template <bool LINEAR>
 __global__ void __launch_bounds__(256)
 bias_grad_lrelu_kernel(const float *__restrict__ g, long long sN, long long sC, long long sH, long long sW,
                        const float *__restrict__ act, float *__restrict__ gb, int N, int C, int H, int W,
@@ -114,18 +117,37 @@ bias_grad_lrelu_kernel(const float *__restrict__ g, long long sN, long long sC, 
   const long long npix = (long long)N * H * W;
   const long long p0 = (long long)blockIdx.x * pix_per_cta;
   const long long p1 = p0 + pix_per_cta < npix ? p0 + pix_per_cta : npix;
-  float s = 0.f;
+  float s0 = 0.f, s1 = 0.f;
   if (c < C) {
-    for (long long p = p0 + row; p < p1; p += 8) {
-      const int x = (int)(p % W);
-      const int y = (int)((p / W) % H);
-      const long long n = p / ((long long)W * H);
-      float v = __ldg(g + n * sN + y * sH + x * sW + c * sC);
-      if (act && __ldg(act + p * C + c) <= 0.0f) v *= slope;
-      s += v;
+    if (LINEAR) {
+      const float *gp = g + c * sC;
+      const float *ap = act ? act + c : nullptr;
+      long long p = p0 + row;
+      for (; p + 8 < p1; p += 16) {           // two independent loads in flight per thread
+        float v0 = __ldg(gp + p * sW), v1 = __ldg(gp + (p + 8) * sW);
+        if (ap) {
+          if (__ldg(ap + p * C) <= 0.0f) v0 *= slope;
+          if (__ldg(ap + (p + 8) * C) <= 0.0f) v1 *= slope;
+        }
+        s0 += v0; s1 += v1;
+      }
+      for (; p < p1; p += 8) {
+        float v = __ldg(gp + p * sW);
+        if (ap && __ldg(ap + p * C) <= 0.0f) v *= slope;
+        s0 += v;
+      }
+    } else {
+      for (long long p = p0 + row; p < p1; p += 8) {
+        const int x = (int)(p % W);
+        const int y = (int)((p / W) % H);
+        const long long n = p / ((long long)W * H);
+        float v = __ldg(g + n * sN + y * sH + x * sW + c * sC);
+        if (act && __ldg(act + p * C + c) <= 0.0f) v *= slope;
+        s0 += v;
+      }
     }
   }
-  red[row][lane] = s;
+  red[row][lane] = s0 + s1;
   __syncthreads();
   if (row == 0 && c < C) {
     float t = 0.f;
@@ -167,7 +189,9 @@ extern "C" int unflow_bias_grad_lrelu(const float *g, long long sN, long long sC
   int pix_per_cta = (int)((npix + strips - 1) / strips);
   if (pix_per_cta < 64) pix_per_cta = 64;
   dim3 grid(ceil_div(npix, pix_per_cta), cblocks);
-  bias_grad_lrelu_kernel<<<grid, 256, 0, s>>>(g, sN, sC, sH, sW, act, gb, N, C, H, W, slope, pix_per_cta);
+  const bool linear = sH == (long long)W * sW && sN == (long long)H * sH;
+  if (linear) bias_grad_lrelu_kernel<true><<<grid, 256, 0, s>>>(g, sN, sC, sH, sW, act, gb, N, C, H, W, slope, pix_per_cta);
+  else bias_grad_lrelu_kernel<false><<<grid, 256, 0, s>>>(g, sN, sC, sH, sW, act, gb, N, C, H, W, slope, pix_per_cta);
   count_launch();
   return check_launch("bias_grad_lrelu");
 }

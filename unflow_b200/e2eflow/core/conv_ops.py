@@ -213,6 +213,8 @@ def conv2d(x, w, b, stride, pads, act=False):
     else:
         x = F.pad(x, (pl, pr, pt, pb))
         padding = (0, 0)
+    if x.is_cuda and _MODE == 'fp32':
+        w = w.contiguous()     # parameters are stored NHWC-ordered; the exact-fp32 path computes in NCHW
     y = F.conv2d(x, w, b, stride=stride, padding=padding)
     return F.leaky_relu(y, LRELU_SLOPE) if act else y
 
@@ -222,5 +224,7 @@ def conv_transpose2d(x, w, b, act=False):
         fuse = act and b is not None and w.shape[1] % 4 == 0
         y = _Deconv3x.apply(x, w, b, fuse)
         return F.leaky_relu(y, LRELU_SLOPE) if (act and not fuse) else y
+    if x.is_cuda and _MODE == 'fp32':
+        w = w.contiguous()
     y = F.conv_transpose2d(x, w, b, stride=2, padding=1)
     return F.leaky_relu(y, LRELU_SLOPE) if act else y

@@ -136,7 +136,10 @@ class FlowNetVariables(nn.Module):
             # layers.variance_scaling_initializer(): factor 2, FAN_IN, truncated normal
             std = math.sqrt(1.3 * 2.0 / fan_in)
             nn.init.trunc_normal_(w, mean=0.0, std=std, a=-2 * std, b=2 * std, generator=gen)
-            self.params[_key(name + '/weights')] = nn.Parameter(w)
+            # stored NHWC-ordered ([dim0, kh, kw, dim1] in memory): cuDNN's tensor-core kernels and
+            # their weight gradients are NHWC, so the operand kernel reads the weights contiguously and
+            # the gradient accumulates into .grad without a layout conversion
+            self.params[_key(name + '/weights')] = nn.Parameter(w.contiguous(memory_format=torch.channels_last))
             self.params[_key(name + '/biases')] = nn.Parameter(torch.zeros(cout))
             self.kinds[name] = kind
         if device is not None:

@@ -90,12 +90,21 @@ class Trainer:
         self.adam_m = torch.zeros(npad, device=self.device, dtype=torch.float32)
         self.adam_v = torch.zeros(npad, device=self.device, dtype=torch.float32)
         off = 0
+
+        def view_like(flat_seg, p):
+            """A view of the flat segment with p's shape; 4-D weights keep their NHWC memory order."""
+            if p.dim() == 4:
+                a, b, kh, kw = p.shape
+                return flat_seg.view(a, kh, kw, b).permute(0, 3, 1, 2)
+            return flat_seg.view_as(p)
+
         with torch.no_grad():
             for p in self.trainable:
                 k = p.numel()
-                self.flat_param[off:off + k].copy_(p.reshape(-1))
-                p.data = self.flat_param[off:off + k].view_as(p)
-                p.grad = self.flat_grad[off:off + k].view_as(p)
+                pv = view_like(self.flat_param[off:off + k], p)
+                pv.copy_(p)
+                p.data = pv
+                p.grad = view_like(self.flat_grad[off:off + k], p)
                 off += k
         self.num_params = n
 
