@@ -20,5 +20,8 @@ Pinning status (see DESIGN.md "Oracle"):
     resize_bilinear, rgb_to_grayscale): PARITY UNPINNED -- the reference holds
     no usable golden values for them (its ternary test is dead code) and
     TensorFlow 1.x cannot run here.  The oracle restates the documented TF1
-    behaviour.
+    behaviour.  The loss assembly is cross-checked against a second,
+    independently written float64 pixel-loop definition (oracle/brute.py,
+    tests/test_oracle_losses_brute.py); that is a self-consistency guard, not
+    a reference pin.
 """

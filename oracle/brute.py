@@ -115,3 +115,107 @@ def downsample(images, scale):
     images = np.asarray(images, np.float64)
     B, H, W, C = images.shape
     return images.reshape(B, H // scale, scale, W // scale, scale, C).mean(axis=(2, 4))
+
+
+# ---------------------------------------------------------------------------------------------
+# Loss terms from their mathematical definition (float64, explicit loops).  Independent of the
+# conv2d / gather formulation the oracle (and the reference) use.
+# ---------------------------------------------------------------------------------------------
+_GRAY = (0.2989, 0.5870, 0.1140)
+
+
+def charbonnier(x, mask=None, beta=1.0, alpha=0.45, eps=0.001):
+    x = np.asarray(x, np.float64)
+    e = ((x * beta) ** 2 + eps ** 2) ** alpha
+    if mask is not None:
+        e = e * np.asarray(mask, np.float64)
+    return e.sum() / x.size
+
+
+def ternary_loss(im1, im2w, mask, max_distance):
+    """sum_q mask(q) * interior(q) * charb( sum_k d_k/(0.1+d_k) ),  d_k = (t1_k - t2_k)^2,
+    t_k = s_k / sqrt(0.81 + s_k^2),  s_k = I(q+k) - I(q) with zero intensity outside the image."""
+    im1, im2w, mask = (np.asarray(a, np.float64) for a in (im1, im2w, mask))
+    B, H, W, _ = im1.shape
+    r = max_distance
+    g1 = (im1[..., 0] * _GRAY[0] + im1[..., 1] * _GRAY[1] + im1[..., 2] * _GRAY[2]) * 255
+    g2 = (im2w[..., 0] * _GRAY[0] + im2w[..., 1] * _GRAY[1] + im2w[..., 2] * _GRAY[2]) * 255
+    total = 0.0
+    for b in range(B):
+        for y in range(H):
+            for x in range(W):
+                if not (r <= y < H - r and r <= x < W - r):
+                    continue                      # transform mask (create_mask) removes the border
+                dist = 0.0
+                for dy in range(-r, r + 1):
+                    for dx in range(-r, r + 1):
+                        s1 = g1[b, y + dy, x + dx] - g1[b, y, x]
+                        s2 = g2[b, y + dy, x + dx] - g2[b, y, x]
+                        t1 = s1 / np.sqrt(0.81 + s1 * s1)
+                        t2 = s2 / np.sqrt(0.81 + s2 * s2)
+                        d = (t1 - t2) ** 2
+                        dist += d / (0.1 + d)
+                total += mask[b, y, x, 0] * (dist ** 2 + 1e-6) ** 0.45
+    return total / (B * H * W)
+
+
+def second_order_loss(flow):
+    flow = np.asarray(flow, np.float64)
+    B, H, W, _ = flow.shape
+    total = 0.0
+    for c in range(2):
+        f = flow[..., c]
+        for b in range(B):
+            for y in range(H):
+                for x in range(W):
+                    ix, iy = 1 <= x < W - 1, 1 <= y < H - 1
+                    if ix:
+                        total += ((f[b, y, x - 1] + f[b, y, x + 1] - 2 * f[b, y, x]) ** 2 + 1e-6) ** 0.45
+                    if iy:
+                        total += ((f[b, y - 1, x] + f[b, y + 1, x] - 2 * f[b, y, x]) ** 2 + 1e-6) ** 0.45
+                    if ix and iy:
+                        total += ((f[b, y - 1, x - 1] + f[b, y + 1, x + 1] - 2 * f[b, y, x]) ** 2 + 1e-6) ** 0.45
+                        total += ((f[b, y - 1, x + 1] + f[b, y + 1, x - 1] - 2 * f[b, y, x]) ** 2 + 1e-6) ** 0.45
+    return total / (B * H * W * 4)
+
+
+def first_order_loss(flow):
+    flow = np.asarray(flow, np.float64)
+    B, H, W, _ = flow.shape
+    total = 0.0
+    for c in range(2):
+        f = flow[..., c]
+        total += (((f[:, :, :-1] - f[:, :, 1:]) ** 2 + 1e-6) ** 0.45).sum()
+        total += (((f[:, :-1, :] - f[:, 1:, :]) ** 2 + 1e-6) ** 0.45).sum()
+    return total / (B * H * W * 2)
+
+
+def compute_losses(im1, im2, flow_fw, flow_bw, border_mask=None, mask_occlusion='', data_max_distance=1):
+    """The terms of losses.py:16-87 that do not need the splat map (occ, photo, smooth_1st,
+    smooth_2nd, fb, ternary), from the definitions above."""
+    im1, im2, flow_fw, flow_bw = (np.asarray(a, np.float64) for a in (im1, im2, flow_fw, flow_bw))
+    B, H, W, _ = im1.shape
+    out = {k: 0.0 for k in ('occ', 'photo', 'smooth_1st', 'smooth_2nd', 'fb', 'ternary')}
+    masks = []
+    for (A, Bi, f, g) in ((im1, im2, flow_fw, flow_bw), (im2, im1, flow_bw, flow_fw)):
+        Bw = backward_warp_clamp(Bi, f)
+        gw = backward_warp_clamp(g, f)
+        fd = f + gw
+        if border_mask is None:
+            ys, xs = np.meshgrid(np.arange(H), np.arange(W), indexing='ij')
+            px, py = xs[None] + f[..., 0], ys[None] + f[..., 1]
+            m = ((px <= W - 1) & (px >= 0) & (py <= H - 1) & (py >= 0)).astype(np.float64)[..., None]
+        else:
+            m = np.asarray(border_mask, np.float64).copy()
+        if mask_occlusion == 'fb':
+            lsq = (fd ** 2).sum(-1, keepdims=True)
+            mag = (f ** 2).sum(-1, keepdims=True) + (gw ** 2).sum(-1, keepdims=True)
+            m = m * (1 - (lsq > 0.01 * mag + 0.5))
+        masks.append(m)
+        out['occ'] += charbonnier(1 - m)
+        out['photo'] += charbonnier(A - Bw, m, beta=255)
+        out['fb'] += charbonnier(fd, m)
+        out['smooth_1st'] += first_order_loss(f)
+        out['smooth_2nd'] += second_order_loss(f)
+        out['ternary'] += ternary_loss(A, Bw, m, data_max_distance)
+    return out, masks

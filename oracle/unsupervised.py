@@ -24,82 +24,69 @@ def regularization_loss(variables, scale=0.0004):
     return total
 
 
+def _pyramid_table(full_resolution):
+    """(weight, census radius) per loss level, finest first (unsupervised.py:87-92)."""
+    table = [(12.7, 3), (4.35, 2), (3.9, 2), (3.4, 1), (1.1, 1)]
+    if full_resolution:
+        table = [(12.7, 3), (5.5, 3), (5.0, 3)] + table[1:]
+    return table
+
+
 def unsupervised_loss(variables, batch, params, normalization=None, augment=False,
                       return_flow=False, return_terms=False):
     if augment:
         raise NotImplementedError("the oracle restates the augment=False graph only")
-    channel_mean = torch.tensor(normalization[0], dtype=torch.float32) / 255.0
-    im1, im2 = batch
-    im1 = im1 / 255.0
-    im2 = im2 / 255.0
-    im_shape = im1.shape[1:3]
+    mean = torch.tensor(normalization[0], dtype=torch.float32) / 255.0        # :31
+    a, b = batch[0] / 255.0, batch[1] / 255.0                                 # :32-33
+    out_hw = a.shape[1:3]
+    valid = create_border_mask(a, 0.1)                                         # :38
 
-    border_mask = create_border_mask(im1, 0.1)
-    im1_norm, im2_norm = im1, im2
-    im1_photo = im1 - channel_mean
-    im2_photo = im2 - channel_mean
+    spec = params.get('flownet', 'S')
+    full = params.get('full_res')
+    # without augmentation the loss images are the inputs and the network images are the
+    # mean-subtracted inputs (:62-68); only the last network of a stack is scored (:79-80)
+    fw_all, bw_all = flownet(variables, a - mean, b - mean, flownet_spec=spec, full_resolution=full,
+                             backward_flow=True, train_all=params.get('train_all'))
+    fw, bw = fw_all[-1], bw_all[-1]
 
-    flownet_spec = params.get('flownet', 'S')
-    full_resolution = params.get('full_res')
-    train_all = params.get('train_all')
+    table = _pyramid_table(full)
+    if full:                                                                   # :93-99
+        unit = FLOW_SCALE * 4
+        pyr = [(a, b, valid)]
+        flow_fw, flow_bw = fw[0] * unit, bw[0] * unit
+    else:                                                                      # :100-106
+        unit = FLOW_SCALE
+        pyr = [(downsample(a, 4), downsample(b, 4), downsample(valid, 4))]
+        flow_fw = tfc.resize_bilinear_legacy(fw[0], out_hw) * unit * 4
+        flow_bw = tfc.resize_bilinear_legacy(bw[0], out_hw) * unit * 4
 
-    flows_fw, flows_bw = flownet(variables, im1_photo, im2_photo, flownet_spec=flownet_spec,
-                                 full_resolution=full_resolution, backward_flow=True,
-                                 train_all=train_all)
-    flows_fw = flows_fw[-1]
-    flows_bw = flows_bw[-1]
+    depth = len(fw) if params.get('pyramid_loss') else 1                       # :113-116
+    while len(pyr) < depth:                                                    # :147-149
+        pyr.append(tuple(downsample(t, 2) for t in pyr[-1]))
 
-    layer_weights = [12.7, 4.35, 3.9, 3.4, 1.1]
-    layer_patch_distances = [3, 2, 2, 1, 1]
-    if full_resolution:
-        layer_weights = [12.7, 5.5, 5.0, 4.35, 3.9, 3.4, 1.1]
-        layer_patch_distances = [3, 3] + layer_patch_distances
-        im1_s, im2_s, mask_s = im1_norm, im2_norm, border_mask
-        final_flow_scale = FLOW_SCALE * 4
-        final_flow_fw = flows_fw[0] * final_flow_scale
-        final_flow_bw = flows_bw[0] * final_flow_scale
-    else:
-        im1_s = downsample(im1_norm, 4)
-        im2_s = downsample(im2_norm, 4)
-        mask_s = downsample(border_mask, 4)
-        final_flow_scale = FLOW_SCALE
-        final_flow_fw = tfc.resize_bilinear_legacy(flows_fw[0], im_shape) * final_flow_scale * 4
-        final_flow_bw = tfc.resize_bilinear_legacy(flows_bw[0], im_shape) * final_flow_scale * 4
+    occlusion = params.get('mask_occlusion', '')
+    assert occlusion in ['fb', 'disocc', '']
+    weighted = [(name, params[name + '_weight']) for name in LOSSES if params.get(name + '_weight')]
 
-    combined_losses = {loss: 0.0 for loss in LOSSES}
-    combined_loss = 0.0
+    by_term = dict.fromkeys(LOSSES, 0.0)
+    objective = 0.0
+    for k in range(depth):                                                     # :118-145
+        (lam, radius), (pa, pb, pm) = table[k], pyr[k]
+        px = unit / (2 ** k)
+        got = compute_losses(pa, pb, fw[k] * px, bw[k] * px,
+                             border_mask=pm if params.get('border_mask') else None,
+                             mask_occlusion=occlusion, data_max_distance=radius)
+        acc = 0.0
+        for name, w in weighted:
+            acc = acc + w * got[name]
+            by_term[name] = by_term[name] + lam * got[name]
+        objective = objective + lam * acc
 
-    if params.get('pyramid_loss'):
-        flow_enum = list(enumerate(zip(flows_fw, flows_bw)))
-    else:
-        flow_enum = [(0, (flows_fw[0], flows_bw[0]))]
+    objective = objective + regularization_loss(variables)                     # :151-152
 
-    for i, (flow_fw_s, flow_bw_s) in flow_enum:
-        flow_scale = final_flow_scale / (2 ** i)
-        layer_weight = layer_weights[i]
-        mask_occlusion = params.get('mask_occlusion', '')
-        assert mask_occlusion in ['fb', 'disocc', '']
-        losses = compute_losses(im1_s, im2_s, flow_fw_s * flow_scale, flow_bw_s * flow_scale,
-                                border_mask=mask_s if params.get('border_mask') else None,
-                                mask_occlusion=mask_occlusion,
-                                data_max_distance=layer_patch_distances[i])
-        layer_loss = 0.0
-        for loss in LOSSES:
-            weight_name = loss + '_weight'
-            if params.get(weight_name):
-                layer_loss = layer_loss + params[weight_name] * losses[loss]
-                combined_losses[loss] = combined_losses[loss] + layer_weight * losses[loss]
-        combined_loss = combined_loss + layer_weight * layer_loss
-
-        im1_s = downsample(im1_s, 2)
-        im2_s = downsample(im2_s, 2)
-        mask_s = downsample(mask_s, 2)
-
-    final_loss = combined_loss + regularization_loss(variables)
-
-    out = (final_loss,)
+    ret = [objective]
     if return_flow:
-        out = out + (final_flow_fw, final_flow_bw)
+        ret += [flow_fw, flow_bw]
     if return_terms:
-        out = out + (combined_losses,)
-    return out[0] if len(out) == 1 else out
+        ret.append(by_term)
+    return ret[0] if len(ret) == 1 else tuple(ret)

@@ -60,80 +60,64 @@ def compute_losses(im1, im2, flow_fw, flow_bw,
     return losses
 
 
+class _Direction:
+    """Everything the eight terms need for one flow direction (a -> b): the second image and the
+    opposite flow sampled along the flow, the forward-backward residual and its occlusion test
+    (reference :21-22, :38-50)."""
+
+    def __init__(self, im_a, im_b, flow_ab, flow_ba):
+        self.image, self.flow = im_a, flow_ab
+        self.other_warped = image_warp(im_b, flow_ab)
+        self.image_diff = im_a - self.other_warped
+        back = image_warp(flow_ba, flow_ab)
+        self.flow_diff = flow_ab + back
+        limit = 0.01 * (length_sq(flow_ab) + length_sq(back)) + 0.5
+        self.fb_occluded = (length_sq(self.flow_diff) > limit).float()
+
+    def disocclusion(self):
+        return (forward_warp(self.flow) < DISOCC_THRESH).float()
+
+
 def _compute_losses_unfused(im1, im2, flow_fw, flow_bw, border_mask, mask_occlusion,
                             data_max_distance, _terms=None):
-    need = (lambda k: True) if _terms is None else (lambda k: k in _terms)
+    """The level loss term by term on stand-alone ops (used when the fused kernels cannot serve
+    the request, and as their cross-check in the tests)."""
+    from .fused_loss import TERM_ORDER
+    wanted = set(TERM_ORDER if _terms is None else _terms)
+    fw = _Direction(im1, im2, flow_fw, flow_bw)
+    bw = _Direction(im2, im1, flow_bw, flow_fw)
+    dirs = (fw, bw)
+
+    if 'sym' in wanted or mask_occlusion == 'disocc':
+        for d in dirs:
+            d.disocc = d.disocclusion()
+
+    # validity: the border mask if given, else "the flow stays inside the image"; then remove
+    # what the chosen occlusion test marks (note the swap: a pixel of frame 1 is disoccluded when
+    # the BACKWARD flow splats nothing onto it)
+    for d, opposite in ((fw, bw), (bw, fw)):
+        d.mask = create_outgoing_mask(d.flow) if border_mask is None else border_mask
+        if mask_occlusion == 'fb':
+            d.mask = d.mask * (1 - d.fb_occluded)
+        elif mask_occlusion == 'disocc':
+            d.mask = d.mask * (1 - opposite.disocc)
+
+    def both(term):
+        return term(fw, bw) + term(bw, fw)
+
+    table = {
+        'sym': lambda d, o: charbonnier_loss((1 - d.mask) - o.disocc),
+        'occ': lambda d, o: charbonnier_loss(1 - d.mask),
+        'photo': lambda d, o: photometric_loss(d.image_diff, d.mask),
+        'grad': lambda d, o: gradient_loss(d.image, d.other_warped, d.mask),
+        'smooth_1st': lambda d, o: smoothness_loss(d.flow),
+        'smooth_2nd': lambda d, o: second_order_loss(d.flow),
+        'fb': lambda d, o: charbonnier_loss(d.flow_diff, d.mask),
+        'ternary': lambda d, o: ternary_loss(d.image, d.other_warped, d.mask,
+                                             max_distance=data_max_distance),
+    }
     zero = torch.zeros((), device=im1.device, dtype=torch.float32)
-    losses = {}
-
-    im2_warped = image_warp(im2, flow_fw)
-    im1_warped = image_warp(im1, flow_bw)
-
-    im_diff_fw = im1 - im2_warped
-    im_diff_bw = im2 - im1_warped
-
-    need_disocc = need('sym') or mask_occlusion == 'disocc'
-    if need_disocc:
-        disocc_fw = (forward_warp(flow_fw) < DISOCC_THRESH).float()
-        disocc_bw = (forward_warp(flow_bw) < DISOCC_THRESH).float()
-
-    if border_mask is None:
-        mask_fw = create_outgoing_mask(flow_fw)
-        mask_bw = create_outgoing_mask(flow_bw)
-    else:
-        mask_fw = border_mask
-        mask_bw = border_mask
-
-    flow_bw_warped = image_warp(flow_bw, flow_fw)
-    flow_fw_warped = image_warp(flow_fw, flow_bw)
-    flow_diff_fw = flow_fw + flow_bw_warped
-    flow_diff_bw = flow_bw + flow_fw_warped
-
-    mag_sq_fw = length_sq(flow_fw) + length_sq(flow_bw_warped)
-    mag_sq_bw = length_sq(flow_bw) + length_sq(flow_fw_warped)
-    occ_thresh_fw = 0.01 * mag_sq_fw + 0.5
-    occ_thresh_bw = 0.01 * mag_sq_bw + 0.5
-
-    fb_occ_fw = (length_sq(flow_diff_fw) > occ_thresh_fw).float()
-    fb_occ_bw = (length_sq(flow_diff_bw) > occ_thresh_bw).float()
-
-    if mask_occlusion == 'fb':
-        mask_fw = mask_fw * (1 - fb_occ_fw)
-        mask_bw = mask_bw * (1 - fb_occ_bw)
-    elif mask_occlusion == 'disocc':
-        mask_fw = mask_fw * (1 - disocc_bw)
-        mask_bw = mask_bw * (1 - disocc_fw)
-
-    occ_fw = 1 - mask_fw
-    occ_bw = 1 - mask_bw
-
-    losses['sym'] = (charbonnier_loss(occ_fw - disocc_bw) +
-                     charbonnier_loss(occ_bw - disocc_fw)) if need('sym') else zero
-
-    losses['occ'] = (charbonnier_loss(occ_fw) +
-                     charbonnier_loss(occ_bw)) if need('occ') else zero
-
-    losses['photo'] = (photometric_loss(im_diff_fw, mask_fw) +
-                       photometric_loss(im_diff_bw, mask_bw)) if need('photo') else zero
-
-    losses['grad'] = (gradient_loss(im1, im2_warped, mask_fw) +
-                      gradient_loss(im2, im1_warped, mask_bw)) if need('grad') else zero
-
-    losses['smooth_1st'] = (smoothness_loss(flow_fw) +
-                            smoothness_loss(flow_bw)) if need('smooth_1st') else zero
-
-    losses['smooth_2nd'] = (second_order_loss(flow_fw) +
-                            second_order_loss(flow_bw)) if need('smooth_2nd') else zero
-
-    losses['fb'] = (charbonnier_loss(flow_diff_fw, mask_fw) +
-                    charbonnier_loss(flow_diff_bw, mask_bw)) if need('fb') else zero
-
-    losses['ternary'] = (ternary_loss(im1, im2_warped, mask_fw,
-                                      max_distance=data_max_distance) +
-                         ternary_loss(im2, im1_warped, mask_bw,
-                                      max_distance=data_max_distance)) if need('ternary') else zero
-
-    return losses
+    return {name: (both(term) if name in wanted else zero) for name, term in table.items()}
 
 
 def _rgb_to_gray(image):
@@ -206,15 +190,14 @@ def divergence(flow):
 
 
 def norm(x, sigma):
-    """Gaussian decay.
-    Result is 1.0 for x = 0 and decays towards 0 for |x > sigma.
-    """
+    """exp(-x^2 / (2 sigma^2)): 1 at x = 0, falling off on the scale of sigma."""
     return torch.exp(-0.5 * torch.square(x / sigma))
 
 
 def diffusion_loss(flow, im, occ):
-    """Forces diffusion weighted by motion, intensity and occlusion label similarity
-    (reference losses.py:173-195; unused by any shipped configuration)."""
+    """8-neighbour flow differences, down-weighted where intensity or flow already differ and
+    gated by the occlusion-label difference (reference losses.py:173-195; no shipped
+    configuration uses it)."""
     def neighbor_diff(x):
         outs = []
         for c in range(x.shape[3]):
@@ -302,17 +285,9 @@ def second_order_loss(flow):
 
 
 def charbonnier_loss(x, mask=None, truncate=None, alpha=0.45, beta=1.0, epsilon=0.001):
-    """Compute the generalized charbonnier loss of the difference tensor x.
-    All positions where mask == 0 are not taken into account.
-
-    Args:
-        x: a tensor of shape [num_batch, height, width, channels].
-        mask: a mask of shape [num_batch, height, width, mask_channels],
-            where mask channels must be either 1 or the same number as
-            the number of channels of x. Entries should be 0 or 1.
-    Returns:
-        loss as a 0-d float32 tensor
-    """
+    """Generalised Charbonnier penalty ((beta*x)^2 + epsilon^2)^alpha, averaged over ALL elements
+    of ``x`` ([B,H,W,C]); elements where ``mask`` ([B,H,W,1] or [B,H,W,C], 0/1) is zero add
+    nothing but still count in the denominator (reference :296-323)."""
     normalization = float(x.numel())
     error = torch.pow(torch.square(x * beta) + epsilon ** 2, alpha)
     if mask is not None:
@@ -340,8 +315,7 @@ def create_border_mask(tensor, border_ratio=0.1):
 
 
 def create_outgoing_mask(flow):
-    """Computes a mask that is zero at all positions where the flow
-    would carry a pixel over the image boundary."""
+    """[B,H,W,1] mask: 1 where pixel + flow lands inside [0,W-1] x [0,H-1], else 0."""
     B, H, W, _ = flow.shape
     grid_x = torch.arange(W, device=flow.device, dtype=torch.float32).view(1, 1, W)
     grid_y = torch.arange(H, device=flow.device, dtype=torch.float32).view(1, H, 1)

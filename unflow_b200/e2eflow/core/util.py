@@ -1,23 +1,27 @@
-"""reference src/e2eflow/core/util.py:12-26 (resize helpers and the downsample wrapper)."""
-import torch
+"""Resize helpers with the reference's names (src/e2eflow/core/util.py:12-26).
 
-from ..ops import downsample as downsample_ops
+``resize_area`` / ``resize_bilinear`` resize to the spatial size of a second NHWC tensor and block
+the gradient; ``downsample`` is the box-mean CUDA op for even sizes and TF's area resize otherwise.
+(``summarized_placeholder`` belongs to the TensorBoard plumbing, which is out of scope.)
+"""
 from . import tf_image
+from ..ops import downsample as _box_downsample
+
+
+def _size_of(nhwc):
+    return [int(nhwc.shape[1]), int(nhwc.shape[2])]
 
 
 def resize_area(tensor, like):
-    _, h, w, _ = like.shape
-    return tf_image.resize_area(tensor, [h, w]).detach()
+    return tf_image.resize_area(tensor, _size_of(like)).detach()
 
 
 def resize_bilinear(tensor, like):
-    _, h, w, _ = like.shape
-    return tf_image.resize_bilinear(tensor, [h, w]).detach()
+    return tf_image.resize_bilinear(tensor, _size_of(like)).detach()
 
 
 def downsample(tensor, num):
-    _, height, width, _ = tensor.shape
-    if height % 2 == 0 and width % 2 == 0:
-        return downsample_ops(tensor, num)
-    else:
-        return tf_image.resize_area(tensor, [int(height / num), int(width / num)])
+    rows, cols = _size_of(tensor)
+    if rows % 2 or cols % 2:     # odd extent: the op's output grid is undefined, use area resize
+        return tf_image.resize_area(tensor, [int(rows / num), int(cols / num)])
+    return _box_downsample(tensor, num)
