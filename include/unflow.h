@@ -201,6 +201,14 @@ int unflow_bias_grad_lrelu(const float *g, long long sN, long long sC, long long
                            const float *act, float *gb, int N, int C, int H, int W, float slope,
                            void *stream);
 
+/* ---- checkpoint formats --------------------------------------------
+ * Host-only helper, no GPU work: CRC-32C (Castagnoli) of ``n`` bytes continuing from ``crc``
+ * (0 to start).  TensorFlow's checkpoint files -- what tf.train.Saver writes and restores in the
+ * reference (src/e2eflow/core/train.py:23-65,258-259) -- guard every index block and every tensor
+ * with this checksum; the importer/exporter (e2eflow/core/tf_checkpoint.py) calls it for the
+ * ~157 MB of weights per network. */
+unsigned int unflow_crc32c(const void *data, size_t n, unsigned int crc);
+
 #ifdef __cplusplus
 }
 #endif

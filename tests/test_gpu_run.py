@@ -63,6 +63,13 @@ def test_run_trains_checkpoints_and_resumes(tmp_path, capsys):
     R.main(["--ex", "t1", "--config", str(ini), "--synthetic", "--ow", "--debug", "--max-iters", "2"])
     assert "-- training from i = 1 to 2" in capsys.readouterr().out
     assert not glob.glob(str(tmp_path / "log" / "checkpoints" / "t1" / "model.ckpt-*.pt"))
+    # the reference's own checkpoint format: write, then resume from it
+    R.main(["--ex", "t2", "--config", str(ini), "--synthetic", "--max-iters", "2", "--ckpt-format", "tf"])
+    capsys.readouterr()
+    d2 = tmp_path / "log" / "checkpoints" / "t2"
+    assert sorted(os.listdir(d2)) == ["checkpoint", "model.ckpt-2.data-00000-of-00001", "model.ckpt-2.index"]
+    R.main(["--ex", "t2", "--config", str(ini), "--synthetic", "--max-iters", "3", "--debug"])
+    assert "-- training from i = 3 to 3" in capsys.readouterr().out
 
 
 def test_evaluate_loop_on_synthetic_ground_truth():

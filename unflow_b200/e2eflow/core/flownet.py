@@ -91,6 +91,8 @@ def layer_specs(flownet_spec='S', full_resolution=False):
         c512, c1024 = int(512 * m), int(1024 * m)
         if name.lower() == 'c':
             assert i == 0, 'FlowNetS must be used for refinement networks'
+            if full_res:   # flownet_c hands no conv1 / inputs to the up-convolutions (flownet.py:235-236)
+                raise ValueError("full_res needs a FlowNetS as the last network of the stack")
             f = root + 'flownet_c_features/'
             specs += [(f + 'conv1', 'conv', 3, c64, 7), (f + 'conv2', 'conv', c64, c128, 5),
                       (f + 'conv3', 'conv', c128, c256, 5)]

@@ -70,10 +70,12 @@ class Trainer:
             scopes = list(self.variables.kinds)
         else:
             scopes = self.variables.scopes_of_net(n_nets - 1)
-        trainable = []
+        trainable, names = [], []
         for sc in scopes:
             w, b = self.variables.weights(sc)
             trainable += [w, b]
+            names += [sc + '/weights', sc + '/biases']
+        self.trainable_names = names
         train_ids = {id(p) for p in trainable}
         for p in self.variables.parameters():
             p.requires_grad_(id(p) in train_ids)
@@ -90,23 +92,52 @@ class Trainer:
         self.adam_m = torch.zeros(npad, device=self.device, dtype=torch.float32)
         self.adam_v = torch.zeros(npad, device=self.device, dtype=torch.float32)
         off = 0
-
-        def view_like(flat_seg, p):
-            """A view of the flat segment with p's shape; 4-D weights keep their NHWC memory order."""
-            if p.dim() == 4:
-                a, b, kh, kw = p.shape
-                return flat_seg.view(a, kh, kw, b).permute(0, 3, 1, 2)
-            return flat_seg.view_as(p)
-
+        self._offsets = []
         with torch.no_grad():
             for p in self.trainable:
                 k = p.numel()
-                pv = view_like(self.flat_param[off:off + k], p)
+                pv = self._view_like(self.flat_param[off:off + k], p)
                 pv.copy_(p)
                 p.data = pv
-                p.grad = view_like(self.flat_grad[off:off + k], p)
+                p.grad = self._view_like(self.flat_grad[off:off + k], p)
+                self._offsets.append(off)
                 off += k
         self.num_params = n
+
+    @staticmethod
+    def _view_like(flat_seg, p):
+        """A view of the flat segment with p's shape; 4-D weights keep their NHWC memory order."""
+        if p.dim() == 4:
+            a, b, kh, kw = p.shape
+            return flat_seg.view(a, kh, kw, b).permute(0, 3, 1, 2)
+        return flat_seg.view_as(p)
+
+    # -- optimizer state in the reference's checkpoint naming --------------------------------------
+    def adam_slots(self):
+        """{variable name: (m, v)} in TF layout -- the ``<name>/Adam`` and ``<name>/Adam_1`` slot
+        variables tf.train.AdamOptimizer creates next to each trained variable (train.py:151-152)."""
+        out = {}
+        for name, p, off in zip(self.trainable_names, self.trainable, self._offsets):
+            pair = []
+            for flat in (self.adam_m, self.adam_v):
+                t = self._view_like(flat[off:off + p.numel()], p)
+                if p.dim() == 4:
+                    t = t.permute(2, 3, 1, 0)
+                pair.append(t.detach().clone(memory_format=torch.contiguous_format).cpu().numpy())
+            out[name] = tuple(pair)
+        return out
+
+    def load_adam_slots(self, slots):
+        """Inverse of ``adam_slots``; variables without an entry keep zero moments."""
+        with torch.no_grad():
+            for name, p, off in zip(self.trainable_names, self.trainable, self._offsets):
+                if name not in slots:
+                    continue
+                for flat, value in zip((self.adam_m, self.adam_v), slots[name]):
+                    t = torch.as_tensor(value, dtype=torch.float32)
+                    if p.dim() == 4:
+                        t = t.permute(3, 2, 0, 1)
+                    self._view_like(flat[off:off + p.numel()], p).copy_(t)
 
     def broadcast_variables(self, src=0):
         if self.world_size > 1:

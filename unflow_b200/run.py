@@ -8,11 +8,20 @@
   coercion (int -> float -> bool -> str); the dataset section overrides [train]
   (run.py:91-92); ``manual_decay_*`` strings become lists and define ``num_iters``.
 * [run] batch_size is the TOTAL batch, divided by the number of GPUs (run.py:48).
-* training runs in chunks of ``save_interval`` iterations; after each chunk a checkpoint
-  ``model.ckpt-<iter>.pt`` (variables under their TF names, TF layout) is written and training
-  resumes from the newest checkpoint by parsing the iteration from the file name
-  (train.py:124-135, 258-259).  ``--ow`` discards an existing experiment, ``--debug`` disables
+* training runs in chunks of ``save_interval`` iterations; after each chunk a checkpoint is
+  written and training resumes from the newest checkpoint by parsing the iteration from the file
+  name (train.py:124-135, 258-259).  ``--ckpt-format pt`` (default) writes ``model.ckpt-<iter>.pt``
+  (variables under their TF names, TF layout); ``--ckpt-format tf`` writes the reference's own
+  format (``model.ckpt-<iter>.index`` / ``.data-00000-of-00001`` + the ``checkpoint`` state file,
+  core/tf_checkpoint.py), which the reference's Saver can restore.  Either kind is accepted on
+  resume and for ``finetune``.  ``--ow`` discards an existing experiment, ``--debug`` disables
   checkpoint writing.
+* ``finetune = exA,exB`` ([train*] sections): network i of the stack is initialised from the
+  newest checkpoint of experiment i -- looked up in [dirs] checkpoints, then [dirs] log /ex --
+  with the reference's rules (util.py:75-85, train.py:23-62): when the experiment has no
+  checkpoint of its own all listed networks are restored; when it resumes and ``train_all`` is off,
+  the fixed networks (all but the last) are restored again from their sources; a checkpoint that
+  lacks the ``full_res`` layers restores the rest.
 * The dataset adapters / TF queue-runner input pipeline of the reference are outside the hot path
   (SURVEY.md section 2): with ``--synthetic`` (or when [dirs] data does not exist) batches are
   seeded synthetic pairs of the configured height x width.
@@ -55,8 +64,9 @@ def config_dict(config_path):
     return d
 
 
-def convert_input_strings(config_dct):
-    """util.py:65-73 (the ``finetune`` checkpoint lookup is handled by load_finetune)."""
+def convert_input_strings(config_dct, dirs=None):
+    """util.py:65-85: the manual decay lists and, given ``dirs``, the ``finetune`` experiment names
+    resolved to their newest checkpoints (``(iteration, path)`` as ``latest_checkpoint`` returns)."""
     if 'manual_decay_iters' in config_dct and 'manual_decay_lrs' in config_dct:
         iters_lst = [int(i) for i in str(config_dct['manual_decay_iters']).split(',')]
         lrs_lst = [float(l) for l in str(config_dct['manual_decay_lrs']).split(',')]
@@ -64,8 +74,23 @@ def convert_input_strings(config_dct):
         config_dct['manual_decay_lrs'] = lrs_lst
         config_dct['num_iters'] = sum(iters_lst)
 
+    if 'finetune' in config_dct and dirs is not None:
+        found = []
+        for name in str(config_dct['finetune']).split(','):
+            name = name.strip()
+            ckpt = latest_checkpoint(os.path.join(dirs.get('checkpoints', ''), name))
+            if ckpt is None:
+                ckpt = latest_checkpoint(os.path.join(dirs.get('log', ''), 'ex', name))
+            assert ckpt, "Could not load experiment " + name
+            found.append(ckpt)
+        config_dct['finetune'] = found
+
 
 def latest_checkpoint(ckpt_dir):
+    """Newest checkpoint of an experiment directory as ``(iteration, path)``: a ``.pt`` file of
+    this implementation or the prefix of a TF checkpoint named by the ``checkpoint`` state file
+    (tf.train.get_checkpoint_state); None when there is none."""
+    from .e2eflow.core import tf_checkpoint
     best = None
     for p in glob.glob(os.path.join(ckpt_dir, "model.ckpt-*.pt")):
         try:
@@ -74,7 +99,54 @@ def latest_checkpoint(ckpt_dir):
             continue
         if best is None or it > best[0]:
             best = (it, p)
+    state = tf_checkpoint.get_checkpoint_state(ckpt_dir)
+    if state is not None and os.path.exists(state[0] + '.index'):
+        try:
+            it = tf_checkpoint.checkpoint_iteration(state[0])
+        except ValueError:
+            it = 0
+        if best is None or it > best[0]:
+            best = (it, state[0])
     return best
+
+
+def restore_checkpoint(trainer, path, nets=None, with_optimizer=False):
+    """Load network variables (and optionally Adam's moments) from either checkpoint kind."""
+    from .e2eflow.core import tf_checkpoint
+    variables = trainer.variables
+    if path.endswith('.pt'):
+        state = torch.load(path, map_location='cpu')
+        tensors = state['variables']
+        if nets is not None:
+            keep = {s for i in nets for s in variables.scopes_of_net(i)}
+            tensors = {k: v for k, v in tensors.items() if k.rsplit('/', 1)[0] in keep}
+        missing = [n for n in variables.variable_names()
+                   if n not in tensors and (nets is None or n.rsplit('/', 1)[0] in keep)]
+        if any('full_res' not in n for n in missing):
+            raise KeyError("checkpoint %s lacks %s" % (path, missing[0]))
+        variables.load_tf_dict(tensors, strict=False)
+        if with_optimizer and 'adam_slots' in state:
+            trainer.load_adam_slots(state['adam_slots'])
+        return
+    tf_checkpoint.restore_variables(variables, path, nets=nets)
+    if with_optimizer:
+        reader = tf_checkpoint.BundleReader(path)
+        slots = {n: (reader.tensor(n + '/Adam'), reader.tensor(n + '/Adam_1'))
+                 for n in trainer.trainable_names if n + '/Adam' in reader and n + '/Adam_1' in reader}
+        trainer.load_adam_slots(slots)
+
+
+def save_checkpoint(trainer, ckpt_dir, iteration, fmt='pt'):
+    """train.py:258-259 ``saver.save(sess, save_path, global_step=i)``.  The reference's Saver
+    holds only the trained networks unless ``train_all`` (train.py:32-37); here every network of
+    the stack is written, so a checkpoint is self-contained (a superset of the reference's)."""
+    from .e2eflow.core import tf_checkpoint
+    prefix = os.path.join(ckpt_dir, 'model.ckpt-%d' % iteration)
+    if fmt == 'tf':
+        return tf_checkpoint.save_variables(trainer.variables, prefix, adam_slots=trainer.adam_slots())
+    slots = {k: (torch.from_numpy(m), torch.from_numpy(v)) for k, (m, v) in trainer.adam_slots().items()}
+    torch.save({'variables': trainer.variables.to_tf_dict(), 'adam_slots': slots}, prefix + '.pt')
+    return prefix + '.pt'
 
 
 def synthetic_batch(batch, height, width, step, rank, device):
@@ -91,6 +163,8 @@ def main(argv=None):
     ap.add_argument('--config', default=os.environ.get('UNFLOW_CONFIG', '../config.ini'))
     ap.add_argument('--synthetic', action='store_true')
     ap.add_argument('--max-iters', type=int, default=None, help='stop early (for smoke runs)')
+    ap.add_argument('--ckpt-format', choices=('pt', 'tf'), default='pt',
+                    help="'tf' writes TensorFlow checkpoints the reference can restore")
     args = ap.parse_args(argv)
 
     cfg = config_dict(args.config)
@@ -98,7 +172,7 @@ def main(argv=None):
     train_dataset = run_config.get('dataset', 'kitti')
     params = copy.deepcopy(cfg['train'])
     params.update(cfg.get('train_' + train_dataset, {}))
-    convert_input_strings(params)
+    convert_input_strings(params, dirs)
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -130,15 +204,26 @@ def main(argv=None):
     save_interval = min(params['save_interval'], max(num_iters, 1))
     start_iter = 1
     ck = latest_checkpoint(ckpt_dir)
+    # restore_networks (train.py:23-62): which networks come from the ``finetune`` experiments
+    finetune = params.get('finetune', [])
+    n_nets = len(params.get('flownet', 'S'))
+    assert len(finetune) <= n_nets
+    if params.get('train_all'):
+        external = finetune if ck is None else []
+    else:
+        external = finetune if ck is None else finetune[:n_nets - 1]
     if ck is not None:
-        state = torch.load(ck[1], map_location='cpu')
-        tr.variables.load_tf_dict(state['variables'])
-        tr.adam_m.copy_(state['adam_m']); tr.adam_v.copy_(state['adam_v'])
+        # continue training
+        restore_checkpoint(tr, ck[1], with_optimizer=True)
         tr.iteration = ck[0]
         start_iter = ck[0] + 1
-        if start_iter > num_iters:
-            print('-- train: max_iter reached')
-            return
+    for i, source in enumerate(external):
+        if rank == 0:
+            print('-- restore', 'network %d' % i, source[1])
+        restore_checkpoint(tr, source[1], nets=[i])
+    if start_iter > num_iters:
+        print('-- train: max_iter reached')
+        return
     tr.broadcast_variables(0)
     if rank == 0:
         print('-- training from i = {} to {}'.format(start_iter, num_iters))
@@ -152,8 +237,7 @@ def main(argv=None):
         if rank == 0 and (i == 1 or i % params['display_interval'] == 0):
             print("-- train: i = {}, loss = {}".format(i, float(loss)))
         if i % save_interval == 0 and not args.debug and rank == 0:
-            torch.save({'variables': tr.variables.to_tf_dict(), 'adam_m': tr.adam_m.cpu(),
-                        'adam_v': tr.adam_v.cpu()}, os.path.join(ckpt_dir, 'model.ckpt-%d.pt' % i))
+            save_checkpoint(tr, ckpt_dir, i, args.ckpt_format)
     if world > 1:
         dist.destroy_process_group()
 
