@@ -91,14 +91,18 @@ def unsupervised_loss(batch, params, normalization=None, augment=True,
         weights, distances = _FULL_RES_WEIGHTS, _FULL_RES_DISTANCES
         level_im1, level_im2, level_mask = loss_im1, loss_im2, border_mask
         top_scale = FLOW_SCALE * 4
-        final_fw, final_bw = pyramid_fw[0] * top_scale, pyramid_bw[0] * top_scale
     else:
         weights, distances = _LEVEL_WEIGHTS, _LEVEL_DISTANCES
         level_im1, level_im2 = downsample(loss_im1, 4), downsample(loss_im2, 4)
         level_mask = downsample(border_mask.contiguous(), 4)
         top_scale = FLOW_SCALE
-        final_fw = tf_image.resize_bilinear(pyramid_fw[0], size) * top_scale * 4
-        final_bw = tf_image.resize_bilinear(pyramid_bw[0], size) * top_scale * 4
+
+    def final_flow(finest):
+        """The full-size output flow in pixels (reference :97-98, :105-106).  Only evaluated when
+        it is returned: a TF session prunes it from the training step, eager code has to ask."""
+        if full_res:
+            return finest * top_scale
+        return tf_image.resize_bilinear(finest, size) * top_scale * 4
 
     n_levels = len(pyramid_fw) if params.get('pyramid_loss') else 1
     active = [t for t in LOSSES if params.get(t + '_weight')]
@@ -132,5 +136,5 @@ def unsupervised_loss(batch, params, normalization=None, augment=True,
         _track_loss(per_term[t], 'loss/' + t)
 
     if return_flow:
-        return final_loss, final_fw, final_bw
+        return final_loss, final_flow(pyramid_fw[0]), final_flow(pyramid_bw[0])
     return final_loss
