@@ -251,7 +251,7 @@ def run_ours(args):
              roof("correlation_bwd", 4 * Bc * hc * wc * (D2 + 4 * C), 2 * corr_flops),
              roof("level_loss_fwd_%dx%d" % (H // 4, W // 4), (44 + 16) * npx0),
              roof("level_loss_bwd_%dx%d" % (H // 4, W // 4), (60 + 16) * npx0),
-             roof("conv_operand"), roof("adam")]
+             roof("conv_operand"), roof("narrow_conv_fwd"), roof("narrow_conv_wgrad"), roof("adam")]
     roofs = [r for r in roofs if r]
     line = {
         "metric": METRIC, "value": round(value, 3), "unit": "frame-pairs/s", "n_gpus": world,

@@ -201,6 +201,24 @@ int unflow_bias_grad_lrelu(const float *g, long long sN, long long sC, long long
                            const float *act, float *gb, int N, int C, int H, int W, float slope,
                            void *stream);
 
+/* ---- flow-prediction heads: 3x3, stride 1, SAME, C_out = 2 (csrc/narrow_conv.cu) ---------------
+ * The reference's `slim.conv2d(concatN, 2, 3, scope='flowN', activation_fn=None)` layers
+ * (src/e2eflow/core/flownet.py:92-131) in exact fp32 on the FMA pipes; two output channels are
+ * no tensor-core shape.
+ *   x    dense NHWC [N,H,W,C], C even, 8-byte aligned
+ *   w    [2][3][3][C]  (OIHW weights stored channels-last = TF's HWIO with O moved to the front)
+ *   bias [2] or NULL;  y dense NHWC [N,H,W,2], 8-byte aligned
+ *   g    gradient w.r.t. y as a logical [N,2,H,W] tensor read through strides (floats)
+ *   gw   [2][3][3][C], written (not accumulated); deterministic two-pass reduction through
+ *        ``workspace`` (unflow_conv3x3_narrow_wgrad_workspace_bytes bytes).
+ * UNFLOW_EINVAL unless C_out == 2 and C is even. */
+int unflow_conv3x3_narrow_fwd(const float *x, const float *w, const float *bias, float *y, int N, int H,
+                              int W, int C, int C_out, void *stream);
+size_t unflow_conv3x3_narrow_wgrad_workspace_bytes(int N, int H, int W, int C);
+int unflow_conv3x3_narrow_wgrad(const float *x, const float *g, long long gsN, long long gsC,
+                                long long gsH, long long gsW, float *gw, void *workspace, int N, int H,
+                                int W, int C, int C_out, void *stream);
+
 /* ---- checkpoint formats --------------------------------------------
  * Host-only helper, no GPU work: CRC-32C (Castagnoli) of ``n`` bytes continuing from ``crc``
  * (0 to start).  TensorFlow's checkpoint files -- what tf.train.Saver writes and restores in the

@@ -147,3 +147,58 @@ def test_fused_bias_leaky_relu_layer_matches_float64(mode3x, deconv):
     for got, want, name in ((a, ad, "a"), (xc.grad, xd.grad, "dx"), (wc.grad, wd.grad, "dw"), (bc.grad, bd.grad, "db")):
         e = rel(got.detach().cpu(), want.detach())
         assert e < 3e-5, "%s: rel err %.2e" % (name, e)
+
+
+@pytest.mark.parametrize("N,C,H,W", [(2, 194, 37, 70), (1, 18, 16, 32), (3, 16, 5, 33), (1, 386, 48, 160)])
+def test_narrow_flow_head_matches_float64(mode3x, N, C, H, W):
+    """csrc/narrow_conv.cu (the 2-channel 3x3 flow heads): forward, weight and bias gradients in
+    exact fp32 against float64; ragged tiles, channel-chunk tails, strided incoming gradient,
+    bit-identical repeats (fixed-order reduction)."""
+    from unflow_b200.e2eflow.core import conv_ops
+    gen = torch.Generator().manual_seed(C * 1000 + H)
+    x = torch.randn(N, C, H, W, generator=gen)
+    w = torch.randn(2, C, 3, 3, generator=gen) * 0.1
+    b = torch.randn(2, generator=gen)
+    # the gradient arrives as a channel slice of a wider NHWC buffer (what the concat backward hands out)
+    gwide = torch.randn(N, H, W, 5, generator=gen)
+    xd, wd, bd = x.double().requires_grad_(True), w.double().requires_grad_(True), b.double().requires_grad_(True)
+    yd = F.conv2d(xd, wd, bd, padding=1)
+    gd = gwide.permute(0, 3, 1, 2)[:, 1:3].double()
+    yd.backward(gd)
+
+    xc = x.cuda().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    wc = w.cuda().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    bc = b.cuda().requires_grad_(True)
+    y = conv_ops._NarrowConv3x3.apply(xc, wc, bc)
+    assert y.shape == (N, 2, H, W) and y.is_contiguous(memory_format=torch.channels_last)
+    gc = gwide.cuda().permute(0, 3, 1, 2)[:, 1:3]
+    y.backward(gc)
+    assert rel(y.detach().cpu(), yd.detach()) < 2e-6
+    assert rel(wc.grad.cpu(), wd.grad) < 2e-6
+    assert rel(bc.grad.cpu(), bd.grad) < 2e-6
+    assert rel(xc.grad.cpu(), xd.grad) < 3e-5                    # 3xTF32 library path
+    # deterministic: a second evaluation gives the same bits
+    wc2 = wc.detach().clone().requires_grad_(True)
+    y2 = conv_ops._NarrowConv3x3.apply(xc.detach(), wc2, bc.detach())
+    y2.backward(gc)
+    assert torch.equal(y2, y) and torch.equal(wc2.grad, wc.grad)
+    # no bias, and the dispatch rule of conv2d
+    y3 = conv_ops._NarrowConv3x3.apply(xc.detach(), wc.detach(), None)
+    assert rel((y3 + bc.detach().view(1, 2, 1, 1)).cpu(), yd.detach()) < 2e-6
+    tiles = N * ((H + 15) // 16) * ((W + 31) // 32)
+    assert conv_ops._use_narrow(xc, wc, 1, (1, 1, 1, 1)) == (tiles >= conv_ops.NARROW_MIN_TILES)
+    assert not conv_ops._use_narrow(xc, wc, 2, (1, 1, 1, 1)) and not conv_ops._use_narrow(xc, wc, 1, (0, 1, 0, 1))
+
+
+def test_narrow_conv_rejects_other_shapes():
+    from unflow_b200 import _native
+    x = torch.zeros(1, 4, 4, 6, device="cuda")
+    y = torch.zeros(1, 4, 4, 2, device="cuda")
+    w = torch.zeros(2, 3, 3, 6, device="cuda")
+    s = torch.cuda.current_stream().cuda_stream
+    lib = _native.lib()
+    assert lib.unflow_conv3x3_narrow_fwd(x.data_ptr(), w.data_ptr(), None, y.data_ptr(), 1, 4, 4, 6, 4, s) == 1
+    assert "2 output channels" in _native.lib().unflow_last_error().decode()
+    assert lib.unflow_conv3x3_narrow_fwd(x.data_ptr(), w.data_ptr(), None, y.data_ptr(), 1, 4, 4, 5, 2, s) == 1
+    assert lib.unflow_conv3x3_narrow_wgrad_workspace_bytes(2, 16, 32, 6) == 2 * 18 * 6 * 4
+    assert lib.unflow_conv3x3_narrow_wgrad_workspace_bytes(2, 17, 33, 6) == 8 * 18 * 6 * 4

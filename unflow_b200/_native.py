@@ -51,6 +51,9 @@ SIGNATURES = {
     "unflow_level_loss_workspace_bytes": (ctypes.c_size_t, [_i] * 3),
     "unflow_level_loss_fwd": (_i, [_vp] * 11 + [_i] * 5 + [ctypes.c_uint, _vp]),
     "unflow_level_loss_bwd": (_i, [_vp] * 11 + [_i] * 5 + [ctypes.c_uint, _vp]),
+    "unflow_conv3x3_narrow_fwd": (_i, [_vp] * 4 + [_i] * 5 + [_vp]),
+    "unflow_conv3x3_narrow_wgrad_workspace_bytes": (ctypes.c_size_t, [_i] * 4),
+    "unflow_conv3x3_narrow_wgrad": (_i, [_vp, _vp] + [ctypes.c_longlong] * 4 + [_vp, _vp] + [_i] * 5 + [_vp]),
     "unflow_crc32c": (ctypes.c_uint, [_vp, ctypes.c_size_t, ctypes.c_uint]),
 }
 

@@ -204,6 +204,71 @@ class _Deconv3x(torch.autograd.Function):
         return gx, gw, gb, None
 
 
+# The narrow kernels pay off where the layer is large enough to fill the GPU with 16x32-pixel
+# tiles (the flow2 / flow3 heads of a training batch); smaller heads stay on the library path.
+NARROW_MIN_TILES = 96
+_NARROW = __import__('os').environ.get('UNFLOW_NARROW_CONV', '1') != '0'
+
+
+def _narrow_tiles(N, H, W):
+    return N * ((H + 15) // 16) * ((W + 31) // 32)
+
+
+def _use_narrow(x, w, stride, pads):
+    return (_NARROW and w.shape[0] == 2 and w.shape[2] == 3 and w.shape[3] == 3 and stride in (1, (1, 1))
+            and tuple(pads) == (1, 1, 1, 1) and x.shape[1] % 2 == 0 and x.dtype == torch.float32
+            and x.is_contiguous(memory_format=torch.channels_last)
+            and _narrow_tiles(x.shape[0], x.shape[2], x.shape[3]) >= NARROW_MIN_TILES)
+
+
+class _NarrowConv3x3(torch.autograd.Function):
+    """The 2-channel flow heads (csrc/narrow_conv.cu): forward and weight gradient in exact fp32 on
+    the FMA pipes, reading the wide input once; the input gradient (C_in wide) keeps the
+    tensor-core path of ``_Conv3x``."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        N, C, H, W = x.shape
+        wl = w if w.is_contiguous(memory_format=torch.channels_last) else \
+            w.contiguous(memory_format=torch.channels_last)
+        y = torch.empty((N, 2, H, W), device=x.device, dtype=torch.float32,
+                        memory_format=torch.channels_last)
+        from ..ops import kernel_timer
+        with torch.cuda.device(x.device), kernel_timer.span("narrow_conv_fwd", 4 * x.numel() + 4 * y.numel()):
+            check(_native.lib().unflow_conv3x3_narrow_fwd(
+                x.data_ptr(), wl.data_ptr(), b.data_ptr() if b is not None else None, y.data_ptr(),
+                N, H, W, C, 2, torch.cuda.current_stream().cuda_stream), "conv3x3_narrow_fwd")
+        ctx.save_for_backward(x, w)
+        ctx.has_b = b is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w = ctx.saved_tensors
+        N, C, H, W = x.shape
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            ci_p = _round4(C)
+            gs = _operand(g, 0, c_pad=4)                                          # [N, 12, H, W]
+            wt = _operand(w, 1, concat_batch=True, c_pad=ci_p, n_out=4)           # [12, Ci_p, 3, 3]
+            gx = _conv_input_grad((H + 2, W + 2), wt, gs, 1)[:, :C, 1:1 + H, 1:1 + W]
+        if ctx.needs_input_grad[1]:
+            lib = _native.lib()
+            ws = torch.empty(lib.unflow_conv3x3_narrow_wgrad_workspace_bytes(N, H, W, C) // 4,
+                             device=x.device, dtype=torch.float32)
+            gw = torch.empty((2, 3, 3, C), device=x.device, dtype=torch.float32)
+            sN, sC, sH, sW = g.stride()
+            from ..ops import kernel_timer
+            with torch.cuda.device(x.device), kernel_timer.span("narrow_conv_wgrad", 4 * x.numel() + 4 * g.numel()):
+                check(lib.unflow_conv3x3_narrow_wgrad(
+                    x.data_ptr(), g.data_ptr(), sN, sC, sH, sW, gw.data_ptr(), ws.data_ptr(),
+                    N, H, W, C, 2, torch.cuda.current_stream().cuda_stream), "conv3x3_narrow_wgrad")
+            gw = gw.permute(0, 3, 1, 2)                                           # [2, C, 3, 3], NHWC-ordered
+        if ctx.has_b and ctx.needs_input_grad[2]:
+            gb = _bias_grad(g, None)
+        return gx, gw, gb
+
+
 def channels_last_active(x):
     """The tensor-core path computes in NHWC (cuDNN's TF32 kernels are NHWC; NCHW costs a layout
     transform around every conv); the exact-fp32 path keeps the reference's NCHW (cuDNN's fp32
@@ -221,6 +286,8 @@ def network_input(x_nhwc):
 def conv2d(x, w, b, stride, pads, act=False):
     """pads = (top, bottom, left, right) TF-SAME padding; act: apply the leaky ReLU."""
     if _MODE == '3xtf32' and x.is_cuda:
+        if not act and _use_narrow(x, w, stride, pads):
+            return _NarrowConv3x3.apply(x, w, b)
         fuse = act and b is not None and w.shape[0] % 4 == 0
         y = _Conv3x.apply(x, w, b, stride, tuple(pads), fuse)
         return F.leaky_relu(y, LRELU_SLOPE) if (act and not fuse) else y
