@@ -34,37 +34,40 @@ constexpr int KC = 16;                     // input channels per chunk
 constexpr int THREADS = 128;
 constexpr int NOUT = 18;                   // 2 output channels x 9 taps
 constexpr int GPITCH = 2 * TW + 2;         // floats per row of the staged gradient tile (wgrad)
+constexpr int FWD_PITCH = 38, FWD_CHS = 706;   // forward staging layout (see narrow_fwd_kernel)
+static_assert(FWD_CHS >= SR * FWD_PITCH && FWD_CHS % 32 == 2 && FWD_PITCH % 4 == 2, "forward smem layout");
 
-// Stage the window of chunk [c0, c0+KC) as xs[ch * CHS + row * PITCH + col]; zero outside the image
-// and beyond C.  x is dense NHWC with C even (8-byte channel pairs).
-template <int CHS>
+// Stage the window of chunk [c0, c0+KC) as xs[ch * CHS + row * PITCH_ + col]; zero outside the image
+// and beyond C.  x is dense NHWC with C even.  A warp instruction covers 4 consecutive pixels x 8
+// channel pairs: four contiguous 64-byte runs in global memory (one 8-byte pair per lane), and in
+// shared memory 32 distinct banks (channel stride = 2 or 9 mod 32 banks, pixels = consecutive banks).
+template <int CHS, int PITCH_>
 __device__ __forceinline__ void stage_x(float *xs, const float *__restrict__ x, int n, int y0, int x0,
                                         int c0, int H, int W, int C, int tid) {
   constexpr int NPIX = SR * SC;
-  for (int p = tid; p < NPIX; p += THREADS) {
+  const int h = tid & 7, q = tid >> 3;
+  const bool chan_ok = c0 + 2 * h < C;
+  const float *xc = x + c0 + 2 * h;
+  float *xd = xs + (2 * h) * CHS;
+#pragma unroll 4
+  for (int p = q; p < NPIX; p += THREADS / 8) {
     const int pr = p / SC, pc = p - pr * SC;
     const int gy = y0 - 1 + pr, gx = x0 - 1 + pc;
-    const bool inside = gy >= 0 && gy < H && gx >= 0 && gx < W;
-    const float *src = x + (((long long)n * H + (inside ? gy : 0)) * W + (inside ? gx : 0)) * C + c0;
-    float2 v[KC / 2];
-#pragma unroll
-    for (int h = 0; h < KC / 2; ++h) {
-      v[h] = make_float2(0.f, 0.f);
-      if (inside && c0 + 2 * h < C) v[h] = __ldg(reinterpret_cast<const float2 *>(src + 2 * h));
-    }
-    float *dst = xs + pr * PITCH + pc;
-#pragma unroll
-    for (int h = 0; h < KC / 2; ++h) {
-      dst[(2 * h) * CHS] = v[h].x;
-      dst[(2 * h + 1) * CHS] = v[h].y;
-    }
+    float2 v = make_float2(0.f, 0.f);
+    if (chan_ok && gy >= 0 && gy < H && gx >= 0 && gx < W)
+      v = __ldg(reinterpret_cast<const float2 *>(xc + (((long long)n * H + gy) * W + gx) * C));
+    float *dst = xd + pr * PITCH_ + pc;
+    dst[0] = v.x;
+    dst[CHS] = v.y;
   }
 }
 
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, 4)
 narrow_fwd_kernel(const float *__restrict__ x, const float *__restrict__ w, const float *__restrict__ bias,
                   float *__restrict__ y, int H, int W, int C) {
-  constexpr int CHS = SR * PITCH;             // 648: multiple of 4 -> 16-byte aligned vector loads
+  // rows 38 floats apart: a half-warp's 8-byte reads (two tile rows) fall on disjoint banks;
+  // channels 706 = 2 (mod 32) floats apart: the staging stores are conflict-free
+  constexpr int CHS = FWD_CHS, FP = FWD_PITCH;
   extern __shared__ __align__(16) float smem[];
   float *xs = smem;                           // [KC][CHS]
   float *ws = smem + KC * CHS;                // [KC][3][8]: co0 kx0..2, co1 kx0..2, 0, 0
@@ -74,7 +77,7 @@ narrow_fwd_kernel(const float *__restrict__ x, const float *__restrict__ w, cons
 
   for (int c0 = 0; c0 < C; c0 += KC) {
     __syncthreads();                          // the previous chunk has been consumed
-    stage_x<CHS>(xs, x, n, y0, x0, c0, H, W, C, tid);
+    stage_x<CHS, FP>(xs, x, n, y0, x0, c0, H, W, C, tid);
     for (int idx = tid; idx < KC * 24; idx += THREADS) {
       const int ch = idx % KC, r = idx / KC, ky = r >> 3, e = r & 7;
       float v = 0.f;
@@ -89,12 +92,13 @@ narrow_fwd_kernel(const float *__restrict__ x, const float *__restrict__ w, cons
     for (int ch = 0; ch < KC; ++ch) {
 #pragma unroll
       for (int ky = 0; ky < 3; ++ky) {
-        const float *xp = xs + ch * CHS + (row + ky) * PITCH + 4 * cg;
-        const float4 a = *reinterpret_cast<const float4 *>(xp);
-        const float2 b = *reinterpret_cast<const float2 *>(xp + 4);
+        const float *xp = xs + ch * CHS + (row + ky) * FP + 4 * cg;
+        const float2 a = *reinterpret_cast<const float2 *>(xp);
+        const float2 b = *reinterpret_cast<const float2 *>(xp + 2);
+        const float2 c = *reinterpret_cast<const float2 *>(xp + 4);
         const float4 wa = *reinterpret_cast<const float4 *>(ws + (ch * 3 + ky) * 8);
         const float4 wb = *reinterpret_cast<const float4 *>(ws + (ch * 3 + ky) * 8 + 4);
-        const float xv[6] = {a.x, a.y, a.z, a.w, b.x, b.y};
+        const float xv[6] = {a.x, a.y, b.x, b.y, c.x, c.y};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           acc0[j] = fmaf(xv[j], wa.x, acc0[j]);
@@ -120,7 +124,7 @@ narrow_fwd_kernel(const float *__restrict__ x, const float *__restrict__ w, cons
   }
 }
 
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, 4)
 narrow_wgrad_kernel(const float *__restrict__ x, const float *__restrict__ g, long long gsN, long long gsC,
                     long long gsH, long long gsW, float *__restrict__ partial, int H, int W, int C) {
   constexpr int CHS = SR * PITCH + 1;         // 649: odd -> lanes on consecutive channels hit distinct banks
@@ -143,7 +147,7 @@ narrow_wgrad_kernel(const float *__restrict__ x, const float *__restrict__ g, lo
 
   for (int c0 = 0; c0 < C; c0 += KC) {
     __syncthreads();                          // red (aliasing xs) has been read; gs is complete
-    stage_x<CHS>(xs, x, n, y0, x0, c0, H, W, C, tid);
+    stage_x<CHS, PITCH>(xs, x, n, y0, x0, c0, H, W, C, tid);
     __syncthreads();
     float acc0[9], acc1[9];
 #pragma unroll
@@ -246,7 +250,7 @@ extern "C" int unflow_conv3x3_narrow_fwd(const float *x, const float *w, const f
   UNFLOW_REQUIRE(x && w && y, "conv3x3_narrow_fwd: null pointer");
   UNFLOW_REQUIRE(((uintptr_t)x & 7) == 0 && ((uintptr_t)y & 7) == 0, "conv3x3_narrow_fwd: x and y must be 8-byte aligned");
   const dim3 grid(ceil_div(W, nc::TW), ceil_div(H, nc::TH), N);
-  const size_t smem = (size_t)(nc::KC * nc::SR * nc::PITCH + nc::KC * 24) * sizeof(float);
+  const size_t smem = (size_t)(nc::KC * nc::FWD_CHS + nc::KC * 24) * sizeof(float);
   nc::narrow_fwd_kernel<<<grid, nc::THREADS, smem, (cudaStream_t)stream>>>(x, w, bias, y, H, W, C);
   count_launch();
   return check_launch("conv3x3_narrow_fwd");
