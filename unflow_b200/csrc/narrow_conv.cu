@@ -62,6 +62,43 @@ __device__ __forceinline__ void stage_x(float *xs, const float *__restrict__ x, 
   }
 }
 
+__device__ __forceinline__ void cp_async_4(unsigned dst, const float *src, unsigned bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// The same staging with asynchronous 4-byte copies (LDGSTS): nothing passes through registers, so
+// all ~77 copies of a thread are in flight at once and the DRAM latency is paid once per chunk
+// instead of once per unrolled batch (the synchronous loader is latency-bound: ~10 us per chunk).
+// A warp instruction covers 2 consecutive pixels x 16 channels = two 64-byte runs; out-of-image /
+// beyond-C elements are zero-filled by a copy of size 0.
+template <int CHS, int PITCH_>
+__device__ __forceinline__ void stage_x_async(float *xs, const float *__restrict__ x, int n, int y0, int x0,
+                                              int c0, int H, int W, int C, int tid) {
+  constexpr int NPIX = SR * SC;
+  const int ch = tid & 15, q = tid >> 4;
+  const bool chan_ok = c0 + ch < C;
+  const float *xc = x + c0 + ch;
+  const unsigned dbase = (unsigned)__cvta_generic_to_shared(xs + ch * CHS);
+#pragma unroll 7
+  for (int p = q; p < NPIX; p += THREADS / 16) {
+    const int pr = p / SC, pc = p - pr * SC;
+    const int gy = y0 - 1 + pr, gx = x0 - 1 + pc;
+    const bool ok = chan_ok && gy >= 0 && gy < H && gx >= 0 && gx < W;
+    const float *src = ok ? xc + (((long long)n * H + gy) * W + gx) * C : x;
+    cp_async_4(dbase + (unsigned)(pr * PITCH_ + pc) * 4u, src, ok ? 4u : 0u);
+  }
+  cp_async_wait_all();
+}
+
+template <bool ASYNC, int CHS, int PITCH_>
+__device__ __forceinline__ void stage(float *xs, const float *__restrict__ x, int n, int y0, int x0, int c0,
+                                      int H, int W, int C, int tid) {
+  if (ASYNC) stage_x_async<CHS, PITCH_>(xs, x, n, y0, x0, c0, H, W, C, tid);
+  else stage_x<CHS, PITCH_>(xs, x, n, y0, x0, c0, H, W, C, tid);
+}
+
+template <bool ASYNC>
 __global__ void __launch_bounds__(THREADS, 4)
 narrow_fwd_kernel(const float *__restrict__ x, const float *__restrict__ w, const float *__restrict__ bias,
                   float *__restrict__ y, int H, int W, int C) {
@@ -77,7 +114,7 @@ narrow_fwd_kernel(const float *__restrict__ x, const float *__restrict__ w, cons
 
   for (int c0 = 0; c0 < C; c0 += KC) {
     __syncthreads();                          // the previous chunk has been consumed
-    stage_x<CHS, FP>(xs, x, n, y0, x0, c0, H, W, C, tid);
+    stage<ASYNC, CHS, FP>(xs, x, n, y0, x0, c0, H, W, C, tid);
     for (int idx = tid; idx < KC * 24; idx += THREADS) {
       const int ch = idx % KC, r = idx / KC, ky = r >> 3, e = r & 7;
       float v = 0.f;
@@ -124,6 +161,7 @@ narrow_fwd_kernel(const float *__restrict__ x, const float *__restrict__ w, cons
   }
 }
 
+template <bool ASYNC>
 __global__ void __launch_bounds__(THREADS, 4)
 narrow_wgrad_kernel(const float *__restrict__ x, const float *__restrict__ g, long long gsN, long long gsC,
                     long long gsH, long long gsW, float *__restrict__ partial, int H, int W, int C) {
@@ -147,7 +185,7 @@ narrow_wgrad_kernel(const float *__restrict__ x, const float *__restrict__ g, lo
 
   for (int c0 = 0; c0 < C; c0 += KC) {
     __syncthreads();                          // red (aliasing xs) has been read; gs is complete
-    stage_x<CHS, PITCH>(xs, x, n, y0, x0, c0, H, W, C, tid);
+    stage<ASYNC, CHS, PITCH>(xs, x, n, y0, x0, c0, H, W, C, tid);
     __syncthreads();
     float acc0[9], acc1[9];
 #pragma unroll
@@ -224,10 +262,14 @@ narrow_wgrad_reduce_kernel(const float *__restrict__ partial, float *__restrict_
   }
 }
 
+int g_loader = 1;   // 1: cp.async staging (default), 0: synchronous float2 staging (unflow_set_int_option "narrow_loader")
+
 inline long long tiles(int N, int H, int W) { return (long long)N * ceil_div(H, TH) * ceil_div(W, TW); }
 
 }  // namespace nc
 }  // namespace unflow
+
+namespace unflow { int set_narrow_loader(int v) { if (v != 0 && v != 1) return 0; nc::g_loader = v; return 1; } }
 
 extern "C" size_t unflow_conv3x3_narrow_wgrad_workspace_bytes(int N, int H, int W, int C) {
   if (N <= 0 || H <= 0 || W <= 0 || C <= 0) return 0;
@@ -251,7 +293,8 @@ extern "C" int unflow_conv3x3_narrow_fwd(const float *x, const float *w, const f
   UNFLOW_REQUIRE(((uintptr_t)x & 7) == 0 && ((uintptr_t)y & 7) == 0, "conv3x3_narrow_fwd: x and y must be 8-byte aligned");
   const dim3 grid(ceil_div(W, nc::TW), ceil_div(H, nc::TH), N);
   const size_t smem = (size_t)(nc::KC * nc::FWD_CHS + nc::KC * 24) * sizeof(float);
-  nc::narrow_fwd_kernel<<<grid, nc::THREADS, smem, (cudaStream_t)stream>>>(x, w, bias, y, H, W, C);
+  if (nc::g_loader) nc::narrow_fwd_kernel<true><<<grid, nc::THREADS, smem, (cudaStream_t)stream>>>(x, w, bias, y, H, W, C);
+  else nc::narrow_fwd_kernel<false><<<grid, nc::THREADS, smem, (cudaStream_t)stream>>>(x, w, bias, y, H, W, C);
   count_launch();
   return check_launch("conv3x3_narrow_fwd");
 }
@@ -273,7 +316,8 @@ extern "C" int unflow_conv3x3_narrow_wgrad(const float *x, const float *g, long 
   const dim3 grid(ceil_div(W, nc::TW), ceil_div(H, nc::TH), N);
   const int nblocks = (int)nc::tiles(N, H, W);
   const size_t smem = (size_t)(nc::KC * (nc::SR * nc::PITCH + 1) + nc::TH * nc::GPITCH) * sizeof(float);
-  nc::narrow_wgrad_kernel<<<grid, nc::THREADS, smem, s>>>(x, g, gsN, gsC, gsH, gsW, (float *)workspace, H, W, C);
+  if (nc::g_loader) nc::narrow_wgrad_kernel<true><<<grid, nc::THREADS, smem, s>>>(x, g, gsN, gsC, gsH, gsW, (float *)workspace, H, W, C);
+  else nc::narrow_wgrad_kernel<false><<<grid, nc::THREADS, smem, s>>>(x, g, gsN, gsC, gsH, gsW, (float *)workspace, H, W, C);
   count_launch();
   if (int rc = check_launch("conv3x3_narrow_wgrad")) return rc;
   const int total = nc::NOUT * C;

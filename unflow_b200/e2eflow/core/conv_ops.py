@@ -210,6 +210,19 @@ NARROW_MIN_TILES = 96
 _NARROW = __import__('os').environ.get('UNFLOW_NARROW_CONV', '1') != '0'
 
 
+NARROW_LOADER = int(__import__('os').environ.get('UNFLOW_NARROW_LOADER', '1'))   # 1: cp.async staging (measured 1.5 % of the step faster), 0: synchronous
+_narrow_ready = False
+
+
+def _narrow_lib():
+    global _narrow_ready
+    lib = _native.lib()
+    if not _narrow_ready:
+        check(lib.unflow_set_int_option(b"narrow_loader", NARROW_LOADER), "narrow_loader option")
+        _narrow_ready = True
+    return lib
+
+
 def _narrow_tiles(N, H, W):
     return N * ((H + 15) // 16) * ((W + 31) // 32)
 
@@ -235,7 +248,7 @@ class _NarrowConv3x3(torch.autograd.Function):
                         memory_format=torch.channels_last)
         from ..ops import kernel_timer
         with torch.cuda.device(x.device), kernel_timer.span("narrow_conv_fwd", 4 * x.numel() + 4 * y.numel()):
-            check(_native.lib().unflow_conv3x3_narrow_fwd(
+            check(_narrow_lib().unflow_conv3x3_narrow_fwd(
                 x.data_ptr(), wl.data_ptr(), b.data_ptr() if b is not None else None, y.data_ptr(),
                 N, H, W, C, 2, torch.cuda.current_stream().cuda_stream), "conv3x3_narrow_fwd")
         ctx.save_for_backward(x, w)
@@ -253,7 +266,7 @@ class _NarrowConv3x3(torch.autograd.Function):
             wt = _operand(w, 1, concat_batch=True, c_pad=ci_p, n_out=4)           # [12, Ci_p, 3, 3]
             gx = _conv_input_grad((H + 2, W + 2), wt, gs, 1)[:, :C, 1:1 + H, 1:1 + W]
         if ctx.needs_input_grad[1]:
-            lib = _native.lib()
+            lib = _narrow_lib()
             ws = torch.empty(lib.unflow_conv3x3_narrow_wgrad_workspace_bytes(N, H, W, C) // 4,
                              device=x.device, dtype=torch.float32)
             gw = torch.empty((2, 3, 3, C), device=x.device, dtype=torch.float32)
