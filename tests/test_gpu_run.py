@@ -90,3 +90,40 @@ def test_evaluate_loop_on_synthetic_ground_truth():
     assert 0.0 < res['AEE/occluded'] < 100.0 and 0.0 < res['AEE/non-occluded'] < 100.0
     assert 0 <= res['outliers/non-occluded'] <= 100
     assert images['flow'].shape == (1, 96, 320, 3) and images['reverse disocc'].dtype == torch.bool
+
+
+def test_run_trains_on_a_kitti_tree_and_evaluates(tmp_path, capsys):
+    """Real-data path of run.py: KITTI raw PNG pairs through the reference's pairing rules, resume
+    shift, evaluation on the 2012 training set after each save_interval chunk."""
+    cv2 = pytest.importorskip("cv2")
+    import numpy as np
+    from unflow_b200 import run as R
+    from unflow_b200.e2eflow.core import flow_io
+    data = tmp_path / "data"
+    rng = np.random.default_rng(0)
+    base = cv2.GaussianBlur(rng.integers(0, 255, (150, 300, 3), dtype=np.uint8), (0, 0), 3)
+    for view in ("image_02", "image_03"):
+        d = data / "kitti_raw" / "2011_09_26" / "2011_09_26_drive_0001_extract" / view / "data"
+        d.mkdir(parents=True)
+        for n in range(6):
+            assert cv2.imwrite(str(d / ("%010d.png" % n)), np.roll(base, 2 * n, axis=1))
+    tr_dir = data / "data_stereo_flow" / "training"
+    for sub in ("colored_0", "flow_occ", "flow_noc"):
+        (tr_dir / sub).mkdir(parents=True)
+    for i in range(2):
+        im = np.roll(base, 5 * i, axis=0)[:120, :280]
+        cv2.imwrite(str(tr_dir / "colored_0" / ("%06d_10.png" % i)), im)
+        cv2.imwrite(str(tr_dir / "colored_0" / ("%06d_11.png" % i)), np.roll(im, 3, axis=1))
+        flow = np.zeros((120, 280, 2), np.float32)
+        flow[..., 0] = 3.0
+        for sub in ("flow_occ", "flow_noc"):
+            flow_io.write_kitti_flow(str(tr_dir / sub / ("%06d_10.png" % i)), flow, np.ones((120, 280)))
+    ini = tmp_path / "config.ini"
+    ini.write_text(CFG.format(d=str(tmp_path)).replace("data = %s/nodata" % tmp_path, "data = %s" % data))
+    R.main(["--ex", "k1", "--config", str(ini), "--max-iters", "2"])
+    out = capsys.readouterr().out
+    assert "Training on 10 frame pairs." in out and "-- train: i = 2, loss" in out
+    assert "-- eval: i = 2" in out and "AEE/occluded" in out and "num_examples = 2" in out
+    assert os.path.exists(str(tmp_path / "log" / "checkpoints" / "k1" / "model.ckpt-2.pt"))
+    R.main(["--ex", "k1", "--config", str(ini), "--max-iters", "4", "--debug"])
+    assert "-- training from i = 3 to 4" in capsys.readouterr().out

@@ -120,7 +120,16 @@ def write_kitti_flow(path, flow, mask=None):
 
 def read_kitti_flow(path):
     """kitti/input.py:12-22 -> (flow [h,w,2] float32, mask [h,w,1] float32)."""
-    gt = read_png16(path).astype(np.float32)
+    gt = None
+    try:                                   # OpenCV decodes a 375x1242 ground-truth file in milliseconds
+        import cv2
+        raw = cv2.imread(path, cv2.IMREAD_UNCHANGED)
+        if raw is not None and raw.dtype == np.uint16 and raw.ndim == 3 and raw.shape[2] == 3:
+            gt = raw[:, :, ::-1].astype(np.float32)       # BGR -> (u, v, valid)
+    except ImportError:
+        pass
+    if gt is None:
+        gt = read_png16(path).astype(np.float32)
     flow = (gt[:, :, 0:2] - 2 ** 15) / 64.0
     mask = gt[:, :, 2:3]
     return flow, mask

@@ -22,9 +22,12 @@
   checkpoint of its own all listed networks are restored; when it resumes and ``train_all`` is off,
   the fixed networks (all but the last) are restored again from their sources; a checkpoint that
   lacks the ``full_res`` layers restores the rest.
-* The dataset adapters / TF queue-runner input pipeline of the reference are outside the hot path
-  (SURVEY.md section 2): with ``--synthetic`` (or when [dirs] data does not exist) batches are
-  seeded synthetic pairs of the configured height x width.
+* ``dataset = kitti`` with an existing [dirs] data directory trains on the KITTI raw sequences
+  through the reference's pairing / shuffling / resume-shift rules (core/input.py, kitti/) and
+  evaluates on the KITTI 2012 training set after every ``save_interval`` chunk; each rank reads
+  its own shard of the batch stream.  With ``--synthetic`` (or when [dirs] data does not exist)
+  batches are seeded synthetic pairs of the configured height x width.  Downloading the datasets
+  and the other dataset adapters (chairs, synthia, cityscapes, middlebury) are out of scope.
 """
 import argparse
 import configparser
@@ -149,6 +152,45 @@ def save_checkpoint(trainer, ckpt_dir, iteration, fmt='pt'):
     return prefix + '.pt'
 
 
+def kitti_inputs(dirs, run_config, params, train_dataset, gpu_batch_size, start_iter, rank, world):
+    """The 'kitti' branch of the reference run.py (:31-58, :96-115): training batches from the raw
+    sequences (``input_raw(swap_images=False, center_crop=True, shift=iterations_done * batch_size)``)
+    and, when present, the KITTI 2012 training set with ground truth for evaluation at 384x1280."""
+    if train_dataset != 'kitti':
+        raise SystemExit("dataset '%s': only the KITTI input pipeline is implemented; use --synthetic"
+                         % train_dataset)
+    from .e2eflow.kitti.data import KITTIData
+    from .e2eflow.kitti.input import KITTIInput
+    kdata = KITTIData(dirs['data'], development=run_config.get('development', True),
+                      fast_dir=dirs.get('fast'))
+    kinput = KITTIInput(data=kdata, batch_size=gpu_batch_size, normalize=False, skipped_frames=True,
+                        dims=(params['height'], params['width']))
+    batches = kinput.input_raw(swap_images=False, center_crop=True,
+                               shift=(start_iter - 1) * run_config['batch_size'],
+                               rank=rank, world_size=world)
+    eval_input = None
+    if os.path.isdir(os.path.join(kdata.current_dir, 'data_stereo_flow', 'training', 'flow_occ')):
+        eval_input = KITTIInput(data=kdata, batch_size=1, normalize=False, dims=(384, 1280))
+    return batches, eval_input
+
+
+def evaluate_kitti(trainer, eval_input, device, hold_out_inv=None):
+    """train.py:265-385 on ``einput.input_train_2012()``: every pair is brought back to its file
+    size (the queue pads to 384x1280), resized bilinearly to 384x1280 for the network, and the flow
+    is resized back before AEE / outlier-% against the occluded and non-occluded ground truth."""
+    from .e2eflow.core.input import resize_image_with_crop_or_pad
+    from .e2eflow.core.train import evaluate
+
+    def examples():
+        for item in eval_input.input_train_2012(hold_out_inv):
+            h, w = int(item[2][0, 0]), int(item[2][0, 1])
+            yield tuple(resize_image_with_crop_or_pad(t[0], h, w).unsqueeze(0).to(device)
+                        for t in (item[0], item[1]) + item[3:])
+
+    result, _ = evaluate(trainer.variables, trainer.params, trainer.normalization, examples())
+    return result
+
+
 def synthetic_batch(batch, height, width, step, rank, device):
     from . import synthetic
     im1, im2, _ = synthetic.image_pair(batch, height, width, seed=1234 + 7919 * step + rank)
@@ -228,16 +270,29 @@ def main(argv=None):
     if rank == 0:
         print('-- training from i = {} to {}'.format(start_iter, num_iters))
 
+    batches, eval_input = None, None
     data_dir = dirs.get('data', '')
     if not args.synthetic and os.path.isdir(data_dir):
-        raise SystemExit("real-data input pipelines are outside the hot path; run with --synthetic")
+        batches, eval_input = kitti_inputs(dirs, run_config, params, train_dataset, gpu_batch_size,
+                                           start_iter, rank, world)
     for i in range(start_iter, num_iters + 1):
-        im1, im2 = synthetic_batch(gpu_batch_size, params['height'], params['width'], i, rank, device)
+        if batches is None:
+            im1, im2 = synthetic_batch(gpu_batch_size, params['height'], params['width'], i, rank, device)
+        else:
+            im1, im2 = (t.to(device, non_blocking=True) for t in next(batches))
         loss = tr.step(im1, im2)     # LR schedule inside (train.py:225-244)
         if rank == 0 and (i == 1 or i % params['display_interval'] == 0):
             print("-- train: i = {}, loss = {}".format(i, float(loss)))
-        if i % save_interval == 0 and not args.debug and rank == 0:
-            save_checkpoint(tr, ckpt_dir, i, args.ckpt_format)
+        if i % save_interval == 0:
+            if not args.debug and rank == 0:
+                save_checkpoint(tr, ckpt_dir, i, args.ckpt_format)
+            if eval_input is not None and rank == 0:      # Trainer.run: self.eval(1) after every chunk
+                result = evaluate_kitti(tr, eval_input, device, params.get('eval_hold_out_inv'))
+                print("-- eval: i = {}".format(i))
+                for k in sorted(result):
+                    print("   {} = {}".format(k, result[k]))
+    if batches is not None:
+        batches.close()
     if world > 1:
         dist.destroy_process_group()
 
