@@ -195,6 +195,7 @@ class Trainer:
         self._hyper_dev = torch.zeros(8, device=self.device, dtype=torch.float32)
         self._static_im1 = im1.to(self.device).clone()
         self._static_im2 = im2.to(self.device).clone()
+        moments = (self.adam_m.clone(), self.adam_v.clone())   # restored below (resumed runs carry state)
         self._set_hyper(0.0, 1.0)                         # lr = 0 while warming up / capturing
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream())
@@ -209,8 +210,8 @@ class Trainer:
             self._static_loss = self._step_impl(self._static_im1, self._static_im2)
         self._graph_launches = _native.launch_count() - n0
         torch.cuda.synchronize(self.device)
-        # lr = 0 left the parameters alone but fed the moments: reset them and the step counter
-        self.adam_m.zero_(); self.adam_v.zero_(); self.flat_grad.zero_()
+        # lr = 0 left the parameters alone but fed the moments: put them back, reset the step counter
+        self.adam_m.copy_(moments[0]); self.adam_v.copy_(moments[1]); self.flat_grad.zero_()
         self._set_hyper(learning_rate_at(self.iteration, self.params), self.iteration + 1)
         self._graph = graph
         self.graph_replays = 0

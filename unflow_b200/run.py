@@ -205,6 +205,8 @@ def main(argv=None):
     ap.add_argument('--config', default=os.environ.get('UNFLOW_CONFIG', '../config.ini'))
     ap.add_argument('--synthetic', action='store_true')
     ap.add_argument('--max-iters', type=int, default=None, help='stop early (for smoke runs)')
+    ap.add_argument('--graph', action='store_true',
+                    help='capture the training step in one CUDA graph (Trainer.capture) and replay it')
     ap.add_argument('--ckpt-format', choices=('pt', 'tf'), default='pt',
                     help="'tf' writes TensorFlow checkpoints the reference can restore")
     args = ap.parse_args(argv)
@@ -280,6 +282,8 @@ def main(argv=None):
             im1, im2 = synthetic_batch(gpu_batch_size, params['height'], params['width'], i, rank, device)
         else:
             im1, im2 = (t.to(device, non_blocking=True) for t in next(batches))
+        if args.graph and tr._graph is None:
+            tr.capture(im1, im2)     # leaves parameters, moments and the iteration counter untouched
         loss = tr.step(im1, im2)     # LR schedule inside (train.py:225-244)
         if rank == 0 and (i == 1 or i % params['display_interval'] == 0):
             print("-- train: i = {}, loss = {}".format(i, float(loss)))
