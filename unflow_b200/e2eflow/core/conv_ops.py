@@ -87,6 +87,36 @@ def _operand(x, order, concat_batch=False, c_pad=None, n_out=None, pads=(0, 0, 0
     return out.view(n_out, Hp, Wp, 3 * c_pad).permute(0, 3, 1, 2)
 
 
+# Opt-in (UNFLOW_BWD_STREAMS=1, not yet measured): the weight gradient of a layer on a second stream
+# next to its input gradient.  The two are independent, and many of the library kernels involved
+# run far below one wave of CTAs (profiles/r1_next_steps.md, item 1).
+BWD_STREAMS = __import__('os').environ.get('UNFLOW_BWD_STREAMS', '0') == '1'
+_side_streams = {}
+
+
+def _side_stream(device):
+    key = torch.device(device).index
+    if key not in _side_streams:
+        _side_streams[key] = torch.cuda.Stream(device=device)
+    return _side_streams[key]
+
+
+def _two_streams(device, main_fn, side_fn):
+    """Run ``side_fn`` on the side stream concurrently with ``main_fn`` on the current stream; both
+    see everything enqueued before the call, and the current stream waits for the side stream at
+    the end.  ``side_fn`` returns ``(result, tensors_used_later_on_the_current_stream)``."""
+    cur = torch.cuda.current_stream(device)
+    side = _side_stream(device)
+    side.wait_stream(cur)
+    with torch.cuda.stream(side):
+        side_result, handed_over = side_fn()
+    main_result = main_fn()
+    cur.wait_stream(side)
+    for t in handed_over:
+        t.record_stream(cur)
+    return main_result, side_result
+
+
 def _conv_input_grad(input_hw, weight, grad_output, stride):
     """Gradient of ``conv2d(x, weight, stride=stride, padding=0)`` w.r.t. ``x`` ([.., input_hw]).
 
@@ -143,16 +173,26 @@ class _Conv3x(torch.autograd.Function):
         N, _, H, W = x.shape
         pt, pb, pl, pr = pads
         gx = gw = gb = None
-        if ctx.needs_input_grad[0]:
+
+        def input_grad():
             gs = _operand(g, 0, c_pad=co_p, act=a)                                 # [N, 3Co_p, ..]
             wt = _operand(w, 1, concat_batch=True, c_pad=ci_p, n_out=co_p)        # [3Co_p, Ci_p, k, k]
             gxp = _conv_input_grad((H + pt + pb, W + pl + pr), wt, gs, stride)
-            gx = gxp[:, :Ci, pt:pt + H, pl:pl + W]
-        if ctx.needs_input_grad[1]:
+            return gxp[:, :Ci, pt:pt + H, pl:pl + W]
+
+        def weight_grad():
             xb = _operand(x, 0, concat_batch=True, c_pad=ci_p, pads=pads)          # [3N, Ci_p, Hp, Wp]
             gb3 = _operand(g, 1, concat_batch=True, c_pad=co_p, act=a)             # [3N, Co_p, ..]
             gwp = nngrad.conv2d_weight(xb, (co_p, ci_p, k, k), gb3, stride=stride, padding=0)
-            gw = gwp[:Co, :Ci]
+            return gwp[:Co, :Ci], (gwp,)
+
+        if BWD_STREAMS and ctx.needs_input_grad[0] and ctx.needs_input_grad[1]:
+            gx, gw = _two_streams(x.device, input_grad, weight_grad)
+        else:
+            if ctx.needs_input_grad[0]:
+                gx = input_grad()
+            if ctx.needs_input_grad[1]:
+                gw = weight_grad()[0]
         if has_b and ctx.needs_input_grad[2]:
             gb = _bias_grad(g, a)
         return gx, gw, gb, None, None, None
@@ -188,17 +228,27 @@ class _Deconv3x(torch.autograd.Function):
         has_b, ci_p, co_p = ctx.cfg
         Ci, Co = w.shape[0], w.shape[1]
         gx = gw = gb = None
-        if ctx.needs_input_grad[0]:
+
+        def input_grad():
             gs = _operand(g, 0, c_pad=co_p, act=a)                                # [N, 3Co_p, 2h, 2w]
             wc = _operand(w, 1, c_pad=co_p, n_out=ci_p)                           # [Ci_p, 3Co_p, 4, 4]
             gxp = F.conv2d(gs, wc, None, stride=2, padding=1)
-            gx = gxp if ci_p == Ci else gxp[:, :Ci]
-        if ctx.needs_input_grad[1]:
+            return gxp if ci_p == Ci else gxp[:, :Ci]
+
+        def weight_grad():
             # d/dw of conv_transpose == weight gradient of the conv whose input is g and output x
             gb3 = _operand(g, 0, concat_batch=True, c_pad=co_p, act=a)
             xb = _operand(x, 1, concat_batch=True, c_pad=ci_p)
             gwp = nngrad.conv2d_weight(gb3, (ci_p, co_p, 4, 4), xb, stride=2, padding=1)
-            gw = gwp[:Ci, :Co]
+            return gwp[:Ci, :Co], (gwp,)
+
+        if BWD_STREAMS and ctx.needs_input_grad[0] and ctx.needs_input_grad[1]:
+            gx, gw = _two_streams(x.device, input_grad, weight_grad)
+        else:
+            if ctx.needs_input_grad[0]:
+                gx = input_grad()
+            if ctx.needs_input_grad[1]:
+                gw = weight_grad()[0]
         if has_b and ctx.needs_input_grad[2]:
             gb = _bias_grad(g, a)
         return gx, gw, gb, None
