@@ -196,9 +196,6 @@ extern "C" int unflow_bias_grad_lrelu(const float *g, long long sN, long long sC
   return check_launch("bias_grad_lrelu");
 }
 
-namespace unflow {
-}
-
 extern "C" int unflow_conv_operand_tf32(const float *x, float *out, int N, int C, int H, int W,
                                         long long sN, long long sC, long long sH, long long sW,
                                         int N_out, int C_pad, int pad_top, int pad_bottom,
