@@ -298,6 +298,15 @@ def main(argv=None):
     if batches is not None:
         batches.close()
     if world > 1:
+        if args.graph:
+            # ncclCommDestroy was observed to hang for minutes when the communicator had been used
+            # inside a captured CUDA graph (bench.py:_finish): leave once every rank is done
+            import sys
+            torch.cuda.synchronize()
+            dist.barrier()
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os._exit(0)
         dist.destroy_process_group()
 
 
