@@ -105,7 +105,7 @@ def main():
         flops = 2 * N * hh * ww * C * 18
         for loader in (1, 0):
             _native.check(_native.lib().unflow_set_int_option(b"narrow_loader", loader), "narrow_loader")
-            xr, wr = x.clone().requires_grad_(True), wgt.clone().requires_grad_(True)
+            wr = wgt.clone().requires_grad_(True)
             with torch.no_grad():
                 t = timeit(lambda: conv_ops._NarrowConv3x3.apply(x, wgt, bias))
             report("narrow_conv_fwd %s loader%d" % (tag, loader), *t, nbytes, flops)
