@@ -35,7 +35,8 @@ def cpu_kernels(monkeypatch):
 
 @pytest.mark.parametrize("stride,k,pads,cin,cout,act", [(1, 3, (1, 1, 1, 1), 6, 8, False), (2, 5, (1, 2, 1, 2), 6, 8, True),
                                                         (2, 7, (2, 3, 2, 3), 3, 8, True), (1, 1, (0, 0, 0, 0), 5, 2, False),
-                                                        (2, 3, (0, 1, 0, 1), 7, 12, True)])
+                                                        (2, 3, (0, 1, 0, 1), 7, 12, True),
+                                                        (1, 4, (0, 0, 0, 0), 12, 8, True)])   # the space-to-depth first layer
 def test_conv3x_function_matches_autograd(cpu_kernels, stride, k, pads, cin, cout, act):
     g = torch.Generator().manual_seed(k * 10 + stride)
     x = torch.randn(2, cin, 12, 14, dtype=torch.float64, generator=g).requires_grad_(True)
@@ -80,3 +81,28 @@ def test_input_grad_as_transposed_conv_equals_conv2d_input():
         want = nngrad.conv2d_input((2, 4, H, W), w, g, stride=s, padding=0)
         got = co._conv_input_grad((H, W), w, g, s)
         assert got.shape == want.shape and float((got - want).abs().max()) < 1e-12
+
+
+@pytest.mark.parametrize("C,H,W,k,pads", [(3, 16, 20, 7, (2, 3, 2, 3)), (6, 17, 21, 7, (3, 3, 3, 3)),
+                                          (14, 12, 12, 7, (2, 3, 2, 3)), (3, 10, 14, 5, (1, 2, 1, 2))])
+def test_space_to_depth_first_layer_is_the_same_convolution(cpu_kernels, C, H, W, k, pads):
+    """7x7 stride-2 conv == 4x4 stride-1 conv over 2x2 pixel blocks (core/conv_ops.py), values and
+    gradients, through the plain conv and through the _Conv3x Function the GPU path uses."""
+    g = torch.Generator().manual_seed(C + H)
+    x = torch.randn(2, C, H, W, dtype=torch.float64, generator=g).requires_grad_(True)
+    w = torch.randn(8, C, k, k, dtype=torch.float64, generator=g).requires_grad_(True)
+    b = torch.randn(8, dtype=torch.float64, generator=g).requires_grad_(True)
+    ref = F.leaky_relu(F.conv2d(F.pad(x, (pads[2], pads[3], pads[0], pads[1])), w, b, stride=2), co.LRELU_SLOPE)
+    xs, ws = co.space_to_depth_operands(x, w, pads)
+    m = (k + 1) // 2
+    assert xs.shape == (2, 4 * C, ref.shape[2] + m - 1, ref.shape[3] + m - 1) and ws.shape == (8, 4 * C, m, m)
+    assert co._use_space_to_depth(x, w, 2) and not co._use_space_to_depth(xs, ws, 1)
+    go = torch.randn(ref.shape, dtype=torch.float64, generator=g)
+    want = torch.autograd.grad(ref, (x, w, b), go)
+    for y in (F.leaky_relu(F.conv2d(xs, ws, b), co.LRELU_SLOPE), co._Conv3x.apply(xs, ws, b, 1, (0, 0, 0, 0), True)):
+        assert y.shape == ref.shape and float((y - ref).abs().max()) < 1e-12
+        got = torch.autograd.grad(y, (x, w, b), go, retain_graph=True)
+        for a_, b_ in zip(got, want):
+            assert a_.shape == b_.shape and float((a_ - b_).abs().max()) < 1e-10
+    wide = torch.randn(8, 64, 5, 5, dtype=torch.float64)
+    assert not co._use_space_to_depth(torch.zeros(1, 64, 8, 8), wide, 2)        # enough channels already

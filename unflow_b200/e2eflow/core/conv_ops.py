@@ -332,6 +332,38 @@ class _NarrowConv3x3(torch.autograd.Function):
         return gx, gw, gb
 
 
+# First layers (7x7, stride 2, 3 / 6 / 14 input channels): with so few channels the implicit-GEMM
+# kernels pad every filter tap to a 32-channel K tile (cuDNN falls back to an indexed sm80 kernel:
+# 0.8 ms fprop, 1.4 ms wgrad + 0.6 ms of layout conversions per step).  Folding the stride into the
+# channels -- 2x2 pixel blocks become 4*C channels, the 7x7 filter (zero-extended to 8x8) a 4x4
+# filter with stride 1 -- is the same sum with a tensor-core-friendly shape (4*C*3 = 36 channels).
+S2D_MAX_CHANNELS = 16
+_S2D = __import__('os').environ.get('UNFLOW_CONV1_S2D', '1') != '0'
+
+
+def _use_space_to_depth(x, w, stride):
+    return (_S2D and stride in (2, (2, 2)) and w.shape[2] == w.shape[3] and w.shape[2] % 2 == 1
+            and w.shape[2] >= 5 and w.shape[1] <= S2D_MAX_CHANNELS)
+
+
+def space_to_depth_operands(x, w, pads):
+    """``conv2d(pad(x, pads), w, stride=2)`` with an odd k x k filter  ==
+    ``conv2d(xs, ws, stride=1)`` with the returned operands: ``xs`` [N, 4C, Ho+m-1, Wo+m-1] holds the
+    padded input in 2x2 pixel blocks (channel = (dy, dx, c)), ``ws`` [Co, 4C, m, m] the filter
+    zero-extended to (k+1) x (k+1) and regrouped the same way, m = (k+1)/2."""
+    N, C, H, W = x.shape
+    Co, _, k, _ = w.shape
+    m = (k + 1) // 2
+    pt, pb, pl, pr = pads
+    Ho, Wo = (H + pt + pb - k) // 2 + 1, (W + pl + pr - k) // 2 + 1
+    Hb, Wb = Ho + m - 1, Wo + m - 1                           # block rows / cols the filter touches
+    xp = F.pad(x, (pl, 2 * Wb - W - pl, pt, 2 * Hb - H - pt))  # extra zero row / col under the 8th tap
+    xs = xp.permute(0, 2, 3, 1).reshape(N, Hb, 2, Wb, 2, C).permute(0, 1, 3, 2, 4, 5).reshape(N, Hb, Wb, 4 * C)
+    xs = xs.permute(0, 3, 1, 2)                               # NCHW-shaped view of NHWC memory
+    ws = F.pad(w, (0, 1, 0, 1)).reshape(Co, C, m, 2, m, 2).permute(0, 3, 5, 1, 2, 4).reshape(Co, 4 * C, m, m)
+    return xs, ws
+
+
 def channels_last_active(x):
     """The tensor-core path computes in NHWC (cuDNN's TF32 kernels are NHWC; NCHW costs a layout
     transform around every conv); the exact-fp32 path keeps the reference's NCHW (cuDNN's fp32
@@ -351,6 +383,9 @@ def conv2d(x, w, b, stride, pads, act=False):
     if _MODE == '3xtf32' and x.is_cuda:
         if not act and _use_narrow(x, w, stride, pads):
             return _NarrowConv3x3.apply(x, w, b)
+        if _use_space_to_depth(x, w, stride):
+            xs, ws = space_to_depth_operands(x, w, pads)
+            return conv2d(xs, ws, b, 1, (0, 0, 0, 0), act=act)
         fuse = act and b is not None and w.shape[0] % 4 == 0
         y = _Conv3x.apply(x, w, b, stride, tuple(pads), fuse)
         return F.leaky_relu(y, LRELU_SLOPE) if (act and not fuse) else y
