@@ -49,7 +49,7 @@ void unflow_reset_launch_count(void);
 /* Tuning knobs for tests / benchmarks.  "corr_fwd_variant": 1 (one row pair per thread) or
  * 3 (three row pairs per thread); default 1 (faster on B200); results are bit-identical.
  * "narrow_loader": staging of the flow-head kernels, 1 = cp.async (default), 0 = synchronous
- * loads; results are bit-identical. */
+ * loads, 2 = row-wise cp.async (experimental); the staged values, hence the results, are the same. */
 int unflow_set_int_option(const char *name, int value);
 
 /* ------------------------------------------------------------------------

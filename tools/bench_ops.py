@@ -103,7 +103,7 @@ def main():
         g = torch.randn(N, 2, hh, ww, device="cuda").contiguous(memory_format=torch.channels_last)
         nbytes = 4 * N * hh * ww * (C + 2)
         flops = 2 * N * hh * ww * C * 18
-        for loader in (1, 0):
+        for loader in (1, 0, 2):
             _native.check(_native.lib().unflow_set_int_option(b"narrow_loader", loader), "narrow_loader")
             wr = wgt.clone().requires_grad_(True)
             with torch.no_grad():

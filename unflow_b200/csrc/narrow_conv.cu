@@ -91,14 +91,52 @@ __device__ __forceinline__ void stage_x_async(float *xs, const float *__restrict
   cp_async_wait_all();
 }
 
-template <bool ASYNC, int CHS, int PITCH_>
+// Loader 2 (experimental, not the default): the same copies issued row by row -- the row pointer and
+// the bounds test of a window row are computed once, the columns of a thread are a fixed unrolled
+// set -- to cut the ~14 index instructions per copy of the loop above (the kernels are issue-bound,
+// profiles/r1_ncu_narrow_conv.md).
+template <int CHS, int PITCH_>
+__device__ __forceinline__ void stage_x_async_rows(float *xs, const float *__restrict__ x, int n, int y0, int x0,
+                                                   int c0, int H, int W, int C, int tid) {
+  const int ch = tid & 15, q = tid >> 4;                  // 8 column slots: pc = q, q+8, q+16, q+24, (q+32)
+  const bool chan_ok = c0 + ch < C;
+  const float *xc = x + (long long)n * H * W * C + c0 + ch;
+  const unsigned dbase = (unsigned)__cvta_generic_to_shared(xs + ch * CHS) + (unsigned)q * 4u;
+  int gxs[5];
+  bool cok[5];
+#pragma unroll
+  for (int j = 0; j < 5; ++j) {
+    const int pc = q + 8 * j;
+    gxs[j] = x0 - 1 + pc;
+    cok[j] = chan_ok && pc < SC && gxs[j] >= 0 && gxs[j] < W;
+  }
+#pragma unroll 3
+  for (int pr = 0; pr < SR; ++pr) {
+    const int gy = y0 - 1 + pr;
+    const bool rok = gy >= 0 && gy < H;
+    const float *rowp = xc + (long long)(rok ? gy : 0) * W * C;
+    const unsigned drow = dbase + (unsigned)(pr * PITCH_) * 4u;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+      if (q + 8 * j < SC) {                               // the fifth column exists for q < 2 only
+        const bool ok = rok && cok[j];
+        const float *src = ok ? rowp + (long long)gxs[j] * C : x;
+        cp_async_4(drow + (unsigned)(8 * j) * 4u, src, ok ? 4u : 0u);
+      }
+    }
+  }
+  cp_async_wait_all();
+}
+
+template <int LOADER, int CHS, int PITCH_>
 __device__ __forceinline__ void stage(float *xs, const float *__restrict__ x, int n, int y0, int x0, int c0,
                                       int H, int W, int C, int tid) {
-  if (ASYNC) stage_x_async<CHS, PITCH_>(xs, x, n, y0, x0, c0, H, W, C, tid);
+  if (LOADER == 2) stage_x_async_rows<CHS, PITCH_>(xs, x, n, y0, x0, c0, H, W, C, tid);
+  else if (LOADER == 1) stage_x_async<CHS, PITCH_>(xs, x, n, y0, x0, c0, H, W, C, tid);
   else stage_x<CHS, PITCH_>(xs, x, n, y0, x0, c0, H, W, C, tid);
 }
 
-template <bool ASYNC>
+template <int LOADER>
 __global__ void __launch_bounds__(THREADS, 4)
 narrow_fwd_kernel(const float *__restrict__ x, const float *__restrict__ w, const float *__restrict__ bias,
                   float *__restrict__ y, int H, int W, int C) {
@@ -114,7 +152,7 @@ narrow_fwd_kernel(const float *__restrict__ x, const float *__restrict__ w, cons
 
   for (int c0 = 0; c0 < C; c0 += KC) {
     __syncthreads();                          // the previous chunk has been consumed
-    stage<ASYNC, CHS, FP>(xs, x, n, y0, x0, c0, H, W, C, tid);
+    stage<LOADER, CHS, FP>(xs, x, n, y0, x0, c0, H, W, C, tid);
     for (int idx = tid; idx < KC * 24; idx += THREADS) {
       const int ch = idx % KC, r = idx / KC, ky = r >> 3, e = r & 7;
       float v = 0.f;
@@ -161,7 +199,7 @@ narrow_fwd_kernel(const float *__restrict__ x, const float *__restrict__ w, cons
   }
 }
 
-template <bool ASYNC>
+template <int LOADER>
 __global__ void __launch_bounds__(THREADS, 4)
 narrow_wgrad_kernel(const float *__restrict__ x, const float *__restrict__ g, long long gsN, long long gsC,
                     long long gsH, long long gsW, float *__restrict__ partial, int H, int W, int C) {
@@ -185,7 +223,7 @@ narrow_wgrad_kernel(const float *__restrict__ x, const float *__restrict__ g, lo
 
   for (int c0 = 0; c0 < C; c0 += KC) {
     __syncthreads();                          // red (aliasing xs) has been read; gs is complete
-    stage<ASYNC, CHS, PITCH>(xs, x, n, y0, x0, c0, H, W, C, tid);
+    stage<LOADER, CHS, PITCH>(xs, x, n, y0, x0, c0, H, W, C, tid);
     __syncthreads();
     float acc0[9], acc1[9];
 #pragma unroll
@@ -262,14 +300,15 @@ narrow_wgrad_reduce_kernel(const float *__restrict__ partial, float *__restrict_
   }
 }
 
-int g_loader = 1;   // 1: cp.async staging (default), 0: synchronous float2 staging (unflow_set_int_option "narrow_loader")
+int g_loader = 1;   // unflow_set_int_option "narrow_loader": 1 cp.async staging (default), 0 synchronous float2
+                    // staging, 2 row-wise cp.async (experimental, unmeasured)
 
 inline long long tiles(int N, int H, int W) { return (long long)N * ceil_div(H, TH) * ceil_div(W, TW); }
 
 }  // namespace nc
 }  // namespace unflow
 
-namespace unflow { int set_narrow_loader(int v) { if (v != 0 && v != 1) return 0; nc::g_loader = v; return 1; } }
+namespace unflow { int set_narrow_loader(int v) { if (v < 0 || v > 2) return 0; nc::g_loader = v; return 1; } }
 
 extern "C" size_t unflow_conv3x3_narrow_wgrad_workspace_bytes(int N, int H, int W, int C) {
   if (N <= 0 || H <= 0 || W <= 0 || C <= 0) return 0;
@@ -293,8 +332,10 @@ extern "C" int unflow_conv3x3_narrow_fwd(const float *x, const float *w, const f
   UNFLOW_REQUIRE(((uintptr_t)x & 7) == 0 && ((uintptr_t)y & 7) == 0, "conv3x3_narrow_fwd: x and y must be 8-byte aligned");
   const dim3 grid(ceil_div(W, nc::TW), ceil_div(H, nc::TH), N);
   const size_t smem = (size_t)(nc::KC * nc::FWD_CHS + nc::KC * 24) * sizeof(float);
-  if (nc::g_loader) nc::narrow_fwd_kernel<true><<<grid, nc::THREADS, smem, (cudaStream_t)stream>>>(x, w, bias, y, H, W, C);
-  else nc::narrow_fwd_kernel<false><<<grid, nc::THREADS, smem, (cudaStream_t)stream>>>(x, w, bias, y, H, W, C);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (nc::g_loader == 2) nc::narrow_fwd_kernel<2><<<grid, nc::THREADS, smem, st>>>(x, w, bias, y, H, W, C);
+  else if (nc::g_loader == 1) nc::narrow_fwd_kernel<1><<<grid, nc::THREADS, smem, st>>>(x, w, bias, y, H, W, C);
+  else nc::narrow_fwd_kernel<0><<<grid, nc::THREADS, smem, st>>>(x, w, bias, y, H, W, C);
   count_launch();
   return check_launch("conv3x3_narrow_fwd");
 }
@@ -316,8 +357,10 @@ extern "C" int unflow_conv3x3_narrow_wgrad(const float *x, const float *g, long 
   const dim3 grid(ceil_div(W, nc::TW), ceil_div(H, nc::TH), N);
   const int nblocks = (int)nc::tiles(N, H, W);
   const size_t smem = (size_t)(nc::KC * (nc::SR * nc::PITCH + 1) + nc::TH * nc::GPITCH) * sizeof(float);
-  if (nc::g_loader) nc::narrow_wgrad_kernel<true><<<grid, nc::THREADS, smem, s>>>(x, g, gsN, gsC, gsH, gsW, (float *)workspace, H, W, C);
-  else nc::narrow_wgrad_kernel<false><<<grid, nc::THREADS, smem, s>>>(x, g, gsN, gsC, gsH, gsW, (float *)workspace, H, W, C);
+  float *part = (float *)workspace;
+  if (nc::g_loader == 2) nc::narrow_wgrad_kernel<2><<<grid, nc::THREADS, smem, s>>>(x, g, gsN, gsC, gsH, gsW, part, H, W, C);
+  else if (nc::g_loader == 1) nc::narrow_wgrad_kernel<1><<<grid, nc::THREADS, smem, s>>>(x, g, gsN, gsC, gsH, gsW, part, H, W, C);
+  else nc::narrow_wgrad_kernel<0><<<grid, nc::THREADS, smem, s>>>(x, g, gsN, gsC, gsH, gsW, part, H, W, C);
   count_launch();
   if (int rc = check_launch("conv3x3_narrow_wgrad")) return rc;
   const int total = nc::NOUT * C;
