@@ -228,3 +228,31 @@ def test_narrow_loader_variants_agree_bitwise(mode3x):
         _native.check(_native.lib().unflow_set_int_option(b"narrow_loader", conv_ops.NARROW_LOADER), "narrow_loader")
     for y, gw in outs[1:]:
         assert torch.equal(y, outs[0][0]) and torch.equal(gw, outs[0][1])
+
+
+@pytest.mark.parametrize("cin,hw", [(3, (20, 28)), (14, (22, 26)), (6, (21, 27))])
+def test_first_layer_space_to_depth_matches_float64(mode3x, cin, hw):
+    """7x7 stride-2 first layers run as 4x4 stride-1 convs over 2x2 pixel blocks (conv_ops.
+    space_to_depth_operands); against the direct float64 convolution with TF SAME padding."""
+    from unflow_b200.e2eflow.core import conv_ops
+    from unflow_b200.e2eflow.core.flownet import _same_pad
+    g = torch.Generator().manual_seed(cin)
+    H, W = hw
+    x = torch.randn(2, cin, H, W, generator=g)
+    w = torch.randn(16, cin, 7, 7, generator=g) * 0.1
+    b = torch.randn(16, generator=g)
+    pads = _same_pad(H, 7, 2) + _same_pad(W, 7, 2)
+    xd = F.pad(x.double(), (pads[2], pads[3], pads[0], pads[1])).requires_grad_(True)
+    wd, bd = w.double().requires_grad_(True), b.double().requires_grad_(True)
+    yd = F.leaky_relu(F.conv2d(xd, wd, bd, stride=2), 0.1)
+    go = torch.randn(yd.shape, generator=g)
+    yd.backward(go.double())
+    xc = x.cuda().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    wc, bc = w.cuda().requires_grad_(True), b.cuda().requires_grad_(True)
+    assert conv_ops._use_space_to_depth(xc, wc, 2)
+    y = conv_ops.conv2d(xc, wc, bc, 2, pads, act=True)
+    y.backward(go.cuda())
+    gx_ref = xd.grad[:, :, pads[0]:pads[0] + H, pads[2]:pads[2] + W]
+    for got, want, name in ((y, yd, "y"), (xc.grad, gx_ref, "dx"), (wc.grad, wd.grad, "dw"), (bc.grad, bd.grad, "db")):
+        e = rel(got.detach().cpu(), want.detach())
+        assert got.shape == want.shape and e < 1e-4, "%s: rel err %.2e" % (name, e)
