@@ -59,6 +59,12 @@ def test_frame_numbers_and_crop_or_pad():
     assert p.shape == (8, 9, 1) and torch.equal(p[1:6, 1:7], t) and float(p.sum()) == float(t.sum())
     m = inp.resize_image_with_crop_or_pad(t.unsqueeze(0), 7, 4)   # pad rows, crop cols, batched
     assert m.shape == (1, 7, 4, 1) and torch.equal(m[0, 1:6, :, 0], t[:, 1:5, 0])
+    assert torch.equal(inp.resize_output_crop(t.unsqueeze(0), 3, 2, 1), c.unsqueeze(0))
+    f = torch.ones(1, 4, 6, 2)
+    r = inp.resize_output_flow(f, 8, 3)                           # u scales with the width, v with the height
+    assert r.shape == (1, 8, 3, 2) and torch.allclose(r[..., 0], torch.full((1, 8, 3), 0.5)) \
+        and torch.allclose(r[..., 1], torch.full((1, 8, 3), 2.0))
+    assert inp.resize_output(torch.zeros(1, 4, 6, 3), 8, 12, 3).shape == (1, 8, 12, 3)
 
 
 def test_kitti_raw_dirs_and_pairs(tree):

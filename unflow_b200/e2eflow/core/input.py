@@ -70,6 +70,23 @@ def resize_input(t, height, width, resized_h, resized_w):
     return tf_image.resize_bilinear(t, [resized_h, resized_w])
 
 
+def resize_output_crop(t, height, width, channels):
+    """core/input.py:17-21: centre crop / zero pad a [1,h,w,c] result back to the file size."""
+    return resize_image_with_crop_or_pad(t[0], height, width).reshape(1, height, width, channels)
+
+
+def resize_output(t, height, width, channels):
+    """core/input.py:24-25."""
+    from . import tf_image
+    return tf_image.resize_bilinear(t, [height, width])
+
+
+def resize_output_flow(t, height, width, channels=2):
+    """core/input.py:28-34 (implemented in core/flow_io.py)."""
+    from .flow_io import resize_output_flow as impl
+    return impl(t, height, width, channels)
+
+
 class _Prefetcher:
     """Iterator over ``make(i)`` for i = first, first+step, ... produced by a daemon thread."""
 
