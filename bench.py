@@ -202,6 +202,15 @@ def run_ours(args):
         loss_host.copy_(loss, non_blocking=True)
         return loss
 
+    if args.prefetch and args.graph:
+        # opt-in: the copy of step i+1's batch overlaps step i (still inside the timed region, still
+        # one H2D of both frames and one D2H of the loss per step)
+        def e2e_step():   # noqa: F811
+            loss = trainer.step_prefetched()
+            trainer.prefetch(h_im1, h_im2)
+            loss_host.copy_(loss, non_blocking=True)
+            return loss
+        trainer.prefetch(h_im1, h_im2)
     for _ in range(min(args.warmup, 2)):
         e2e_step()
     ms_e2e, _, _, _ = timed(e2e_step, args.steps)
@@ -393,6 +402,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--prefetch", type=int, default=0,
+                    help="1: overlap the host->device copy of the next batch with the running step in the "
+                         "e2e loop (Trainer.prefetch / step_prefetched; opt-in, not yet measured)")
     ap.add_argument("--conv", default=os.environ.get("UNFLOW_CONV_PRECISION", "3xtf32"),
                     choices=["fp32", "3xtf32"],
                     help="arithmetic of the conv stacks: 3xtf32 = tensor cores at fp32-level accuracy "

@@ -217,6 +217,43 @@ class Trainer:
         self.graph_replays = 0
         return self
 
+    # -- input prefetch (opt-in; graph mode) -----------------------------------------------------
+    def prefetch(self, h_im1, h_im2):
+        """Start copying the NEXT batch (pinned host tensors) into staging buffers on a copy stream;
+        it overlaps the step that is currently running.  Pair with ``step_prefetched``."""
+        assert self._graph is not None, "prefetch() needs a captured step (capture())"
+        if getattr(self, '_copy_stream', None) is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._stage_im1 = torch.empty_like(self._static_im1)
+            self._stage_im2 = torch.empty_like(self._static_im2)
+            self._stage_free = None
+        cs = self._copy_stream
+        if self._stage_free is not None:
+            cs.wait_event(self._stage_free)            # the previous contents have been consumed
+        with torch.cuda.stream(cs):
+            self._stage_im1.copy_(h_im1, non_blocking=True)
+            self._stage_im2.copy_(h_im2, non_blocking=True)
+            self._stage_ready = torch.cuda.Event()
+            self._stage_ready.record(cs)
+
+    def step_prefetched(self, lr=None):
+        """``step`` on the batch handed to the last ``prefetch`` call: the compute stream waits for the
+        staged copy, moves it into the graph's static input buffers (device to device) and replays."""
+        self.iteration += 1
+        if lr is None:
+            lr = learning_rate_at(self.iteration - 1, self.params)
+        if lr != self._hyper_lr:
+            self._set_hyper(lr, self.iteration)
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(self._stage_ready)
+        self._static_im1.copy_(self._stage_im1, non_blocking=True)
+        self._static_im2.copy_(self._stage_im2, non_blocking=True)
+        self._stage_free = torch.cuda.Event()
+        self._stage_free.record(cur)
+        self._graph.replay()
+        self.graph_replays += 1
+        return self._static_loss
+
     def step(self, im1, im2, lr=None):
         """One optimisation step on this rank's shard; returns the (local) loss tensor."""
         self.iteration += 1
