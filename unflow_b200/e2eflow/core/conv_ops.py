@@ -332,9 +332,9 @@ class _NarrowConv3x3(torch.autograd.Function):
         return gx, gw, gb
 
 
-# First layers (7x7, stride 2, 3 / 6 / 14 input channels): with so few channels the implicit-GEMM
-# kernels pad every filter tap to a 32-channel K tile (cuDNN falls back to an indexed sm80 kernel:
-# 0.8 ms fprop, 1.4 ms wgrad + 0.6 ms of layout conversions per step).  Folding the stride into the
+# First layers (7x7, stride 2, 3 / 6 / 14 input channels): with so few channels per filter tap cuDNN
+# does not pick its sm100 implicit-GEMM kernels but an indexed sm80 one (measured: 0.8 ms fprop,
+# 1.4 ms wgrad + 0.6 ms of layout conversions per step).  Folding the stride into the
 # channels -- 2x2 pixel blocks become 4*C channels, the 7x7 filter (zero-extended to 8x8) a 4x4
 # filter with stride 1 -- is the same sum with a tensor-core-friendly shape (4*C*3 = 36 channels).
 S2D_MAX_CHANNELS = 16
