@@ -15,13 +15,20 @@ Pinning status (see DESIGN.md "Oracle"):
   * image_warp / smoothness deltas / outgoing mask / gradient loss: pinned by
     the reference KATs in src/e2eflow/test/test_image_warp.py and
     src/e2eflow/test/test_losses.py.
-  * ternary loss, compute_losses, flownet, unsupervised_loss and every
-    TensorFlow-supplied primitive they rest on (SAME padding, legacy
-    resize_bilinear, rgb_to_grayscale): PARITY UNPINNED -- the reference holds
-    no usable golden values for them (its ternary test is dead code) and
-    TensorFlow 1.x cannot run here.  The oracle restates the documented TF1
-    behaviour.  The loss assembly is cross-checked against a second,
-    independently written float64 pixel-loop definition (oracle/brute.py,
-    tests/test_oracle_losses_brute.py); that is a self-consistency guard, not
-    a reference pin.
+  * ternary loss, compute_losses (all occlusion modes, values and flow
+    gradients), flownet (C, S, stacked: every output of every network),
+    unsupervised_loss (value, output flows, variable gradients): pinned against
+    the reference's OWN Python source, executed unmodified under a
+    TensorFlow-API stand-in (tests/golden/tf_shim.py ->
+    tests/golden/make_reference_run.py -> tests/golden/reference_run.npz,
+    tests/test_oracle_vs_reference_run.py).  That pins the graph -- op order,
+    constants, masks, weights, pyramid bookkeeping, variable scopes / names /
+    shapes, stop_gradient placement.
+  * STILL PARITY UNPINNED: the arithmetic inside the TensorFlow-supplied
+    primitives the graph rests on (SAME padding rule, legacy resize_bilinear,
+    rgb_to_grayscale weights, conv2d_transpose) -- TensorFlow 1.x cannot run
+    here and the reference holds no golden values for them; the stand-in and
+    the oracle both restate the documented TF1 behaviour.  A second,
+    independently written float64 pixel-loop definition of the loss assembly
+    (oracle/brute.py, tests/test_oracle_losses_brute.py) guards against slips.
 """

@@ -1,0 +1,158 @@
+#!/usr/bin/env python
+"""Run the reference's OWN Python source (unmodified, from /root/reference/src/e2eflow/core) under
+the TensorFlow-API stand-in of tests/golden/tf_shim.py and store inputs + outputs as golden vectors
+in tests/golden/reference_run.npz.
+
+    python tests/golden/make_reference_run.py          (needs /root/reference; run in the build container)
+
+What this pins: the graph the reference builds -- op order, constants, masks, loss weights, pyramid
+bookkeeping, variable scopes / names / shapes, gradient flow (stop_gradient, casts) -- for
+``image_warp``, every loss term, ``compute_losses`` (all three occlusion modes), ``flownet`` (C, S,
+stacked) and ``unsupervised_loss``.  What it does not pin: the arithmetic inside TensorFlow's own
+primitives (SAME padding, legacy bilinear resize, grayscale weights, conv2d_transpose), which the
+stand-in restates from the TF documentation, and the custom CUDA ops, which are served by
+oracle/oracle_ops.c (pinned by the reference's known-answer tests, tests/golden/reference_kats.json).
+tests/test_oracle_vs_reference_run.py compares the oracle with these vectors.
+"""
+import importlib
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
+REF_SRC = os.environ.get("UNFLOW_REFERENCE_SRC", "/root/reference/src")
+
+import tf_shim  # noqa: E402
+from oracle import flownet as oflownet  # noqa: E402
+from oracle import ops as oops  # noqa: E402
+from unflow_b200 import synthetic as synth  # noqa: E402
+
+
+def load_reference():
+    """Import the reference's e2eflow.core modules with the stand-ins for tensorflow and for the
+    compiled-op loader (e2eflow/ops.py JIT-compiles CUDA at import)."""
+    tf = tf_shim.install()
+    sys.path.insert(0, REF_SRC)
+    pkg = importlib.import_module('e2eflow')
+    assert os.path.realpath(os.path.dirname(pkg.__file__)).startswith(os.path.realpath(REF_SRC)), pkg.__file__
+    ops = types.ModuleType('e2eflow.ops')
+    wrap = lambda t: t.as_subclass(tf_shim.Tensor)
+    ops.correlation = lambda first, second, **kw: wrap(oops.correlation(first.contiguous(), second.contiguous(), **kw))
+    ops.backward_warp = lambda images, flows: wrap(oops.backward_warp(images, flows))
+    ops.forward_warp = lambda flows: wrap(oops.forward_warp(flows))
+    ops.downsample = lambda images, scale: wrap(oops.downsample(images, scale))
+    sys.modules['e2eflow.ops'] = ops
+    pkg.ops = ops
+    mods = {n: importlib.import_module('e2eflow.core.' + n) for n in ('image_warp', 'losses', 'flownet', 'unsupervised')}
+    for m in mods.values():
+        assert os.path.realpath(m.__file__).startswith(os.path.realpath(REF_SRC)), m.__file__
+    return tf, mods
+
+
+def T(x, grad=False):
+    t = torch.as_tensor(np.asarray(x), dtype=torch.float32).clone().requires_grad_(grad)
+    return t.as_subclass(tf_shim.Tensor)
+
+
+def N(t):
+    return t.detach().cpu().numpy().astype(np.float32) if isinstance(t, torch.Tensor) else np.float32(t)
+
+
+def checksum(variables):
+    s = sum(float(v.double().sum()) for v in variables.values())
+    a = sum(float(v.double().abs().sum()) for v in variables.values())
+    return np.array([s, a], dtype=np.float64)
+
+
+def main():
+    tf, ref = load_reference()
+    out = {}
+
+    # ---- image_warp, individual loss terms, masks ---------------------------------------------
+    im1, im2, ffw, fbw = synth.level_inputs(2, 20, 28, seed=5)
+    out['L_im1'], out['L_im2'], out['L_ffw'], out['L_fbw'] = map(N, (im1, im2, ffw, fbw))
+    tf_shim.STATE.reset({})
+    a, f = T(im1, True), T(ffw, True)
+    w = ref['image_warp'].image_warp(a, f)
+    gsel = torch.linspace(-1, 1, w.numel()).reshape(w.shape)
+    ga, gf = torch.autograd.grad((w * gsel).sum(), (a, f))
+    out['warp_out'], out['warp_dim'], out['warp_dflow'] = N(w), N(ga), N(gf)
+    L = ref['losses']
+    out['border_mask'] = N(L.create_border_mask(T(im1), 0.1))
+    out['outgoing_mask'] = N(L.create_outgoing_mask(T(ffw * 4)))
+    occ = L.occlusion(T(ffw), T(fbw))
+    out['occ_fw'], out['occ_bw'] = N(occ[0]), N(occ[1])
+    mask = L.create_border_mask(T(im1), 0.1)
+    for d in (1, 2, 3):
+        out['ternary_d%d' % d] = N(L.ternary_loss(T(im1), T(im2), mask, max_distance=d))
+    out['photometric'] = N(L.photometric_loss(T(im1) - T(im2), mask))
+    out['gradient_loss'] = N(L.gradient_loss(T(im1), T(im2), mask))
+    out['smoothness_1st'] = N(L.smoothness_loss(T(ffw)))
+    out['smoothness_2nd'] = N(L.second_order_loss(T(ffw)))
+    out['charbonnier_trunc'] = N(L.charbonnier_loss(T(ffw), mask, truncate=0.7, alpha=0.3, beta=2.0))
+
+    # ---- compute_losses: every term, three occlusion modes, with / without border mask ----------
+    weights = dict(ternary=1.0, smooth_2nd=3.0, fb=0.2, occ=12.4, photo=0.5, grad=0.25, smooth_1st=0.75, sym=0.3)
+    for tag, mode, use_border, dist in (('fb', 'fb', True, 3), ('none', '', False, 1), ('disocc', 'disocc', True, 2)):
+        fw, bw = T(ffw, True), T(fbw, True)
+        border = L.create_border_mask(T(im1), 0.1) if use_border else None
+        res = L.compute_losses(T(im1), T(im2), fw, bw, border_mask=border, mask_occlusion=mode,
+                               data_max_distance=dist)
+        assert sorted(res) == sorted(weights), sorted(res)
+        total = 0.0
+        for k in sorted(res):
+            out['cl_%s_%s' % (tag, k)] = N(res[k])
+            total = total + weights[k] * res[k]
+        gfw, gbw = torch.autograd.grad(total, (fw, bw))
+        out['cl_%s_dfw' % tag], out['cl_%s_dbw' % tag] = N(gfw), N(gbw)
+
+    # ---- flownet: C, S and a stacked net, both directions -----------------------------------------
+    for tag, spec, hw, seed in (('c', 'c', (64, 128), 21), ('s', 's', (64, 64), 22), ('cs', 'cs', (64, 64), 23)):
+        variables = oflownet.init_variables(spec, False, seed=seed)
+        tf_shim.STATE.reset({k: v for k, v in variables.items()})
+        i1, i2, _ = synth.image_pair(1, hw[0], hw[1], seed=seed + 100)
+        i1, i2 = i1 / 255.0 - 0.4, i2 / 255.0 - 0.4
+        fw, bw = ref['flownet'].flownet(T(i1), T(i2), flownet_spec=spec, backward_flow=True)
+        assert sorted(tf_shim.STATE.created) == sorted(variables), "variable names differ from the reference graph"
+        out['fn_%s_im1' % tag], out['fn_%s_im2' % tag] = N(i1), N(i2)
+        out['fn_%s_vars' % tag] = checksum(variables)
+        for n, (nf, nb) in enumerate(zip(fw, bw)):
+            for lvl, (a_, b_) in enumerate(zip(nf, nb)):
+                out['fn_%s_net%d_fw%d' % (tag, n, lvl)] = N(a_)
+                out['fn_%s_net%d_bw%d' % (tag, n, lvl)] = N(b_)
+
+    # ---- unsupervised_loss: value, output flows, gradient norms ---------------------------------
+    for tag, spec, hw, seed, extra in (('c', 'c', (128, 128), 31, {}), ('s', 's', (128, 128), 32, {'pyramid_loss': False}),
+                                       ('cs', 'cs', (128, 128), 33, {'train_all': True})):
+        params = dict(synth.KITTI_PARAMS, flownet=spec, **extra)
+        variables = oflownet.init_variables(spec, False, seed=seed)
+        leaves = {k: v.clone().requires_grad_(True) for k, v in variables.items()}
+        tf_shim.STATE.reset(leaves)
+        i1, i2, _ = synth.image_pair(1, hw[0], hw[1], seed=seed + 100)
+        loss, ffw_, fbw_ = ref['unsupervised'].unsupervised_loss((T(i1), T(i2)), params, synth.KITTI_NORMALIZATION,
+                                                                 augment=False, return_flow=True)
+        names = sorted(leaves)
+        grads = torch.autograd.grad(loss, [leaves[k] for k in names], allow_unused=True)
+        out['ul_%s_im1' % tag], out['ul_%s_im2' % tag] = N(i1), N(i2)
+        out['ul_%s_vars' % tag] = checksum(variables)
+        out['ul_%s_loss' % tag] = N(loss)
+        out['ul_%s_flow_fw' % tag], out['ul_%s_flow_bw' % tag] = N(ffw_), N(fbw_)
+        out['ul_%s_grad_names' % tag] = np.array(names)
+        out['ul_%s_grad_norms' % tag] = np.array([0.0 if g is None else float(g.double().norm()) for g in grads])
+        for k, g in zip(names, grads):          # the small gradients in full
+            if g is not None and g.numel() <= 4096:
+                out['ul_%s_grad/%s' % (tag, k)] = N(g)
+
+    path = os.path.join(HERE, 'reference_run.npz')
+    np.savez_compressed(path, **out)
+    print("wrote %s: %d arrays, %.1f KB" % (path, len(out), os.path.getsize(path) / 1024.0))
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,118 @@
+"""The oracle against golden vectors produced by the reference's OWN Python source
+(/root/reference/src/e2eflow/core/*.py, unmodified) executed under the TensorFlow-API stand-in of
+tests/golden/tf_shim.py -- see tests/golden/make_reference_run.py for what that does and does not
+pin.  Runs without /root/reference: only the committed fixture is read."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import flownet as oflownet
+from oracle import image_warp as oimage_warp
+from oracle import losses as olosses
+from oracle import unsupervised as ounsup
+import synth
+
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_run.npz"))
+WEIGHTS = dict(ternary=1.0, smooth_2nd=3.0, fb=0.2, occ=12.4, photo=0.5, grad=0.25, smooth_1st=0.75, sym=0.3)
+
+
+def t(name, grad=False):
+    return torch.from_numpy(G[name]).clone().requires_grad_(grad)
+
+
+def close(got, want, rtol=2e-5, atol_rel=2e-6, msg=""):
+    got = got.detach().numpy() if isinstance(got, torch.Tensor) else np.asarray(got)
+    want = np.asarray(want)
+    atol = atol_rel * max(float(np.abs(want).max()), 1e-12)
+    np.testing.assert_allclose(got, want, rtol=rtol, atol=atol, err_msg=msg)
+
+
+def test_image_warp_values_and_gradients():
+    im, flow = t('L_im1', True), t('L_ffw', True)
+    w = oimage_warp.image_warp(im, flow)
+    close(w, G['warp_out'])
+    gsel = torch.linspace(-1, 1, w.numel()).reshape(w.shape)
+    gi, gf = torch.autograd.grad((w * gsel).sum(), (im, flow))
+    close(gi, G['warp_dim'])
+    close(gf, G['warp_dflow'], rtol=1e-4, atol_rel=1e-5)
+
+
+def test_masks_and_single_terms():
+    im1, im2, ffw, fbw = t('L_im1'), t('L_im2'), t('L_ffw'), t('L_fbw')
+    mask = olosses.create_border_mask(im1, 0.1)
+    assert np.array_equal(mask.numpy(), G['border_mask'])
+    assert np.array_equal(olosses.create_outgoing_mask(ffw * 4).numpy(), G['outgoing_mask'])
+    occ = olosses.occlusion(ffw, fbw)
+    assert np.array_equal(occ[0].numpy(), G['occ_fw']) and np.array_equal(occ[1].numpy(), G['occ_bw'])
+    assert 0 < G['occ_fw'].mean() < 1 and 0 < G['outgoing_mask'].mean() < 1          # non-trivial masks
+    for d in (1, 2, 3):
+        close(olosses.ternary_loss(im1, im2, mask, max_distance=d), G['ternary_d%d' % d], msg="ternary %d" % d)
+    close(olosses.photometric_loss(im1 - im2, mask), G['photometric'])
+    close(olosses.gradient_loss(im1, im2, mask), G['gradient_loss'])
+    close(olosses.smoothness_loss(ffw), G['smoothness_1st'])
+    close(olosses.second_order_loss(ffw), G['smoothness_2nd'])
+    close(olosses.charbonnier_loss(ffw, mask, truncate=0.7, alpha=0.3, beta=2.0), G['charbonnier_trunc'])
+
+
+@pytest.mark.parametrize("tag,mode,use_border,dist", [('fb', 'fb', True, 3), ('none', '', False, 1), ('disocc', 'disocc', True, 2)])
+def test_compute_losses_all_terms_and_flow_gradients(tag, mode, use_border, dist):
+    im1, im2 = t('L_im1'), t('L_im2')
+    fw, bw = t('L_ffw', True), t('L_fbw', True)
+    border = olosses.create_border_mask(im1, 0.1) if use_border else None
+    res = olosses.compute_losses(im1, im2, fw, bw, border_mask=border, mask_occlusion=mode, data_max_distance=dist)
+    total = 0.0
+    for k in sorted(WEIGHTS):
+        close(res[k], G['cl_%s_%s' % (tag, k)], msg=k)
+        total = total + WEIGHTS[k] * res[k]
+    gfw, gbw = torch.autograd.grad(total, (fw, bw))
+    close(gfw, G['cl_%s_dfw' % tag], rtol=2e-4, atol_rel=2e-5, msg="dflow_fw")
+    close(gbw, G['cl_%s_dbw' % tag], rtol=2e-4, atol_rel=2e-5, msg="dflow_bw")
+
+
+def _variables(spec, seed, key):
+    v = oflownet.init_variables(spec, False, seed=seed)
+    s = sum(float(x.double().sum()) for x in v.values())
+    a = sum(float(x.double().abs().sum()) for x in v.values())
+    if not np.allclose([s, a], G[key], rtol=1e-12):
+        pytest.skip("this torch build draws different random weights than the one the fixture was made with")
+    return v
+
+
+@pytest.mark.parametrize("tag,spec,seed", [('c', 'c', 21), ('s', 's', 22), ('cs', 'cs', 23)])
+def test_flownet_every_output_of_every_network(tag, spec, seed):
+    v = _variables(spec, seed, 'fn_%s_vars' % tag)
+    fw, bw = oflownet.flownet(v, t('fn_%s_im1' % tag), t('fn_%s_im2' % tag), spec, backward_flow=True)
+    assert len(fw) == len(spec)
+    for n in range(len(spec)):
+        assert len(fw[n]) == 5
+        for lvl in range(5):
+            close(fw[n][lvl], G['fn_%s_net%d_fw%d' % (tag, n, lvl)], rtol=1e-4, atol_rel=1e-5, msg="net %d fw %d" % (n, lvl))
+            close(bw[n][lvl], G['fn_%s_net%d_bw%d' % (tag, n, lvl)], rtol=1e-4, atol_rel=1e-5, msg="net %d bw %d" % (n, lvl))
+
+
+@pytest.mark.parametrize("tag,spec,seed,extra", [('c', 'c', 31, {}), ('s', 's', 32, {'pyramid_loss': False}),
+                                                 ('cs', 'cs', 33, {'train_all': True})])
+def test_unsupervised_loss_value_flows_and_gradients(tag, spec, seed, extra):
+    v = _variables(spec, seed, 'ul_%s_vars' % tag)
+    leaves = {k: x.clone().requires_grad_(True) for k, x in v.items()}
+    params = dict(synth.KITTI_PARAMS, flownet=spec, **extra)
+    loss, ffw, fbw = ounsup.unsupervised_loss(leaves, (t('ul_%s_im1' % tag), t('ul_%s_im2' % tag)), params,
+                                              synth.KITTI_NORMALIZATION, augment=False, return_flow=True)
+    close(loss, G['ul_%s_loss' % tag], rtol=2e-5)
+    close(ffw, G['ul_%s_flow_fw' % tag], rtol=1e-4, atol_rel=1e-5)
+    close(fbw, G['ul_%s_flow_bw' % tag], rtol=1e-4, atol_rel=1e-5)
+    names = [str(n) for n in G['ul_%s_grad_names' % tag]]
+    assert names == sorted(leaves)
+    grads = torch.autograd.grad(loss, [leaves[k] for k in names], allow_unused=True)
+    norms = np.array([0.0 if g is None else float(g.double().norm()) for g in grads])
+    want = G['ul_%s_grad_norms' % tag]
+    assert np.array_equal(norms == 0.0, want == 0.0)       # the same variables are (not) trained
+    # hard masks can flip on 1e-7 differences: norms to 1e-3, small gradients in full
+    np.testing.assert_allclose(norms, want, rtol=2e-3)
+    for k, g in zip(names, grads):
+        key = 'ul_%s_grad/%s' % (tag, k)
+        if key in G.files:
+            err = float((g - torch.from_numpy(G[key])).norm() / max(float(torch.from_numpy(G[key]).norm()), 1e-20))
+            assert err < 2e-3, "%s: relative L2 gradient error %.2e" % (k, err)
