@@ -1,8 +1,13 @@
 """CPU restatement of the reference FlowNetC / FlowNetS / stacked model (TEST INFRASTRUCTURE ONLY).
 
-Follows /root/reference/src/e2eflow/core/flownet.py (whole file).  PARITY
-UNPINNED: the reference has no test for the model and TF1/slim cannot run
-here; the TF primitives are restated in oracle/tf_compat.py.
+Follows /root/reference/src/e2eflow/core/flownet.py (whole file).  Pinned
+against that file itself, executed unmodified under the TensorFlow-API stand-in
+of tests/golden/ (every output of every network for specs c / s / cs, and the
+variable names / shapes the graph asks for: tests/test_oracle_vs_reference_run.py).
+PARITY UNPINNED below that: the reference has no test for the model and TF1 /
+slim cannot run here, so the TF primitives (SAME padding, conv2d_transpose,
+legacy resize_bilinear) are restated in oracle/tf_compat.py from their
+documentation.
 
 Variables are passed explicitly as a dict  TF-variable-name -> tensor in TF
 layout (conv ``weights``: [kh,kw,in,out]; conv2d_transpose ``weights``:

@@ -7,8 +7,12 @@ them in the reference (casts and masks carry no gradient).
 
 Pinned by reference KATs (tests/test_oracle_reference_kats.py):
 ``_smoothness_deltas``, ``create_outgoing_mask``, ``gradient_loss``.
-PARITY UNPINNED for the rest (ternary_loss, compute_losses, ...): the
-reference has no live test for them.
+The rest (ternary_loss, compute_losses in all occlusion modes, masks, single
+terms; values and gradients) is pinned against the reference file itself,
+executed unmodified under the TensorFlow-API stand-in of tests/golden/
+(tests/test_oracle_vs_reference_run.py).  PARITY UNPINNED below that: the
+arithmetic of the TF primitives (rgb_to_grayscale, conv2d SAME), restated from
+their documentation.
 """
 import math
 

@@ -2,7 +2,11 @@
 
 Follows /root/reference/src/e2eflow/core/unsupervised.py:27-164 with
 ``augment=False`` (the random augmentation cannot be parity-pinned and is out
-of scope).  PARITY UNPINNED (no reference test).
+of scope).  Pinned against the reference file itself,
+executed unmodified under the TensorFlow-API stand-in of tests/golden/ (loss
+value, output flows and variable gradients for specs c / s / cs, pyramid on /
+off, train_all: tests/test_oracle_vs_reference_run.py); PARITY UNPINNED below
+that for the TF primitives it rests on (see oracle/__init__.py).
 """
 import torch
 
