@@ -17,7 +17,9 @@ Pinning status (see DESIGN.md "Oracle"):
     src/e2eflow/test/test_losses.py.
   * ternary loss, compute_losses (all occlusion modes, values and flow
     gradients), flownet (C, S, stacked: every output of every network),
-    unsupervised_loss (value, output flows, variable gradients): pinned against
+    unsupervised_loss (value, output flows, variable gradients), the
+    augmentation cores (spatial transformer, random_affine, random_photometric
+    with recorded draws): pinned against
     the reference's OWN Python source, executed unmodified under a
     TensorFlow-API stand-in (tests/golden/tf_shim.py ->
     tests/golden/make_reference_run.py -> tests/golden/reference_run.npz,

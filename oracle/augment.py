@@ -2,8 +2,10 @@
 
 Follows /root/reference/src/e2eflow/core/spatial_transformer.py:57-175 (``transformer`` with its
 ``_meshgrid`` / ``_interpolate``) and /root/reference/src/e2eflow/core/augment.py:30-48,91-106.
-The random draws are inputs here: augmentation cannot be parity-pinned sample by sample.
-PARITY UNPINNED (the reference has no test for the augmentation)."""
+The random draws are inputs here.  Pinned against the reference files themselves, executed
+unmodified under the TensorFlow-API stand-in of tests/golden/ with the random draws recorded
+(transformer, random_affine incl. the flip branch, random_photometric:
+tests/test_oracle_vs_reference_run.py); the reference has no test of its own for the augmentation."""
 import math
 
 import torch

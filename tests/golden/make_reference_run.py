@@ -49,7 +49,8 @@ def load_reference():
     ops.downsample = lambda images, scale: wrap(oops.downsample(images, scale))
     sys.modules['e2eflow.ops'] = ops
     pkg.ops = ops
-    mods = {n: importlib.import_module('e2eflow.core.' + n) for n in ('image_warp', 'losses', 'flownet', 'unsupervised')}
+    mods = {n: importlib.import_module('e2eflow.core.' + n)
+            for n in ('image_warp', 'losses', 'flownet', 'unsupervised', 'augment', 'spatial_transformer')}
     for m in mods.values():
         assert os.path.realpath(m.__file__).startswith(os.path.realpath(REF_SRC)), m.__file__
     return tf, mods
@@ -148,6 +149,34 @@ def main():
         for k, g in zip(names, grads):          # the small gradients in full
             if g is not None and g.numel() <= 4096:
                 out['ul_%s_grad/%s' % (tag, k)] = N(g)
+
+    # ---- augmentation: the random draws are recorded and stored as inputs -------
+    a1, a2, _ = synth.image_pair(3, 24, 36, seed=41)
+    a1, a2 = a1 / 255.0, a2 / 255.0
+    amask = ref['losses'].create_border_mask(T(a1), 0.1)
+    out['aug_im1'], out['aug_im2'], out['aug_mask'] = N(a1), N(a2), N(amask)
+    theta = torch.tensor([[1.05, 0.1, 0.02, -0.08, 0.93, -0.03], [0.9, 0.0, 0.0, 0.0, 1.1, 0.0],
+                          [-1.0, 0.2, 0.1, 0.15, 1.0, 0.05]])
+    out['aug_theta'] = N(theta)
+    out['aug_transformer'] = N(ref['spatial_transformer'].transformer(T(a1), T(theta), (20, 30)))
+    tf_shim.STATE.reset({})
+    tf_shim.STATE.rng.manual_seed(1)
+    res = ref['augment'].random_affine([T(a1), T(a2), amask], horizontal_flipping=True, min_scale=0.9, max_scale=1.1,
+                                       max_translation_x=0.1, max_translation_y=0.05, max_rotation=10.0)
+    for name, d in zip(('tx', 'ty', 'rot', 'scale', 'flip'), tf_shim.STATE.draws):
+        out['aug_affine_' + name] = N(d)
+    assert len(tf_shim.STATE.draws) == 5
+    for i, r in enumerate(res):
+        out['aug_affine_out%d' % i] = N(r)
+    tf_shim.STATE.reset({})
+    tf_shim.STATE.rng.manual_seed(8)
+    res = ref['augment'].random_photometric([T(a1), T(a2)], noise_stddev=0.04, min_contrast=-0.3, max_contrast=0.3,
+                                            brightness_stddev=0.02, min_colour=0.9, max_colour=1.1,
+                                            min_gamma=0.7, max_gamma=1.5)
+    for name, d in zip(('contrast', 'gamma', 'colour', 'noise', 'brightness'), tf_shim.STATE.draws):
+        out['aug_photo_' + name] = N(d)
+    assert len(tf_shim.STATE.draws) == 5
+    out['aug_photo_out0'], out['aug_photo_out1'] = N(res[0]), N(res[1])
 
     path = os.path.join(HERE, 'reference_run.npz')
     np.savez_compressed(path, **out)

@@ -16,6 +16,7 @@ Conventions: tensors are ``Tensor`` (a torch.Tensor subclass whose ``.shape`` ha
 ``tf.shape`` returns a list of Python ints and scalar shape arithmetic stays in Python / numpy
 float32, which is what a TF session would constant-fold to.
 """
+import builtins
 import contextlib
 import math
 import sys
@@ -61,6 +62,8 @@ def _t(x, dtype=None):
     """anything -> Tensor (python scalars / lists / numpy included)."""
     if isinstance(x, torch.Tensor):
         out = x
+    elif isinstance(x, (list, tuple)) and any(isinstance(e, (torch.Tensor, list, tuple)) for e in x):
+        out = torch.stack([_t(e) for e in x])                  # nested lists holding tensors
     else:
         out = torch.as_tensor(np.asarray(x))
         if out.dtype == torch.float64:
@@ -92,6 +95,8 @@ class _State:
         self.reg_losses = []
         self.collections = {}
         self.arg_scope = []                 # stack of (functions, kwargs)
+        self.rng = torch.Generator().manual_seed(0)
+        self.draws = []                     # every random tensor handed out, in call order
 
 
 STATE = _State()
@@ -173,12 +178,12 @@ def to_int32(x):
     return cast(x, 'int32')
 
 
-def zeros(shape_, dtype='float32'):
-    return _t(torch.zeros([int(s) for s in shape_], dtype=_TORCH_DTYPE[dtype]))
+def zeros(shape=None, dtype='float32'):       # noqa: A002
+    return _t(torch.zeros([int(s) for s in shape], dtype=_TORCH_DTYPE[dtype]))
 
 
-def ones(shape_, dtype='float32'):
-    return _t(torch.ones([int(s) for s in shape_], dtype=_TORCH_DTYPE[dtype]))
+def ones(shape=None, dtype='float32'):        # noqa: A002
+    return _t(torch.ones([int(s) for s in shape], dtype=_TORCH_DTYPE[dtype]))
 
 
 def ones_like(x):
@@ -201,6 +206,35 @@ def transpose(x, perm):
     return _t(x).permute(*perm).as_subclass(Tensor)
 
 
+def matmul(a, b):
+    a, b = _t(a), _t(b)
+    if not a.is_floating_point():               # integer outer products (spatial_transformer._repeat)
+        return _t((a.long() @ b.long()).to(a.dtype))
+    return _t(a @ b)
+
+
+def linspace(start, stop, num):
+    return _t(torch.linspace(float(start), float(stop), int(num)))
+
+
+def slice(x, begin, size):                  # noqa: A001  (tf.slice)
+    x = _t(x)
+    idx = tuple(builtins.slice(int(b), None if int(n) == -1 else int(b) + int(n)) for b, n in zip(begin, size))
+    return x[idx].as_subclass(Tensor)
+
+
+def random_uniform(shape=None, minval=0, maxval=1, dtype='float32', seed=None):       # noqa: A002
+    u = torch.rand([int(s) for s in shape], generator=STATE.rng) * (float(maxval) - float(minval)) + float(minval)
+    STATE.draws.append(u.clone())
+    return _t(u)
+
+
+def random_normal(shape=None, mean=0.0, stddev=1.0, dtype='float32', seed=None):     # noqa: A002
+    g = torch.randn([int(s) for s in shape], generator=STATE.rng) * float(stddev) + float(mean)
+    STATE.draws.append(g.clone())
+    return _t(g)
+
+
 def tile(x, multiples):
     return _t(x).repeat(*[int(m) for m in multiples]).as_subclass(Tensor)
 
@@ -212,6 +246,8 @@ def concat(values=None, axis=None, name=None, **kw):
 
 
 def stack(values, axis=0):
+    if all(_is_scalar(v) for v in values):      # shape vectors stay Python lists
+        return [int(v) for v in values]
     return _t(torch.stack([_t(v) for v in values], dim=axis))
 
 
@@ -265,6 +301,8 @@ maximum = _ew(torch.maximum, lambda a, b: max(a, b))
 multiply = _ew(torch.mul, lambda a, b: a * b)
 logical_and = _ew(torch.logical_and, lambda a, b: bool(a) and bool(b))
 greater = _ew(torch.gt, lambda a, b: a > b)
+sin = _ew(torch.sin, lambda x: np.sin(np.float32(x)))
+cos = _ew(torch.cos, lambda x: np.cos(np.float32(x)))
 
 
 def pow(x, y):                          # noqa: A001
@@ -293,8 +331,7 @@ def _unsupported(name):
     return fn
 
 
-for _n in ('random_uniform', 'random_normal', 'matmul', 'slice', 'sin', 'cos', 'linspace', 'round', 'placeholder',
-           'Variable', 'extract_image_patches'):
+for _n in ('round', 'placeholder', 'Variable', 'extract_image_patches'):
     globals()[_n] = _unsupported(_n)
 
 

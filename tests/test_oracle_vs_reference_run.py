@@ -116,3 +116,23 @@ def test_unsupervised_loss_value_flows_and_gradients(tag, spec, seed, extra):
         if key in G.files:
             err = float((g - torch.from_numpy(G[key])).norm() / max(float(torch.from_numpy(G[key]).norm()), 1e-20))
             assert err < 2e-3, "%s: relative L2 gradient error %.2e" % (k, err)
+
+
+def test_augmentation_cores_against_the_reference_run():
+    """spatial_transformer.transformer, random_affine and random_photometric of the reference, run
+    with recorded random draws; the oracle's deterministic cores get the same draws as inputs."""
+    from oracle import augment as oaug
+    a1, a2, mask = t('aug_im1'), t('aug_im2'), t('aug_mask')
+    close(oaug.transformer(a1, t('aug_theta'), (20, 30)), G['aug_transformer'], rtol=1e-4, atol_rel=1e-5)
+    flip = torch.where(t('aug_affine_flip') > 0.5, -torch.ones(3), torch.ones(3))      # augment.py:38-41
+    assert (flip < 0).any() and (flip > 0).any()                                        # both branches drawn
+    theta = oaug.affine_matrices(t('aug_affine_tx'), t('aug_affine_ty'), t('aug_affine_rot'), t('aug_affine_scale'), flip)
+    for i, x in enumerate((a1, a2, mask)):
+        got = oaug.transformer(x, theta, (x.shape[1], x.shape[2]))
+        # positions that land within float rounding of a pixel edge may pick the other neighbour
+        diff = (got - torch.from_numpy(G['aug_affine_out%d' % i])).abs()
+        assert float((diff > 1e-4).float().mean()) < 2e-3, float((diff > 1e-4).float().mean())
+    got = oaug.photometric([a1, a2], t('aug_photo_contrast'), t('aug_photo_gamma'), t('aug_photo_colour'),
+                           t('aug_photo_noise'), t('aug_photo_brightness'))
+    close(got[0], G['aug_photo_out0'], rtol=1e-5, atol_rel=1e-6)
+    close(got[1], G['aug_photo_out1'], rtol=1e-5, atol_rel=1e-6)
