@@ -50,7 +50,8 @@ def load_reference():
     sys.modules['e2eflow.ops'] = ops
     pkg.ops = ops
     mods = {n: importlib.import_module('e2eflow.core.' + n)
-            for n in ('image_warp', 'losses', 'flownet', 'unsupervised', 'augment', 'spatial_transformer')}
+            for n in ('image_warp', 'losses', 'flownet', 'unsupervised', 'augment', 'spatial_transformer',
+                      'flow_util', 'input')}
     for m in mods.values():
         assert os.path.realpath(m.__file__).startswith(os.path.realpath(REF_SRC)), m.__file__
     return tf, mods
@@ -177,6 +178,34 @@ def main():
         out['aug_photo_' + name] = N(d)
     assert len(tf_shim.STATE.draws) == 5
     out['aug_photo_out0'], out['aug_photo_out1'] = N(res[0]), N(res[1])
+
+    # ---- evaluation utilities: flow_util.py, the resize helpers of input.py -----
+    FU, IN = ref['flow_util'], ref['input']
+    g = torch.Generator().manual_seed(51)
+    fl = torch.randn(2, 12, 16, 2, generator=g) * 6
+    fl[0, 0, 0] = 0.0                                   # atan2(0, 0) -> NaN hue in the reference
+    fl[0, 0, 1] = torch.tensor([0.0, 2.0])
+    fl[0, 0, 2] = torch.tensor([0.0, -2.0])
+    fl[0, 0, 3] = torch.tensor([-3.0, 0.0])
+    gt = fl + torch.randn(2, 12, 16, 2, generator=g) * 2
+    mocc = (torch.rand(2, 12, 16, 1, generator=g) > 0.2).float()
+    mnoc = mocc * (torch.rand(2, 12, 16, 1, generator=g) > 0.3).float()
+    out['fu_flow'], out['fu_gt'], out['fu_mocc'], out['fu_mnoc'] = N(fl), N(gt), N(mocc), N(mnoc)
+    out['fu_color'] = N(FU.flow_to_color(T(fl)))
+    out['fu_color_mask_max'] = N(FU.flow_to_color(T(fl), T(mocc), max_flow=10.0))
+    out['fu_error_log'] = N(FU.flow_error_image(T(fl), T(gt), T(mocc), T(mnoc)))
+    out['fu_error_lin'] = N(FU.flow_error_image(T(fl), T(gt), T(mocc), T(mnoc), log_colors=False))
+    out['fu_error_log_nonoc'] = N(FU.flow_error_image(T(fl), T(gt), T(mocc)))
+    out['fu_aee'] = N(FU.flow_error_avg(T(gt), T(fl), T(mocc)))
+    out['fu_outlier_pct'] = N(FU.outlier_pct(T(gt), T(fl), T(mocc)))
+    out['fu_outlier_ratio_abs'] = N(FU.outlier_ratio(T(gt), T(fl), T(mnoc), threshold=2.0, relative=None))
+    img = torch.rand(1, 14, 20, 3, generator=g) * 255
+    out['in_img'] = N(img)
+    out['in_resize_input'] = N(IN.resize_input(T(img.reshape(-1)), 10, 16, 14, 20))
+    out['in_resize_output_crop'] = N(IN.resize_output_crop(T(img), 10, 24, 3))
+    out['in_resize_output'] = N(IN.resize_output(T(img), 7, 30, 3))
+    out['in_resize_output_flow'] = N(IN.resize_output_flow(T(fl[:1]), 18, 8, 2))
+    out['in_frame_nums'] = np.array([IN.frame_name_to_num(n) for n in ('0000000000.png', '0000000120.png', '7.png')])
 
     path = os.path.join(HERE, 'reference_run.npz')
     np.savez_compressed(path, **out)

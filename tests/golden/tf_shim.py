@@ -26,8 +26,8 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-float32, int32 = 'float32', 'int32'
-_TORCH_DTYPE = {'float32': torch.float32, 'int32': torch.int32, float32: torch.float32}
+float32, int32, bool = 'float32', 'int32', 'bool'          # noqa: A001  (tf.bool)
+_TORCH_DTYPE = {'float32': torch.float32, 'int32': torch.int32, 'bool': torch.bool}
 
 
 class Shape(tuple):
@@ -76,7 +76,7 @@ def _t(x, dtype=None):
 
 
 def _is_scalar(x):
-    return isinstance(x, (int, float, np.integer, np.floating)) and not isinstance(x, bool)
+    return isinstance(x, (int, float, np.integer, np.floating)) and not isinstance(x, builtins.bool)
 
 
 # ---- graph bookkeeping -----------------------------------------------------------------------------
@@ -190,6 +190,15 @@ def ones_like(x):
     return _t(torch.ones_like(x))
 
 
+def zeros_like(x):
+    return _t(torch.zeros_like(x))
+
+
+def reduce_max(x, axis=None, keepdims=False):
+    x = _t(x)
+    return _t(x.max() if axis is None else x.amax(dim=axis, keepdim=keepdims))
+
+
 def range(*args):                      # noqa: A001  (tf.range)
     return _t(torch.arange(*[int(a) for a in args], dtype=torch.int32))
 
@@ -299,8 +308,13 @@ abs = _ew(torch.abs, lambda x: np.abs(x))          # noqa: A001
 minimum = _ew(torch.minimum, lambda a, b: min(a, b))
 maximum = _ew(torch.maximum, lambda a, b: max(a, b))
 multiply = _ew(torch.mul, lambda a, b: a * b)
-logical_and = _ew(torch.logical_and, lambda a, b: bool(a) and bool(b))
+logical_and = _ew(torch.logical_and, lambda a, b: builtins.bool(a) and builtins.bool(b))
 greater = _ew(torch.gt, lambda a, b: a > b)
+greater_equal = _ew(torch.ge, lambda a, b: a >= b)
+less = _ew(torch.lt, lambda a, b: a < b)
+equal = _ew(torch.eq, lambda a, b: a == b)
+atan = _ew(torch.atan, lambda x: np.arctan(np.float32(x)))
+mod = _ew(torch.remainder, lambda a, b: a % b)          # floored modulo, like tf.mod
 sin = _ew(torch.sin, lambda x: np.sin(np.float32(x)))
 cos = _ew(torch.cos, lambda x: np.cos(np.float32(x)))
 
@@ -389,6 +403,38 @@ class _Image:
         top = x[:, y0][:, :, x0] + (x[:, y0][:, :, x1] - x[:, y0][:, :, x0]) * fx.view(1, 1, ow, 1)
         bot = x[:, y1][:, :, x0] + (x[:, y1][:, :, x1] - x[:, y1][:, :, x0]) * fx.view(1, 1, ow, 1)
         return _t(top + (bot - top) * fy.view(1, oh, 1, 1))
+
+    @staticmethod
+    def hsv_to_rgb(images):
+        """TF's kernel (colorspace_op.h): h in [0,1) scaled to 6 sectors, piecewise-linear channels,
+        clamped with cwiseMax / cwiseMin -- fmaxf / fminf on the GPU the reference runs on, which
+        drop a NaN operand (flow_util.atan2 yields a NaN hue for a zero flow vector)."""
+        x = _t(images)
+        h, s_, v = x[..., 0], x[..., 1], x[..., 2]
+        nh = h * 6
+        zero, one = torch.zeros(()), torch.ones(())
+        clamp01 = lambda z: torch.fmin(torch.fmax(z, zero), one)
+        dr = clamp01((nh - 3).abs() - 1)
+        dg = clamp01(2 - (nh - 2).abs())
+        db = clamp01(2 - (nh - 4).abs())
+        oms = 1 - s_
+        return _t(torch.stack([(oms + s_ * dr) * v, (oms + s_ * dg) * v, (oms + s_ * db) * v], -1))
+
+    @staticmethod
+    def resize_image_with_crop_or_pad(image, target_height, target_width):
+        """Centre crop ((in - target) // 2 from the start) and / or centre zero pad ((target - in) // 2
+        before), per axis; [h,w,c] or [b,h,w,c]."""
+        x = _t(image)
+        hd = x.dim() - 3
+        for d, target in ((hd, int(target_height)), (hd + 1, int(target_width))):
+            n = x.shape[d]
+            if n > target:
+                x = x.narrow(d, (n - target) // 2, target)
+            elif n < target:
+                before = (target - n) // 2
+                pad_spec = [0, 0] * (x.dim() - 1 - d) + [before, target - n - before]
+                x = F.pad(x, pad_spec)
+        return _t(x)
 
     @staticmethod
     def resize_area(images, size, align_corners=False):

@@ -136,3 +136,33 @@ def test_augmentation_cores_against_the_reference_run():
                            t('aug_photo_noise'), t('aug_photo_brightness'))
     close(got[0], G['aug_photo_out0'], rtol=1e-5, atol_rel=1e-6)
     close(got[1], G['aug_photo_out1'], rtol=1e-5, atol_rel=1e-6)
+
+
+def test_product_evaluation_utilities_against_the_reference_run():
+    """core/flow_util.py and the resize helpers of core/input.py are plain torch in the product and
+    run on the CPU: compared directly with the reference files' own output."""
+    from unflow_b200.e2eflow.core import flow_util as FU
+    from unflow_b200.e2eflow.core import input as IN
+    fl, gt, mocc, mnoc = t('fu_flow'), t('fu_gt'), t('fu_mocc'), t('fu_mnoc')
+
+    def same(got, key, tol=2e-5):
+        want = G[key]
+        got = got.detach().numpy() if isinstance(got, torch.Tensor) else np.asarray(got)
+        assert got.shape == want.shape, (key, got.shape, want.shape)
+        assert np.array_equal(np.isnan(got), np.isnan(want)), key          # atan2(0,0) is NaN in the reference
+        np.testing.assert_allclose(np.nan_to_num(got), np.nan_to_num(want), rtol=tol, atol=tol, err_msg=key)
+
+    same(FU.flow_to_color(fl), 'fu_color')
+    same(FU.flow_to_color(fl, mocc, max_flow=10.0), 'fu_color_mask_max')
+    same(FU.flow_error_image(fl, gt, mocc, mnoc), 'fu_error_log')
+    same(FU.flow_error_image(fl, gt, mocc, mnoc, log_colors=False), 'fu_error_lin')
+    same(FU.flow_error_image(fl, gt, mocc), 'fu_error_log_nonoc')
+    same(FU.flow_error_avg(gt, fl, mocc), 'fu_aee')
+    same(FU.outlier_pct(gt, fl, mocc), 'fu_outlier_pct')
+    same(FU.outlier_ratio(gt, fl, mnoc, threshold=2.0, relative=None), 'fu_outlier_ratio_abs')
+    img = t('in_img')
+    same(IN.resize_input(img.reshape(-1), 10, 16, 14, 20), 'in_resize_input', tol=1e-4)
+    same(IN.resize_output_crop(img, 10, 24, 3), 'in_resize_output_crop')
+    same(IN.resize_output(img, 7, 30, 3), 'in_resize_output', tol=1e-4)
+    same(IN.resize_output_flow(fl[:1], 18, 8, 2), 'in_resize_output_flow', tol=1e-4)
+    assert [IN.frame_name_to_num(n) for n in ('0000000000.png', '0000000120.png', '7.png')] == G['in_frame_nums'].tolist()
