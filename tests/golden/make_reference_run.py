@@ -52,6 +52,8 @@ def load_reference():
     mods = {n: importlib.import_module('e2eflow.core.' + n)
             for n in ('image_warp', 'losses', 'flownet', 'unsupervised', 'augment', 'spatial_transformer',
                       'flow_util', 'input')}
+    mods['kitti_input'] = importlib.import_module('e2eflow.kitti.input')
+    mods['util'] = importlib.import_module('e2eflow.util')
     for m in mods.values():
         assert os.path.realpath(m.__file__).startswith(os.path.realpath(REF_SRC)), m.__file__
     return tf, mods
@@ -206,6 +208,64 @@ def main():
     out['in_resize_output'] = N(IN.resize_output(T(img), 7, 30, 3))
     out['in_resize_output_flow'] = N(IN.resize_output_flow(T(fl[:1]), 18, 8, 2))
     out['in_frame_nums'] = np.array([IN.frame_name_to_num(n) for n in ('0000000000.png', '0000000120.png', '7.png')])
+
+    # ---- input pipeline: which files are paired, in which order ------------------
+    import json
+    import tempfile
+    listing = {}
+    with tempfile.TemporaryDirectory() as root:
+        tree = {'raw/a/image_02/data': [0, 1, 2, 3, 5, 6], 'raw/a/image_03/data': [0, 1, 2],
+                'raw/b/image_02/data': [10, 11, 12, 14], 'raw/b/image_03/data': [7, 8]}
+        for d, nums in tree.items():
+            os.makedirs(os.path.join(root, d))
+            for n in nums:
+                open(os.path.join(root, d, '%010d.png' % n), 'w').close()
+        for sub, names in (('data_stereo_flow/training/colored_0', ['%06d_%d.png' % (i, j) for i in range(5) for j in (10, 11)]),
+                           ('data_stereo_flow/training/flow_occ', ['%06d_10.png' % i for i in range(5)]),
+                           ('data_stereo_flow/training/flow_noc', ['%06d_10.png' % i for i in range(5)])):
+            os.makedirs(os.path.join(root, sub))
+            for n in names:
+                open(os.path.join(root, sub, n), 'w').close()
+
+        class Data:
+            current_dir = root
+
+            def get_raw_dirs(self):
+                return [os.path.join(root, d) for d in sorted(tree)]
+
+        rel = lambda files: [os.path.relpath(f, root) for f in files]
+        KI = ref['kitti_input'].KITTIInput
+        cases = {'plain': dict(kw={}, call=dict(swap_images=False)),
+                 'skipped_swap_shift3': dict(kw=dict(skipped_frames=True), call=dict(swap_images=True, shift=3)),
+                 'skipped_shift4_seed5': dict(kw=dict(skipped_frames=True), call=dict(swap_images=False, shift=4, seed=5)),
+                 'skip01': dict(kw={}, call=dict(swap_images=False, skip=[0, 1]))}
+        for tag, c in cases.items():
+            tf_shim.STATE.reset({})
+            tf_shim.STATE.decode_shape = (4, 6, 3)
+            inp = KI(Data(), batch_size=2, dims=(4, 6), normalize=False, **c['kw'])
+            inp.input_raw(needs_crop=False, **c['call'])
+            first, second = tf_shim.STATE.queues[:2]
+            listing['raw_' + tag] = [rel(first), rel(second)]
+        for tag, hold in (('all', None), ('hold3', 3)):
+            tf_shim.STATE.reset({})
+            inp = KI(Data(), batch_size=1, dims=(4, 6), normalize=False)
+            inp.input_train_2012(hold)
+            q = tf_shim.STATE.queues
+            listing['train2012_' + tag] = [rel(x) for x in q[:4]]      # frame 1, frame 2, flow_occ, flow_noc
+    out['input_listing_json'] = np.array(json.dumps(listing))
+    ini = ("[dirs]\nlog = ../log\ndata = /data\n[run]\nbatch_size = 4\ngpu_list = 0,1\ndevelopment = False\n"
+           "dataset = kitti\n[train]\nlearning_rate = 1.0e-4\ndecay_interval = 100000\nflownet = CSS\n"
+           "pyramid_loss = True\nmask_occlusion = fb\nternary_weight = 1.0\nnum_iters = 500000\n"
+           "[train_kitti_ft]\nmanual_decay_iters = 45000,20000\nmanual_decay_lrs = 0.5e-5,0.25e-5\nheight = 320\n")
+    with tempfile.TemporaryDirectory() as d:
+        path_ini = os.path.join(d, 'config.ini')
+        open(path_ini, 'w').write(ini)
+        cfg = ref['util'].config_dict(path_ini)
+        ft = dict(cfg['train'])
+        ft.update(cfg['train_kitti_ft'])
+        ref['util'].convert_input_strings(ft, cfg['dirs'])
+    out['config_ini'] = np.array(ini)
+    out['config_json'] = np.array(json.dumps({'config': cfg, 'kitti_ft': ft}, sort_keys=True))
 
     path = os.path.join(HERE, 'reference_run.npz')
     np.savez_compressed(path, **out)

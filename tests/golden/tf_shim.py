@@ -27,7 +27,7 @@ import torch
 import torch.nn.functional as F
 
 float32, int32, bool = 'float32', 'int32', 'bool'          # noqa: A001  (tf.bool)
-_TORCH_DTYPE = {'float32': torch.float32, 'int32': torch.int32, 'bool': torch.bool}
+_TORCH_DTYPE = {'float32': torch.float32, 'int32': torch.int32, 'bool': torch.bool, 'uint16': torch.int32}
 
 
 class Shape(tuple):
@@ -97,6 +97,8 @@ class _State:
         self.arg_scope = []                 # stack of (functions, kwargs)
         self.rng = torch.Generator().manual_seed(0)
         self.draws = []                     # every random tensor handed out, in call order
+        self.queues = []                    # file-name lists handed to string_input_producer, in call order
+        self.decode_shape = (4, 6, 3)       # what the stand-in decode_png "reads"
 
 
 STATE = _State()
@@ -532,6 +534,40 @@ def slim_l2_regularizer(scale):
     def reg(v):
         return _t(scale * (torch.sum(torch.square(v)) / 2))       # scale * tf.nn.l2_loss(v)
     return reg
+
+
+# ---- input queues: only the FILE LISTS matter (core/input.py, kitti/input.py) --------------------
+class _Train:
+    @staticmethod
+    def string_input_producer(string_tensor, num_epochs=None, shuffle=True, capacity=32, **kw):
+        assert shuffle is False              # the reference never lets TF reorder the files
+        STATE.queues.append([str(f) for f in string_tensor])
+        return len(STATE.queues) - 1
+
+    @staticmethod
+    def batch(tensors, batch_size=1, num_threads=1, allow_smaller_final_batch=False, **kw):
+        return tensors
+
+    @staticmethod
+    def get_checkpoint_state(path):
+        return None
+
+
+train = _Train()
+
+
+class WholeFileReader:
+    def read(self, queue):
+        return None, queue
+
+
+def _decode_png(contents, channels=None, dtype=None, name=None):
+    h, w, c = STATE.decode_shape
+    return _t(torch.zeros(h, w, c if channels is None else channels))
+
+
+image.decode_png = staticmethod(_decode_png)
+uint16 = 'uint16'
 
 
 def install():

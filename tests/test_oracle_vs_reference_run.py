@@ -166,3 +166,59 @@ def test_product_evaluation_utilities_against_the_reference_run():
     same(IN.resize_output(img, 7, 30, 3), 'in_resize_output', tol=1e-4)
     same(IN.resize_output_flow(fl[:1], 18, 8, 2), 'in_resize_output_flow', tol=1e-4)
     assert [IN.frame_name_to_num(n) for n in ('0000000000.png', '0000000120.png', '7.png')] == G['in_frame_nums'].tolist()
+
+
+def test_input_pairing_and_config_parsing_against_the_reference_run(tmp_path):
+    """File pairing / ordering of core/input.py + kitti/input.py and config parsing of util.py: the
+    reference code ran with stub queues that only record the file lists."""
+    import json
+    from unflow_b200 import run as R
+    from unflow_b200.e2eflow.kitti.input import KITTIInput
+    listing = json.loads(str(G['input_listing_json']))
+    root = str(tmp_path)
+    tree = {'raw/a/image_02/data': [0, 1, 2, 3, 5, 6], 'raw/a/image_03/data': [0, 1, 2],
+            'raw/b/image_02/data': [10, 11, 12, 14], 'raw/b/image_03/data': [7, 8]}
+    for d, nums in tree.items():
+        os.makedirs(os.path.join(root, d))
+        for n in nums:
+            open(os.path.join(root, d, '%010d.png' % n), 'w').close()
+    for sub, names in (('data_stereo_flow/training/colored_0', ['%06d_%d.png' % (i, j) for i in range(5) for j in (10, 11)]),
+                       ('data_stereo_flow/training/flow_occ', ['%06d_10.png' % i for i in range(5)]),
+                       ('data_stereo_flow/training/flow_noc', ['%06d_10.png' % i for i in range(5)])):
+        os.makedirs(os.path.join(root, sub))
+        for n in names:
+            open(os.path.join(root, sub, n), 'w').close()
+
+    class Data:
+        current_dir = root
+
+        def get_raw_dirs(self):
+            return [os.path.join(root, d) for d in sorted(tree)]
+
+    rel = lambda f: os.path.relpath(f, root)
+    cases = {'plain': (dict(), dict(swap_images=False)),
+             'skipped_swap_shift3': (dict(skipped_frames=True), dict(swap_images=True, shift=3)),
+             'skipped_shift4_seed5': (dict(skipped_frames=True), dict(swap_images=False, shift=4, seed=5)),
+             'skip01': (dict(), dict(swap_images=False, skip=[0, 1]))}
+    for tag, (kw, call) in cases.items():
+        pairs = KITTIInput(Data(), batch_size=2, dims=(4, 6), normalize=False, **kw).raw_pairs(**call)
+        want_first, want_second = listing['raw_' + tag]
+        assert [rel(a) for a, _ in pairs] == want_first, tag
+        assert [rel(b) for _, b in pairs] == want_second, tag
+    ki = KITTIInput(Data(), batch_size=1, dims=(4, 6), normalize=False)
+    for tag, hold in (('all', None), ('hold3', 3)):
+        f1, f2, occ, noc = listing['train2012_' + tag]
+        pairs = ki.image_pairs('data_stereo_flow/training/colored_0', hold)
+        got_occ, got_noc = ki._flow_files('data_stereo_flow/training', hold)
+        assert [rel(a) for a, _ in pairs] == f1 and [rel(b) for _, b in pairs] == f2, tag
+        assert [rel(x) for x in got_occ] == occ and [rel(x) for x in got_noc] == noc, tag
+
+    want = json.loads(str(G['config_json']))
+    ini = tmp_path / 'config.ini'
+    ini.write_text(str(G['config_ini']))
+    cfg = R.config_dict(str(ini))
+    assert cfg == want['config']
+    ft = dict(cfg['train'])
+    ft.update(cfg['train_kitti_ft'])
+    R.convert_input_strings(ft, cfg['dirs'])
+    assert ft == want['kitti_ft']
