@@ -131,6 +131,17 @@ def main():
                 out['fn_%s_net%d_fw%d' % (tag, n, lvl)] = N(a_)
                 out['fn_%s_net%d_bw%d' % (tag, n, lvl)] = N(b_)
 
+    # full-resolution variant (two more up-convolutions under the scope 'full_res')
+    variables = oflownet.init_variables('s', True, seed=24)
+    tf_shim.STATE.reset(dict(variables))
+    i1, i2, _ = synth.image_pair(1, 64, 64, seed=124)
+    i1, i2 = i1 / 255.0 - 0.4, i2 / 255.0 - 0.4
+    fw, bw = ref['flownet'].flownet(T(i1), T(i2), flownet_spec='s', full_resolution=True, backward_flow=True)
+    assert sorted(tf_shim.STATE.created) == sorted(variables) and len(fw[0]) == 7
+    out['fn_sfull_im1'], out['fn_sfull_im2'], out['fn_sfull_vars'] = N(i1), N(i2), checksum(variables)
+    for lvl in range(7):
+        out['fn_sfull_fw%d' % lvl], out['fn_sfull_bw%d' % lvl] = N(fw[0][lvl]), N(bw[0][lvl])
+
     # ---- unsupervised_loss: value, output flows, gradient norms ---------------------------------
     for tag, spec, hw, seed, extra in (('c', 'c', (128, 128), 31, {}), ('s', 's', (128, 128), 32, {'pyramid_loss': False}),
                                        ('cs', 'cs', (128, 128), 33, {'train_all': True})):

@@ -92,6 +92,19 @@ def test_flownet_every_output_of_every_network(tag, spec, seed):
             close(bw[n][lvl], G['fn_%s_net%d_bw%d' % (tag, n, lvl)], rtol=1e-4, atol_rel=1e-5, msg="net %d bw %d" % (n, lvl))
 
 
+def test_flownet_full_resolution_variant():
+    v = oflownet.init_variables('s', True, seed=24)
+    s_ = sum(float(x.double().sum()) for x in v.values())
+    a_ = sum(float(x.double().abs().sum()) for x in v.values())
+    if not np.allclose([s_, a_], G['fn_sfull_vars'], rtol=1e-12):
+        pytest.skip("different random weights")
+    fw, bw = oflownet.flownet(v, t('fn_sfull_im1'), t('fn_sfull_im2'), 's', full_resolution=True, backward_flow=True)
+    assert len(fw[0]) == 7 and tuple(fw[0][0].shape) == (1, 64, 64, 2)
+    for lvl in range(7):
+        close(fw[0][lvl], G['fn_sfull_fw%d' % lvl], rtol=1e-4, atol_rel=1e-5, msg="fw %d" % lvl)
+        close(bw[0][lvl], G['fn_sfull_bw%d' % lvl], rtol=1e-4, atol_rel=1e-5, msg="bw %d" % lvl)
+
+
 @pytest.mark.parametrize("tag,spec,seed,extra", [('c', 'c', 31, {}), ('s', 's', 32, {'pyramid_loss': False}),
                                                  ('cs', 'cs', 33, {'train_all': True})])
 def test_unsupervised_loss_value_flows_and_gradients(tag, spec, seed, extra):
