@@ -278,6 +278,31 @@ def main():
     out['config_ini'] = np.array(ini)
     out['config_json'] = np.array(json.dumps({'config': cfg, 'kitti_ft': ft}, sort_keys=True))
 
+    # ---- learning-rate schedule: the reference computes it inline in Trainer.train (train.py:224-244);
+    # those source lines are cut out and executed as they are -----------------------------------
+    import textwrap
+    src = open(os.path.join(REF_SRC, 'e2eflow', 'core', 'train.py')).read().split('\n')
+    first = next(i for i, l in enumerate(src) if 'decay_iters = local_i + iter_offset' in l)
+    last = next(i for i in range(first, len(src)) if 'feed_dict = {learning_rate_' in src[i])
+    block = textwrap.dedent('\n'.join(src[first + 1:last]))
+    assert "learning_rate = self.params['learning_rate'] / (2 ** decay)" in block
+
+    def reference_lr(params, decay_iters):
+        scope = {'self': types.SimpleNamespace(params=params), 'decay_iters': decay_iters}
+        exec(block, scope)
+        return scope['learning_rate']
+
+    schedules = {'halving': dict(learning_rate=1.0e-4, decay_interval=100000, decay_after=300000),
+                 'halving_from_start': dict(learning_rate=2.0e-4, decay_interval=50000),
+                 'manual': dict(learning_rate=1.0e-4, decay_interval=100000, manual_decay_iters=[45000, 20000, 5000],
+                                manual_decay_lrs=[0.5e-5, 0.25e-5, 0.1e-5])}
+    probes = [0, 1, 44999, 45000, 45001, 49999, 50000, 65000, 65001, 70000, 99999, 100000, 299999, 300000, 300001,
+              399999, 400000, 500000, 750000]
+    out['lr_probes'] = np.array(probes)
+    out['lr_schedules_json'] = np.array(json.dumps(schedules))
+    for name, prm in schedules.items():
+        out['lr_' + name] = np.array([reference_lr(prm, it) for it in probes], dtype=np.float64)
+
     path = os.path.join(HERE, 'reference_run.npz')
     np.savez_compressed(path, **out)
     print("wrote %s: %d arrays, %.1f KB" % (path, len(out), os.path.getsize(path) / 1024.0))

@@ -235,3 +235,14 @@ def test_input_pairing_and_config_parsing_against_the_reference_run(tmp_path):
     ft.update(cfg['train_kitti_ft'])
     R.convert_input_strings(ft, cfg['dirs'])
     assert ft == want['kitti_ft']
+
+
+def test_learning_rate_schedule_against_the_reference_lines():
+    """train.py:224-244 (cut out of the reference source and executed at fixture time) vs
+    core/train.py: learning_rate_at."""
+    import json
+    from unflow_b200.e2eflow.core.train import learning_rate_at
+    schedules = json.loads(str(G['lr_schedules_json']))
+    for name, prm in schedules.items():
+        got = [learning_rate_at(int(it), prm) for it in G['lr_probes']]
+        np.testing.assert_allclose(got, G['lr_' + name], rtol=0, atol=0, err_msg=name)
