@@ -303,6 +303,23 @@ def main():
     for name, prm in schedules.items():
         out['lr_' + name] = np.array([reference_lr(prm, it) for it in probes], dtype=np.float64)
 
+    # ---- restore_networks (train.py:23-37): which finetune sources are loaded -----------------------
+    first = next(i for i, l in enumerate(src) if l.startswith('def restore_networks('))
+    last = next(i for i in range(first, len(src)) if 'saver = tf.train.Saver(variables_to_save' in src[i])
+    block = textwrap.dedent('\n'.join(src[first + 1:last]))
+    plans = {}
+    for spec in ('C', 'CS', 'CSS'):
+        for train_all in (None, True):
+            for n_ft in range(0, len(spec) + 1):
+                for has_ckpt in (False, True):
+                    scope = {'params': {'flownet': spec, 'train_all': train_all, 'finetune': ['ex%d' % i for i in range(n_ft)]},
+                             'ckpt': object() if has_ckpt else None,
+                             'slim': types.SimpleNamespace(get_variables_to_restore=lambda include=None: include)}
+                    exec(block, scope)
+                    plans['%s|%s|%d|%d' % (spec, bool(train_all), n_ft, int(has_ckpt))] = {
+                        'external': scope['restore_external_nets'], 'net_names': scope['net_names']}
+    out['restore_plans_json'] = np.array(json.dumps(plans))
+
     path = os.path.join(HERE, 'reference_run.npz')
     np.savez_compressed(path, **out)
     print("wrote %s: %d arrays, %.1f KB" % (path, len(out), os.path.getsize(path) / 1024.0))

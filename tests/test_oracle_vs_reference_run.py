@@ -246,3 +246,18 @@ def test_learning_rate_schedule_against_the_reference_lines():
     for name, prm in schedules.items():
         got = [learning_rate_at(int(it), prm) for it in G['lr_probes']]
         np.testing.assert_allclose(got, G['lr_' + name], rtol=0, atol=0, err_msg=name)
+
+
+def test_finetune_restore_plan_against_the_reference_lines():
+    """train.py:23-37 (executed at fixture time) vs run.py: external_restores and
+    tf_checkpoint.net_names."""
+    import json
+    from unflow_b200 import run as R
+    from unflow_b200.e2eflow.core import tf_checkpoint as ck
+    plans = json.loads(str(G['restore_plans_json']))
+    assert len(plans) == 36
+    for key, want in plans.items():
+        spec, train_all, n_ft, has = key.split('|')
+        params = {'flownet': spec, 'train_all': train_all == 'True', 'finetune': ['ex%d' % i for i in range(int(n_ft))]}
+        assert R.external_restores(params, has == '1') == want['external'], key
+        assert ck.net_names(spec) == want['net_names'], key

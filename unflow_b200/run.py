@@ -113,6 +113,17 @@ def latest_checkpoint(ckpt_dir):
     return best
 
 
+def external_restores(params, has_own_checkpoint):
+    """restore_networks (train.py:23-37): which entries of ``finetune`` (one per network of the
+    stack, in order) are loaded from their source experiments."""
+    finetune = params.get('finetune', [])
+    n_nets = len(params.get('flownet', 'S'))
+    assert len(finetune) <= n_nets
+    if params.get('train_all'):
+        return finetune if not has_own_checkpoint else []
+    return finetune if not has_own_checkpoint else finetune[:n_nets - 1]
+
+
 def restore_checkpoint(trainer, path, nets=None, with_optimizer=False):
     """Load network variables (and optionally Adam's moments) from either checkpoint kind."""
     from .e2eflow.core import tf_checkpoint
@@ -248,14 +259,7 @@ def main(argv=None):
     save_interval = min(params['save_interval'], max(num_iters, 1))
     start_iter = 1
     ck = latest_checkpoint(ckpt_dir)
-    # restore_networks (train.py:23-62): which networks come from the ``finetune`` experiments
-    finetune = params.get('finetune', [])
-    n_nets = len(params.get('flownet', 'S'))
-    assert len(finetune) <= n_nets
-    if params.get('train_all'):
-        external = finetune if ck is None else []
-    else:
-        external = finetune if ck is None else finetune[:n_nets - 1]
+    external = external_restores(params, ck is not None)
     if ck is not None:
         # continue training
         restore_checkpoint(tr, ck[1], with_optimizer=True)
