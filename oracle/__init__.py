@@ -7,6 +7,10 @@ line by line.  Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s
 ``cpu_baseline`` / ``--impl reference`` legs may import it; the product never
 does (tests/test_no_oracle_in_product.py enforces that).
 
+oracle/_ref/libref_ops.so (oracle/ref_kernels.py, oracle/ref_ops/, oracle/tf_stub/) holds the
+reference's own CUDA kernels, compiled where they lie against stand-in TensorFlow headers: the GPU
+ground truth for the four ops (built here, not yet run on a GPU).
+
 Pinning status (see DESIGN.md "Oracle"):
   * custom ops (oracle_ops.c): pinned by the reference's own known-answer
     tests (tests/golden/reference_kats.json, transcribed from
