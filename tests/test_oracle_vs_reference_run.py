@@ -261,3 +261,21 @@ def test_finetune_restore_plan_against_the_reference_lines():
         params = {'flownet': spec, 'train_all': train_all == 'True', 'finetune': ['ex%d' % i for i in range(int(n_ft))]}
         assert R.external_restores(params, has == '1') == want['external'], key
         assert ck.net_names(spec) == want['net_names'], key
+
+
+@pytest.mark.parametrize("tag,full,seed,levels", [('s', False, 22, 5), ('sfull', True, 24, 7)])
+def test_product_flownet_s_on_the_cpu_against_the_reference_run(tag, full, seed, levels):
+    """FlowNetS needs none of the custom CUDA ops, so the PRODUCT's network definition
+    (core/flownet.py on the plain conv path) runs on the CPU and is held directly to the output of
+    the reference's own flownet.py."""
+    from unflow_b200.e2eflow.core.flownet import FlowNetVariables, flownet
+    tfv = _variables('s', seed, 'fn_%s_vars' % tag) if not full else oflownet.init_variables('s', True, seed=seed)
+    v = FlowNetVariables('s', full, seed=0).load_tf_dict(tfv)
+    with torch.no_grad():
+        fw, bw = flownet(t('fn_%s_im1' % tag), t('fn_%s_im2' % tag), 's', full_resolution=full, backward_flow=True,
+                         variables=v)
+    assert len(fw[0]) == levels
+    for lvl in range(levels):
+        key = ('fn_s_net0_%s%d' if not full else 'fn_sfull_%s%d')
+        close(fw[0][lvl], G[key % ('fw', lvl)], rtol=1e-4, atol_rel=1e-5, msg="fw %d" % lvl)
+        close(bw[0][lvl], G[key % ('bw', lvl)], rtol=1e-4, atol_rel=1e-5, msg="bw %d" % lvl)
