@@ -279,3 +279,21 @@ def test_product_flownet_s_on_the_cpu_against_the_reference_run(tag, full, seed,
         key = ('fn_s_net0_%s%d' if not full else 'fn_sfull_%s%d')
         close(fw[0][lvl], G[key % ('fw', lvl)], rtol=1e-4, atol_rel=1e-5, msg="fw %d" % lvl)
         close(bw[0][lvl], G[key % ('bw', lvl)], rtol=1e-4, atol_rel=1e-5, msg="bw %d" % lvl)
+
+
+@pytest.mark.parametrize("tag,spec,seed", [('c', 'c', 21), ('cs', 'cs', 23)])
+def test_product_flownet_c_and_stack_on_the_cpu_against_the_reference_run(monkeypatch, tag, spec, seed):
+    """The product's FlowNetC / stacked definition with its two CUDA entry points (correlation,
+    image_warp) swapped for the oracle's CPU ops, against the reference's own flownet.py output."""
+    from oracle import ops as oops
+    from unflow_b200.e2eflow.core import flownet as F
+    monkeypatch.setattr(F, 'correlation', oops.correlation)
+    monkeypatch.setattr(F, 'image_warp', oimage_warp.image_warp)
+    v = F.FlowNetVariables(spec, False, seed=0).load_tf_dict(_variables(spec, seed, 'fn_%s_vars' % tag))
+    with torch.no_grad():
+        fw, bw = F.flownet(t('fn_%s_im1' % tag), t('fn_%s_im2' % tag), spec, backward_flow=True, variables=v)
+    assert len(fw) == len(spec)
+    for n in range(len(spec)):
+        for lvl in range(5):
+            close(fw[n][lvl], G['fn_%s_net%d_fw%d' % (tag, n, lvl)], rtol=1e-4, atol_rel=1e-5, msg="net %d fw %d" % (n, lvl))
+            close(bw[n][lvl], G['fn_%s_net%d_bw%d' % (tag, n, lvl)], rtol=1e-4, atol_rel=1e-5, msg="net %d bw %d" % (n, lvl))
