@@ -297,3 +297,37 @@ def test_product_flownet_c_and_stack_on_the_cpu_against_the_reference_run(monkey
         for lvl in range(5):
             close(fw[n][lvl], G['fn_%s_net%d_fw%d' % (tag, n, lvl)], rtol=1e-4, atol_rel=1e-5, msg="net %d fw %d" % (n, lvl))
             close(bw[n][lvl], G['fn_%s_net%d_bw%d' % (tag, n, lvl)], rtol=1e-4, atol_rel=1e-5, msg="net %d bw %d" % (n, lvl))
+
+
+@pytest.mark.parametrize("tag,spec,seed,extra", [('c', 'c', 31, {}), ('s', 's', 32, {'pyramid_loss': False}),
+                                                 ('cs', 'cs', 33, {'train_all': True})])
+def test_product_unsupervised_loss_host_path_on_the_cpu_against_the_reference_run(monkeypatch, tag, spec, seed, extra):
+    """The product's whole Python host path -- unsupervised_loss, flownet, the unfused compute_losses
+    and every loss term -- with only the CUDA entry points (correlation, image_warp, forward_warp,
+    downsample) swapped for the oracle's CPU ops, against the reference's own unsupervised.py run."""
+    from oracle import ops as oops
+    from oracle import util as outil
+    from unflow_b200.e2eflow.core import flownet as F
+    from unflow_b200.e2eflow.core import losses as L
+    from unflow_b200.e2eflow.core import unsupervised as U
+    monkeypatch.setattr(F, 'correlation', oops.correlation)
+    monkeypatch.setattr(F, 'image_warp', oimage_warp.image_warp)
+    monkeypatch.setattr(L, 'image_warp', oimage_warp.image_warp)
+    monkeypatch.setattr(L, 'forward_warp', oops.forward_warp)
+    monkeypatch.setattr(U, 'downsample', outil.downsample)
+    v = F.FlowNetVariables(spec, False, seed=0).load_tf_dict(_variables(spec, seed, 'ul_%s_vars' % tag))
+    params = dict(synth.KITTI_PARAMS, flownet=spec, **extra)
+    loss, ffw, fbw = U.unsupervised_loss((t('ul_%s_im1' % tag), t('ul_%s_im2' % tag)), params,
+                                         synth.KITTI_NORMALIZATION, augment=False, return_flow=True, variables=v)
+    close(loss, G['ul_%s_loss' % tag], rtol=2e-5)
+    close(ffw, G['ul_%s_flow_fw' % tag], rtol=1e-4, atol_rel=1e-5)
+    close(fbw, G['ul_%s_flow_bw' % tag], rtol=1e-4, atol_rel=1e-5)
+    loss.backward()
+    names = [str(n) for n in G['ul_%s_grad_names' % tag]]
+    want = dict(zip(names, G['ul_%s_grad_norms' % tag]))
+    for scope in v.kinds:
+        w, b = v.weights(scope)
+        for p, name in ((w, scope + '/weights'), (b, scope + '/biases')):
+            norm = 0.0 if p.grad is None else float(p.grad.double().norm())
+            assert (norm == 0.0) == (want[name] == 0.0), name
+            np.testing.assert_allclose(norm, want[name], rtol=2e-3, err_msg=name)
