@@ -217,16 +217,27 @@ def run_ours(args):
     torch.cuda.synchronize()
     final_loss = float(loss_host.item())
     fp32_exact = None
-    if args.also_fp32 and args.conv != "fp32":
+    if args.also_fp32 and args.conv != "fp32" and world == 1:
         conv_ops.set_mode("fp32")
+        saved_graph, trainer._graph = trainer._graph, None     # eager: the captured graph is the 3xTF32 step
         for _ in range(3):
             resident_step()
         ms32, _, _, _ = timed(resident_step, max(3, args.steps // 2))
+        trainer._graph = saved_graph
         fp32_exact = {"ms_per_step": round(ms32 / max(3, args.steps // 2), 3),
                       "value": round(PER_GPU_BATCH * world / (ms32 / max(3, args.steps // 2) * 1e-3), 3),
                       "unit": "frame-pairs/s", "conv_precision": "fp32 (cuDNN, no tensor cores)"}
         conv_ops.set_mode(args.conv)
 
+    params_in_sync = None
+    if world > 1:
+        # every rank must hold bit-identical variables after the timed steps (same all-reduced
+        # gradient, same Adam update): min == max over ranks of an order-independent integer checksum
+        chk = trainer.flat_param.view(torch.int32).to(torch.int64).sum().reshape(1)
+        lo, hi = chk.clone(), chk.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        params_in_sync = bool(int(lo.item()) == int(hi.item()))
     if rank != 0:
         _finish(world)
         return
@@ -284,6 +295,8 @@ def run_ours(args):
     }
     if fp32_exact:
         line["fp32_exact"] = fp32_exact
+    if params_in_sync is not None:
+        line["params_in_sync"] = params_in_sync
     if roofs:
         line["roofline"] = roofs[0]
         line["rooflines_other"] = roofs[1:]
@@ -414,8 +427,9 @@ def main():
     ap.add_argument("--graph", type=int, default=int(os.environ.get("UNFLOW_CUDA_GRAPH", "1")),
                     help="1: replay the whole training step as one CUDA graph (value and e2e); the "
                          "per-kernel roofline timings always come from an eager pass")
-    ap.add_argument("--also-fp32", action="store_true",
-                    help="additionally time the plain-fp32 conv mode and report it as fp32_exact")
+    ap.add_argument("--also-fp32", type=int, nargs="?", const=1, default=1,
+                    help="1 (default, N=1 only): additionally time the exact-fp32 conv mode (no tensor "
+                         "cores) for a few steps and report it as fp32_exact next to the 3xTF32 headline")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -17,9 +17,13 @@
  *   - return value: UNFLOW_OK, UNFLOW_EINVAL (argument check failed -- mirrors
  *     the reference's OP_REQUIRES -> InvalidArgument), UNFLOW_ECUDA (launch
  *     failed); unflow_last_error() returns a thread-local message;
- *   - re-entrant: no global mutable state apart from the launch counter and
- *     the thread-local error string; safe to call from several host threads on
- *     distinct streams.
+ *   - re-entrant: safe to call from several host threads on distinct streams.
+ *     Process-global state: the atomic launch counter, the thread-local error
+ *     string, the once-resolved driver entry point used to encode TMA tensor
+ *     maps, and the tuning options set
+ *     through unflow_set_int_option() (kernel-variant selectors only -- every
+ *     variant computes the same result; set them before launching, not while
+ *     other threads launch).
  */
 #ifndef UNFLOW_H_
 #define UNFLOW_H_

@@ -86,10 +86,12 @@ def calibrate_threads(cap=None):
     for c in cands:
         set_num_threads(c)
         F.conv2d(x, w, padding=1)
-        t0 = time.perf_counter()
-        F.conv2d(x, w, padding=1)
-        correlation(a, a, max_displacement=8, pad=8)
-        dt = time.perf_counter() - t0
+        dt = float("inf")
+        for _ in range(3):          # best of 3: one noisy sample moved the choice (and the baseline) by 40 %
+            t0 = time.perf_counter()
+            F.conv2d(x, w, padding=1)
+            correlation(a, a, max_displacement=8, pad=8)
+            dt = min(dt, time.perf_counter() - t0)
         if dt < best_t * 0.95:
             best, best_t = c, dt
     set_num_threads(best)

@@ -8,9 +8,7 @@ The op-registration files (*_op.cc) need the whole TensorFlow op framework and a
 the letter of the task the reference is therefore "unbuildable", what IS built are its GPU kernels
 and their launchers, which is where the arithmetic lives.
 
-Status: built and symbol-checked in the CPU container; NOT YET RUN on a GPU (the round's GPU
-budget was spent when it was written) -- the GPU tests that use it are opt-in
-(UNFLOW_TEST_REFERENCE_KERNELS=1) until a run has confirmed them.
+Used by tests/test_reference_kernels.py (every ``-m gpu`` run) and tools/bench_reference_kernels.py.
 
 All functions take / return float32 CUDA tensors in the reference's layouts (correlation NCHW, the
 warps and downsample NHWC) and synchronise before returning; the kernels run on the legacy default
@@ -28,8 +26,12 @@ _lib = None
 
 
 def build():
-    """(Re)build when the reference tree is present; a no-op elsewhere."""
+    """(Re)build when the reference tree is present (the build container) and fail loudly if that
+    leaves no library; where the tree is absent (the GPU box) the prebuilt file must have travelled."""
     subprocess.check_call(["bash", os.path.join(HERE, "ref_ops", "build.sh")])
+    if not available():
+        raise RuntimeError("%s is missing: the reference kernels are the GPU ground truth of the "
+                           "parity tests (oracle/ref_ops/build.sh needs /root/reference)" % LIB_PATH)
 
 
 def available():

@@ -71,3 +71,28 @@ def test_unsupervised_loss_with_augmentation_runs_and_backprops():
     again = unsupervised_loss((im1.cuda(), im2.cuda()), dict(synth.KITTI_PARAMS), synth.KITTI_NORMALIZATION,
                               augment=True, variables=v)
     assert abs(float(again) - float(loss)) / abs(float(loss)) < 1e-4   # same draws -> same loss
+
+
+def test_trainer_augment_changes_the_step_and_survives_graph_capture():
+    """the reference trains with augment=True (train.py:160,169).  Trainer(augment=True)
+    must (a) give a loss that depends on the augmentation seed, (b) reproduce with the same seed,
+    (c) draw fresh parameters on every replay of the captured CUDA graph."""
+    from unflow_b200.e2eflow.core import augment as A
+    from unflow_b200.e2eflow.core.train import Trainer
+    params = dict(synth.KITTI_PARAMS, learning_rate=0.0)       # lr 0: the variables stay put
+    im1, im2, _ = synth.image_pair(1, 128, 256, seed=6)
+    im1, im2 = im1.cuda(), im2.cuda()
+    try:
+        tr = Trainer(params, synth.KITTI_NORMALIZATION, "cuda", seed=2, augment=True)
+        plain = Trainer(params, synth.KITTI_NORMALIZATION, "cuda", seed=2)
+        A.seed(1); l1 = float(tr.step(im1, im2))
+        A.seed(2); l2 = float(tr.step(im1, im2))
+        A.seed(1); l3 = float(tr.step(im1, im2))
+        l0 = float(plain.step(im1, im2))
+        assert abs(l1 - l3) <= 1e-4 * abs(l1)
+        assert abs(l1 - l2) > 1e-3 * abs(l1) and abs(l1 - l0) > 1e-3 * abs(l1)
+        tr.capture(im1, im2)
+        reps = [float(tr.step(im1, im2)) for _ in range(3)]
+        assert all(np.isfinite(reps)) and len({round(r, 3) for r in reps}) == 3, reps
+    finally:
+        A.set_device_rng(False)

@@ -1,0 +1,120 @@
+"""Parity at BASELINE.json's own config sizes, B=1 per case so the
+CPU oracle finishes in seconds:
+
+  configs[0]  FlowNetS, 384x512: unsupervised_loss (forward + warp + census loss) vs oracle
+  configs[1/2] FlowNetC, 384x1280: unsupervised_loss value, final flows fw/bw, variable gradients
+  configs[4]  stacked CSS, 384x1280: every network's flows of the bidirectional forward pass
+  level 0 of the real pyramid (B=4, 96x320): binary masks bit-exact, terms, flow gradients
+
+Tolerances are north_star's: flows within 1e-4 of the flow magnitude, loss 2e-4 relative; both conv
+arithmetic modes (exact fp32 and the benchmark's 3xTF32 tensor-core mode) are held to them.
+Reference graph: src/e2eflow/core/unsupervised.py:27-164, flownet.py:14-81, losses.py:16-87."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import flownet as oflownet
+from oracle import losses as olosses
+from oracle import unsupervised as ounsup
+import synth
+
+
+def rel_err(got, want):
+    want = want.detach().cpu().double()
+    got = got.detach().cpu().double()
+    return float((got - want).abs().max() / want.abs().max().clamp_min(1e-12))
+
+
+@pytest.fixture(scope="module")
+def modes():
+    from unflow_b200.e2eflow.core import conv_ops
+    prev = conv_ops.get_mode()
+    yield conv_ops
+    conv_ops.set_mode(prev)
+
+
+@pytest.mark.parametrize("spec,hw", [("C", (384, 1280)), ("S", (384, 512))])
+def test_unsupervised_loss_full_size(spec, hw, modes):
+    from unflow_b200.e2eflow.core.flownet import FlowNetVariables
+    from unflow_b200.e2eflow.core.unsupervised import unsupervised_loss
+    params = dict(synth.KITTI_PARAMS, flownet=spec)
+    tfv = oflownet.init_variables(spec, False, seed=17)
+    for k in tfv:
+        tfv[k] = tfv[k].clone().requires_grad_(True)
+    im1, im2, _ = synth.image_pair(1, hw[0], hw[1], seed=33)
+    want_loss, want_fw, want_bw = ounsup.unsupervised_loss(tfv, (im1, im2), params, synth.KITTI_NORMALIZATION,
+                                                           augment=False, return_flow=True)
+    want_loss.backward()
+    report = {}
+    for mode in ("fp32", "3xtf32"):
+        modes.set_mode(mode)
+        v = FlowNetVariables(spec, False, seed=0).load_tf_dict({k: t.detach() for k, t in tfv.items()}).cuda()
+        got_loss, got_fw, got_bw = unsupervised_loss((im1.cuda(), im2.cuda()), params, synth.KITTI_NORMALIZATION,
+                                                     augment=False, return_flow=True, variables=v)
+        got_loss.backward()
+        e_loss = abs(float(got_loss) - float(want_loss)) / abs(float(want_loss))
+        e_fw, e_bw = rel_err(got_fw, want_fw), rel_err(got_bw, want_bw)
+        worst_g = 0.0
+        for scope in v.kinds:
+            w, b = v.weights(scope)
+            for got, want in ((w.grad.cpu(), tfv[scope + '/weights'].grad.permute(3, 2, 0, 1)),
+                              (b.grad.cpu(), tfv[scope + '/biases'].grad)):
+                worst_g = max(worst_g, float((got - want).norm() / want.norm().clamp_min(1e-20)))
+        report[mode] = (e_loss, e_fw, e_bw, worst_g)
+        print("full-size %s %s %s: loss rel %.2e, flow_fw %.2e, flow_bw %.2e, worst grad L2 %.2e"
+              % (spec, hw, mode, e_loss, e_fw, e_bw, worst_g))
+    for mode, (e_loss, e_fw, e_bw, worst_g) in report.items():
+        assert e_loss < 2e-4, (mode, e_loss)
+        assert e_fw < 1e-4 and e_bw < 1e-4, (mode, e_fw, e_bw)
+        assert worst_g < 5e-3, (mode, worst_g)   # hard masks: L2 per variable
+
+
+def test_flownet_css_forward_full_size(modes):
+    """configs[4]: FlowNetC + 2x FlowNetS (warp + diff inputs between the networks), 384x1280."""
+    from unflow_b200.e2eflow.core.flownet import FlowNetVariables, flownet
+    spec = "CSS"
+    tfv = oflownet.init_variables(spec, False, seed=23)
+    im1, im2, _ = synth.image_pair(1, 384, 1280, seed=41)
+    a, b = im1 / 255.0 - 0.4, im2 / 255.0 - 0.4
+    with torch.no_grad():
+        want_fw, want_bw = oflownet.flownet(tfv, a, b, spec, backward_flow=True)
+    for mode in ("fp32", "3xtf32"):
+        modes.set_mode(mode)
+        v = FlowNetVariables(spec, False, seed=0).load_tf_dict(tfv).cuda()
+        with torch.no_grad():
+            got_fw, got_bw = flownet(a.cuda(), b.cuda(), spec, backward_flow=True, variables=v)
+        assert len(got_fw) == 3 and len(got_bw) == 3
+        worst = 0.0
+        for net in range(3):
+            for w, g in zip(want_fw[net] + want_bw[net], got_fw[net] + got_bw[net]):
+                assert tuple(g.shape) == tuple(w.shape)
+                worst = max(worst, rel_err(g, w))
+        print("CSS 384x1280 %s: worst flow error over 3 nets x 5 levels x 2 directions %.2e" % (mode, worst))
+        assert worst < 1e-4, (mode, worst)
+
+
+def test_level0_loss_at_the_real_pyramid_size():
+    """compute_losses at level 0 of configs[2] (B=4, 96x320, census 7x7, fb masks): masks bit-exact,
+    every term, both flow gradients."""
+    from unflow_b200.e2eflow.core import fused_loss
+    im1, im2, ffw, fbw = synth.level_inputs(4, 96, 320, seed=77)
+    border = olosses.create_border_mask(im1, 0.1)
+    fo, bo = ffw.clone().requires_grad_(True), fbw.clone().requires_grad_(True)
+    fg, bg = ffw.cuda().requires_grad_(True), fbw.cuda().requires_grad_(True)
+    want = olosses.compute_losses(im1, im2, fo, bo, border_mask=border, mask_occlusion='fb', data_max_distance=3)
+    terms = ['ternary', 'smooth_2nd', 'fb', 'occ']
+    got, mfw, mbw = fused_loss.compute_losses_fused(im1.cuda(), im2.cuda(), fg, bg, border.cuda(), 'fb', 3, terms,
+                                                    return_masks=True)
+    aux = want['_aux']
+    assert torch.equal(mfw.cpu(), aux['mask_fw'].expand_as(mfw.cpu()))
+    assert torch.equal(mbw.cpu(), aux['mask_bw'].expand_as(mbw.cpu()))
+    wts = dict(ternary=1.0, smooth_2nd=3.0, fb=0.2, occ=12.4)
+    for k in terms:
+        assert abs(float(got[k]) - float(want[k])) <= 2e-4 * abs(float(want[k])) + 1e-9, k
+    sum(wts[k] * want[k] for k in terms).backward()
+    sum(wts[k] * got[k] for k in terms).backward()
+    for g, w, name in ((fg.grad, fo.grad, "fw"), (bg.grad, bo.grad, "bw")):
+        np.testing.assert_allclose(g.cpu().numpy(), w.numpy(), rtol=2e-3,
+                                   atol=2e-4 * float(w.abs().max()), err_msg=name)

@@ -149,7 +149,7 @@ def test_correlation_forward_variants_bit_identical():
         assert lib.unflow_set_int_option(b"corr_fwd_variant", 3) == 0
         o3 = _ops().correlation(a, b)
     finally:
-        lib.unflow_set_int_option(b"corr_fwd_variant", 3)
+        lib.unflow_set_int_option(b"corr_fwd_variant", 1)     # back to the default variant
     assert torch.equal(o1, o3)
     assert lib.unflow_set_int_option(b"corr_fwd_variant", 2) == 1
 

@@ -3,9 +3,10 @@ oracle/_ref/libref_ops.so (oracle/ref_kernels.py), as ground truth for the four 
 
 * CPU part (always on where the library exists): the correlation geometry comes from the reference's
   ``CorrelationState`` host code -- compared with the oracle and with the product's C ABI.
-* GPU part: opt-in (UNFLOW_TEST_REFERENCE_KERNELS=1) until the library has been exercised on a GPU
-  once; it compares the oracle's C restatement and the product's kernels with the reference kernels
-  on the same inputs."""
+* GPU part (runs with every ``-m gpu`` pass): the oracle's C restatement and the product's kernels
+  are compared with the reference kernels on the same inputs -- forward and gradients of all four
+  ops, including displacement > 0 / C > 1 / K = 3 / strides, which the reference's own KATs never
+  exercise (test/ops/correlation.py:30-89)."""
 import ctypes
 import itertools
 import os
@@ -18,8 +19,6 @@ from oracle import ops as oops
 from oracle import ref_kernels as RK
 
 needs_lib = pytest.mark.skipif(not RK.available(), reason="oracle/_ref/libref_ops.so not built (needs the reference tree)")
-opt_in = pytest.mark.skipif(os.environ.get("UNFLOW_TEST_REFERENCE_KERNELS") != "1",
-                            reason="reference-kernel GPU checks are opt-in until confirmed on a GPU")
 
 
 @needs_lib
@@ -51,13 +50,12 @@ def _close(a, b, tol=1e-5):
 
 
 @pytest.mark.gpu
-@needs_lib
-@opt_in
 @pytest.mark.parametrize("B,C,H,W,attrs", [(2, 32, 12, 20, dict(kernel_size=1, max_displacement=4, pad=4, stride_1=1, stride_2=2)),
                                            (1, 16, 10, 14, dict(kernel_size=3, max_displacement=3, pad=4, stride_1=2, stride_2=1)),
                                            (1, 256, 48, 160, dict(kernel_size=1, max_displacement=20, pad=20, stride_1=1, stride_2=2))])
 def test_correlation_kernels(B, C, H, W, attrs):
     from unflow_b200.e2eflow import ops
+    assert RK.available(), "oracle/_ref/libref_ops.so did not travel to the GPU box"
     g = torch.Generator().manual_seed(C + H)
     a, b = torch.randn(B, C, H, W, generator=g), torch.randn(B, C, H, W, generator=g)
     ref, p0, p1 = RK.correlation(a.cuda(), b.cuda(), **attrs)
@@ -77,10 +75,9 @@ def test_correlation_kernels(B, C, H, W, attrs):
 
 
 @pytest.mark.gpu
-@needs_lib
-@opt_in
 def test_warp_and_downsample_kernels():
     from unflow_b200.e2eflow import ops
+    assert RK.available(), "oracle/_ref/libref_ops.so did not travel to the GPU box"
     g = torch.Generator().manual_seed(3)
     im = torch.rand(2, 18, 26, 3, generator=g)
     fl = torch.randn(2, 18, 26, 2, generator=g) * 4
@@ -104,6 +101,9 @@ def test_warp_and_downsample_kernels():
     fo = fl.clone().requires_grad_(True)
     oops.forward_warp(fo).backward(go)
     _close(fo.grad, rg, 1e-4)
+    fc = fl.cuda().requires_grad_(True)
+    ops.forward_warp(fc).backward(go.cuda())
+    _close(fc.grad, rg, 1e-4)
 
     x = torch.rand(2, 16, 24, 3, generator=g)
     for scale in (2, 4):

@@ -15,19 +15,36 @@ from ... import _native
 from .._native_shim import BORDER_STN, check, stream
 
 _gen = None
+_device_rng = False
 
 
 def seed(s):
-    """Seed the augmentation random stream (torch.Generator on the CPU; draws are tiny)."""
+    """Seed the augmentation random stream (torch.Generator on the CPU; draws are tiny) and the
+    device generator used in ``set_device_rng(True)`` mode."""
     global _gen
     _gen = torch.Generator().manual_seed(int(s))
+    if torch.cuda.is_available():
+        torch.cuda.manual_seed(int(s))
+
+
+def set_device_rng(flag=True):
+    """Draw the augmentation parameters on the device from torch's default CUDA generator instead of
+    a CPU generator + host->device copies.  That generator is CUDA-graph safe (its Philox offset
+    lives in device memory while capturing), so a training step captured by ``Trainer.capture``
+    draws fresh parameters on every replay; the CPU path cannot be captured at all."""
+    global _device_rng
+    _device_rng = bool(flag)
 
 
 def _uniform(n, lo, hi, device):
+    if _device_rng and torch.device(device).type == "cuda":
+        return torch.rand(n, device=device) * (hi - lo) + lo
     return (torch.rand(n, generator=_gen) * (hi - lo) + lo).to(device)
 
 
 def _normal(n, std, device):
+    if _device_rng and torch.device(device).type == "cuda":
+        return torch.randn(n, device=device) * std
     return (torch.randn(n, generator=_gen) * std).to(device)
 
 

@@ -53,7 +53,17 @@ def learning_rate_at(decay_iters, params):
 
 class Trainer:
     def __init__(self, params, normalization, device, variables=None, seed=1234,
-                 loss_fn=unsupervised_loss, process_group=None):
+                 loss_fn=unsupervised_loss, process_group=None, augment=False):
+        """``augment``: run the reference's training-time augmentation (random_affine x3 +
+        random_photometric, unsupervised.py:39-60) inside every step, as the reference Trainer does
+        (``loss_fn(batch, params, normalization)`` with the default ``augment=True``,
+        train.py:160,169).  run.py trains with it on; bench.py and the parity tests keep it off
+        (random draws cannot be parity-pinned).  The draws come from the device generator so the
+        step stays capturable in a CUDA graph."""
+        self.augment = bool(augment)
+        if self.augment:
+            from . import augment as _aug
+            _aug.set_device_rng(True)
         self.params = dict(params)
         self.normalization = normalization
         self.device = torch.device(device)
@@ -144,7 +154,7 @@ class Trainer:
             dist.broadcast(self.flat_param, src, group=self.pg)
 
     def loss(self, im1, im2):
-        return self.loss_fn((im1, im2), self.params, self.normalization, augment=False,
+        return self.loss_fn((im1, im2), self.params, self.normalization, augment=self.augment,
                             variables=self.variables)
 
     def reduce_gradients(self):

@@ -218,6 +218,9 @@ def main(argv=None):
     ap.add_argument('--max-iters', type=int, default=None, help='stop early (for smoke runs)')
     ap.add_argument('--graph', action='store_true',
                     help='capture the training step in one CUDA graph (Trainer.capture) and replay it')
+    ap.add_argument('--no-augment', action='store_true',
+                    help='train without the random affine / photometric augmentation (the reference '
+                         'always trains with it, train.py:160,169)')
     ap.add_argument('--ckpt-format', choices=('pt', 'tf'), default='pt',
                     help="'tf' writes TensorFlow checkpoints the reference can restore")
     args = ap.parse_args(argv)
@@ -251,7 +254,10 @@ def main(argv=None):
         dist.barrier()
 
     from .e2eflow.core.train import Trainer
-    tr = Trainer(params, KITTI_NORMALIZATION, device, seed=1234)
+    tr = Trainer(params, KITTI_NORMALIZATION, device, seed=1234, augment=not args.no_augment)
+    if tr.augment:
+        from .e2eflow.core import augment as _augment
+        _augment.seed(4321 + rank)      # towers / ranks differ in their augmentation draws (train.py:169)
 
     num_iters = params.get('num_iters', 0)
     if args.max_iters is not None:
