@@ -51,9 +51,7 @@ const char *unflow_last_error(void);
 unsigned long long unflow_launch_count(void);
 void unflow_reset_launch_count(void);
 /* Tuning knobs for tests / benchmarks.  "corr_fwd_variant": 1 (one row pair per thread) or
- * 3 (three row pairs per thread); default 1 (faster on B200); results are bit-identical.
- * "narrow_loader": staging of the flow-head kernels, 1 = cp.async (default), 0 = synchronous
- * loads, 2 = row-wise cp.async (experimental); the staged values, hence the results, are the same. */
+ * 3 (three row pairs per thread); default 1 (faster on B200); results are bit-identical. */
 int unflow_set_int_option(const char *name, int value);
 
 /* ------------------------------------------------------------------------
@@ -203,6 +201,12 @@ int unflow_conv_operand_tf32(const float *x, float *out, int N, int C, int H, in
  * unflow_bias_grad_lrelu: gb[c] = sum_pixels g * lrelu'(act)  (act NULL: plain bias gradient);
  * g is read through strides, gb is zeroed by the launcher. */
 int unflow_bias_lrelu(float *y, const float *bias, long long pixels, int C, float slope, void *stream);
+/* unflow_lrelu_bwd_bias: unflow_bias_grad_lrelu that also writes gpre = g * lrelu'(act) as dense
+ * NHWC [N,H,W,C] (NULL: skip) -- the gradient w.r.t. the pre-activation output, the operand of the
+ * tensor-core input / weight gradient kernels (one pass over g instead of two). */
+int unflow_lrelu_bwd_bias(const float *g, long long sN, long long sC, long long sH, long long sW,
+                          const float *act, float *gpre, float *gb, int N, int C, int H, int W,
+                          float slope, void *stream);
 int unflow_bias_grad_lrelu(const float *g, long long sN, long long sC, long long sH, long long sW,
                            const float *act, float *gb, int N, int C, int H, int W, float slope,
                            void *stream);
@@ -211,19 +215,52 @@ int unflow_bias_grad_lrelu(const float *g, long long sN, long long sC, long long
  * The reference's `slim.conv2d(concatN, 2, 3, scope='flowN', activation_fn=None)` layers
  * (src/e2eflow/core/flownet.py:92-131) in exact fp32 on the FMA pipes; two output channels are
  * no tensor-core shape.
- *   x    dense NHWC [N,H,W,C], C even, 8-byte aligned
+ *   x    NHWC [N,H,W,C] with `x_pitch` floats between pixels (>= C: a channel slice of a concat
+ *        buffer is allowed), C even
  *   w    [2][3][3][C]  (OIHW weights stored channels-last = TF's HWIO with O moved to the front)
  *   bias [2] or NULL;  y dense NHWC [N,H,W,2], 8-byte aligned
  *   g    gradient w.r.t. y as a logical [N,2,H,W] tensor read through strides (floats)
  *   gw   [2][3][3][C], written (not accumulated); deterministic two-pass reduction through
  *        ``workspace`` (unflow_conv3x3_narrow_wgrad_workspace_bytes bytes).
  * UNFLOW_EINVAL unless C_out == 2 and C is even. */
-int unflow_conv3x3_narrow_fwd(const float *x, const float *w, const float *bias, float *y, int N, int H,
-                              int W, int C, int C_out, void *stream);
+int unflow_conv3x3_narrow_fwd(const float *x, long long x_pitch, const float *w, const float *bias, float *y,
+                              int N, int H, int W, int C, int C_out, void *stream);
 size_t unflow_conv3x3_narrow_wgrad_workspace_bytes(int N, int H, int W, int C);
-int unflow_conv3x3_narrow_wgrad(const float *x, const float *g, long long gsN, long long gsC,
+int unflow_conv3x3_narrow_wgrad(const float *x, long long x_pitch, const float *g, long long gsN, long long gsC,
                                 long long gsH, long long gsW, float *gw, void *workspace, int N, int H,
                                 int W, int C, int C_out, void *stream);
+
+/* ---- conv / deconv stacks on the tensor cores (csrc/tc_conv.cu) --------------------------------
+ * The reference's slim.conv2d / slim.conv2d_transpose layers (src/e2eflow/core/flownet.py:166-233,
+ * _flownet_upconv :89-155; cuDNN behind TensorFlow) as a hand-written tcgen05 implicit GEMM:
+ * fp32 activations are read from HBM once (TMA), split into TF32 hi / lo planes in shared memory,
+ * three kind::tf32 MMAs per K step accumulate in tensor memory (fp32-level accuracy, "3xTF32"),
+ * the epilogue adds the bias, applies max(slope*x, x) (flownet.py:84-86) and writes -- or, with
+ * `accumulate`, adds -- float4 vectors into the destination.
+ *
+ * unflow_tc_wsplit: weight planes hi = tf32(w), lo = w - hi in the layout [taps][R][Cp]
+ *   (R = the GEMM's output channels, C = contraction channels, Cp = C rounded up to 4, tail zero);
+ *   element (t, r, c) is read from w[t*s_t + r*s_r + c*s_c] (strides in floats).
+ * unflow_tc_conv:
+ *   x  NHWC [N,Hin,Win,Cin], `x_pitch` floats between pixels (a channel slice of a wider buffer is
+ *      allowed); y NHWC [N,Hout,Wout,Cout] with `y_pitch`; pitches % 4 == 0, pointers 16-byte
+ *      aligned.
+ *   mode 0  y[oy,ox] = sum_k x[stride*oy - pad_t + ky, stride*ox - pad_l + kx] W[ky*kw+kx]
+ *           (slim.conv2d; TF SAME padding enters as the offsets pad_t / pad_l, zero outside)
+ *   mode 1  y[stride*iy - pad_t + ky, stride*ix - pad_l + kx] += x[iy,ix] W[ky*kw+kx]
+ *           (slim.conv2d_transpose and the input gradient of mode 0; Hout, Wout % stride == 0)
+ *   stride 1 or 2, kh*kw <= 64.  UNFLOW_EINVAL otherwise. */
+/* unflow_tc_conv_plan (host only, for the CPU tests): the tap / class / tile plan the launcher builds,
+ * as integers (layout in csrc/tc_conv.cu); returns the count written, -needed when `cap` is too
+ * small, -1 on invalid arguments. */
+int unflow_tc_conv_plan(int N, int Hin, int Win, int Cin, int Hout, int Wout, int Cout, int mode,
+                        int stride, int kh, int kw, int pad_t, int pad_l, int *out, int cap);
+int unflow_tc_wsplit(const float *w, float *w_hi, float *w_lo, int taps, int R, int C, long long s_t,
+                     long long s_r, long long s_c, void *stream);
+int unflow_tc_conv(const float *x, int N, int Hin, int Win, int Cin, long long x_pitch,
+                   const float *w_hi, const float *w_lo, float *y, int Hout, int Wout, int Cout,
+                   long long y_pitch, const float *bias, float slope, int act, int accumulate,
+                   int mode, int stride, int kh, int kw, int pad_t, int pad_l, void *stream);
 
 /* ---- checkpoint formats --------------------------------------------
  * Host-only helper, no GPU work: CRC-32C (Castagnoli) of ``n`` bytes continuing from ``crc``

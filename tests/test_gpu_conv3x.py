@@ -197,37 +197,32 @@ def test_narrow_conv_rejects_other_shapes():
     w = torch.zeros(2, 3, 3, 6, device="cuda")
     s = torch.cuda.current_stream().cuda_stream
     lib = _native.lib()
-    assert lib.unflow_conv3x3_narrow_fwd(x.data_ptr(), w.data_ptr(), None, y.data_ptr(), 1, 4, 4, 6, 4, s) == 1
+    assert lib.unflow_conv3x3_narrow_fwd(x.data_ptr(), 6, w.data_ptr(), None, y.data_ptr(), 1, 4, 4, 6, 4, s) == 1
     assert "2 output channels" in _native.lib().unflow_last_error().decode()
-    assert lib.unflow_conv3x3_narrow_fwd(x.data_ptr(), w.data_ptr(), None, y.data_ptr(), 1, 4, 4, 5, 2, s) == 1
+    assert lib.unflow_conv3x3_narrow_fwd(x.data_ptr(), 6, w.data_ptr(), None, y.data_ptr(), 1, 4, 4, 5, 2, s) == 1
+    assert lib.unflow_conv3x3_narrow_fwd(x.data_ptr(), 4, w.data_ptr(), None, y.data_ptr(), 1, 4, 4, 6, 2, s) == 1   # pitch < C
     assert lib.unflow_conv3x3_narrow_wgrad_workspace_bytes(2, 16, 32, 6) == 2 * 18 * 6 * 4
     assert lib.unflow_conv3x3_narrow_wgrad_workspace_bytes(2, 17, 33, 6) == 8 * 18 * 6 * 4
 
 
-@pytest.mark.skipif(__import__("os").environ.get("UNFLOW_TEST_EXPERIMENTAL") != "1",
-                    reason="experimental staging loader (narrow_loader=2): enable with UNFLOW_TEST_EXPERIMENTAL=1")
-def test_narrow_loader_variants_agree_bitwise(mode3x):
-    """All staging loaders of csrc/narrow_conv.cu fill shared memory with the same values, so the
-    results must be bit-identical."""
-    from unflow_b200 import _native
+def test_narrow_conv_on_a_channel_slice_of_a_wider_buffer(mode3x):
+    """The flow heads read their input in place from the (pitch-padded) concat buffers: a channel slice
+    with a larger pixel pitch must give bit-identical results to the dense copy."""
     from unflow_b200.e2eflow.core import conv_ops
     gen = torch.Generator().manual_seed(3)
-    x = torch.randn(2, 194, 37, 70, generator=gen).cuda().contiguous(memory_format=torch.channels_last)
+    buf = torch.randn(2, 37, 70, 200, generator=gen).cuda()
+    xs = buf[..., 4:198].permute(0, 3, 1, 2)                            # 194 channels, pitch 200
+    xd = xs.contiguous(memory_format=torch.channels_last)
     w = (torch.randn(2, 194, 3, 3, generator=gen) * 0.1).cuda().contiguous(memory_format=torch.channels_last)
     b = torch.randn(2, generator=gen).cuda()
     g = torch.randn(2, 2, 37, 70, generator=gen).cuda()
     outs = []
-    try:
-        for loader in (1, 0, 2):
-            _native.check(_native.lib().unflow_set_int_option(b"narrow_loader", loader), "narrow_loader")
-            wr = w.clone().requires_grad_(True)
-            y = conv_ops._NarrowConv3x3.apply(x, wr, b)
-            y.backward(g)
-            outs.append((y.detach().clone(), wr.grad.clone()))
-    finally:
-        _native.check(_native.lib().unflow_set_int_option(b"narrow_loader", conv_ops.NARROW_LOADER), "narrow_loader")
-    for y, gw in outs[1:]:
-        assert torch.equal(y, outs[0][0]) and torch.equal(gw, outs[0][1])
+    for x in (xd, xs):
+        wr = w.clone().requires_grad_(True)
+        y = conv_ops._NarrowConv3x3.apply(x, wr, b)
+        y.backward(g)
+        outs.append((y.detach().clone(), wr.grad.clone()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
 
 
 @pytest.mark.parametrize("cin,hw", [(3, (20, 28)), (14, (22, 26)), (6, (21, 27))])

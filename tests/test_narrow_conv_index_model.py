@@ -1,7 +1,7 @@
 """Index model of the staging / shared-memory layout of csrc/narrow_conv.cu, executed on the CPU.
 
 The CUDA kernels cannot run here; what can be checked without a GPU is the integer arithmetic the
-design rests on: every staging loader (synchronous float2, cp.async per pixel, cp.async row-wise)
+design rests on: the staging loader (row-wise cp.async, with a pixel pitch for channel slices)
 covers each element of the (16+2)x(32+2)x16 window exactly once with the right source element, and
 the strides chosen for the layouts (forward 706/38, wgrad 649/36, gradient tile pitch 66) give the
 bank-conflict-free access patterns the comments claim.  The constants are parsed from the source so
@@ -27,8 +27,9 @@ WG_CHS = SR * PITCH + 1
 GPITCH = 2 * TW + 2
 
 
-def window_reference(H, W, C, y0, x0, c0):
-    """ref[ch, pr, pc] = linear index into x[n] (pixel-major, channel-minor) or -1 for a zero."""
+def window_reference(H, W, C, y0, x0, c0, XP=None):
+    """ref[ch, pr, pc] = linear index into x[n] (pixel-major with pitch XP, channel-minor) or -1 for a zero."""
+    XP = C if XP is None else XP
     ref = -np.ones((KC, SR, SC), dtype=np.int64)
     for pr in range(SR):
         for pc in range(SC):
@@ -36,40 +37,12 @@ def window_reference(H, W, C, y0, x0, c0):
             if 0 <= gy < H and 0 <= gx < W:
                 for ch in range(KC):
                     if c0 + ch < C:
-                        ref[ch, pr, pc] = (gy * W + gx) * C + c0 + ch
+                        ref[ch, pr, pc] = (gy * W + gx) * XP + c0 + ch
     return ref
 
 
-def loader_sync(H, W, C, y0, x0, c0, CHS, P):
-    out = {}
-    for tid in range(THREADS):
-        h, q = tid & 7, tid >> 3
-        for p in range(q, SR * SC, THREADS // 8):
-            pr, pc = divmod(p, SC)
-            gy, gx = y0 - 1 + pr, x0 - 1 + pc
-            ok = c0 + 2 * h < C and 0 <= gy < H and 0 <= gx < W
-            for k in range(2):
-                addr = (2 * h + k) * CHS + pr * P + pc
-                assert addr not in out
-                out[addr] = (gy * W + gx) * C + c0 + 2 * h + k if ok else -1
-    return out
-
-
-def loader_async(H, W, C, y0, x0, c0, CHS, P):
-    out = {}
-    for tid in range(THREADS):
-        ch, q = tid & 15, tid >> 4
-        for p in range(q, SR * SC, THREADS // 16):
-            pr, pc = divmod(p, SC)
-            gy, gx = y0 - 1 + pr, x0 - 1 + pc
-            ok = c0 + ch < C and 0 <= gy < H and 0 <= gx < W
-            addr = ch * CHS + pr * P + pc
-            assert addr not in out
-            out[addr] = (gy * W + gx) * C + c0 + ch if ok else -1
-    return out
-
-
-def loader_rows(H, W, C, y0, x0, c0, CHS, P):
+def loader_rows(H, W, C, y0, x0, c0, CHS, P, XP=None):
+    XP = C if XP is None else XP
     out = {}
     for tid in range(THREADS):
         ch, q = tid & 15, tid >> 4
@@ -83,18 +56,18 @@ def loader_rows(H, W, C, y0, x0, c0, CHS, P):
                 ok = c0 + ch < C and 0 <= gy < H and 0 <= gx < W
                 addr = ch * CHS + pr * P + q + 8 * j
                 assert addr not in out
-                out[addr] = (gy * W + gx) * C + c0 + ch if ok else -1
+                out[addr] = (gy * W + gx) * XP + c0 + ch if ok else -1
     return out
 
 
 def test_every_loader_fills_the_window_exactly():
-    cases = [(37, 70, 194, 0, 0, 0), (37, 70, 194, 32, 64, 192), (48, 160, 386, 16, 128, 368), (5, 33, 16, 0, 32, 0),
-             (16, 32, 18, 0, 0, 16)]
-    for H, W, C, y0, x0, c0 in cases:
-        ref = window_reference(H, W, C, y0, x0, c0)
+    cases = [(37, 70, 194, 0, 0, 0, None), (37, 70, 194, 32, 64, 192, 196), (48, 160, 386, 16, 128, 368, 388),
+             (5, 33, 16, 0, 32, 0, None), (16, 32, 18, 0, 0, 16, 20)]
+    for H, W, C, y0, x0, c0, XP in cases:
+        ref = window_reference(H, W, C, y0, x0, c0, XP)
         for CHS, P in ((FWD_CHS, FWD_PITCH), (WG_CHS, PITCH)):
-            for loader in (loader_sync, loader_async, loader_rows):
-                got = loader(H, W, C, y0, x0, c0, CHS, P)
+            for loader in (loader_rows,):
+                got = loader(H, W, C, y0, x0, c0, CHS, P, XP)
                 assert len(got) == KC * SR * SC
                 for ch in range(KC):
                     for pr in range(SR):
@@ -128,10 +101,6 @@ def test_layout_strides_are_bank_conflict_free():
         for pix in range(0, SC - 1):
             addrs = [(t & 15) * CHS + pix + (t >> 4) for t in range(32)]
             assert conflict_free(banks(addrs, 1))
-    # synchronous loader stores: lanes = 8 channel pairs x 4 adjacent pixels, one store per pair element
-    for k in range(2):
-        addrs = [(2 * (t & 7) + k) * FWD_CHS + (t >> 3) for t in range(32)]
-        assert conflict_free(banks(addrs, 1))
     # wgrad compute reads (4-byte): lanes = 16 channels x 2 row groups 4 rows apart, any row / column
     for r in range(0, 4):
         for c in range(0, SC):

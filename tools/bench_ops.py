@@ -103,8 +103,7 @@ def main():
         g = torch.randn(N, 2, hh, ww, device="cuda").contiguous(memory_format=torch.channels_last)
         nbytes = 4 * N * hh * ww * (C + 2)
         flops = 2 * N * hh * ww * C * 18
-        for loader in (1, 0, 2):
-            _native.check(_native.lib().unflow_set_int_option(b"narrow_loader", loader), "narrow_loader")
+        for loader in (2,):          # the one staging loader left (row-wise cp.async)
             wr = wgt.clone().requires_grad_(True)
             with torch.no_grad():
                 t = timeit(lambda: conv_ops._NarrowConv3x3.apply(x, wgt, bias))
@@ -115,7 +114,6 @@ def main():
                 y.backward(g)
             t = timeit(fwd_bwd)
             report("narrow_conv fwd+wgrad %s loader%d" % (tag, loader), *t, 2 * nbytes, 2 * flops)
-    _native.check(_native.lib().unflow_set_int_option(b"narrow_loader", conv_ops.NARROW_LOADER), "narrow_loader")
 
 
 if __name__ == "__main__":

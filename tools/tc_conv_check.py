@@ -1,0 +1,205 @@
+#!/usr/bin/env python
+"""GPU check of csrc/tc_conv.cu (tcgen05 3xTF32 implicit-GEMM conv): correctness against float64
+convolutions on small cases of every mode, then accuracy and timing on the FlowNetC layer shapes next
+to the library path it replaces (cuDNN 3xTF32 via core/conv_ops.py) and plain fp32 cuDNN.
+
+    python tools/tc_conv_check.py [--quick]      (one JSON line per case)
+"""
+import json
+import os
+import sys
+import time
+
+import torch
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from unflow_b200.e2eflow.core import tc_conv as T  # noqa: E402
+from unflow_b200.e2eflow.core import conv_ops  # noqa: E402
+
+dev = torch.device("cuda")
+
+
+def say(**kw):
+    print(json.dumps(kw), flush=True)
+
+
+def cl(t):
+    return t.contiguous(memory_format=torch.channels_last)
+
+
+def rel(a, b):
+    return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
+
+
+def make_x(N, C, H, W, pitch=None, seed=0, image_like=False):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    if image_like:
+        x = torch.rand(N, C, H, W, generator=g) * 0.8 - 0.4
+        x = F.avg_pool2d(F.pad(x, (1, 1, 1, 1), mode="replicate"), 3, 1)
+    else:
+        x = torch.randn(N, C, H, W, generator=g)
+    pitch = pitch or T.round4(C)
+    buf = torch.full((N, H, W, pitch), 7.25, device=dev)          # poison the slack channels
+    view = buf[..., :C].permute(0, 3, 1, 2)
+    view.copy_(x.to(dev))
+    return view
+
+
+def case_conv(name, N, Cin, Cout, H, W, k, stride, pads, bias=True, act=True, pitch=None, accumulate=False,
+              image_like=False, time_it=False, compare_lib=False):
+    pt, pb, pl, pr = pads
+    x = make_x(N, Cin, H, W, pitch, seed=Cin + H, image_like=image_like)
+    g = torch.Generator().manual_seed(Cout + k)
+    w = cl((torch.randn(Cout, Cin, k, k, generator=g) * (2.0 / (Cin * k * k)) ** 0.5).to(dev))
+    b = (torch.randn(Cout, generator=g) * 0.1).to(dev) if bias else None
+    Ho, Wo = (H + pt + pb - k) // stride + 1, (W + pl + pr - k) // stride + 1
+    ref = F.conv2d(F.pad(x.double(), (pl, pr, pt, pb)), w.double(), b.double() if bias else None, stride=stride)
+    base = torch.randn(N, Cout, Ho, Wo, device=dev).contiguous(memory_format=torch.channels_last) if accumulate else None
+    if act:
+        ref = F.leaky_relu(ref, 0.1)
+    if accumulate:
+        ref = ref + base.double()
+    planes = T.split_weights(w)
+    out, obuf = out_buf(N, Cout, Ho, Wo)
+    if accumulate:
+        out.copy_(base)
+    T.run(x, planes, out, mode=0, stride=stride, kh=k, kw=k, pad_t=pt, pad_l=pl, bias=b, act=act,
+          accumulate=accumulate)
+    torch.cuda.synchronize()
+    rec = dict(case=name, mode="conv", N=N, Cin=Cin, Cout=Cout, H=H, W=W, k=k, stride=stride, err=rel(out, ref),
+               finite=bool(torch.isfinite(out).all()), slack_untouched=bool((obuf[..., Cout:] == -3.5).all()))
+    if compare_lib:
+        conv_ops.set_mode("3xtf32")
+        with torch.no_grad():
+            y3 = conv_ops.conv2d(x if x.is_contiguous(memory_format=torch.channels_last) else cl(x), w, b, stride, pads, act=act)
+        conv_ops.set_mode("fp32")
+        with torch.no_grad():
+            y32 = conv_ops.conv2d(x.contiguous(), w, b, stride, pads, act=act)
+        rec["err_cudnn_3xtf32"] = rel(y3, ref)
+        rec["err_cudnn_fp32"] = rel(y32, ref)
+    if time_it:
+        rec["us"] = bench(lambda: T.run(x, planes, out, mode=0, stride=stride, kh=k, kw=k, pad_t=pt, pad_l=pl,
+                                        bias=b, act=act))
+        flops = 2.0 * N * Ho * Wo * Cout * Cin * k * k
+        rec["tflops_fp32_equiv"] = round(flops / rec["us"] / 1e6, 1)
+        if compare_lib:
+            conv_ops.set_mode("3xtf32")
+            xc = x if x.is_contiguous(memory_format=torch.channels_last) else cl(x)
+            with torch.no_grad():
+                rec["us_cudnn_3xtf32_with_operand_passes"] = bench(lambda: conv_ops.conv2d(xc, w, b, stride, pads, act=act))
+            conv_ops.set_mode("fp32")
+    say(**rec)
+    return rec
+
+
+def case_deconv(name, N, Cin, Cout, H, W, k, stride, pad, bias=True, act=True, pitch=None, time_it=False,
+                out_hw=None, compare_lib=False):
+    """mode 1 against F.conv_transpose2d (output_padding chosen to reach out_hw)."""
+    x = make_x(N, Cin, H, W, pitch, seed=Cin + W)
+    g = torch.Generator().manual_seed(Cout + 3 * k)
+    w = cl((torch.randn(Cin, Cout, k, k, generator=g) * (2.0 / (Cin * k * k / stride ** 2)) ** 0.5).to(dev))   # IOHW
+    b = (torch.randn(Cout, generator=g) * 0.1).to(dev) if bias else None
+    Ho = (H - 1) * stride - 2 * pad + k
+    Wo = (W - 1) * stride - 2 * pad + k
+    oph = opw = 0
+    if out_hw is not None:
+        oph, opw = out_hw[0] - Ho, out_hw[1] - Wo
+        Ho, Wo = out_hw
+    ref = F.conv_transpose2d(x.double(), w.double(), b.double() if bias else None, stride=stride, padding=pad,
+                             output_padding=(max(oph, 0), max(opw, 0)))[:, :, :Ho, :Wo]   # crop = SAME's bottom/right pad
+    if act:
+        ref = F.leaky_relu(ref, 0.1)
+    planes = T.split_weights(w, transpose=True)      # rows = Cout, contraction = Cin
+    out, obuf = out_buf(N, Cout, Ho, Wo)
+    T.run(x, planes, out, mode=1, stride=stride, kh=k, kw=k, pad_t=pad, pad_l=pad, bias=b, act=act)
+    torch.cuda.synchronize()
+    rec = dict(case=name, mode="transposed", N=N, Cin=Cin, Cout=Cout, H=H, W=W, k=k, stride=stride,
+               err=rel(out, ref), finite=bool(torch.isfinite(out).all()),
+               slack_untouched=bool((obuf[..., Cout:] == -3.5).all()))
+    if time_it:
+        rec["us"] = bench(lambda: T.run(x, planes, out, mode=1, stride=stride, kh=k, kw=k, pad_t=pad, pad_l=pad,
+                                        bias=b, act=act))
+        flops = 2.0 * N * H * W * Cout * Cin * k * k
+        rec["tflops_fp32_equiv"] = round(flops / rec["us"] / 1e6, 1)
+        if compare_lib and stride == 2 and k == 4:
+            conv_ops.set_mode("3xtf32")
+            xc = x if x.is_contiguous(memory_format=torch.channels_last) else cl(x)
+            with torch.no_grad():
+                rec["us_cudnn_3xtf32_with_operand_passes"] = bench(lambda: conv_ops.conv_transpose2d(xc, w, b, act=act))
+            conv_ops.set_mode("fp32")
+    say(**rec)
+    return rec
+
+
+def out_buf(N, C, H, W, fill=float("nan")):
+    """NCHW-shaped view with NHWC memory and a channel pitch that is a multiple of 4 (poisoned slack)."""
+    buf = torch.full((N, H, W, T.round4(C) + 4), -3.5, device=dev)
+    v = buf[..., :C].permute(0, 3, 1, 2)
+    v.fill_(fill)
+    return v, buf
+
+
+def bench(fn, iters=10, warmup=3):
+    scratch = torch.empty(256 * 1024 * 1024 // 4, device=dev)
+    for _ in range(warmup):
+        fn()
+    ts = []
+    for _ in range(iters):
+        scratch.zero_()                       # flush L2
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b) * 1e3)
+    ts.sort()
+    return round(ts[len(ts) // 2], 2)
+
+
+def main():
+    quick = "--quick" in sys.argv
+    torch.backends.cudnn.benchmark = True
+    t0 = time.time()
+    # --- smallest possible first: one tile, one K block, one tap -----------------------------------
+    case_conv("1x1 one tile", 1, 32, 32, 8, 16, 1, 1, (0, 0, 0, 0), bias=False, act=False)
+    case_conv("1x1 K=64 N=128", 1, 64, 128, 8, 16, 1, 1, (0, 0, 0, 0), bias=False, act=False)
+    case_conv("3x3 s1", 2, 64, 128, 16, 24, 3, 1, (1, 1, 1, 1))
+    case_conv("3x3 s1 ragged channels + pitch", 2, 70, 64, 13, 21, 3, 1, (1, 1, 1, 1), pitch=80)
+    case_conv("3x3 s1 C_out tail 70", 1, 32, 70, 9, 11, 3, 1, (1, 1, 1, 1))
+    case_conv("3x3 s1 C_out 30", 1, 40, 30, 9, 11, 3, 1, (1, 1, 1, 1))
+    case_conv("3x3 s1 accumulate, no act", 2, 64, 96, 12, 20, 3, 1, (1, 1, 1, 1), bias=False, act=False, accumulate=True)
+    case_conv("3x3 s2 SAME(0,1)", 2, 64, 128, 16, 24, 3, 2, (0, 1, 0, 1))
+    case_conv("5x5 s2 SAME(1,2)", 2, 64, 128, 16, 24, 5, 2, (1, 2, 1, 2))
+    case_conv("7x7 s2 SAME(2,3) 6ch image", 2, 6, 64, 32, 48, 7, 2, (2, 3, 2, 3), pitch=8, image_like=True)
+    case_deconv("deconv k4 s2 p1", 2, 64, 128, 6, 10, 4, 2, 1)
+    case_deconv("deconv k4 s2 p1 ragged", 2, 130, 64, 6, 20, 4, 2, 1, pitch=132)
+    case_deconv("dgrad of 3x3 s2 SAME(0,1)", 2, 128, 64, 8, 12, 3, 2, 0, bias=False, act=False, out_hw=(16, 24))
+    case_deconv("dgrad of 5x5 s2 SAME(1,2)", 2, 128, 64, 8, 12, 5, 2, 1, bias=False, act=False, out_hw=(16, 24))
+    case_deconv("dgrad of 3x3 s1", 2, 128, 64, 9, 14, 3, 1, 1, bias=False, act=False)
+    say(phase="small cases done", seconds=round(time.time() - t0, 1))
+    if quick:
+        return
+    # --- FlowNetC layer shapes at 384x1280, 2B = 8 samples ---------------------------------------------
+    B = 8
+    case_conv("conv3_1", B, 473, 256, 48, 160, 3, 1, (1, 1, 1, 1), pitch=476, time_it=True, compare_lib=True)
+    case_conv("conv4_1", B, 512, 512, 24, 80, 3, 1, (1, 1, 1, 1), time_it=True, compare_lib=True)
+    case_conv("conv5_1", B, 512, 512, 12, 40, 3, 1, (1, 1, 1, 1), time_it=True, compare_lib=True)
+    case_conv("conv6_1", B, 1024, 1024, 6, 20, 3, 1, (1, 1, 1, 1), time_it=True, compare_lib=True)
+    case_conv("conv4 (s2)", B, 256, 512, 48, 160, 3, 2, (0, 1, 0, 1), time_it=True, compare_lib=True)
+    case_conv("conv2 (5x5 s2)", B, 64, 128, 192, 640, 5, 2, (1, 2, 1, 2), time_it=True, compare_lib=True)
+    case_conv("conv3 (5x5 s2)", B, 128, 256, 96, 320, 5, 2, (1, 2, 1, 2), time_it=True, compare_lib=True)
+    case_conv("conv1 (7x7 s2, 3ch image)", B, 3, 64, 384, 1280, 7, 2, (2, 3, 2, 3), pitch=4, image_like=True,
+              time_it=True, compare_lib=False)
+    case_conv("conv_redir 1x1", B, 256, 32, 48, 160, 1, 1, (0, 0, 0, 0), time_it=True, compare_lib=True)
+    case_deconv("deconv5", B, 1024, 512, 6, 20, 4, 2, 1, time_it=True, compare_lib=True)
+    case_deconv("deconv4", B, 1026, 256, 12, 40, 4, 2, 1, pitch=1028, time_it=True, compare_lib=False)
+    case_deconv("deconv3", B, 770, 128, 24, 80, 4, 2, 1, pitch=772, time_it=True, compare_lib=False)
+    case_deconv("deconv2", B, 386, 64, 48, 160, 4, 2, 1, pitch=388, time_it=True, compare_lib=False)
+    case_deconv("dgrad conv3_1", B, 256, 473, 48, 160, 3, 1, 1, bias=False, act=False, time_it=True)
+    say(phase="done", seconds=round(time.time() - t0, 1))
+
+
+if __name__ == "__main__":
+    main()

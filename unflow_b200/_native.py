@@ -45,16 +45,22 @@ SIGNATURES = {
     "unflow_bias_lrelu": (_i, [_vp, _vp, ctypes.c_longlong, _i, ctypes.c_float, _vp]),
     "unflow_bias_grad_lrelu": (_i, [_vp] + [ctypes.c_longlong] * 4 + [_vp, _vp] + [_i] * 4 +
                                [ctypes.c_float, _vp]),
+    "unflow_lrelu_bwd_bias": (_i, [_vp] + [ctypes.c_longlong] * 4 + [_vp, _vp, _vp] + [_i] * 4 +
+                              [ctypes.c_float, _vp]),
     "unflow_adam_step": (_i, [_vp] * 4 + [ctypes.c_longlong] + [ctypes.c_float] * 4 +
                          [ctypes.c_longlong, ctypes.c_float, _i, _vp]),
     "unflow_adam_step_dev": (_i, [_vp] * 4 + [ctypes.c_longlong, _vp, _i, _vp]),
     "unflow_level_loss_workspace_bytes": (ctypes.c_size_t, [_i] * 3),
     "unflow_level_loss_fwd": (_i, [_vp] * 11 + [_i] * 5 + [ctypes.c_uint, _vp]),
     "unflow_level_loss_bwd": (_i, [_vp] * 11 + [_i] * 5 + [ctypes.c_uint, _vp]),
-    "unflow_conv3x3_narrow_fwd": (_i, [_vp] * 4 + [_i] * 5 + [_vp]),
+    "unflow_conv3x3_narrow_fwd": (_i, [_vp, ctypes.c_longlong] + [_vp] * 3 + [_i] * 5 + [_vp]),
     "unflow_conv3x3_narrow_wgrad_workspace_bytes": (ctypes.c_size_t, [_i] * 4),
-    "unflow_conv3x3_narrow_wgrad": (_i, [_vp, _vp] + [ctypes.c_longlong] * 4 + [_vp, _vp] + [_i] * 5 + [_vp]),
+    "unflow_conv3x3_narrow_wgrad": (_i, [_vp, ctypes.c_longlong, _vp] + [ctypes.c_longlong] * 4 + [_vp, _vp] + [_i] * 5 + [_vp]),
     "unflow_crc32c": (ctypes.c_uint, [_vp, ctypes.c_size_t, ctypes.c_uint]),
+    "unflow_tc_wsplit": (_i, [_vp, _vp, _vp, _i, _i, _i] + [ctypes.c_longlong] * 3 + [_vp]),
+    "unflow_tc_conv_plan": (_i, [_i] * 13 + [ctypes.POINTER(_i), _i]),
+    "unflow_tc_conv": (_i, [_vp, _i, _i, _i, _i, ctypes.c_longlong, _vp, _vp, _vp, _i, _i, _i,
+                            ctypes.c_longlong, _vp, ctypes.c_float, _i, _i] + [_i] * 6 + [_vp]),
 }
 
 

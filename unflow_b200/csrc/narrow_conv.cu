@@ -37,70 +37,26 @@ constexpr int GPITCH = 2 * TW + 2;         // floats per row of the staged gradi
 constexpr int FWD_PITCH = 38, FWD_CHS = 706;   // forward staging layout (see narrow_fwd_kernel)
 static_assert(FWD_CHS >= SR * FWD_PITCH && FWD_CHS % 32 == 2 && FWD_PITCH % 4 == 2, "forward smem layout");
 
-// Stage the window of chunk [c0, c0+KC) as xs[ch * CHS + row * PITCH_ + col]; zero outside the image
-// and beyond C.  x is dense NHWC with C even.  A warp instruction covers 4 consecutive pixels x 8
-// channel pairs: four contiguous 64-byte runs in global memory (one 8-byte pair per lane), and in
-// shared memory 32 distinct banks (channel stride = 2 or 9 mod 32 banks, pixels = consecutive banks).
-template <int CHS, int PITCH_>
-__device__ __forceinline__ void stage_x(float *xs, const float *__restrict__ x, int n, int y0, int x0,
-                                        int c0, int H, int W, int C, int tid) {
-  constexpr int NPIX = SR * SC;
-  const int h = tid & 7, q = tid >> 3;
-  const bool chan_ok = c0 + 2 * h < C;
-  const float *xc = x + c0 + 2 * h;
-  float *xd = xs + (2 * h) * CHS;
-#pragma unroll 4
-  for (int p = q; p < NPIX; p += THREADS / 8) {
-    const int pr = p / SC, pc = p - pr * SC;
-    const int gy = y0 - 1 + pr, gx = x0 - 1 + pc;
-    float2 v = make_float2(0.f, 0.f);
-    if (chan_ok && gy >= 0 && gy < H && gx >= 0 && gx < W)
-      v = __ldg(reinterpret_cast<const float2 *>(xc + (((long long)n * H + gy) * W + gx) * C));
-    float *dst = xd + pr * PITCH_ + pc;
-    dst[0] = v.x;
-    dst[CHS] = v.y;
-  }
-}
-
 __device__ __forceinline__ void cp_async_4(unsigned dst, const float *src, unsigned bytes) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-// The same staging with asynchronous 4-byte copies (LDGSTS): nothing passes through registers, so
-// all ~77 copies of a thread are in flight at once and the DRAM latency is paid once per chunk
-// instead of once per unrolled batch (the synchronous loader is latency-bound: ~10 us per chunk).
-// A warp instruction covers 2 consecutive pixels x 16 channels = two 64-byte runs; out-of-image /
-// beyond-C elements are zero-filled by a copy of size 0.
+// Stage the window of chunk [c0, c0+KC) as xs[ch * CHS + row * PITCH_ + col]; zero outside the image
+// and beyond C.  x is NHWC with XP floats between pixels (XP >= C: a channel slice of a concat buffer).
+// Asynchronous 4-byte copies (LDGSTS), nothing passes through registers, so all ~77 copies of a thread
+// are in flight at once and the DRAM latency is paid once per chunk.  A warp instruction covers 2
+// consecutive pixels x 16 channels = two 64-byte runs; out-of-image / beyond-C elements are
+// zero-filled by a copy of size 0.  The copies are issued row by row: the row pointer and the bounds
+// test of a window row are computed once, the columns of a thread are a fixed unrolled set.
+// (Round 2 A/B on B200, same lease: this loader 21.43 ms/step, the per-pixel cp.async loop 21.80, the
+// synchronous float2 loader slower still -- the two losers were removed, profiles/r2_ab.md.)
 template <int CHS, int PITCH_>
-__device__ __forceinline__ void stage_x_async(float *xs, const float *__restrict__ x, int n, int y0, int x0,
-                                              int c0, int H, int W, int C, int tid) {
-  constexpr int NPIX = SR * SC;
-  const int ch = tid & 15, q = tid >> 4;
-  const bool chan_ok = c0 + ch < C;
-  const float *xc = x + c0 + ch;
-  const unsigned dbase = (unsigned)__cvta_generic_to_shared(xs + ch * CHS);
-#pragma unroll 7
-  for (int p = q; p < NPIX; p += THREADS / 16) {
-    const int pr = p / SC, pc = p - pr * SC;
-    const int gy = y0 - 1 + pr, gx = x0 - 1 + pc;
-    const bool ok = chan_ok && gy >= 0 && gy < H && gx >= 0 && gx < W;
-    const float *src = ok ? xc + (((long long)n * H + gy) * W + gx) * C : x;
-    cp_async_4(dbase + (unsigned)(pr * PITCH_ + pc) * 4u, src, ok ? 4u : 0u);
-  }
-  cp_async_wait_all();
-}
-
-// Loader 2 (experimental, not the default): the same copies issued row by row -- the row pointer and
-// the bounds test of a window row are computed once, the columns of a thread are a fixed unrolled
-// set -- to cut the ~14 index instructions per copy of the loop above (the kernels are issue-bound,
-// profiles/r1_ncu_narrow_conv.md).
-template <int CHS, int PITCH_>
-__device__ __forceinline__ void stage_x_async_rows(float *xs, const float *__restrict__ x, int n, int y0, int x0,
-                                                   int c0, int H, int W, int C, int tid) {
+__device__ __forceinline__ void stage(float *xs, const float *__restrict__ x, int n, int y0, int x0, int c0,
+                                      int H, int W, int C, long long XP, int tid) {
   const int ch = tid & 15, q = tid >> 4;                  // 8 column slots: pc = q, q+8, q+16, q+24, (q+32)
   const bool chan_ok = c0 + ch < C;
-  const float *xc = x + (long long)n * H * W * C + c0 + ch;
+  const float *xc = x + (long long)n * H * W * XP + c0 + ch;
   const unsigned dbase = (unsigned)__cvta_generic_to_shared(xs + ch * CHS) + (unsigned)q * 4u;
   int gxs[5];
   bool cok[5];
@@ -114,13 +70,13 @@ __device__ __forceinline__ void stage_x_async_rows(float *xs, const float *__res
   for (int pr = 0; pr < SR; ++pr) {
     const int gy = y0 - 1 + pr;
     const bool rok = gy >= 0 && gy < H;
-    const float *rowp = xc + (long long)(rok ? gy : 0) * W * C;
+    const float *rowp = xc + (long long)(rok ? gy : 0) * W * XP;
     const unsigned drow = dbase + (unsigned)(pr * PITCH_) * 4u;
 #pragma unroll
     for (int j = 0; j < 5; ++j) {
       if (q + 8 * j < SC) {                               // the fifth column exists for q < 2 only
         const bool ok = rok && cok[j];
-        const float *src = ok ? rowp + (long long)gxs[j] * C : x;
+        const float *src = ok ? rowp + (long long)gxs[j] * XP : x;
         cp_async_4(drow + (unsigned)(8 * j) * 4u, src, ok ? 4u : 0u);
       }
     }
@@ -128,18 +84,9 @@ __device__ __forceinline__ void stage_x_async_rows(float *xs, const float *__res
   cp_async_wait_all();
 }
 
-template <int LOADER, int CHS, int PITCH_>
-__device__ __forceinline__ void stage(float *xs, const float *__restrict__ x, int n, int y0, int x0, int c0,
-                                      int H, int W, int C, int tid) {
-  if (LOADER == 2) stage_x_async_rows<CHS, PITCH_>(xs, x, n, y0, x0, c0, H, W, C, tid);
-  else if (LOADER == 1) stage_x_async<CHS, PITCH_>(xs, x, n, y0, x0, c0, H, W, C, tid);
-  else stage_x<CHS, PITCH_>(xs, x, n, y0, x0, c0, H, W, C, tid);
-}
-
-template <int LOADER>
 __global__ void __launch_bounds__(THREADS, 4)
 narrow_fwd_kernel(const float *__restrict__ x, const float *__restrict__ w, const float *__restrict__ bias,
-                  float *__restrict__ y, int H, int W, int C) {
+                  float *__restrict__ y, int H, int W, int C, long long XP) {
   // rows 38 floats apart: a half-warp's 8-byte reads (two tile rows) fall on disjoint banks;
   // channels 706 = 2 (mod 32) floats apart: the staging stores are conflict-free
   constexpr int CHS = FWD_CHS, FP = FWD_PITCH;
@@ -152,7 +99,7 @@ narrow_fwd_kernel(const float *__restrict__ x, const float *__restrict__ w, cons
 
   for (int c0 = 0; c0 < C; c0 += KC) {
     __syncthreads();                          // the previous chunk has been consumed
-    stage<LOADER, CHS, FP>(xs, x, n, y0, x0, c0, H, W, C, tid);
+    stage<CHS, FP>(xs, x, n, y0, x0, c0, H, W, C, XP, tid);
     for (int idx = tid; idx < KC * 24; idx += THREADS) {
       const int ch = idx % KC, r = idx / KC, ky = r >> 3, e = r & 7;
       float v = 0.f;
@@ -199,10 +146,9 @@ narrow_fwd_kernel(const float *__restrict__ x, const float *__restrict__ w, cons
   }
 }
 
-template <int LOADER>
 __global__ void __launch_bounds__(THREADS, 4)
 narrow_wgrad_kernel(const float *__restrict__ x, const float *__restrict__ g, long long gsN, long long gsC,
-                    long long gsH, long long gsW, float *__restrict__ partial, int H, int W, int C) {
+                    long long gsH, long long gsW, float *__restrict__ partial, int H, int W, int C, long long XP) {
   constexpr int CHS = SR * PITCH + 1;         // 649: odd -> lanes on consecutive channels hit distinct banks
   extern __shared__ __align__(16) float smem[];
   float *xs = smem;                           // [KC][CHS]; reused as red[8][KC][NOUT] after the arithmetic
@@ -223,7 +169,7 @@ narrow_wgrad_kernel(const float *__restrict__ x, const float *__restrict__ g, lo
 
   for (int c0 = 0; c0 < C; c0 += KC) {
     __syncthreads();                          // red (aliasing xs) has been read; gs is complete
-    stage<LOADER, CHS, PITCH>(xs, x, n, y0, x0, c0, H, W, C, tid);
+    stage<CHS, PITCH>(xs, x, n, y0, x0, c0, H, W, C, XP, tid);
     __syncthreads();
     float acc0[9], acc1[9];
 #pragma unroll
@@ -300,15 +246,10 @@ narrow_wgrad_reduce_kernel(const float *__restrict__ partial, float *__restrict_
   }
 }
 
-int g_loader = 1;   // unflow_set_int_option "narrow_loader": 1 cp.async staging (default), 0 synchronous float2
-                    // staging, 2 row-wise cp.async (experimental, unmeasured)
-
 inline long long tiles(int N, int H, int W) { return (long long)N * ceil_div(H, TH) * ceil_div(W, TW); }
 
 }  // namespace nc
 }  // namespace unflow
-
-namespace unflow { int set_narrow_loader(int v) { if (v < 0 || v > 2) return 0; nc::g_loader = v; return 1; } }
 
 extern "C" size_t unflow_conv3x3_narrow_wgrad_workspace_bytes(int N, int H, int W, int C) {
   if (N <= 0 || H <= 0 || W <= 0 || C <= 0) return 0;
@@ -323,24 +264,23 @@ static int narrow_check(const char *what, int N, int H, int W, int C, int Co) {
   return UNFLOW_OK;
 }
 
-extern "C" int unflow_conv3x3_narrow_fwd(const float *x, const float *w, const float *bias, float *y, int N,
-                                         int H, int W, int C, int Co, void *stream) {
+extern "C" int unflow_conv3x3_narrow_fwd(const float *x, long long x_pitch, const float *w, const float *bias,
+                                         float *y, int N, int H, int W, int C, int Co, void *stream) {
   using namespace unflow;
   if (int rc = narrow_check("conv3x3_narrow_fwd", N, H, W, C, Co)) return rc;
   if (N == 0) return UNFLOW_OK;
   UNFLOW_REQUIRE(x && w && y, "conv3x3_narrow_fwd: null pointer");
-  UNFLOW_REQUIRE(((uintptr_t)x & 7) == 0 && ((uintptr_t)y & 7) == 0, "conv3x3_narrow_fwd: x and y must be 8-byte aligned");
+  UNFLOW_REQUIRE(((uintptr_t)y & 7) == 0, "conv3x3_narrow_fwd: y must be 8-byte aligned");
+  UNFLOW_REQUIRE(x_pitch >= C, "conv3x3_narrow_fwd: pixel pitch smaller than C");
   const dim3 grid(ceil_div(W, nc::TW), ceil_div(H, nc::TH), N);
   const size_t smem = (size_t)(nc::KC * nc::FWD_CHS + nc::KC * 24) * sizeof(float);
   cudaStream_t st = (cudaStream_t)stream;
-  if (nc::g_loader == 2) nc::narrow_fwd_kernel<2><<<grid, nc::THREADS, smem, st>>>(x, w, bias, y, H, W, C);
-  else if (nc::g_loader == 1) nc::narrow_fwd_kernel<1><<<grid, nc::THREADS, smem, st>>>(x, w, bias, y, H, W, C);
-  else nc::narrow_fwd_kernel<0><<<grid, nc::THREADS, smem, st>>>(x, w, bias, y, H, W, C);
+  nc::narrow_fwd_kernel<<<grid, nc::THREADS, smem, st>>>(x, w, bias, y, H, W, C, x_pitch);
   count_launch();
   return check_launch("conv3x3_narrow_fwd");
 }
 
-extern "C" int unflow_conv3x3_narrow_wgrad(const float *x, const float *g, long long gsN, long long gsC,
+extern "C" int unflow_conv3x3_narrow_wgrad(const float *x, long long x_pitch, const float *g, long long gsN, long long gsC,
                                            long long gsH, long long gsW, float *gw, void *workspace, int N,
                                            int H, int W, int C, int Co, void *stream) {
   using namespace unflow;
@@ -353,14 +293,12 @@ extern "C" int unflow_conv3x3_narrow_wgrad(const float *x, const float *g, long 
     return UNFLOW_OK;
   }
   UNFLOW_REQUIRE(x && g && workspace, "conv3x3_narrow_wgrad: null pointer");
-  UNFLOW_REQUIRE(((uintptr_t)x & 7) == 0, "conv3x3_narrow_wgrad: x must be 8-byte aligned");
+  UNFLOW_REQUIRE(x_pitch >= C, "conv3x3_narrow_wgrad: pixel pitch smaller than C");
   const dim3 grid(ceil_div(W, nc::TW), ceil_div(H, nc::TH), N);
   const int nblocks = (int)nc::tiles(N, H, W);
   const size_t smem = (size_t)(nc::KC * (nc::SR * nc::PITCH + 1) + nc::TH * nc::GPITCH) * sizeof(float);
   float *part = (float *)workspace;
-  if (nc::g_loader == 2) nc::narrow_wgrad_kernel<2><<<grid, nc::THREADS, smem, s>>>(x, g, gsN, gsC, gsH, gsW, part, H, W, C);
-  else if (nc::g_loader == 1) nc::narrow_wgrad_kernel<1><<<grid, nc::THREADS, smem, s>>>(x, g, gsN, gsC, gsH, gsW, part, H, W, C);
-  else nc::narrow_wgrad_kernel<0><<<grid, nc::THREADS, smem, s>>>(x, g, gsN, gsC, gsH, gsW, part, H, W, C);
+  nc::narrow_wgrad_kernel<<<grid, nc::THREADS, smem, s>>>(x, g, gsN, gsC, gsH, gsW, part, H, W, C, x_pitch);
   count_launch();
   if (int rc = check_launch("conv3x3_narrow_wgrad")) return rc;
   const int total = nc::NOUT * C;

@@ -110,7 +110,7 @@ template <bool LINEAR>
 __global__ void __launch_bounds__(256)
 bias_grad_lrelu_kernel(const float *__restrict__ g, long long sN, long long sC, long long sH, long long sW,
                        const float *__restrict__ act, float *__restrict__ gb, int N, int C, int H, int W,
-                       float slope, int pix_per_cta) {
+                       float slope, int pix_per_cta, float *__restrict__ gpre) {
   __shared__ float red[8][32];
   const int lane = threadIdx.x & 31, row = threadIdx.x >> 5;
   const int c = blockIdx.y * 32 + lane;
@@ -129,11 +129,13 @@ bias_grad_lrelu_kernel(const float *__restrict__ g, long long sN, long long sC, 
           if (__ldg(ap + p * C) <= 0.0f) v0 *= slope;
           if (__ldg(ap + (p + 8) * C) <= 0.0f) v1 *= slope;
         }
+        if (gpre) { gpre[p * C + c] = v0; gpre[(p + 8) * C + c] = v1; }
         s0 += v0; s1 += v1;
       }
       for (; p < p1; p += 8) {
         float v = __ldg(gp + p * sW);
         if (ap && __ldg(ap + p * C) <= 0.0f) v *= slope;
+        if (gpre) gpre[p * C + c] = v;
         s0 += v;
       }
     } else {
@@ -143,6 +145,7 @@ bias_grad_lrelu_kernel(const float *__restrict__ g, long long sN, long long sC, 
         const long long n = p / ((long long)W * H);
         float v = __ldg(g + n * sN + y * sH + x * sW + c * sC);
         if (act && __ldg(act + p * C + c) <= 0.0f) v *= slope;
+        if (gpre) gpre[p * C + c] = v;
         s0 += v;
       }
     }
@@ -172,9 +175,19 @@ extern "C" int unflow_bias_lrelu(float *y, const float *bias, long long pixels, 
   return check_launch("bias_lrelu");
 }
 
+extern "C" int unflow_lrelu_bwd_bias(const float *g, long long sN, long long sC, long long sH, long long sW,
+                                     const float *act, float *gpre, float *gb, int N, int C, int H, int W,
+                                     float slope, void *stream);
+
 extern "C" int unflow_bias_grad_lrelu(const float *g, long long sN, long long sC, long long sH,
                                       long long sW, const float *act, float *gb, int N, int C, int H,
                                       int W, float slope, void *stream) {
+  return unflow_lrelu_bwd_bias(g, sN, sC, sH, sW, act, nullptr, gb, N, C, H, W, slope, stream);
+}
+
+extern "C" int unflow_lrelu_bwd_bias(const float *g, long long sN, long long sC, long long sH, long long sW,
+                                     const float *act, float *gpre, float *gb, int N, int C, int H, int W,
+                                     float slope, void *stream) {
   using namespace unflow;
   UNFLOW_REQUIRE(N >= 0 && C >= 1 && H >= 1 && W >= 1, "bias_grad: bad shape");
   UNFLOW_REQUIRE(g && gb, "bias_grad: null pointer");
@@ -190,8 +203,8 @@ extern "C" int unflow_bias_grad_lrelu(const float *g, long long sN, long long sC
   if (pix_per_cta < 64) pix_per_cta = 64;
   dim3 grid(ceil_div(npix, pix_per_cta), cblocks);
   const bool linear = sH == (long long)W * sW && sN == (long long)H * sH;
-  if (linear) bias_grad_lrelu_kernel<true><<<grid, 256, 0, s>>>(g, sN, sC, sH, sW, act, gb, N, C, H, W, slope, pix_per_cta);
-  else bias_grad_lrelu_kernel<false><<<grid, 256, 0, s>>>(g, sN, sC, sH, sW, act, gb, N, C, H, W, slope, pix_per_cta);
+  if (linear) bias_grad_lrelu_kernel<true><<<grid, 256, 0, s>>>(g, sN, sC, sH, sW, act, gb, N, C, H, W, slope, pix_per_cta, gpre);
+  else bias_grad_lrelu_kernel<false><<<grid, 256, 0, s>>>(g, sN, sC, sH, sW, act, gb, N, C, H, W, slope, pix_per_cta, gpre);
   count_launch();
   return check_launch("bias_grad_lrelu");
 }

@@ -1,0 +1,599 @@
+// tc_conv.cu -- the conv / deconv stacks of FlowNet on the 5th-generation tensor cores:
+// a tcgen05 implicit GEMM with the 3xTF32 operand split done in shared memory.
+//
+// Replaces the library convolutions behind slim.conv2d / slim.conv2d_transpose
+// (reference src/e2eflow/core/flownet.py:166-233, _flownet_upconv :89-155) for the forward pass
+// and the input gradient.  One kernel serves every case because the host describes a layer as a
+// list of TAPS over an iteration space of output positions:
+//
+//     out[n, s_out*iy + py, s_out*ix + px, co] (+)= act( bias[co] +
+//         sum_{t in taps(class)} sum_ci  in[n, s_in*iy + dy_t, s_in*ix + dx_t, ci] * W[t.widx][co][ci] )
+//
+//   * convolution, stride 1 or 2 (TF SAME padding = the tap offsets): one class, s_out = 1;
+//   * transposed convolution with stride 2 (deconvN forward, input gradient of a stride-2 conv):
+//     four output-parity classes, each a stride-1 gather over its own subset of the taps;
+//   * input gradient of a stride-1 convolution: one class, mirrored tap offsets.
+//
+// GEMM view per tile: M = 128 output positions (a TW x TH x TN box of one class), N = BN output
+// channels, K = taps x Cin walked in blocks of 32 channels (one 128-byte swizzle row of fp32).
+//
+// Pipeline (one CTA per SM, persistent over tiles, warp-specialised):
+//   warp 0     TMA producer: per K block one 4-D box of the ACTIVATIONS as they lie in HBM (fp32,
+//              NHWC, any channel pitch -- e.g. a channel slice of a concat buffer; image borders,
+//              the TF SAME padding and the channel tail are TMA zero fill, stride 2 is the tensor
+//              map's element stride) plus the hi and lo planes of the weights.
+//   warps 4-7  split the activation tile in shared memory: hi = tf32(x) in place, lo = x - hi
+//              into a second buffer (same swizzled layout: the split is element-wise).
+//   warp 1     one thread issues tcgen05.mma kind::tf32, three per K step:
+//              lo*hi' + hi*lo' + hi*hi' accumulate in fp32 in TENSOR MEMORY (double-buffered).
+//   warps 8-11 epilogue: tcgen05.ld -> bias + leaky ReLU (or += for gradient accumulation) ->
+//              float4 stores straight into the destination (which may be a channel slice of a
+//              concat buffer, with stride 2 for the transposed classes).
+// The activations are read from HBM once, as fp32; no [hi,hi,lo] operand copies exist, no layout
+// conversion, no separate bias / activation pass (round 1 spent 30 % of the step on those).
+//
+// Accuracy: hi carries 11 significant bits, lo the next 11; the dropped lo*lo' term and the
+// truncation of lo are ~2^-22 relative -- the same 3xTF32 arithmetic the parity tests accept.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace unflow {
+namespace tc {
+
+constexpr int BM = 128;          // UMMA M: output positions per tile
+constexpr int BK = 32;           // fp32 channels per K block = 128 bytes = one swizzle row
+constexpr int MAX_TAPS = 64;
+constexpr int NTHREADS = 384;    // 12 warps, see the role table above
+constexpr int A_BYTES = BM * BK * 4;   // 16 KB
+
+struct Tap {
+  short dx, dy;
+  int widx;
+};
+
+struct ConvParams {
+  int N, Hit, Wit;            // images; iteration rows / columns of one class
+  int TW, TH, TN;             // tile box, TW*TH*TN <= 128
+  int tiles_x, tiles_y, tiles_n, n_blocks, n_classes;
+  int s_in, s_out;
+  int Cin, Cout, kblocks;
+  float *out;
+  long long out_pitch;        // floats between consecutive output pixels
+  int Hout, Wout;
+  const float *bias;          // [Cout] or nullptr
+  float slope;                // leaky-ReLU slope when act != 0
+  int act, accumulate;
+  int class_start[5];
+  short class_px[4], class_py[4];
+  Tap taps[MAX_TAPS];
+};
+
+template <int BN>
+struct Cfg {
+  static constexpr int B_BYTES = BN * BK * 4;
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  static constexpr int STAGES = (200 * 1024 / STAGE_BYTES) < 6 ? (200 * 1024 / STAGE_BYTES) : 6;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+  static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;   // two accumulator buffers
+};
+
+// ------------------------------------------------------------------------------------------
+// PTX helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned s32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  unsigned done;
+  do {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        " selp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_4d(unsigned dst, const CUtensorMap *map, unsigned bar, int c0, int c1,
+                                       int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_3d(unsigned dst, const CUtensorMap *map, unsigned bar, int c0, int c1,
+                                       int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major operand tile, 128-byte swizzle: rows of 128 B, 8-row atoms of 1024 B (SBO), descriptor
+// version 1 (sm_100), layout type 2 = SWIZZLE_128B.  (cute::UMMA::SmemDescriptor bit layout.)
+__device__ __forceinline__ unsigned long long umma_desc_k128(unsigned saddr) {
+  return (unsigned long long)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) |
+         (2ull << 61);
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, tf32 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_tf32(unsigned d_tmem, unsigned long long adesc, unsigned long long bdesc,
+                                          unsigned idesc, unsigned accumulate) {
+  asm volatile(
+      "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n"
+      " tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(unsigned bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(unsigned taddr, unsigned (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float tf32_rna(float x) {
+  unsigned u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+
+struct TileCoord {
+  int cls, n0, iy0, ix0, nb;
+};
+__device__ __forceinline__ TileCoord decode_tile(const ConvParams &p, int tile) {
+  TileCoord t;
+  t.nb = tile % p.n_blocks; tile /= p.n_blocks;
+  t.ix0 = (tile % p.tiles_x) * p.TW; tile /= p.tiles_x;
+  t.iy0 = (tile % p.tiles_y) * p.TH; tile /= p.tiles_y;
+  t.n0 = (tile % p.tiles_n) * p.TN; tile /= p.tiles_n;
+  t.cls = tile;
+  return t;
+}
+
+// ------------------------------------------------------------------------------------------
+// The kernel
+// ------------------------------------------------------------------------------------------
+template <int BN>
+__global__ void __launch_bounds__(NTHREADS, 1)
+tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapBhi,
+               const __grid_constant__ CUtensorMap mapBlo, const __grid_constant__ ConvParams p) {
+  using C = Cfg<BN>;
+  extern __shared__ unsigned char smem_raw[];
+  const unsigned base = (s32(smem_raw) + 1023u) & ~1023u;          // 128B swizzle atoms need 1024 B alignment
+  unsigned char *gbase = smem_raw + (base - s32(smem_raw));
+  // stage layout: [A hi (raw)] [A lo] [B hi] [B lo]
+  const unsigned bars = base + C::STAGES * C::STAGE_BYTES;
+  auto full_raw = [&](int s) { return bars + 8u * s; };
+  auto full_cvt = [&](int s) { return bars + 8u * (C::STAGES + s); };
+  auto empty = [&](int s) { return bars + 8u * (2 * C::STAGES + s); };
+  auto tmem_full = [&](int a) { return bars + 8u * (3 * C::STAGES + a); };
+  auto tmem_empty = [&](int a) { return bars + 8u * (3 * C::STAGES + 2 + a); };
+  const unsigned tmem_slot = bars + 8u * (3 * C::STAGES + 4);
+  volatile unsigned *tmem_slot_ptr = (volatile unsigned *)(gbase + C::STAGES * C::STAGE_BYTES + 8 * (3 * C::STAGES + 4));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_tiles = p.n_classes * p.tiles_n * p.tiles_y * p.tiles_x * p.n_blocks;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(full_raw(s), 1);
+      mbar_init(full_cvt(s), 4);
+      mbar_init(empty(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tmem_full(a), 1);
+      mbar_init(tmem_empty(a), 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapBhi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapBlo) : "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                 "r"((unsigned)C::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const unsigned tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int s = 0;
+      unsigned ph = 0;
+      const unsigned a_box_bytes = (unsigned)(p.TW * p.TH * p.TN) * BK * 4u;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(p, tile);
+        const int x0 = p.s_in * t.ix0, y0 = p.s_in * t.iy0;
+        for (int ti = p.class_start[t.cls]; ti < p.class_start[t.cls + 1]; ++ti) {
+          const Tap tap = p.taps[ti];
+          for (int kc = 0; kc < p.kblocks; ++kc) {
+            mbar_wait(empty(s), ph ^ 1u);
+            const unsigned st = base + s * C::STAGE_BYTES;
+            mbar_expect_tx(full_raw(s), a_box_bytes + 2u * C::B_BYTES);
+            tma_4d(st, &mapA, full_raw(s), kc * BK, x0 + tap.dx, y0 + tap.dy, t.n0);
+            tma_3d(st + 2 * A_BYTES, &mapBhi, full_raw(s), kc * BK, t.nb * BN, tap.widx);
+            tma_3d(st + 2 * A_BYTES + C::B_BYTES, &mapBlo, full_raw(s), kc * BK, t.nb * BN, tap.widx);
+            if (++s == C::STAGES) { s = 0; ph ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      // instruction descriptor: D fp32, A/B tf32, both K-major, N = BN, M = 128
+      const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(BN >> 3) << 17) | ((unsigned)(BM >> 4) << 24);
+      int s = 0, acc = 0;
+      unsigned ph = 0, aph = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(p, tile);
+        const int iters = (p.class_start[t.cls + 1] - p.class_start[t.cls]) * p.kblocks;
+        mbar_wait(tmem_empty(acc), aph ^ 1u);
+        tc_fence_after();
+        const unsigned d = tmem_base + (unsigned)(acc * BN);
+        for (int it = 0; it < iters; ++it) {
+          mbar_wait(full_raw(s), ph);        // weights landed (TMA)
+          mbar_wait(full_cvt(s), ph);        // activations split (converter warps)
+          tc_fence_after();
+          const unsigned st = base + s * C::STAGE_BYTES;
+          const unsigned long long a_hi = umma_desc_k128(st), a_lo = umma_desc_k128(st + A_BYTES);
+          const unsigned long long b_hi = umma_desc_k128(st + 2 * A_BYTES);
+          const unsigned long long b_lo = umma_desc_k128(st + 2 * A_BYTES + C::B_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 8; ++k) {            // UMMA K = 8 tf32 = 32 bytes: +2 in 16-byte units
+            const unsigned long long adv = (unsigned long long)(2 * k);
+            umma_tf32(d, a_lo + adv, b_hi + adv, idesc, (it | k) != 0);
+            umma_tf32(d, a_hi + adv, b_lo + adv, idesc, 1u);
+            umma_tf32(d, a_hi + adv, b_hi + adv, idesc, 1u);
+          }
+          umma_commit(empty(s));             // frees the stage when these MMAs have read it
+          if (++s == C::STAGES) { s = 0; ph ^= 1u; }
+        }
+        umma_commit(tmem_full(acc));         // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; aph ^= 1u; }
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ===================== activation split: hi in place, lo beside it =====================
+    const int tid = threadIdx.x - 128;
+    int s = 0;
+    unsigned ph = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(p, tile);
+      const int iters = (p.class_start[t.cls + 1] - p.class_start[t.cls]) * p.kblocks;
+      for (int it = 0; it < iters; ++it) {
+        mbar_wait(full_raw(s), ph);
+        float4 *a = reinterpret_cast<float4 *>(gbase + s * C::STAGE_BYTES);
+        float4 *l = reinterpret_cast<float4 *>(gbase + s * C::STAGE_BYTES + A_BYTES);
+#pragma unroll
+        for (int j = 0; j < A_BYTES / 16 / 128; ++j) {
+          const int i = tid + 128 * j;
+          const float4 v = a[i];
+          float4 h, r;
+          h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
+          r.x = v.x - h.x; r.y = v.y - h.y; r.z = v.z - h.z; r.w = v.w - h.w;
+          a[i] = h;
+          l[i] = r;
+        }
+        fence_proxy_async();                 // generic-proxy writes -> visible to the tensor core
+        __syncwarp();
+        if (lane == 0) mbar_arrive(full_cvt(s));
+        if (++s == C::STAGES) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp >= 8) {
+    // ===================== epilogue =====================
+    const int q = warp - 8;                  // == warp % 4: the TMEM lane quarter this warp may read
+    const int row = q * 32 + lane;
+    const int per_img = p.TW * p.TH;
+    const int tn = row / per_img, rem = row - tn * per_img;
+    const int ty = rem / p.TW, tx = rem - ty * p.TW;
+    int acc = 0;
+    unsigned aph = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(p, tile);
+      const int n = t.n0 + tn, iy = t.iy0 + ty, ix = t.ix0 + tx;
+      const bool valid = tn < p.TN && n < p.N && iy < p.Hit && ix < p.Wit;
+      const int oy = p.s_out * iy + p.class_py[t.cls], ox = p.s_out * ix + p.class_px[t.cls];
+      float *dst = p.out + (((long long)n * p.Hout + oy) * p.Wout + ox) * p.out_pitch + t.nb * BN;
+      mbar_wait(tmem_full(acc), aph);
+      tc_fence_after();
+#pragma unroll 1
+      for (int ch = 0; ch < BN / 32; ++ch) {
+        unsigned r[32];
+        tmem_ld32(tmem_base + ((unsigned)(q * 32) << 16) + (unsigned)(acc * BN + ch * 32), r);
+        const int c0 = t.nb * BN + ch * 32;          // first output channel of this chunk
+        if (valid && c0 < p.Cout) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int c = c0 + 4 * j;
+            float v[4] = {__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                          __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])};
+            if (c + 4 <= p.Cout) {
+              if (p.bias) {
+                const float4 b = __ldg(reinterpret_cast<const float4 *>(p.bias + c));
+                v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
+              }
+              if (p.act) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) v[e] = v[e] > 0.f ? v[e] : p.slope * v[e];
+              }
+              float4 *o = reinterpret_cast<float4 *>(dst + ch * 32) + j;
+              if (p.accumulate) {
+                const float4 old = *o;
+                v[0] += old.x; v[1] += old.y; v[2] += old.z; v[3] += old.w;
+              }
+              *o = make_float4(v[0], v[1], v[2], v[3]);
+            } else if (c < p.Cout) {               // channel tail (C_out not a multiple of 4)
+              for (int e = 0; e < 4 && c + e < p.Cout; ++e) {
+                float u = v[e] + (p.bias ? __ldg(p.bias + c + e) : 0.f);
+                if (p.act) u = u > 0.f ? u : p.slope * u;
+                float *o = dst + ch * 32 + 4 * j + e;
+                *o = p.accumulate ? *o + u : u;
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty(acc));
+      if (++acc == 2) { acc = 0; aph ^= 1u; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((unsigned)C::TMEM_COLS) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Weight planes: w -> hi = tf32(w), lo = w - hi, in the K-major layout [tap][R][Cp] the kernel's
+// B operand wants (R = output channels of the GEMM, C = contraction channels, Cp = C rounded up to
+// 4 so every TMA stride is a multiple of 16 bytes; the tail is zero).  The source is read through
+// strides, so the same kernel serves [Cout][kh][kw][Cin] and [Cin][kh][kw][Cout] variables and
+// their transposes (forward / input-gradient operands).  Runs once per optimiser step per layer.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+wsplit_kernel(const float *__restrict__ w, float *__restrict__ hi, float *__restrict__ lo, int taps, int R,
+              int C, int Cp, long long s_t, long long s_r, long long s_c, int r_fast) {
+  __shared__ float tile[32][33];
+  const int t = blockIdx.z;
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
+  for (int k = ty; k < 32; k += 8) {
+    // r_fast: consecutive threads walk r (the source is contiguous in r), else they walk c
+    const int r = r0 + (r_fast ? tx : k), c = c0 + (r_fast ? k : tx);
+    float v = 0.f;
+    if (r < R && c < C) v = w[t * s_t + r * s_r + c * s_c];
+    if (r_fast) tile[tx][k] = v; else tile[k][tx] = v;          // tile[r][c]
+  }
+  __syncthreads();
+  for (int k = ty; k < 32; k += 8) {
+    const int r = r0 + k, c = c0 + tx;
+    if (r < R && c < Cp) {
+      const float v = tile[k][tx];
+      const float h = tf32_rna(v);
+      const long long o = ((long long)t * R + r) * Cp + c;
+      hi[o] = h;
+      lo[o] = v - h;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Host side
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void *ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)ptr;
+  }
+  return fn;
+}
+static int encode(CUtensorMap *m, const float *basep, int rank, const cuuint64_t *dims,
+                  const cuuint64_t *strides_bytes, const cuuint32_t *box, const cuuint32_t *estr) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return UNFLOW_ECUDA; }
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, (void *)basep, dims, strides_bytes, box,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return UNFLOW_ECUDA; }
+  return UNFLOW_OK;
+}
+
+static int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+
+template <int BN>
+static int launch(const CUtensorMap &mA, const CUtensorMap &mBh, const CUtensorMap &mBl, const ConvParams &p,
+                  int total_tiles, cudaStream_t stream) {
+  using C = Cfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(tc_conv_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (e != cudaSuccess) { set_error("tc_conv: cannot opt in to %d bytes of shared memory: %s", C::SMEM_BYTES, cudaGetErrorString(e)); return UNFLOW_ECUDA; }
+    attr_set = true;
+  }
+  const int grid = total_tiles < kNumSMs ? total_tiles : kNumSMs;
+  tc_conv_kernel<BN><<<grid, NTHREADS, C::SMEM_BYTES, stream>>>(mA, mBh, mBl, p);
+  count_launch();
+  return check_launch("tc_conv_kernel");
+}
+
+}  // namespace tc
+}  // namespace unflow
+
+using namespace unflow;
+
+extern "C" int unflow_tc_wsplit(const float *w, float *w_hi, float *w_lo, int taps, int R, int C, long long s_t,
+                                long long s_r, long long s_c, void *stream) {
+  UNFLOW_REQUIRE(w && w_hi && w_lo && taps > 0 && R > 0 && C > 0, "tc_wsplit: bad arguments");
+  UNFLOW_REQUIRE(taps <= 65535 && (R + 31) / 32 <= 65535, "tc_wsplit: too many taps / rows");
+  const int Cp = (C + 3) / 4 * 4;
+  dim3 grid((Cp + 31) / 32, (R + 31) / 32, taps);
+  tc::wsplit_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(w, w_hi, w_lo, taps, R, C, Cp, s_t, s_r, s_c,
+                                                           (s_r == 1 && s_c != 1) ? 1 : 0);
+  count_launch();
+  return check_launch("tc_wsplit_kernel");
+}
+
+// Build the tap / class / tile description of one layer (host only; shared by the launcher and by
+// unflow_tc_conv_plan, which lets the CPU tests execute the same plan with plain loops).
+static int make_plan(tc::ConvParams &p, int &BN, int N, int Hin, int Win, int Cin, int Hout, int Wout, int Cout,
+                     int mode, int stride, int kh, int kw, int pad_t, int pad_l) {
+  UNFLOW_REQUIRE(N > 0 && Hin > 0 && Win > 0 && Cin > 0 && Hout > 0 && Wout > 0 && Cout > 0, "tc_conv: bad extents");
+  UNFLOW_REQUIRE(mode == 0 || mode == 1, "tc_conv: mode must be 0 (conv) or 1 (transposed)");
+  UNFLOW_REQUIRE(stride == 1 || stride == 2, "tc_conv: stride must be 1 or 2");
+  UNFLOW_REQUIRE(kh > 0 && kw > 0 && kh * kw <= tc::MAX_TAPS, "tc_conv: at most %d taps", tc::MAX_TAPS);
+  p.N = N; p.Cin = Cin; p.Cout = Cout; p.kblocks = (Cin + tc::BK - 1) / tc::BK;
+  p.Hout = Hout; p.Wout = Wout;
+  int nt = 0;
+  if (mode == 0) {
+    p.n_classes = 1; p.s_in = stride; p.s_out = 1; p.Hit = Hout; p.Wit = Wout;
+    p.class_px[0] = p.class_py[0] = 0;
+    p.class_start[0] = 0;
+    for (int ky = 0; ky < kh; ++ky)
+      for (int kx = 0; kx < kw; ++kx) p.taps[nt++] = tc::Tap{(short)(kx - pad_l), (short)(ky - pad_t), ky * kw + kx};
+    p.class_start[1] = nt;
+  } else {
+    UNFLOW_REQUIRE(Hout % stride == 0 && Wout % stride == 0, "tc_conv: transposed output extents must be multiples of the stride");
+    p.n_classes = stride * stride; p.s_in = 1; p.s_out = stride; p.Hit = Hout / stride; p.Wit = Wout / stride;
+    int c = 0;
+    for (int py = 0; py < stride; ++py)
+      for (int px = 0; px < stride; ++px, ++c) {
+        p.class_px[c] = (short)px; p.class_py[c] = (short)py;
+        p.class_start[c] = nt;
+        for (int ky = 0; ky < kh; ++ky) {
+          if (((py + pad_t - ky) % stride + stride) % stride) continue;
+          for (int kx = 0; kx < kw; ++kx) {
+            if (((px + pad_l - kx) % stride + stride) % stride) continue;
+            UNFLOW_REQUIRE(nt < tc::MAX_TAPS, "tc_conv: too many taps");
+            p.taps[nt++] = tc::Tap{(short)tc::floordiv(px + pad_l - kx, stride),
+                                   (short)tc::floordiv(py + pad_t - ky, stride), ky * kw + kx};
+          }
+        }
+      }
+    p.class_start[p.n_classes] = nt;
+    for (int c2 = 0; c2 < p.n_classes; ++c2)
+      UNFLOW_REQUIRE(p.class_start[c2 + 1] > p.class_start[c2], "tc_conv: an output parity class has no taps");
+  }
+  // tile box: fewest tiles over (TW, TH, TN) with TW*TH*TN <= 128 (ties: the widest rows)
+  long long best = -1;
+  for (int TW = 1; TW <= p.Wit && TW <= 128; ++TW)
+    for (int TH = 1; TH <= p.Hit && TW * TH <= 128; ++TH) {
+      int TN = 128 / (TW * TH);
+      if (TN > N) TN = N;
+      const long long tiles = (long long)((p.Wit + TW - 1) / TW) * ((p.Hit + TH - 1) / TH) * ((N + TN - 1) / TN);
+      if (best < 0 || tiles < best || (tiles == best && TW > p.TW)) {
+        best = tiles; p.TW = TW; p.TH = TH; p.TN = TN;
+      }
+    }
+  p.tiles_x = (p.Wit + p.TW - 1) / p.TW; p.tiles_y = (p.Hit + p.TH - 1) / p.TH; p.tiles_n = (N + p.TN - 1) / p.TN;
+  BN = Cout > 64 ? 128 : (Cout > 32 ? 64 : 32);     // channel tail: TMA zero rows, masked stores
+  p.n_blocks = (Cout + BN - 1) / BN;
+  const long long total = (long long)p.n_classes * p.tiles_n * p.tiles_y * p.tiles_x * p.n_blocks;
+  UNFLOW_REQUIRE(total < (1ll << 30), "tc_conv: too many tiles");
+  return UNFLOW_OK;
+}
+
+// Debug / test hook: the plan as integers --
+// [n_classes, s_in, s_out, Hit, Wit, TW, TH, TN, tiles_x, tiles_y, tiles_n, n_blocks, BN, kblocks, ntaps,
+//  class_start[5], (class_px, class_py)[4], (dx, dy, widx)[ntaps]]; returns the count written.
+extern "C" int unflow_tc_conv_plan(int N, int Hin, int Win, int Cin, int Hout, int Wout, int Cout, int mode,
+                                   int stride, int kh, int kw, int pad_t, int pad_l, int *out, int cap) {
+  tc::ConvParams p{};
+  int BN = 0;
+  if (make_plan(p, BN, N, Hin, Win, Cin, Hout, Wout, Cout, mode, stride, kh, kw, pad_t, pad_l)) return -1;
+  const int nt = p.class_start[p.n_classes];
+  const int need = 15 + 5 + 8 + 3 * nt;
+  if (!out || cap < need) return -need;
+  int i = 0;
+  const int head[15] = {p.n_classes, p.s_in, p.s_out, p.Hit, p.Wit, p.TW, p.TH, p.TN, p.tiles_x, p.tiles_y,
+                        p.tiles_n, p.n_blocks, BN, p.kblocks, nt};
+  for (int k = 0; k < 15; ++k) out[i++] = head[k];
+  for (int k = 0; k < 5; ++k) out[i++] = p.class_start[k];
+  for (int k = 0; k < 4; ++k) { out[i++] = p.class_px[k]; out[i++] = p.class_py[k]; }
+  for (int k = 0; k < nt; ++k) { out[i++] = p.taps[k].dx; out[i++] = p.taps[k].dy; out[i++] = p.taps[k].widx; }
+  return i;
+}
+
+// mode 0: y = conv(x, W; stride, TF-SAME offsets pad_t / pad_l)          taps (ky,kx) -> offset (ky-pad_t, kx-pad_l)
+// mode 1: y = conv_transpose(x, W; stride, padding pad_t / pad_l)        o = stride*i - pad + k
+// The weight planes are [kh*kw][Cout][Cin_p] (see unflow_tc_wsplit); tap index = ky*kw + kx.
+extern "C" int unflow_tc_conv(const float *x, int N, int Hin, int Win, int Cin, long long x_pitch,
+                              const float *w_hi, const float *w_lo, float *y, int Hout, int Wout, int Cout,
+                              long long y_pitch, const float *bias, float slope, int act, int accumulate,
+                              int mode, int stride, int kh, int kw, int pad_t, int pad_l, void *stream) {
+  UNFLOW_REQUIRE(x && w_hi && w_lo && y, "tc_conv: null pointer");
+  UNFLOW_REQUIRE(x_pitch % 4 == 0 && y_pitch % 4 == 0 && x_pitch >= Cin && y_pitch >= Cout,
+                 "tc_conv: channel pitches must be multiples of 4 floats");
+  UNFLOW_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0 && ((uintptr_t)w_hi & 15) == 0 &&
+                 ((uintptr_t)w_lo & 15) == 0 && (!bias || ((uintptr_t)bias & 15) == 0),
+                 "tc_conv: pointers must be 16-byte aligned");
+  tc::ConvParams p{};
+  int BN = 0;
+  int rc0 = make_plan(p, BN, N, Hin, Win, Cin, Hout, Wout, Cout, mode, stride, kh, kw, pad_t, pad_l);
+  if (rc0) return rc0;
+  p.out = y; p.out_pitch = y_pitch;
+  p.bias = bias; p.slope = slope; p.act = act; p.accumulate = accumulate;
+  const long long total = (long long)p.n_classes * p.tiles_n * p.tiles_y * p.tiles_x * p.n_blocks;
+
+  CUtensorMap mA, mBh, mBl;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)Win, (cuuint64_t)Hin, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)x_pitch * 4, (cuuint64_t)x_pitch * 4 * Win, (cuuint64_t)x_pitch * 4 * Win * Hin};
+    cuuint32_t box[4] = {(cuuint32_t)tc::BK, (cuuint32_t)(p.TW * p.s_in), (cuuint32_t)(p.TH * p.s_in), (cuuint32_t)p.TN};
+    cuuint32_t estr[4] = {1, (cuuint32_t)p.s_in, (cuuint32_t)p.s_in, 1};
+    int rc = tc::encode(&mA, x, 4, dims, strides, box, estr);
+    if (rc) return rc;
+  }
+  {
+    const int Cp = (Cin + 3) / 4 * 4;
+    cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)Cout, (cuuint64_t)(kh * kw)};
+    cuuint64_t strides[2] = {(cuuint64_t)Cp * 4, (cuuint64_t)Cp * 4 * Cout};
+    cuuint32_t box[3] = {(cuuint32_t)tc::BK, (cuuint32_t)BN, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    int rc = tc::encode(&mBh, w_hi, 3, dims, strides, box, estr);
+    if (rc) return rc;
+    rc = tc::encode(&mBl, w_lo, 3, dims, strides, box, estr);
+    if (rc) return rc;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (BN == 128) return tc::launch<128>(mA, mBh, mBl, p, (int)total, st);
+  if (BN == 64) return tc::launch<64>(mA, mBh, mBl, p, (int)total, st);
+  return tc::launch<32>(mA, mBh, mBl, p, (int)total, st);
+}

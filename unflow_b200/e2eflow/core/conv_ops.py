@@ -87,36 +87,6 @@ def _operand(x, order, concat_batch=False, c_pad=None, n_out=None, pads=(0, 0, 0
     return out.view(n_out, Hp, Wp, 3 * c_pad).permute(0, 3, 1, 2)
 
 
-# Opt-in (UNFLOW_BWD_STREAMS=1, not yet measured): the weight gradient of a layer on a second stream
-# next to its input gradient.  The two are independent, and many of the library kernels involved
-# run far below one wave of CTAs (profiles/r1_next_steps.md, item 1).
-BWD_STREAMS = __import__('os').environ.get('UNFLOW_BWD_STREAMS', '0') == '1'
-_side_streams = {}
-
-
-def _side_stream(device):
-    key = torch.device(device).index
-    if key not in _side_streams:
-        _side_streams[key] = torch.cuda.Stream(device=device)
-    return _side_streams[key]
-
-
-def _two_streams(device, main_fn, side_fn):
-    """Run ``side_fn`` on the side stream concurrently with ``main_fn`` on the current stream; both
-    see everything enqueued before the call, and the current stream waits for the side stream at
-    the end.  ``side_fn`` returns ``(result, tensors_used_later_on_the_current_stream)``."""
-    cur = torch.cuda.current_stream(device)
-    side = _side_stream(device)
-    side.wait_stream(cur)
-    with torch.cuda.stream(side):
-        side_result, handed_over = side_fn()
-    main_result = main_fn()
-    cur.wait_stream(side)
-    for t in handed_over:
-        t.record_stream(cur)
-    return main_result, side_result
-
-
 def _conv_input_grad(input_hw, weight, grad_output, stride):
     """Gradient of ``conv2d(x, weight, stride=stride, padding=0)`` w.r.t. ``x`` ([.., input_hw]).
 
@@ -186,13 +156,10 @@ class _Conv3x(torch.autograd.Function):
             gwp = nngrad.conv2d_weight(xb, (co_p, ci_p, k, k), gb3, stride=stride, padding=0)
             return gwp[:Co, :Ci], (gwp,)
 
-        if BWD_STREAMS and ctx.needs_input_grad[0] and ctx.needs_input_grad[1]:
-            gx, gw = _two_streams(x.device, input_grad, weight_grad)
-        else:
-            if ctx.needs_input_grad[0]:
-                gx = input_grad()
-            if ctx.needs_input_grad[1]:
-                gw = weight_grad()[0]
+        if ctx.needs_input_grad[0]:
+            gx = input_grad()
+        if ctx.needs_input_grad[1]:
+            gw = weight_grad()[0]
         if has_b and ctx.needs_input_grad[2]:
             gb = _bias_grad(g, a)
         return gx, gw, gb, None, None, None
@@ -242,15 +209,145 @@ class _Deconv3x(torch.autograd.Function):
             gwp = nngrad.conv2d_weight(gb3, (ci_p, co_p, 4, 4), xb, stride=2, padding=1)
             return gwp[:Ci, :Co], (gwp,)
 
-        if BWD_STREAMS and ctx.needs_input_grad[0] and ctx.needs_input_grad[1]:
-            gx, gw = _two_streams(x.device, input_grad, weight_grad)
-        else:
-            if ctx.needs_input_grad[0]:
-                gx = input_grad()
-            if ctx.needs_input_grad[1]:
-                gw = weight_grad()[0]
+        if ctx.needs_input_grad[0]:
+            gx = input_grad()
+        if ctx.needs_input_grad[1]:
+            gw = weight_grad()[0]
         if has_b and ctx.needs_input_grad[2]:
             gb = _bias_grad(g, a)
+        return gx, gw, gb, None
+
+
+# ---------------------------------------------------------------------------------------------
+# Hand-written tensor-core path (csrc/tc_conv.cu): tcgen05 implicit GEMM, 3xTF32 split in shared
+# memory, fused bias / leaky ReLU.  Forward and input gradient; the weight gradient still goes
+# through the library path below (round-2 work in progress: csrc/tc_wgrad).
+# ---------------------------------------------------------------------------------------------
+_TC = __import__('os').environ.get('UNFLOW_TC_CONV', '1') != '0'
+
+
+def _tc_ok(x, stride):
+    from . import tc_conv
+    return (_TC and _MODE == '3xtf32' and x.is_cuda and tc_conv.supported(x)
+            and (stride == 1 or (x.shape[2] % 2 == 0 and x.shape[3] % 2 == 0)))
+
+
+def _khwc(w):
+    """The variable in the memory order [dim0][kh][kw][dim1] the weight-plane kernel reads (how
+    FlowNetVariables stores it; derived tensors such as the space-to-depth filter are converted)."""
+    A, B, kh, kw = w.shape
+    want = (kh * kw * B, 1, kw * B, B)
+    if all(n == 1 or s == t for n, s, t in zip(w.shape, w.stride(), want)):
+        return w
+    return w.detach().contiguous(memory_format=torch.channels_last)
+
+
+def _lrelu_bwd_bias(g, act, want_bias):
+    """One pass over the incoming gradient: gpre = g * lrelu'(act) as a dense NHWC tensor and the bias
+    gradient sum_pixels gpre.  ``act`` None: no activation (gpre is g made dense)."""
+    from . import tc_conv
+    N, C, H, W = g.shape
+    dense = tc_conv.nhwc_geometry(g)
+    if act is None and not want_bias and dense is not None and dense[4] % 4 == 0 and g.data_ptr() % 16 == 0:
+        return g, None
+    gpre = tc_conv.empty_nhwc(N, C, H, W, g.device)
+    gb = torch.empty(C, device=g.device, dtype=torch.float32)
+    sN, sC, sH, sW = g.stride()
+    with torch.cuda.device(g.device):
+        check(_native.lib().unflow_lrelu_bwd_bias(g.data_ptr(), sN, sC, sH, sW,
+                                                  act.data_ptr() if act is not None else None,
+                                                  gpre.data_ptr(), gb.data_ptr(), N, C, H, W, LRELU_SLOPE,
+                                                  torch.cuda.current_stream().cuda_stream), "lrelu_bwd_bias")
+    return gpre, gb
+
+
+class _ConvTC(torch.autograd.Function):
+    """slim.conv2d on the hand-written tcgen05 kernel: y = act(conv(x, w; stride, TF SAME) + b)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, stride, pads, act):
+        from . import tc_conv
+        Co, Ci, k = w.shape[0], w.shape[1], w.shape[2]
+        N, _, H, W = x.shape
+        pt, pb, pl, pr = pads
+        Ho, Wo = (H + pt + pb - k) // stride + 1, (W + pl + pr - k) // stride + 1
+        buf = torch.empty((N, Ho, Wo, _round4(Co)), device=x.device, dtype=torch.float32)
+        y = buf[..., :Co].permute(0, 3, 1, 2)
+        tc_conv.run(x, tc_conv.split_weights(_khwc(w)), y, mode=0, stride=stride, kh=k, kw=k, pad_t=pt, pad_l=pl,
+                    bias=b, act=bool(act))
+        ctx.save_for_backward(x, w, y if act else None)
+        ctx.cfg = (stride, tuple(pads), b is not None, bool(act))
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        from . import tc_conv
+        x, w, a = ctx.saved_tensors
+        stride, pads, has_b, act = ctx.cfg
+        Co, Ci, k = w.shape[0], w.shape[1], w.shape[2]
+        N, _, H, W = x.shape
+        pt, pb, pl, pr = pads
+        gx = gw = gb = None
+        a_dense = a
+        if act and (tc_conv.nhwc_geometry(a)[4] != Co):
+            a_dense = a.contiguous(memory_format=torch.channels_last)       # C_out % 4 != 0 only
+        gpre, gb_all = _lrelu_bwd_bias(g, a_dense if act else None, has_b and ctx.needs_input_grad[2])
+        if has_b and ctx.needs_input_grad[2]:
+            gb = gb_all
+        if ctx.needs_input_grad[0]:
+            # dx = conv_transpose(gpre, w): rows of the GEMM = C_in, contraction = C_out
+            buf = torch.empty((N, H, W, _round4(Ci)), device=x.device, dtype=torch.float32)
+            gx = buf[..., :Ci].permute(0, 3, 1, 2)
+            tc_conv.run(gpre, tc_conv.split_weights(_khwc(w), transpose=True), gx, mode=1, stride=stride, kh=k, kw=k,
+                        pad_t=pt, pad_l=pl)
+        if ctx.needs_input_grad[1]:
+            ci_p, co_p = _round4(Ci), _round4(Co)
+            xb = _operand(x, 0, concat_batch=True, c_pad=ci_p, pads=pads)          # [3N, Ci_p, Hp, Wp]
+            gb3 = _operand(gpre, 1, concat_batch=True, c_pad=co_p)                 # [3N, Co_p, ..]
+            gw = nngrad.conv2d_weight(xb, (co_p, ci_p, k, k), gb3, stride=stride, padding=0)[:Co, :Ci]
+        return gx, gw, gb, None, None, None
+
+
+class _DeconvTC(torch.autograd.Function):
+    """slim.conv2d_transpose(k=4, stride=2, SAME) on the same kernel (four output-parity classes)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, act):
+        from . import tc_conv
+        Ci, Co = w.shape[0], w.shape[1]
+        N, _, H, W = x.shape
+        buf = torch.empty((N, 2 * H, 2 * W, _round4(Co)), device=x.device, dtype=torch.float32)
+        y = buf[..., :Co].permute(0, 3, 1, 2)
+        tc_conv.run(x, tc_conv.split_weights(_khwc(w), transpose=True), y, mode=1, stride=2, kh=4, kw=4, pad_t=1,
+                    pad_l=1, bias=b, act=bool(act))
+        ctx.save_for_backward(x, w, y if act else None)
+        ctx.cfg = (b is not None, bool(act))
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        from . import tc_conv
+        x, w, a = ctx.saved_tensors
+        has_b, act = ctx.cfg
+        Ci, Co = w.shape[0], w.shape[1]
+        N, _, H, W = x.shape
+        gx = gw = gb = None
+        a_dense = a
+        if act and (tc_conv.nhwc_geometry(a)[4] != Co):
+            a_dense = a.contiguous(memory_format=torch.channels_last)
+        gpre, gb_all = _lrelu_bwd_bias(g, a_dense if act else None, has_b and ctx.needs_input_grad[2])
+        if has_b and ctx.needs_input_grad[2]:
+            gb = gb_all
+        if ctx.needs_input_grad[0]:
+            # dx = conv(gpre, w; stride 2, pad 1): rows = C_in (dim 0 of the IOHW variable), contraction = C_out
+            buf = torch.empty((N, H, W, _round4(Ci)), device=x.device, dtype=torch.float32)
+            gx = buf[..., :Ci].permute(0, 3, 1, 2)
+            tc_conv.run(gpre, tc_conv.split_weights(_khwc(w)), gx, mode=0, stride=2, kh=4, kw=4, pad_t=1, pad_l=1)
+        if ctx.needs_input_grad[1]:
+            ci_p, co_p = _round4(Ci), _round4(Co)
+            gb3 = _operand(gpre, 0, concat_batch=True, c_pad=co_p)
+            xb = _operand(x, 1, concat_batch=True, c_pad=ci_p)
+            gw = nngrad.conv2d_weight(gb3, (ci_p, co_p, 4, 4), xb, stride=2, padding=1)[:Ci, :Co]
         return gx, gw, gb, None
 
 
@@ -260,17 +357,8 @@ NARROW_MIN_TILES = 96
 _NARROW = __import__('os').environ.get('UNFLOW_NARROW_CONV', '1') != '0'
 
 
-NARROW_LOADER = int(__import__('os').environ.get('UNFLOW_NARROW_LOADER', '1'))   # 1: cp.async staging (measured 1.5 % of the step faster), 0: synchronous
-_narrow_ready = False
-
-
 def _narrow_lib():
-    global _narrow_ready
-    lib = _native.lib()
-    if not _narrow_ready:
-        check(lib.unflow_set_int_option(b"narrow_loader", NARROW_LOADER), "narrow_loader option")
-        _narrow_ready = True
-    return lib
+    return _native.lib()
 
 
 def _narrow_tiles(N, H, W):
@@ -278,10 +366,16 @@ def _narrow_tiles(N, H, W):
 
 
 def _use_narrow(x, w, stride, pads):
+    from . import tc_conv
     return (_NARROW and w.shape[0] == 2 and w.shape[2] == 3 and w.shape[3] == 3 and stride in (1, (1, 1))
             and tuple(pads) == (1, 1, 1, 1) and x.shape[1] % 2 == 0 and x.dtype == torch.float32
-            and x.is_contiguous(memory_format=torch.channels_last)
+            and tc_conv.nhwc_geometry(x) is not None        # NHWC memory, possibly a slice of a concat buffer
             and _narrow_tiles(x.shape[0], x.shape[2], x.shape[3]) >= NARROW_MIN_TILES)
+
+
+def _pixel_pitch(x):
+    from . import tc_conv
+    return tc_conv.nhwc_geometry(x)[4]
 
 
 class _NarrowConv3x3(torch.autograd.Function):
@@ -299,7 +393,7 @@ class _NarrowConv3x3(torch.autograd.Function):
         from ..ops import kernel_timer
         with torch.cuda.device(x.device), kernel_timer.span("narrow_conv_fwd", 4 * x.numel() + 4 * y.numel()):
             check(_narrow_lib().unflow_conv3x3_narrow_fwd(
-                x.data_ptr(), wl.data_ptr(), b.data_ptr() if b is not None else None, y.data_ptr(),
+                x.data_ptr(), _pixel_pitch(x), wl.data_ptr(), b.data_ptr() if b is not None else None, y.data_ptr(),
                 N, H, W, C, 2, torch.cuda.current_stream().cuda_stream), "conv3x3_narrow_fwd")
         ctx.save_for_backward(x, w)
         ctx.has_b = b is not None
@@ -324,7 +418,7 @@ class _NarrowConv3x3(torch.autograd.Function):
             from ..ops import kernel_timer
             with torch.cuda.device(x.device), kernel_timer.span("narrow_conv_wgrad", 4 * x.numel() + 4 * g.numel()):
                 check(lib.unflow_conv3x3_narrow_wgrad(
-                    x.data_ptr(), g.data_ptr(), sN, sC, sH, sW, gw.data_ptr(), ws.data_ptr(),
+                    x.data_ptr(), _pixel_pitch(x), g.data_ptr(), sN, sC, sH, sW, gw.data_ptr(), ws.data_ptr(),
                     N, H, W, C, 2, torch.cuda.current_stream().cuda_stream), "conv3x3_narrow_wgrad")
             gw = gw.permute(0, 3, 1, 2)                                           # [2, C, 3, 3], NHWC-ordered
         if ctx.has_b and ctx.needs_input_grad[2]:
@@ -386,6 +480,8 @@ def conv2d(x, w, b, stride, pads, act=False):
         if _use_space_to_depth(x, w, stride):
             xs, ws = space_to_depth_operands(x, w, pads)
             return conv2d(xs, ws, b, 1, (0, 0, 0, 0), act=act)
+        if _tc_ok(x, stride) and w.shape[2] == w.shape[3] and w.shape[2] * w.shape[3] <= 64:
+            return _ConvTC.apply(x, w, b, stride, tuple(pads), bool(act))
         fuse = act and b is not None and w.shape[0] % 4 == 0
         y = _Conv3x.apply(x, w, b, stride, tuple(pads), fuse)
         return F.leaky_relu(y, LRELU_SLOPE) if (act and not fuse) else y
@@ -403,6 +499,8 @@ def conv2d(x, w, b, stride, pads, act=False):
 
 def conv_transpose2d(x, w, b, act=False):
     if _MODE == '3xtf32' and x.is_cuda:
+        if _tc_ok(x, 1):
+            return _DeconvTC.apply(x, w, b, bool(act))
         fuse = act and b is not None and w.shape[1] % 4 == 0
         y = _Deconv3x.apply(x, w, b, fuse)
         return F.leaky_relu(y, LRELU_SLOPE) if (act and not fuse) else y

@@ -371,8 +371,11 @@ class _ConcatCL(torch.autograd.Function):
         n = first[0].shape[0]
         c = sum(t.shape[1] for t in first) + (second[0].shape[1] if second else 0)
         h, w = first[0].shape[2], first[0].shape[3]
-        out = torch.empty((n, c, h, w), device=first[0].device, dtype=first[0].dtype,
-                          memory_format=torch.channels_last)
+        # NHWC buffer whose pixel pitch is a multiple of 4 floats (16 bytes): the tensor-core conv
+        # kernels read channel slices of it in place through TMA tensor maps (csrc/tc_conv.cu); the
+        # returned tensor is the [:, :c] view (the 1..3 slack channels are never read)
+        buf = torch.empty((n, h, w, (c + 3) // 4 * 4), device=first[0].device, dtype=first[0].dtype)
+        out = buf[..., :c].permute(0, 3, 1, 2)
         spans, off = [], 0
         for t in first:
             out[:, off:off + t.shape[1]].copy_(t)

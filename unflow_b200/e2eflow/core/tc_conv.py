@@ -1,0 +1,98 @@
+"""Host side of csrc/tc_conv.cu: the hand-written tcgen05 (3xTF32, TMEM accumulators) implicit-GEMM
+convolution behind the conv / deconv stacks (reference slim.conv2d / slim.conv2d_transpose,
+src/e2eflow/core/flownet.py:166-233, :89-155).
+
+All tensors are NHWC in memory (what torch calls channels_last); a tensor may be a channel slice of
+a wider buffer (a concat buffer): the kernels take the channel PITCH separately.  No fallback: the
+functions raise when the CUDA library is missing or the shape is not served (``supported`` says which
+shapes are)."""
+import torch
+
+from ... import _native
+from ..._native import check
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def round4(c):
+    return (c + 3) // 4 * 4
+
+
+def nhwc_geometry(t):
+    """(N, H, W, C, channel pitch) of an NCHW-shaped tensor whose memory is NHWC (channels_last),
+    possibly a channel slice of a wider NHWC buffer; None when the memory is laid out otherwise."""
+    if t.dim() != 4:
+        return None
+    N, C, H, W = t.shape
+    sN, sC, sH, sW = t.stride()
+    if C > 1 and sC != 1:
+        return None
+    pitch = sW if W > 1 else (sH if H > 1 else max(C, 1))
+    if pitch < C or (W > 1 and sW != pitch) or (H > 1 and sH != W * pitch) or (N > 1 and sN != H * W * pitch):
+        return None
+    return N, H, W, C, pitch
+
+
+def supported(x):
+    """Tensors the tensor-core kernel reads or writes: NHWC memory, 16-byte aligned base, channel
+    pitch a multiple of 4 floats."""
+    g = nhwc_geometry(x)
+    return (x.is_cuda and x.dtype == torch.float32 and g is not None and g[4] % 4 == 0
+            and x.data_ptr() % 16 == 0)
+
+
+class WeightPlanes:
+    """hi / lo TF32 planes of one variable in the K-major layout [taps][rows][Cp] (rows = the GEMM's
+    output channels, Cp = contraction channels rounded up to 4)."""
+
+    def __init__(self, hi, lo, taps, rows, cols):
+        self.hi, self.lo, self.taps, self.rows, self.cols = hi, lo, taps, rows, cols
+
+
+def split_weights(w, transpose=False):
+    """``w``: a conv variable [A, B, kh, kw] stored NHWC-ordered ([A][kh][kw][B] in memory -- OIHW
+    convolution weights or IOHW transposed-convolution weights, core/flownet.py FlowNetVariables).
+    Returns planes with rows = A and contraction = B (``transpose=False``) or rows = B and
+    contraction = A (``transpose=True``)."""
+    A, B, kh, kw = w.shape
+    want = (kh * kw * B, 1, kw * B, B)
+    assert all(n == 1 or s == t for n, s, t in zip(w.shape, w.stride(), want)), \
+        "weights must be stored [A][kh][kw][B] (got strides %s)" % (w.stride(),)
+    taps = kh * kw
+    if transpose:
+        rows, cols, s_t, s_r, s_c = B, A, B, 1, taps * B
+    else:
+        rows, cols, s_t, s_r, s_c = A, B, B, taps * B, 1
+    cp = round4(cols)
+    hi = torch.empty((taps, rows, cp), device=w.device, dtype=torch.float32)
+    lo = torch.empty_like(hi)
+    with torch.cuda.device(w.device):
+        check(_native.lib().unflow_tc_wsplit(w.data_ptr(), hi.data_ptr(), lo.data_ptr(), taps, rows, cols,
+                                             s_t, s_r, s_c, _stream()), "tc_wsplit")
+    return WeightPlanes(hi, lo, taps, rows, cols)
+
+
+def run(x, planes, out, *, mode, stride, kh, kw, pad_t, pad_l, bias=None, act=False, accumulate=False,
+        slope=0.1):
+    """out (+)= act(bias + conv(x)) -- ``x`` / ``out``: NCHW-shaped tensors with NHWC memory (channel
+    slices allowed).  mode 0: convolution with offsets (pad_t, pad_l); mode 1: transposed convolution
+    (o = stride * i - pad + k)."""
+    gx, go = nhwc_geometry(x), nhwc_geometry(out)
+    assert gx is not None and go is not None, "tc_conv needs NHWC (channels_last) memory"
+    N, Hin, Win, Cin, xp = gx
+    No, Hout, Wout, Cout, yp = go
+    assert No == N and planes.rows == Cout and planes.cols == Cin and planes.taps == kh * kw
+    with torch.cuda.device(x.device):
+        check(_native.lib().unflow_tc_conv(
+            x.data_ptr(), N, Hin, Win, Cin, xp, planes.hi.data_ptr(), planes.lo.data_ptr(),
+            out.data_ptr(), Hout, Wout, Cout, yp, bias.data_ptr() if bias is not None else None,
+            float(slope), 1 if act else 0, 1 if accumulate else 0, mode, stride, kh, kw, pad_t, pad_l,
+            _stream()), "tc_conv")
+    return out
+
+
+def empty_nhwc(N, C, H, W, device):
+    """An NCHW-shaped tensor with dense NHWC memory."""
+    return torch.empty((N, H, W, C), device=device, dtype=torch.float32).permute(0, 3, 1, 2)
