@@ -243,8 +243,8 @@ int unflow_conv3x3_narrow_wgrad(const float *x, long long x_pitch, const float *
  *   element (t, r, c) is read from w[t*s_t + r*s_r + c*s_c] (strides in floats).
  * unflow_tc_conv:
  *   x  NHWC [N,Hin,Win,Cin], `x_pitch` floats between pixels (a channel slice of a wider buffer is
- *      allowed); y NHWC [N,Hout,Wout,Cout] with `y_pitch`; pitches % 4 == 0, pointers 16-byte
- *      aligned.
+ *      allowed); y NHWC [N,Hout,Wout,Cout] with `y_pitch`; pitches % 4 == 0; x, y and the weight
+ *      planes 16-byte aligned (bias: any float address).
  *   mode 0  y[oy,ox] = sum_k x[stride*oy - pad_t + ky, stride*ox - pad_l + kx] W[ky*kw+kx]
  *           (slim.conv2d; TF SAME padding enters as the offsets pad_t / pad_l, zero outside)
  *   mode 1  y[stride*iy - pad_t + ky, stride*ix - pad_l + kx] += x[iy,ix] W[ky*kw+kx]

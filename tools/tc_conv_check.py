@@ -53,7 +53,7 @@ def case_conv(name, N, Cin, Cout, H, W, k, stride, pads, bias=True, act=True, pi
     x = make_x(N, Cin, H, W, pitch, seed=Cin + H, image_like=image_like)
     g = torch.Generator().manual_seed(Cout + k)
     w = cl((torch.randn(Cout, Cin, k, k, generator=g) * (2.0 / (Cin * k * k)) ** 0.5).to(dev))
-    b = (torch.randn(Cout, generator=g) * 0.1).to(dev) if bias else None
+    b = (torch.randn(Cout + 1, generator=g) * 0.1).to(dev)[1:] if bias else None     # 4-byte aligned only
     Ho, Wo = (H + pt + pb - k) // stride + 1, (W + pl + pr - k) // stride + 1
     ref = F.conv2d(F.pad(x.double(), (pl, pr, pt, pb)), w.double(), b.double() if bias else None, stride=stride)
     base = torch.randn(N, Cout, Ho, Wo, device=dev).contiguous(memory_format=torch.channels_last) if accumulate else None

@@ -26,26 +26,30 @@
 //              into a second buffer (same swizzled layout: the split is element-wise).
 //   warp 1     one thread issues tcgen05.mma kind::tf32, three per K step:
 //              lo*hi' + hi*lo' + hi*hi' accumulate in fp32 in TENSOR MEMORY (double-buffered).
-//   warps 8-11 epilogue: tcgen05.ld -> bias + leaky ReLU (or += for gradient accumulation) ->
-//              float4 stores straight into the destination (which may be a channel slice of a
-//              concat buffer, with stride 2 for the transposed classes).
+//   warps 8-15 epilogue: the K loop is cut into CHUNKS of 4 K blocks; the tensor core accumulates one
+//              chunk in tensor memory, these warps read it back (tcgen05.ld) and add it to fp32
+//              REGISTER accumulators with round-to-nearest while the next chunk is being multiplied
+//              into the other TMEM buffer (see "Accuracy"); after the last chunk: bias + leaky ReLU
+//              (or += for gradient accumulation) -> float4 stores straight into the destination
+//              (which may be a channel slice of a concat buffer, with stride 2 for the transposed
+//              classes).  Two warps share a TMEM lane quarter, each owns half of the BN columns.
 // The activations are read from HBM once, as fp32; no [hi,hi,lo] operand copies exist, no layout
 // conversion, no separate bias / activation pass (round 1 spent 30 % of the step on those).
 //
 // Accuracy: hi carries 11 significant bits, lo the next 11; the dropped lo*lo' term and the
-// truncation of lo are ~2^-22 relative -- the same 3xTF32 arithmetic the parity tests accept.
-#include <cuda.h>
-
-#include "common.cuh"
+// truncation of lo are ~2^-22 relative.  What limits a long tensor-core accumulation is not the
+// split but the accumulator itself: the MMA adds with truncation, a bias of a fraction of an ulp
+// per instruction that grows LINEARLY with K (measured on B200, this kernel with one accumulation
+// over all of K and cuDNN's TF32 kernels alike: max error / max|y| = 6.8e-9 * K, i.e. 6e-5 at
+// K = 9216 where an fp32 FMA loop has 2e-5; profiles/r2_tc_conv.md).  Cutting K into chunks of
+// 128 and summing the chunks in fp32 registers (round to nearest) removes that term.
+#include "tc_common.cuh"
 
 namespace unflow {
 namespace tc {
 
-constexpr int BM = 128;          // UMMA M: output positions per tile
-constexpr int BK = 32;           // fp32 channels per K block = 128 bytes = one swizzle row
 constexpr int MAX_TAPS = 64;
-constexpr int NTHREADS = 384;    // 12 warps, see the role table above
-constexpr int A_BYTES = BM * BK * 4;   // 16 KB
+constexpr int NTHREADS = 512;    // 16 warps, see the role table above
 
 struct Tap {
   short dx, dy;
@@ -77,84 +81,6 @@ struct Cfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;   // two accumulator buffers
 };
-
-// ------------------------------------------------------------------------------------------
-// PTX helpers
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned s32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(unsigned bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(unsigned bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
-  unsigned done;
-  do {
-    asm volatile(
-        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        " selp.u32 %0, 1, 0, p;\n}\n"
-        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-  } while (!done);
-}
-__device__ __forceinline__ void tma_4d(unsigned dst, const CUtensorMap *map, unsigned bar, int c0, int c1,
-                                       int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-}
-__device__ __forceinline__ void tma_3d(unsigned dst, const CUtensorMap *map, unsigned bar, int c0, int c1,
-                                       int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() {
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-// K-major operand tile, 128-byte swizzle: rows of 128 B, 8-row atoms of 1024 B (SBO), descriptor
-// version 1 (sm_100), layout type 2 = SWIZZLE_128B.  (cute::UMMA::SmemDescriptor bit layout.)
-__device__ __forceinline__ unsigned long long umma_desc_k128(unsigned saddr) {
-  return (unsigned long long)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) |
-         (2ull << 61);
-}
-// D[tmem] (+)= A[smem] * B[smem]^T, tf32 inputs, fp32 accumulate
-__device__ __forceinline__ void umma_tf32(unsigned d_tmem, unsigned long long adesc, unsigned long long bdesc,
-                                          unsigned idesc, unsigned accumulate) {
-  asm volatile(
-      "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n"
-      " tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n"
-      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit(unsigned bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(unsigned taddr, unsigned (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
-      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr) : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ float tf32_rna(float x) {
-  unsigned u;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-  return __uint_as_float(u);
-}
 
 struct TileCoord {
   int cls, n0, iy0, ix0, nb;
@@ -201,7 +127,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tmem_full(a), 1);
-      mbar_init(tmem_empty(a), 4);
+      mbar_init(tmem_empty(a), 8);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
@@ -251,10 +177,13 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const TileCoord t = decode_tile(p, tile);
         const int iters = (p.class_start[t.cls + 1] - p.class_start[t.cls]) * p.kblocks;
-        mbar_wait(tmem_empty(acc), aph ^ 1u);
-        tc_fence_after();
-        const unsigned d = tmem_base + (unsigned)(acc * BN);
         for (int it = 0; it < iters; ++it) {
+          const int in_chunk = it % CHUNK;
+          if (in_chunk == 0) {               // a fresh TMEM accumulator for every chunk of K
+            mbar_wait(tmem_empty(acc), aph ^ 1u);
+            tc_fence_after();
+          }
+          const unsigned d = tmem_base + (unsigned)(acc * BN);
           mbar_wait(full_raw(s), ph);        // weights landed (TMA)
           mbar_wait(full_cvt(s), ph);        // activations split (converter warps)
           tc_fence_after();
@@ -265,15 +194,17 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll
           for (int k = 0; k < BK / 8; ++k) {            // UMMA K = 8 tf32 = 32 bytes: +2 in 16-byte units
             const unsigned long long adv = (unsigned long long)(2 * k);
-            umma_tf32(d, a_lo + adv, b_hi + adv, idesc, (it | k) != 0);
+            umma_tf32(d, a_lo + adv, b_hi + adv, idesc, (in_chunk | k) != 0);
             umma_tf32(d, a_hi + adv, b_lo + adv, idesc, 1u);
             umma_tf32(d, a_hi + adv, b_hi + adv, idesc, 1u);
           }
           umma_commit(empty(s));             // frees the stage when these MMAs have read it
           if (++s == C::STAGES) { s = 0; ph ^= 1u; }
+          if (in_chunk == CHUNK - 1 || it == iters - 1) {
+            umma_commit(tmem_full(acc));     // chunk complete -> epilogue warps add it to their registers
+            if (++acc == 2) { acc = 0; aph ^= 1u; }
+          }
         }
-        umma_commit(tmem_full(acc));         // accumulator complete -> epilogue
-        if (++acc == 2) { acc = 0; aph ^= 1u; }
       }
     }
   } else if (warp >= 4 && warp < 8) {
@@ -305,8 +236,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       }
     }
   } else if (warp >= 8) {
-    // ===================== epilogue =====================
-    const int q = warp - 8;                  // == warp % 4: the TMEM lane quarter this warp may read
+    // ===================== epilogue: fp32 register accumulation over the K chunks =====================
+    constexpr int COLS = BN / 2;             // columns per thread: warps 8-11 take the low half, 12-15 the high half
+    const int q = warp & 3;                  // the TMEM lane quarter this warp may read (warp id % 4)
+    const int half = (warp - 8) >> 2;
     const int row = q * 32 + lane;
     const int per_img = p.TW * p.TH;
     const int tn = row / per_img, rem = row - tn * per_img;
@@ -315,53 +248,62 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     unsigned aph = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile(p, tile);
+      const int iters = (p.class_start[t.cls + 1] - p.class_start[t.cls]) * p.kblocks;
+      const int chunks = (iters + CHUNK - 1) / CHUNK;
+      float sum[COLS];
+#pragma unroll
+      for (int c = 0; c < COLS; ++c) sum[c] = 0.f;
+      for (int ck = 0; ck < chunks; ++ck) {
+        mbar_wait(tmem_full(acc), aph);
+        tc_fence_after();
+        const unsigned taddr = tmem_base + ((unsigned)(q * 32) << 16) + (unsigned)(acc * BN + half * COLS);
+#pragma unroll
+        for (int c0 = 0; c0 < COLS; c0 += 16) {
+          unsigned r[16];
+          tmem_ld16(taddr + (unsigned)c0, r);
+#pragma unroll
+          for (int e = 0; e < 16; ++e) sum[c0 + e] += __uint_as_float(r[e]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tmem_empty(acc));
+        if (++acc == 2) { acc = 0; aph ^= 1u; }
+      }
       const int n = t.n0 + tn, iy = t.iy0 + ty, ix = t.ix0 + tx;
       const bool valid = tn < p.TN && n < p.N && iy < p.Hit && ix < p.Wit;
       const int oy = p.s_out * iy + p.class_py[t.cls], ox = p.s_out * ix + p.class_px[t.cls];
-      float *dst = p.out + (((long long)n * p.Hout + oy) * p.Wout + ox) * p.out_pitch + t.nb * BN;
-      mbar_wait(tmem_full(acc), aph);
-      tc_fence_after();
-#pragma unroll 1
-      for (int ch = 0; ch < BN / 32; ++ch) {
-        unsigned r[32];
-        tmem_ld32(tmem_base + ((unsigned)(q * 32) << 16) + (unsigned)(acc * BN + ch * 32), r);
-        const int c0 = t.nb * BN + ch * 32;          // first output channel of this chunk
-        if (valid && c0 < p.Cout) {
+      const int cbase = t.nb * BN + half * COLS;          // first output channel of this thread
+      if (valid && cbase < p.Cout) {
+        float *dst = p.out + (((long long)n * p.Hout + oy) * p.Wout + ox) * p.out_pitch + cbase;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int c = c0 + 4 * j;
-            float v[4] = {__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
-                          __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])};
-            if (c + 4 <= p.Cout) {
-              if (p.bias) {
-                const float4 b = __ldg(reinterpret_cast<const float4 *>(p.bias + c));
-                v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
-              }
-              if (p.act) {
+        for (int j = 0; j < COLS / 4; ++j) {
+          const int c = cbase + 4 * j;
+          float v[4] = {sum[4 * j], sum[4 * j + 1], sum[4 * j + 2], sum[4 * j + 3]};
+          if (c + 4 <= p.Cout) {
+            if (p.bias) {                          // scalar loads: a bias is a view into the flat variable
+#pragma unroll                                     // buffer at any 4-byte offset
+              for (int e = 0; e < 4; ++e) v[e] += __ldg(p.bias + c + e);
+            }
+            if (p.act) {
 #pragma unroll
-                for (int e = 0; e < 4; ++e) v[e] = v[e] > 0.f ? v[e] : p.slope * v[e];
-              }
-              float4 *o = reinterpret_cast<float4 *>(dst + ch * 32) + j;
-              if (p.accumulate) {
-                const float4 old = *o;
-                v[0] += old.x; v[1] += old.y; v[2] += old.z; v[3] += old.w;
-              }
-              *o = make_float4(v[0], v[1], v[2], v[3]);
-            } else if (c < p.Cout) {               // channel tail (C_out not a multiple of 4)
-              for (int e = 0; e < 4 && c + e < p.Cout; ++e) {
-                float u = v[e] + (p.bias ? __ldg(p.bias + c + e) : 0.f);
-                if (p.act) u = u > 0.f ? u : p.slope * u;
-                float *o = dst + ch * 32 + 4 * j + e;
-                *o = p.accumulate ? *o + u : u;
-              }
+              for (int e = 0; e < 4; ++e) v[e] = v[e] > 0.f ? v[e] : p.slope * v[e];
+            }
+            float4 *o = reinterpret_cast<float4 *>(dst) + j;
+            if (p.accumulate) {
+              const float4 old = *o;
+              v[0] += old.x; v[1] += old.y; v[2] += old.z; v[3] += old.w;
+            }
+            *o = make_float4(v[0], v[1], v[2], v[3]);
+          } else if (c < p.Cout) {                 // channel tail (C_out not a multiple of 4)
+            for (int e = 0; e < 4 && c + e < p.Cout; ++e) {
+              float u = v[e] + (p.bias ? __ldg(p.bias + c + e) : 0.f);
+              if (p.act) u = u > 0.f ? u : p.slope * u;
+              float *o = dst + 4 * j + e;
+              *o = p.accumulate ? *o + u : u;
             }
           }
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tmem_empty(acc));
-      if (++acc == 2) { acc = 0; aph ^= 1u; }
     }
   }
   tc_fence_before();
@@ -408,34 +350,6 @@ wsplit_kernel(const float *__restrict__ w, float *__restrict__ hi, float *__rest
 // ------------------------------------------------------------------------------------------
 // Host side
 // ------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
-                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
-                                  CUtensorMapFloatOOBfill);
-static EncodeTiledFn encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
-    void *ptr = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = (EncodeTiledFn)ptr;
-  }
-  return fn;
-}
-static int encode(CUtensorMap *m, const float *basep, int rank, const cuuint64_t *dims,
-                  const cuuint64_t *strides_bytes, const cuuint32_t *box, const cuuint32_t *estr) {
-  EncodeTiledFn fn = encode_fn();
-  if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return UNFLOW_ECUDA; }
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, (void *)basep, dims, strides_bytes, box,
-                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return UNFLOW_ECUDA; }
-  return UNFLOW_OK;
-}
-
 static int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
 
 template <int BN>
@@ -562,8 +476,7 @@ extern "C" int unflow_tc_conv(const float *x, int N, int Hin, int Win, int Cin, 
   UNFLOW_REQUIRE(x_pitch % 4 == 0 && y_pitch % 4 == 0 && x_pitch >= Cin && y_pitch >= Cout,
                  "tc_conv: channel pitches must be multiples of 4 floats");
   UNFLOW_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0 && ((uintptr_t)w_hi & 15) == 0 &&
-                 ((uintptr_t)w_lo & 15) == 0 && (!bias || ((uintptr_t)bias & 15) == 0),
-                 "tc_conv: pointers must be 16-byte aligned");
+                 ((uintptr_t)w_lo & 15) == 0, "tc_conv: x, y and the weight planes must be 16-byte aligned");
   tc::ConvParams p{};
   int BN = 0;
   int rc0 = make_plan(p, BN, N, Hin, Win, Cin, Hout, Wout, Cout, mode, stride, kh, kw, pad_t, pad_l);

@@ -480,7 +480,8 @@ def conv2d(x, w, b, stride, pads, act=False):
         if _use_space_to_depth(x, w, stride):
             xs, ws = space_to_depth_operands(x, w, pads)
             return conv2d(xs, ws, b, 1, (0, 0, 0, 0), act=act)
-        if _tc_ok(x, stride) and w.shape[2] == w.shape[3] and w.shape[2] * w.shape[3] <= 64:
+        if (_tc_ok(x, stride) and w.shape[2] == w.shape[3] and w.shape[2] * w.shape[3] <= 64
+                and w.shape[0] % 4 == 0):       # (the 2-channel flow heads keep their own kernels / the library)
             return _ConvTC.apply(x, w, b, stride, tuple(pads), bool(act))
         fuse = act and b is not None and w.shape[0] % 4 == 0
         y = _Conv3x.apply(x, w, b, stride, tuple(pads), fuse)
@@ -499,7 +500,7 @@ def conv2d(x, w, b, stride, pads, act=False):
 
 def conv_transpose2d(x, w, b, act=False):
     if _MODE == '3xtf32' and x.is_cuda:
-        if _tc_ok(x, 1):
+        if _tc_ok(x, 1) and w.shape[1] % 4 == 0:
             return _DeconvTC.apply(x, w, b, bool(act))
         fuse = act and b is not None and w.shape[1] % 4 == 0
         y = _Deconv3x.apply(x, w, b, fuse)
