@@ -262,6 +262,21 @@ int unflow_tc_conv(const float *x, int N, int Hin, int Win, int Cin, long long x
                    long long y_pitch, const float *bias, float slope, int act, int accumulate,
                    int mode, int stride, int kh, int kw, int pad_t, int pad_l, void *stream);
 
+/* unflow_tc_wgrad (csrc/tc_wgrad.cu): weight gradient of the same layers, same arithmetic (both operands
+ * split in shared memory, MN-major tcgen05 operands straight from the NHWC activations, fp32 register
+ * accumulation, split-K):
+ *     dw[r * pitch_r + t * pitch_t + c] += sum_p P[p][r] * G[stride * p + (k - pad)][c],   t = ky*kw + kx
+ *   slim.conv2d:            P = dL/dy [N,Hp,Wp,R=C_out],  G = x     [N,Hg,Wg,C=C_in]
+ *   slim.conv2d_transpose:  P = x     [N,Hp,Wp,R=C_in],   G = dL/dy [N,Hg,Wg,C=C_out], stride 2
+ * P / G: NHWC with pixel pitches (multiples of 4 floats), 16-byte aligned.  dw is ACCUMULATED with
+ * fp32 atomics (the caller zeroes it); the summation order is not fixed.  unflow_tc_wgrad_plan: the
+ * launcher's K-block box / split-K plan as integers, host only (tests). */
+int unflow_tc_wgrad_plan(int N, int Hp, int Wp, int R, int C, int stride, int kh, int kw, int pad_t,
+                         int pad_l, int *out);
+int unflow_tc_wgrad(const float *P, int N, int Hp, int Wp, int R, long long p_pitch, const float *G,
+                    int Hg, int Wg, int C, long long g_pitch, float *dw, long long pitch_r,
+                    long long pitch_t, int stride, int kh, int kw, int pad_t, int pad_l, void *stream);
+
 /* ---- checkpoint formats --------------------------------------------
  * Host-only helper, no GPU work: CRC-32C (Castagnoli) of ``n`` bytes continuing from ``crc``
  * (0 to start).  TensorFlow's checkpoint files -- what tf.train.Saver writes and restores in the

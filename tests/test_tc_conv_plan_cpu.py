@@ -126,3 +126,102 @@ def test_plan_rejects_bad_arguments():
     assert lib.unflow_tc_conv_plan(1, 8, 8, 4, 8, 8, 4, 2, 1, 3, 3, 1, 1, None, 0) == -1      # mode 2
     assert lib.unflow_tc_conv_plan(1, 8, 8, 4, 8, 8, 4, 0, 1, 9, 9, 4, 4, None, 0) == -1      # 81 taps
     assert lib.unflow_tc_conv_plan(1, 8, 8, 4, 8, 8, 4, 0, 1, 3, 3, 1, 1, None, 0) < -1       # needs a buffer
+
+
+# ---------------------------------------------------------------------------------------------
+# weight gradient (csrc/tc_wgrad.cu): the K-block pixel boxes / split-K plan executed on the CPU
+# ---------------------------------------------------------------------------------------------
+def wgrad_plan(N, Hp, Wp, R, C, stride, kh, kw, pt, pl):
+    buf = (ctypes.c_int * 15)()
+    assert _native.lib().unflow_tc_wgrad_plan(N, Hp, Wp, R, C, stride, kh, kw, pt, pl, buf) == 15
+    keys = ["TW", "TH", "TN", "tiles_x", "tiles_y", "tiles_n", "n_ptiles", "kc", "n_chunks", "r_blocks",
+            "c_blocks", "BN", "taps", "cgroups", "vgroups"]
+    return dict(zip(keys, list(buf)))
+
+
+def execute_wgrad(p, P, G, stride, kh, kw, pt, pl):
+    """P [N,Hp,Wp,R], G [N,Hg,Wg,C] (NHWC) -> dw [R, taps, C], K block by K block, chunk by chunk."""
+    N, Hp, Wp, R = P.shape
+    _, Hg, Wg, C = G.shape
+    assert p["TW"] * p["TH"] * p["TN"] == 32
+    assert p["n_ptiles"] == p["tiles_x"] * p["tiles_y"] * p["tiles_n"]
+    assert (p["n_chunks"] - 1) * p["kc"] < p["n_ptiles"] <= p["n_chunks"] * p["kc"]
+    dw = torch.zeros(R, kh * kw, C, dtype=P.dtype)
+    assert p["cgroups"] == -(-C // 32) and p["vgroups"] == kh * kw * p["cgroups"]
+    gpb = p["BN"] // 32                                  # (tap, 32-channel group) pairs per column block
+    assert p["c_blocks"] == -(-p["vgroups"] // gpb) and p["r_blocks"] == -(-R // 128)
+    for chunk in range(p["n_chunks"]):
+        for cb in range(p["c_blocks"]):
+            groups = []
+            for j in range(gpb):
+                v = cb * gpb + j
+                if v < p["vgroups"]:
+                    tap, cg = divmod(v, p["cgroups"])
+                    groups.append((tap, cg))
+            parts = {g_: torch.zeros(R, 32, dtype=P.dtype) for g_ in groups}
+            for kb in range(chunk * p["kc"], min((chunk + 1) * p["kc"], p["n_ptiles"])):
+                q = kb
+                px = (q % p["tiles_x"]) * p["TW"]; q //= p["tiles_x"]
+                py = (q % p["tiles_y"]) * p["TH"]; q //= p["tiles_y"]
+                pn = q * p["TN"]
+                pb = torch.zeros(32, R, dtype=P.dtype)
+                gbs = {g_: torch.zeros(32, 32, dtype=P.dtype) for g_ in groups}
+                i = 0
+                for a in range(p["TN"]):
+                    for b in range(p["TH"]):
+                        for c in range(p["TW"]):
+                            n, y, x = pn + a, py + b, px + c
+                            if n < N and y < Hp and x < Wp:
+                                pb[i] = P[n, y, x]
+                            for (tap, cg) in groups:
+                                ky, kx = divmod(tap, kw)
+                                gy, gx = stride * y + ky - pt, stride * x + kx - pl
+                                if n < N and 0 <= gy < Hg and 0 <= gx < Wg:
+                                    ch = G[n, gy, gx, cg * 32:cg * 32 + 32]
+                                    gbs[(tap, cg)][i, :ch.numel()] = ch
+                            i += 1
+                for g_ in groups:
+                    parts[g_] += pb.t() @ gbs[g_]
+            for (tap, cg) in groups:
+                w_ = min(32, C - cg * 32)
+                dw[:, tap, cg * 32:cg * 32 + w_] += parts[(tap, cg)][:, :w_]
+    return dw
+
+
+@pytest.mark.parametrize("N,Cin,H,W,Cout,k,stride,pads", CONV)
+def test_wgrad_plan_conv(N, Cin, H, W, Cout, k, stride, pads):
+    pt, pb, pl, pr = pads
+    g = torch.Generator().manual_seed(k * 11 + Cin)
+    x = torch.randn(N, Cin, H, W, generator=g, dtype=torch.float64)
+    xp = F.pad(x, (pl, pr, pt, pb))
+    Ho, Wo = (xp.shape[2] - k) // stride + 1, (xp.shape[3] - k) // stride + 1
+    gy = torch.randn(N, Cout, Ho, Wo, generator=g, dtype=torch.float64)
+    ref = torch.nn.grad.conv2d_weight(xp, (Cout, Cin, k, k), gy, stride=stride)      # [Cout, Cin, k, k]
+    p = wgrad_plan(N, Ho, Wo, Cout, Cin, stride, k, k, pt, pl)
+    got = execute_wgrad(p, gy.permute(0, 2, 3, 1), x.permute(0, 2, 3, 1), stride, k, k, pt, pl)
+    torch.testing.assert_close(got.reshape(Cout, k, k, Cin).permute(0, 3, 1, 2), ref, rtol=1e-11, atol=1e-11)
+
+
+def test_wgrad_plan_deconv():
+    """slim.conv2d_transpose(k=4, s=2, SAME): dW[ci, co, ky, kx] = sum_p x[p, ci] * gy[2p - 1 + k, co]."""
+    N, Ci, Co, H, W = 2, 5, 6, 4, 6
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(N, Ci, H, W, generator=g, dtype=torch.float64, requires_grad=True)
+    w = torch.randn(Ci, Co, 4, 4, generator=g, dtype=torch.float64, requires_grad=True)
+    gy = torch.randn(N, Co, 2 * H, 2 * W, generator=g, dtype=torch.float64)
+    F.conv_transpose2d(x, w, stride=2, padding=1).backward(gy)
+    p = wgrad_plan(N, H, W, Ci, Co, 2, 4, 4, 1, 1)
+    got = execute_wgrad(p, x.detach().permute(0, 2, 3, 1), gy.permute(0, 2, 3, 1), 2, 4, 4, 1, 1)
+    torch.testing.assert_close(got.reshape(Ci, 4, 4, Co).permute(0, 3, 1, 2), w.grad, rtol=1e-11, atol=1e-11)
+
+
+def test_wgrad_split_k_fills_the_gpu():
+    """conv3_1 at the benchmark geometry: 9 taps x 2 x 4 blocks = 72 tiles -> K is split so that the grid
+    has several waves of work items, each with at least 8 K blocks."""
+    p = wgrad_plan(8, 48, 160, 256, 473, 1, 3, 3, 1, 1)
+    items = p["n_chunks"] * p["r_blocks"] * p["c_blocks"]
+    assert p["BN"] == 128 and p["r_blocks"] == 2 and p["cgroups"] == 15 and p["c_blocks"] == 34 and p["n_ptiles"] == 1920
+    assert items >= 4 * 148 and p["kc"] >= 8
+    # conv2 (64 input channels, 25 taps): two taps share one 128-wide block instead of half-empty MMAs
+    p = wgrad_plan(8, 96, 320, 128, 64, 2, 5, 5, 1, 1)
+    assert p["BN"] == 128 and p["cgroups"] == 2 and p["c_blocks"] == 13

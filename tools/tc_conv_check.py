@@ -133,6 +133,39 @@ def case_deconv(name, N, Cin, Cout, H, W, k, stride, pad, bias=True, act=True, p
     return rec
 
 
+def case_wgrad(name, N, Cin, Cout, H, W, k, stride, pads, pitch_x=None, time_it=False, deconv=False):
+    """csrc/tc_wgrad.cu against torch's float64 weight gradient.  conv: y = conv(x, w); deconv: k4 s2 p1."""
+    g = torch.Generator().manual_seed(Cin + 5 * k)
+    if deconv:
+        x = make_x(N, Cin, H, W, pitch_x, seed=Cin + 1)
+        gy = make_x(N, Cout, 2 * H, 2 * W, None, seed=Cout + 2)
+        xr = x.double().clone().requires_grad_(True)
+        wr = torch.zeros(Cin, Cout, 4, 4, device=dev, dtype=torch.float64, requires_grad=True)
+        F.conv_transpose2d(xr, wr, stride=2, padding=1).backward(gy.double())
+        ref = wr.grad
+        dw = torch.zeros(Cin, Cout, 4, 4, device=dev).contiguous(memory_format=torch.channels_last)
+        run = lambda: T.wgrad(x, gy, dw, stride=2, kh=4, kw=4, pad_t=1, pad_l=1)
+        flops = 2.0 * N * H * W * Cout * Cin * 16
+    else:
+        pt, pb, pl, pr = pads
+        x = make_x(N, Cin, H, W, pitch_x, seed=Cin + 1)
+        Ho, Wo = (H + pt + pb - k) // stride + 1, (W + pl + pr - k) // stride + 1
+        gy = make_x(N, Cout, Ho, Wo, None, seed=Cout + 2)
+        ref = torch.nn.grad.conv2d_weight(F.pad(x.double(), (pl, pr, pt, pb)), (Cout, Cin, k, k), gy.double(), stride=stride)
+        dw = torch.zeros(Cout, Cin, k, k, device=dev).contiguous(memory_format=torch.channels_last)
+        run = lambda: T.wgrad(gy, x, dw, stride=stride, kh=k, kw=k, pad_t=pt, pad_l=pl)
+        flops = 2.0 * N * Ho * Wo * Cout * Cin * k * k
+    run()
+    torch.cuda.synchronize()
+    rec = dict(case=name, mode="wgrad", N=N, Cin=Cin, Cout=Cout, H=H, W=W, k=k, stride=stride, err=rel(dw, ref),
+               finite=bool(torch.isfinite(dw).all()), slack_untouched=True)
+    if time_it:
+        rec["us"] = bench(run)
+        rec["tflops_fp32_equiv"] = round(flops / rec["us"] / 1e6, 1)
+    say(**rec)
+    return rec
+
+
 def out_buf(N, C, H, W, fill=float("nan")):
     """NCHW-shaped view with NHWC memory and a channel pitch that is a multiple of 4 (poisoned slack)."""
     buf = torch.full((N, H, W, T.round4(C) + 4), -3.5, device=dev)
@@ -162,6 +195,22 @@ def main():
     quick = "--quick" in sys.argv
     torch.backends.cudnn.benchmark = True
     t0 = time.time()
+    if "--wgrad-only" in sys.argv:
+        case_wgrad("wgrad 1x1", 1, 32, 128, 8, 16, 1, 1, (0, 0, 0, 0))
+        case_wgrad("wgrad 3x3 s1", 2, 64, 128, 16, 24, 3, 1, (1, 1, 1, 1))
+        case_wgrad("wgrad 3x3 s1 ragged", 2, 70, 50, 13, 21, 3, 1, (1, 1, 1, 1), pitch_x=80)
+        case_wgrad("wgrad 3x3 s2 SAME(0,1)", 2, 64, 128, 16, 24, 3, 2, (0, 1, 0, 1))
+        case_wgrad("wgrad 5x5 s2 SAME(1,2)", 2, 24, 64, 16, 24, 5, 2, (1, 2, 1, 2))
+        case_wgrad("wgrad deconv k4 s2", 2, 130, 64, 6, 10, 4, 2, None, pitch_x=132, deconv=True)
+        B = 8
+        case_wgrad("wgrad conv3_1", B, 473, 256, 48, 160, 3, 1, (1, 1, 1, 1), pitch_x=476, time_it=True)
+        case_wgrad("wgrad conv4_1", B, 512, 512, 24, 80, 3, 1, (1, 1, 1, 1), time_it=True)
+        case_wgrad("wgrad conv6_1", B, 1024, 1024, 6, 20, 3, 1, (1, 1, 1, 1), time_it=True)
+        case_wgrad("wgrad conv4 (s2)", B, 256, 512, 48, 160, 3, 2, (0, 1, 0, 1), time_it=True)
+        case_wgrad("wgrad conv2 (5x5 s2)", B, 64, 128, 192, 640, 5, 2, (1, 2, 1, 2), time_it=True)
+        case_wgrad("wgrad deconv2", B, 386, 64, 48, 160, 4, 2, None, pitch_x=388, time_it=True, deconv=True)
+        case_wgrad("wgrad deconv5", B, 1024, 512, 6, 20, 4, 2, None, time_it=True, deconv=True)
+        return
     # --- smallest possible first: one tile, one K block, one tap -----------------------------------
     case_conv("1x1 one tile", 1, 32, 32, 8, 16, 1, 1, (0, 0, 0, 0), bias=False, act=False)
     case_conv("1x1 K=64 N=128", 1, 64, 128, 8, 16, 1, 1, (0, 0, 0, 0), bias=False, act=False)
@@ -178,6 +227,12 @@ def main():
     case_deconv("dgrad of 3x3 s2 SAME(0,1)", 2, 128, 64, 8, 12, 3, 2, 0, bias=False, act=False, out_hw=(16, 24))
     case_deconv("dgrad of 5x5 s2 SAME(1,2)", 2, 128, 64, 8, 12, 5, 2, 1, bias=False, act=False, out_hw=(16, 24))
     case_deconv("dgrad of 3x3 s1", 2, 128, 64, 9, 14, 3, 1, 1, bias=False, act=False)
+    case_wgrad("wgrad 1x1", 1, 32, 128, 8, 16, 1, 1, (0, 0, 0, 0))
+    case_wgrad("wgrad 3x3 s1", 2, 64, 128, 16, 24, 3, 1, (1, 1, 1, 1))
+    case_wgrad("wgrad 3x3 s1 ragged", 2, 70, 50, 13, 21, 3, 1, (1, 1, 1, 1), pitch_x=80)
+    case_wgrad("wgrad 3x3 s2 SAME(0,1)", 2, 64, 128, 16, 24, 3, 2, (0, 1, 0, 1))
+    case_wgrad("wgrad 5x5 s2 SAME(1,2)", 2, 24, 64, 16, 24, 5, 2, (1, 2, 1, 2))
+    case_wgrad("wgrad deconv k4 s2", 2, 130, 64, 6, 10, 4, 2, None, pitch_x=132, deconv=True)
     say(phase="small cases done", seconds=round(time.time() - t0, 1))
     if quick:
         return
@@ -198,6 +253,13 @@ def main():
     case_deconv("deconv3", B, 770, 128, 24, 80, 4, 2, 1, pitch=772, time_it=True, compare_lib=False)
     case_deconv("deconv2", B, 386, 64, 48, 160, 4, 2, 1, pitch=388, time_it=True, compare_lib=False)
     case_deconv("dgrad conv3_1", B, 256, 473, 48, 160, 3, 1, 1, bias=False, act=False, time_it=True)
+    case_wgrad("wgrad conv3_1", B, 473, 256, 48, 160, 3, 1, (1, 1, 1, 1), pitch_x=476, time_it=True)
+    case_wgrad("wgrad conv4_1", B, 512, 512, 24, 80, 3, 1, (1, 1, 1, 1), time_it=True)
+    case_wgrad("wgrad conv6_1", B, 1024, 1024, 6, 20, 3, 1, (1, 1, 1, 1), time_it=True)
+    case_wgrad("wgrad conv4 (s2)", B, 256, 512, 48, 160, 3, 2, (0, 1, 0, 1), time_it=True)
+    case_wgrad("wgrad conv2 (5x5 s2)", B, 64, 128, 192, 640, 5, 2, (1, 2, 1, 2), time_it=True)
+    case_wgrad("wgrad deconv2", B, 386, 64, 48, 160, 4, 2, None, pitch_x=388, time_it=True, deconv=True)
+    case_wgrad("wgrad deconv5", B, 1024, 512, 6, 20, 4, 2, None, time_it=True, deconv=True)
     say(phase="done", seconds=round(time.time() - t0, 1))
 
 

@@ -59,6 +59,9 @@ SIGNATURES = {
     "unflow_crc32c": (ctypes.c_uint, [_vp, ctypes.c_size_t, ctypes.c_uint]),
     "unflow_tc_wsplit": (_i, [_vp, _vp, _vp, _i, _i, _i] + [ctypes.c_longlong] * 3 + [_vp]),
     "unflow_tc_conv_plan": (_i, [_i] * 13 + [ctypes.POINTER(_i), _i]),
+    "unflow_tc_wgrad_plan": (_i, [_i] * 10 + [ctypes.POINTER(_i)]),
+    "unflow_tc_wgrad": (_i, [_vp, _i, _i, _i, _i, ctypes.c_longlong, _vp, _i, _i, _i, ctypes.c_longlong, _vp,
+                             ctypes.c_longlong, ctypes.c_longlong] + [_i] * 5 + [_vp]),
     "unflow_tc_conv": (_i, [_vp, _i, _i, _i, _i, ctypes.c_longlong, _vp, _vp, _vp, _i, _i, _i,
                             ctypes.c_longlong, _vp, ctypes.c_float, _i, _i] + [_i] * 6 + [_vp]),
 }

@@ -100,12 +100,15 @@ __device__ __forceinline__ float tf32_rna(float x) {
   return __uint_as_float(u);
 }
 
-// MN-major operand tile (the contraction index runs over ROWS of 128 bytes, 32 consecutive M/N
-// elements per row), 128-byte swizzle: 8-row groups of 1024 B along K (SBO), 32-element groups
-// along M/N `lbo_bytes` apart (LBO).  cute::UMMA canonical layout ((T,8,m),(8,k)):((1,T,LBO),(8T,SBO)).
+// MN-major fp32 / tf32 operand tile: the contraction index runs over ROWS of 128 bytes, 32 consecutive
+// M/N elements per row.  For 4-byte types the tensor core accepts exactly one MN-major shared-memory
+// layout: the 128-byte swizzle with 32-BYTE atoms (byte-address bits [5,7) ^= bits [7,9); TMA writes it
+// with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B; descriptor layout type 1, cute::UMMA
+// SWIZZLE_128B_BASE32B, canonical form ((T,8,m),(4,k)):((1,T,LBO),(8T,SBO))): 4-row groups of 512 B
+// along K (SBO), 32-element groups along M/N `lbo_bytes` apart (LBO).
 __device__ __forceinline__ unsigned long long umma_desc_mn128(unsigned saddr, unsigned lbo_bytes) {
   return (unsigned long long)((saddr >> 4) & 0x3FFFu) | ((unsigned long long)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
-         (64ull << 32) | (1ull << 46) | (2ull << 61);
+         (32ull << 32) | (1ull << 46) | (1ull << 61);
 }
 __device__ __forceinline__ void red_add_f32(float *addr, float v) {
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
@@ -130,11 +133,12 @@ inline EncodeTiledFn encode_fn() {
   return fn;
 }
 inline int encode(CUtensorMap *m, const float *basep, int rank, const cuuint64_t *dims,
-                  const cuuint64_t *strides_bytes, const cuuint32_t *box, const cuuint32_t *estr) {
+                  const cuuint64_t *strides_bytes, const cuuint32_t *box, const cuuint32_t *estr,
+                  CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return UNFLOW_ECUDA; }
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, (void *)basep, dims, strides_bytes, box,
-                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return UNFLOW_ECUDA; }
   return UNFLOW_OK;

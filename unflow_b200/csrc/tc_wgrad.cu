@@ -1,0 +1,395 @@
+// tc_wgrad.cu -- weight gradients of the conv / deconv stacks on the tensor cores (tcgen05,
+// 3xTF32 split of BOTH operands in shared memory, fp32 register accumulation, split-K).
+//
+// Replaces the library weight-gradient kernels behind tf.gradients of slim.conv2d /
+// slim.conv2d_transpose (reference src/e2eflow/core/flownet.py:166-233, :89-155; train.py:151-152)
+// and the two 3x-wide operand copies each of them needed.
+//
+//   dW[r][t][c] += sum over pixels p of  P[p][r] * G[stride * p + d_t][c]          (zero outside G)
+//
+//   convolution   y = conv(x, W):     P = dL/dy (rows r = C_out), G = x   (cols c = C_in),  d_t = k - pad
+//   transposed    y = deconv(x, W):   P = x     (rows r = C_in),  G = dL/dy (cols c = C_out), stride 2
+//
+// GEMM view per work item: M = 128 rows of P's channels, N = BN channels of G, K = pixels.  Both
+// operands are "MN-major" for the tensor core: NHWC memory has the channels contiguous and the
+// contraction index (pixels) across rows, which is exactly what a TMA box of 32 pixels x 32 channels
+// (one 128-byte row per pixel, written in the 32-byte-atom swizzle the tensor core requires of MN-major
+// tf32 operands) delivers -- no transposed copy of any activation exists.
+//
+// Work item = (pixel chunk, 128-row block, BN-column block); the BN columns are BN/32 consecutive
+// (tap, 32-channel group) pairs, so a layer with few input channels fills the 128-wide MMA with
+// several taps at once (conv2: 64 channels -> two taps per block).  A chunk is a run of 32-pixel K
+// blocks sized so that the grid has a few waves of items; items of one chunk are adjacent in the
+// schedule, so the chunk's activations are read from HBM once and re-read from L2.
+//   warp 0      TMA: per K block 4 boxes of P (32 px x 32 ch each) and BN/32 boxes of G (element
+//               stride = the conv stride, tap offset in the start coordinate, zero fill outside)
+//   warps 4-7   split both tiles: hi = tf32(v) in place, lo = v - hi beside it
+//   warp 1      tcgen05.mma kind::tf32, A and B MN-major: lo*hi + hi*lo + hi*hi per 8-pixel K step
+//   warps 8-15  every 4 K blocks: tcgen05.ld the TMEM accumulator and add it to fp32 registers (see
+//               tc_conv.cu, "Accuracy"); at the end of the item: red.global.add into dW
+// dW is accumulated with fp32 atomics (split-K partial sums from several CTAs): the caller zeroes
+// it; the order of the additions, hence the last bits, vary from run to run.
+#include "tc_common.cuh"
+
+namespace unflow {
+namespace tcw {
+
+using namespace unflow::tc;
+
+constexpr int NTHREADS = 512;
+constexpr int KP = 32;              // pixels per K block
+
+struct WgradParams {
+  int N, Hp, Wp;                    // pixel grid of the plain operand P
+  int TW, TH, TN;                   // pixel box of one K block, TW*TH*TN == 32
+  int tiles_x, tiles_y, tiles_n;    // boxes covering the grid
+  int n_ptiles, kc, n_chunks;       // K blocks in total / per chunk, chunks
+  int R, C;                         // rows (channels of P) / columns (channels of G) of dW
+  int cgroups, vgroups;             // 32-channel groups of G per tap; (tap, group) pairs = "virtual" column groups
+  int r_blocks, c_blocks, taps, kw;  // c_blocks: blocks of BN/32 consecutive virtual groups
+  int stride, pad_t, pad_l;
+  float *dw;
+  long long pitch_r, pitch_t;       // dW[r * pitch_r + t * pitch_t + c]
+};
+
+template <int BN>
+struct Cfg {
+  static constexpr int B_BYTES = BN * KP * 4;
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  static constexpr int STAGES = (200 * 1024 / STAGE_BYTES) < 6 ? (200 * 1024 / STAGE_BYTES) : 6;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+};
+
+struct Item {
+  int chunk, rb, cb;
+};
+__device__ __forceinline__ Item decode_item(const WgradParams &p, int it) {
+  Item w;
+  w.cb = it % p.c_blocks; it /= p.c_blocks;
+  w.rb = it % p.r_blocks; it /= p.r_blocks;
+  w.chunk = it;
+  return w;
+}
+__device__ __forceinline__ int chunk_len(const WgradParams &p, int chunk) {
+  const int k0 = chunk * p.kc;
+  return (k0 + p.kc <= p.n_ptiles) ? p.kc : p.n_ptiles - k0;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(NTHREADS, 1)
+tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ CUtensorMap mapG,
+                const __grid_constant__ WgradParams p) {
+  using C = Cfg<BN>;
+  extern __shared__ unsigned char smem_raw[];
+  const unsigned base = (s32(smem_raw) + 1023u) & ~1023u;
+  unsigned char *gbase = smem_raw + (base - s32(smem_raw));
+  // stage layout: [P hi (raw)] [P lo] [G hi (raw)] [G lo]; each tile = channel groups of 32 (4096 B each)
+  const unsigned bars = base + C::STAGES * C::STAGE_BYTES;
+  auto full_raw = [&](int s) { return bars + 8u * s; };
+  auto full_cvt = [&](int s) { return bars + 8u * (C::STAGES + s); };
+  auto empty = [&](int s) { return bars + 8u * (2 * C::STAGES + s); };
+  auto tmem_full = [&](int a) { return bars + 8u * (3 * C::STAGES + a); };
+  auto tmem_empty = [&](int a) { return bars + 8u * (3 * C::STAGES + 2 + a); };
+  const unsigned tmem_slot = bars + 8u * (3 * C::STAGES + 4);
+  volatile unsigned *tmem_slot_ptr = (volatile unsigned *)(gbase + C::STAGES * C::STAGE_BYTES + 8 * (3 * C::STAGES + 4));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_items = p.n_chunks * p.r_blocks * p.c_blocks;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(full_raw(s), 1);
+      mbar_init(full_cvt(s), 4);
+      mbar_init(empty(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tmem_full(a), 1);
+      mbar_init(tmem_empty(a), 8);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapP) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapG) : "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                 "r"((unsigned)C::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const unsigned tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int s = 0;
+      unsigned ph = 0;
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+        const Item w = decode_item(p, item);
+        int gch[BN / 32], gdx[BN / 32], gdy[BN / 32];        // per column group: channel, tap offset
+#pragma unroll
+        for (int j = 0; j < BN / 32; ++j) {
+          const int v = w.cb * (BN / 32) + j;
+          if (v < p.vgroups) {
+            const int tap = v / p.cgroups, ky = tap / p.kw;
+            gch[j] = (v - tap * p.cgroups) * 32; gdy[j] = ky - p.pad_t; gdx[j] = tap - ky * p.kw - p.pad_l;
+          } else {
+            gch[j] = p.cgroups * 32; gdx[j] = gdy[j] = 0;    // past the last group: channels >= C, TMA zero fill
+          }
+        }
+        const int k0 = w.chunk * p.kc, klen = chunk_len(p, w.chunk);
+        for (int kb = k0; kb < k0 + klen; ++kb) {
+          int q = kb;
+          const int px = (q % p.tiles_x) * p.TW; q /= p.tiles_x;
+          const int py = (q % p.tiles_y) * p.TH; q /= p.tiles_y;
+          const int pn = q * p.TN;
+          mbar_wait(empty(s), ph ^ 1u);
+          const unsigned st = base + s * C::STAGE_BYTES;
+          mbar_expect_tx(full_raw(s), (unsigned)(A_BYTES + C::B_BYTES));
+#pragma unroll
+          for (int j = 0; j < BM / 32; ++j)       // channels past R are TMA zero fill
+            tma_4d(st + j * 4096, &mapP, full_raw(s), w.rb * BM + 32 * j, px, py, pn);
+#pragma unroll
+          for (int j = 0; j < BN / 32; ++j)
+            tma_4d(st + 2 * A_BYTES + j * 4096, &mapG, full_raw(s), gch[j], p.stride * px + gdx[j],
+                   p.stride * py + gdy[j], pn);
+          if (++s == C::STAGES) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      // D fp32, A / B tf32, both MN-major (bits 15, 16), N = BN, M = 128
+      const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
+                             ((unsigned)(BN >> 3) << 17) | ((unsigned)(BM >> 4) << 24);
+      int s = 0, acc = 0;
+      unsigned ph = 0, aph = 0;
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+        const Item w = decode_item(p, item);
+        const int iters = chunk_len(p, w.chunk);
+        for (int it = 0; it < iters; ++it) {
+          const int in_chunk = it % CHUNK;
+          if (in_chunk == 0) {
+            mbar_wait(tmem_empty(acc), aph ^ 1u);
+            tc_fence_after();
+          }
+          const unsigned d = tmem_base + (unsigned)(acc * BN);
+          mbar_wait(full_raw(s), ph);
+          mbar_wait(full_cvt(s), ph);
+          tc_fence_after();
+          const unsigned st = base + s * C::STAGE_BYTES;
+          const unsigned long long a_hi = umma_desc_mn128(st, 4096), a_lo = umma_desc_mn128(st + A_BYTES, 4096);
+          const unsigned long long b_hi = umma_desc_mn128(st + 2 * A_BYTES, 4096);
+          const unsigned long long b_lo = umma_desc_mn128(st + 2 * A_BYTES + C::B_BYTES, 4096);
+#pragma unroll
+          for (int k = 0; k < KP / 8; ++k) {            // 8 pixels = 8 rows of 128 B = 1024 B: +64 in 16-byte units
+            const unsigned long long adv = (unsigned long long)(64 * k);
+            umma_tf32(d, a_lo + adv, b_hi + adv, idesc, (in_chunk | k) != 0);
+            umma_tf32(d, a_hi + adv, b_lo + adv, idesc, 1u);
+            umma_tf32(d, a_hi + adv, b_hi + adv, idesc, 1u);
+          }
+          umma_commit(empty(s));
+          if (++s == C::STAGES) { s = 0; ph ^= 1u; }
+          if (in_chunk == CHUNK - 1 || it == iters - 1) {
+            umma_commit(tmem_full(acc));
+            if (++acc == 2) { acc = 0; aph ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ===================== split both tiles =====================
+    const int tid = threadIdx.x - 128;
+    int s = 0;
+    unsigned ph = 0;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+      const Item w = decode_item(p, item);
+      const int iters = chunk_len(p, w.chunk);
+      for (int it = 0; it < iters; ++it) {
+        mbar_wait(full_raw(s), ph);
+        unsigned char *stp = gbase + s * C::STAGE_BYTES;
+#pragma unroll
+        for (int part = 0; part < 2; ++part) {
+          float4 *a = reinterpret_cast<float4 *>(stp + (part ? 2 * A_BYTES : 0));
+          float4 *l = reinterpret_cast<float4 *>(stp + (part ? 2 * A_BYTES + C::B_BYTES : A_BYTES));
+          const int n16 = (part ? C::B_BYTES : A_BYTES) / 16;
+#pragma unroll
+          for (int i = tid; i < n16; i += 128) {
+            const float4 v = a[i];
+            float4 h, r;
+            h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
+            r.x = v.x - h.x; r.y = v.y - h.y; r.z = v.z - h.z; r.w = v.w - h.w;
+            a[i] = h;
+            l[i] = r;
+          }
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(full_cvt(s));
+        if (++s == C::STAGES) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp >= 8) {
+    // ===================== epilogue: fp32 register accumulation, then red.add into dW =====================
+    constexpr int COLS = BN / 2;
+    const int q = warp & 3;
+    const int half = (warp - 8) >> 2;
+    const int row = q * 32 + lane;
+    int acc = 0;
+    unsigned aph = 0;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+      const Item w = decode_item(p, item);
+      const int iters = chunk_len(p, w.chunk);
+      const int chunks = (iters + CHUNK - 1) / CHUNK;
+      float sum[COLS];
+#pragma unroll
+      for (int c = 0; c < COLS; ++c) sum[c] = 0.f;
+      for (int ck = 0; ck < chunks; ++ck) {
+        mbar_wait(tmem_full(acc), aph);
+        tc_fence_after();
+        const unsigned taddr = tmem_base + ((unsigned)(q * 32) << 16) + (unsigned)(acc * BN + half * COLS);
+#pragma unroll
+        for (int c0 = 0; c0 < COLS; c0 += 16) {
+          unsigned r[16];
+          tmem_ld16(taddr + (unsigned)c0, r);
+#pragma unroll
+          for (int e = 0; e < 16; ++e) sum[c0 + e] += __uint_as_float(r[e]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tmem_empty(acc));
+        if (++acc == 2) { acc = 0; aph ^= 1u; }
+      }
+      const int r = w.rb * BM + row;
+      if (r < p.R) {
+#pragma unroll
+        for (int g = 0; g < (COLS + 31) / 32; ++g) {       // the (tap, channel group) pairs this thread holds
+          const int col0 = half * COLS + 32 * g;             // column within the BN block
+          const int v = w.cb * (BN / 32) + col0 / 32;
+          if (v < p.vgroups) {
+            const int tap = v / p.cgroups, c0 = (v - tap * p.cgroups) * 32 + (col0 & 31);
+            float *dst = p.dw + (long long)r * p.pitch_r + (long long)tap * p.pitch_t + c0;
+#pragma unroll
+            for (int c = 0; c < (COLS < 32 ? COLS : 32); ++c)
+              if (c0 + c < p.C) red_add_f32(dst + c, sum[32 * g + c]);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((unsigned)C::TMEM_COLS) : "memory");
+  }
+}
+
+template <int BN>
+static int launch(const CUtensorMap &mP, const CUtensorMap &mG, const WgradParams &p, int total, cudaStream_t stream) {
+  using C = Cfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(tc_wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (e != cudaSuccess) { set_error("tc_wgrad: cannot opt in to %d bytes of shared memory: %s", C::SMEM_BYTES, cudaGetErrorString(e)); return UNFLOW_ECUDA; }
+    attr_set = true;
+  }
+  const int grid = total < kNumSMs ? total : kNumSMs;
+  tc_wgrad_kernel<BN><<<grid, NTHREADS, C::SMEM_BYTES, stream>>>(mP, mG, p);
+  count_launch();
+  return check_launch("tc_wgrad_kernel");
+}
+
+// the K-block pixel box: TW*TH*TN == 32 exactly (rows past the tensor are TMA zero fill), fewest boxes
+static void choose_box(WgradParams &p) {
+  long long best = -1;
+  for (int TW = 1; TW <= 32; TW *= 2)
+    for (int TH = 1; TW * TH <= 32; TH *= 2) {
+      const int TN = 32 / (TW * TH);
+      const long long tiles = (long long)((p.Wp + TW - 1) / TW) * ((p.Hp + TH - 1) / TH) * ((p.N + TN - 1) / TN);
+      if (best < 0 || tiles < best || (tiles == best && TW > p.TW)) {
+        best = tiles; p.TW = TW; p.TH = TH; p.TN = TN;
+      }
+    }
+  p.tiles_x = (p.Wp + p.TW - 1) / p.TW; p.tiles_y = (p.Hp + p.TH - 1) / p.TH; p.tiles_n = (p.N + p.TN - 1) / p.TN;
+  p.n_ptiles = p.tiles_x * p.tiles_y * p.tiles_n;
+}
+
+static int make_plan(WgradParams &p, int &BN, int N, int Hp, int Wp, int R, int C, int stride, int kh, int kw,
+                     int pad_t, int pad_l) {
+  UNFLOW_REQUIRE(N > 0 && Hp > 0 && Wp > 0 && R > 0 && C > 0, "tc_wgrad: bad extents");
+  UNFLOW_REQUIRE(stride == 1 || stride == 2, "tc_wgrad: stride must be 1 or 2");
+  UNFLOW_REQUIRE(kh > 0 && kw > 0 && kh * kw <= 64, "tc_wgrad: at most 64 taps");
+  p.N = N; p.Hp = Hp; p.Wp = Wp; p.R = R; p.C = C;
+  p.taps = kh * kw; p.kw = kw; p.stride = stride; p.pad_t = pad_t; p.pad_l = pad_l;
+  choose_box(p);
+  p.cgroups = (C + 31) / 32; p.vgroups = p.taps * p.cgroups;
+  BN = p.vgroups >= 4 ? 128 : (p.vgroups >= 2 ? 64 : 32);
+  p.r_blocks = (R + BM - 1) / BM; p.c_blocks = (p.vgroups + BN / 32 - 1) / (BN / 32);
+  // split K so that the grid has ~6 waves of items; at least 8 K blocks per item
+  const long long tiles = (long long)p.r_blocks * p.c_blocks;
+  long long want = (6ll * kNumSMs + tiles - 1) / tiles;
+  if (want < 1) want = 1;
+  int kc = (int)((p.n_ptiles + want - 1) / want);
+  if (kc < 8) kc = p.n_ptiles < 8 ? p.n_ptiles : 8;
+  p.kc = kc; p.n_chunks = (p.n_ptiles + kc - 1) / kc;
+  UNFLOW_REQUIRE(tiles * p.n_chunks < (1ll << 30), "tc_wgrad: too many work items");
+  return UNFLOW_OK;
+}
+
+}  // namespace tcw
+}  // namespace unflow
+
+using namespace unflow;
+
+// Debug / test hook (host only): [TW, TH, TN, tiles_x, tiles_y, tiles_n, n_ptiles, kc, n_chunks, r_blocks,
+// c_blocks, BN, taps, cgroups, vgroups]; returns 15 or -1.
+extern "C" int unflow_tc_wgrad_plan(int N, int Hp, int Wp, int R, int C, int stride, int kh, int kw, int pad_t,
+                                    int pad_l, int *out) {
+  tcw::WgradParams p{};
+  int BN = 0;
+  if (tcw::make_plan(p, BN, N, Hp, Wp, R, C, stride, kh, kw, pad_t, pad_l) || !out) return -1;
+  const int v[15] = {p.TW, p.TH, p.TN, p.tiles_x, p.tiles_y, p.tiles_n, p.n_ptiles, p.kc, p.n_chunks, p.r_blocks,
+                     p.c_blocks, BN, p.taps, p.cgroups, p.vgroups};
+  for (int i = 0; i < 15; ++i) out[i] = v[i];
+  return 15;
+}
+
+extern "C" int unflow_tc_wgrad(const float *P, int N, int Hp, int Wp, int R, long long p_pitch, const float *G,
+                               int Hg, int Wg, int C, long long g_pitch, float *dw, long long pitch_r,
+                               long long pitch_t, int stride, int kh, int kw, int pad_t, int pad_l, void *stream) {
+  UNFLOW_REQUIRE(P && G && dw, "tc_wgrad: null pointer");
+  UNFLOW_REQUIRE(Hg > 0 && Wg > 0, "tc_wgrad: bad extents");
+  UNFLOW_REQUIRE(p_pitch % 4 == 0 && g_pitch % 4 == 0 && p_pitch >= R && g_pitch >= C,
+                 "tc_wgrad: channel pitches must be multiples of 4 floats");
+  UNFLOW_REQUIRE(((uintptr_t)P & 15) == 0 && ((uintptr_t)G & 15) == 0, "tc_wgrad: P and G must be 16-byte aligned");
+  tcw::WgradParams p{};
+  int BN = 0;
+  int rc = tcw::make_plan(p, BN, N, Hp, Wp, R, C, stride, kh, kw, pad_t, pad_l);
+  if (rc) return rc;
+  p.dw = dw; p.pitch_r = pitch_r; p.pitch_t = pitch_t;
+  const long long total = (long long)p.n_chunks * p.r_blocks * p.c_blocks;
+  CUtensorMap mP, mG;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)R, (cuuint64_t)Wp, (cuuint64_t)Hp, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)p_pitch * 4, (cuuint64_t)p_pitch * 4 * Wp, (cuuint64_t)p_pitch * 4 * Wp * Hp};
+    cuuint32_t box[4] = {32, (cuuint32_t)p.TW, (cuuint32_t)p.TH, (cuuint32_t)p.TN};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    rc = tc::encode(&mP, P, 4, dims, strides, box, estr, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    if (rc) return rc;
+  }
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)Wg, (cuuint64_t)Hg, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)g_pitch * 4, (cuuint64_t)g_pitch * 4 * Wg, (cuuint64_t)g_pitch * 4 * Wg * Hg};
+    cuuint32_t box[4] = {32, (cuuint32_t)(p.TW * stride), (cuuint32_t)(p.TH * stride), (cuuint32_t)p.TN};
+    cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+    rc = tc::encode(&mG, G, 4, dims, strides, box, estr, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    if (rc) return rc;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (BN == 128) return tcw::launch<128>(mP, mG, p, (int)total, st);
+  if (BN == 64) return tcw::launch<64>(mP, mG, p, (int)total, st);
+  return tcw::launch<32>(mP, mG, p, (int)total, st);
+}

@@ -224,6 +224,15 @@ class _Deconv3x(torch.autograd.Function):
 # through the library path below (round-2 work in progress: csrc/tc_wgrad).
 # ---------------------------------------------------------------------------------------------
 _TC = __import__('os').environ.get('UNFLOW_TC_CONV', '1') != '0'
+_TC_WGRAD = __import__('os').environ.get('UNFLOW_TC_WGRAD', '1') != '0'
+
+
+def _tc_weight_grad(P, G, w, stride, pad_t, pad_l):
+    """dL/dw on csrc/tc_wgrad.cu: a zeroed tensor in the variable's memory order, accumulated by the kernel."""
+    from . import tc_conv
+    A, B, kh, kw = w.shape
+    gw = torch.zeros((A, kh, kw, B), device=w.device, dtype=torch.float32).permute(0, 3, 1, 2)
+    return tc_conv.wgrad(P, G, gw, stride=stride, kh=kh, kw=kw, pad_t=pad_t, pad_l=pad_l)
 
 
 def _tc_ok(x, stride):
@@ -301,10 +310,13 @@ class _ConvTC(torch.autograd.Function):
             tc_conv.run(gpre, tc_conv.split_weights(_khwc(w), transpose=True), gx, mode=1, stride=stride, kh=k, kw=k,
                         pad_t=pt, pad_l=pl)
         if ctx.needs_input_grad[1]:
-            ci_p, co_p = _round4(Ci), _round4(Co)
-            xb = _operand(x, 0, concat_batch=True, c_pad=ci_p, pads=pads)          # [3N, Ci_p, Hp, Wp]
-            gb3 = _operand(gpre, 1, concat_batch=True, c_pad=co_p)                 # [3N, Co_p, ..]
-            gw = nngrad.conv2d_weight(xb, (co_p, ci_p, k, k), gb3, stride=stride, padding=0)[:Co, :Ci]
+            if _TC_WGRAD and tc_conv.supported(gpre):
+                gw = _tc_weight_grad(gpre, x, w, stride, pt, pl)                   # rows C_out, columns C_in
+            else:
+                ci_p, co_p = _round4(Ci), _round4(Co)
+                xb = _operand(x, 0, concat_batch=True, c_pad=ci_p, pads=pads)      # [3N, Ci_p, Hp, Wp]
+                gb3 = _operand(gpre, 1, concat_batch=True, c_pad=co_p)             # [3N, Co_p, ..]
+                gw = nngrad.conv2d_weight(xb, (co_p, ci_p, k, k), gb3, stride=stride, padding=0)[:Co, :Ci]
         return gx, gw, gb, None, None, None
 
 
@@ -344,10 +356,13 @@ class _DeconvTC(torch.autograd.Function):
             gx = buf[..., :Ci].permute(0, 3, 1, 2)
             tc_conv.run(gpre, tc_conv.split_weights(_khwc(w)), gx, mode=0, stride=2, kh=4, kw=4, pad_t=1, pad_l=1)
         if ctx.needs_input_grad[1]:
-            ci_p, co_p = _round4(Ci), _round4(Co)
-            gb3 = _operand(gpre, 0, concat_batch=True, c_pad=co_p)
-            xb = _operand(x, 1, concat_batch=True, c_pad=ci_p)
-            gw = nngrad.conv2d_weight(gb3, (ci_p, co_p, 4, 4), xb, stride=2, padding=1)[:Ci, :Co]
+            if _TC_WGRAD and tc_conv.supported(gpre):
+                gw = _tc_weight_grad(x, gpre, w, 2, 1, 1)                          # rows C_in, columns C_out
+            else:
+                ci_p, co_p = _round4(Ci), _round4(Co)
+                gb3 = _operand(gpre, 0, concat_batch=True, c_pad=co_p)
+                xb = _operand(x, 1, concat_batch=True, c_pad=ci_p)
+                gw = nngrad.conv2d_weight(gb3, (ci_p, co_p, 4, 4), xb, stride=2, padding=1)[:Ci, :Co]
         return gx, gw, gb, None
 
 

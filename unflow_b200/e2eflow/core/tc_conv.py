@@ -96,3 +96,22 @@ def run(x, planes, out, *, mode, stride, kh, kw, pad_t, pad_l, bias=None, act=Fa
 def empty_nhwc(N, C, H, W, device):
     """An NCHW-shaped tensor with dense NHWC memory."""
     return torch.empty((N, H, W, C), device=device, dtype=torch.float32).permute(0, 3, 1, 2)
+
+
+def wgrad(P, G, dw, *, stride, kh, kw, pad_t, pad_l):
+    """dw[r, t, c] += sum_p P[p, r] * G[stride * p + (k - pad), c]  (csrc/tc_wgrad.cu).  ``P`` / ``G``:
+    NCHW-shaped tensors with NHWC memory; ``dw``: a ZEROED (or to-be-accumulated) variable-shaped tensor
+    [rows, cols, kh, kw] stored [rows][kh][kw][cols]."""
+    gp, gg = nhwc_geometry(P), nhwc_geometry(G)
+    assert gp is not None and gg is not None, "tc_wgrad needs NHWC (channels_last) memory"
+    N, Hp, Wp, R, pp = gp
+    Ng, Hg, Wg, C, gpitch = gg
+    A, B, k1, k2 = dw.shape
+    assert (A, B, k1, k2) == (R, C, kh, kw) and Ng == N
+    want = (kh * kw * C, 1, kw * C, C)
+    assert all(n == 1 or s == t for n, s, t in zip(dw.shape, dw.stride(), want)), "dw must be stored [rows][kh][kw][cols]"
+    with torch.cuda.device(P.device):
+        check(_native.lib().unflow_tc_wgrad(P.data_ptr(), N, Hp, Wp, R, pp, G.data_ptr(), Hg, Wg, C, gpitch,
+                                            dw.data_ptr(), kh * kw * C, C, stride, kh, kw, pad_t, pad_l,
+                                            _stream()), "tc_wgrad")
+    return dw
