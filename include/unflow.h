@@ -277,6 +277,18 @@ int unflow_tc_wgrad(const float *P, int N, int Hp, int Wp, int R, long long p_pi
                     int Hg, int Wg, int C, long long g_pitch, float *dw, long long pitch_r,
                     long long pitch_t, int stride, int kh, int kw, int pad_t, int pad_l, void *stream);
 
+/* First layers (7x7 stride 2 on 3 / 6 / 14 channels; flownet.py:174-176,203): the row-window form.
+ * `xp` is the input as NHWC with Cp = 4 / 8 / 16 floats per pixel (channel tail zero) and rows of Wp
+ * pixels that already contain the TF SAME padding in x (pad_l zero pixels on the left, zeros on the
+ * right up to Wp >= stride*(Wout-1) + 8); rows outside [0,H) are zero fill.  The kw taps of a filter
+ * row are one contiguous 8*Cp-float window, so the layer is a convolution with kh taps and an
+ * 8*Cp-wide contraction: weight planes / dw are [Cout][kh][8*Cp] with column kx*Cp + c. */
+int unflow_tc_conv_window(const float *xp, int N, int H, int Wp, int Cp, const float *w_hi, const float *w_lo,
+                          float *y, int Hout, int Wout, int Cout, long long y_pitch, const float *bias,
+                          float slope, int act, int kh, int stride, int pad_t, void *stream);
+int unflow_tc_wgrad_window(const float *P, int N, int Ho, int Wo, int R, long long p_pitch, const float *xp,
+                           int H, int Wp, int Cp, float *dw, int kh, int stride, int pad_t, void *stream);
+
 /* ---- checkpoint formats --------------------------------------------
  * Host-only helper, no GPU work: CRC-32C (Castagnoli) of ``n`` bytes continuing from ``crc``
  * (0 to start).  TensorFlow's checkpoint files -- what tf.train.Saver writes and restores in the

@@ -166,6 +166,34 @@ def case_wgrad(name, N, Cin, Cout, H, W, k, stride, pads, pitch_x=None, time_it=
     return rec
 
 
+def case_window(name, N, Ci, H, W, Co=64, time_it=True):
+    """7x7 stride-2 first layer in the row-window form: forward + weight gradient, timing."""
+    k = 7
+    g = torch.Generator().manual_seed(Ci)
+    x = (torch.rand(N, Ci, H, W, generator=g) - 0.4).to(dev)
+    w = cl((torch.randn(Co, Ci, k, k, generator=g) * 0.05).to(dev))
+    b = (torch.randn(Co, generator=g) * 0.1).to(dev)
+    ref = F.leaky_relu(F.conv2d(F.pad(x.double(), (2, 3, 2, 3)), w.double(), b.double(), stride=2), 0.1)
+    Ho, Wo = ref.shape[2:]
+    cp = T.window_channels(Ci)
+    xp = T.window_input(x, 2, 2, Wo)
+    planes = T.split_weights(T.window_weights(w, cp))
+    out = T.empty_nhwc(N, Co, Ho, Wo, dev)
+    T.run_window(xp, planes, out, kh=k, stride=2, pad_t=2, bias=b, act=True)
+    gy = cl(torch.randn(N, Co, Ho, Wo, generator=g).to(dev))
+    dw = torch.zeros((Co, k, 1, 8 * cp), device=dev).permute(0, 3, 1, 2)
+    T.wgrad_window(gy, xp, dw, kh=k, stride=2, pad_t=2)
+    refw = torch.nn.grad.conv2d_weight(F.pad(x.double(), (2, 3, 2, 3)), (Co, Ci, k, k), gy.double(), stride=2)
+    got = dw.permute(0, 2, 3, 1).reshape(Co, k, 8, cp)[:, :, :k, :Ci].permute(0, 3, 1, 2)
+    rec = dict(case=name, mode="window", N=N, Cin=Ci, Cout=Co, H=H, W=W, k=k, stride=2, err=rel(out, ref),
+               err_wgrad=rel(got, refw), finite=bool(torch.isfinite(out).all()), slack_untouched=True)
+    if time_it:
+        rec["us"] = bench(lambda: T.run_window(xp, planes, out, kh=k, stride=2, pad_t=2, bias=b, act=True))
+        rec["us_wgrad"] = bench(lambda: T.wgrad_window(gy, xp, dw, kh=k, stride=2, pad_t=2))
+        rec["us_window_input"] = bench(lambda: T.window_input(x, 2, 2, Wo))
+    say(**rec)
+
+
 def out_buf(N, C, H, W, fill=float("nan")):
     """NCHW-shaped view with NHWC memory and a channel pitch that is a multiple of 4 (poisoned slack)."""
     buf = torch.full((N, H, W, T.round4(C) + 4), -3.5, device=dev)
@@ -195,6 +223,12 @@ def main():
     quick = "--quick" in sys.argv
     torch.backends.cudnn.benchmark = True
     t0 = time.time()
+    if "--profile" in sys.argv:          # one launch of each big kernel, for ncu
+        B = 8
+        case_conv("conv3_1", B, 473, 256, 48, 160, 3, 1, (1, 1, 1, 1), pitch=476)
+        case_deconv("deconv3", B, 770, 128, 24, 80, 4, 2, 1, pitch=772)
+        case_wgrad("wgrad conv3_1", B, 473, 256, 48, 160, 3, 1, (1, 1, 1, 1), pitch_x=476)
+        return
     if "--wgrad-only" in sys.argv:
         case_wgrad("wgrad 1x1", 1, 32, 128, 8, 16, 1, 1, (0, 0, 0, 0))
         case_wgrad("wgrad 3x3 s1", 2, 64, 128, 16, 24, 3, 1, (1, 1, 1, 1))
@@ -210,6 +244,9 @@ def main():
         case_wgrad("wgrad conv2 (5x5 s2)", B, 64, 128, 192, 640, 5, 2, (1, 2, 1, 2), time_it=True)
         case_wgrad("wgrad deconv2", B, 386, 64, 48, 160, 4, 2, None, pitch_x=388, time_it=True, deconv=True)
         case_wgrad("wgrad deconv5", B, 1024, 512, 6, 20, 4, 2, None, time_it=True, deconv=True)
+        case_window("window conv1 FlowNetC", B, 3, 384, 1280)
+        case_window("window conv1 FlowNetS", B, 6, 384, 1280)
+        case_window("window conv1 stacked S", 4, 14, 384, 1280)
         return
     # --- smallest possible first: one tile, one K block, one tap -----------------------------------
     case_conv("1x1 one tile", 1, 32, 32, 8, 16, 1, 1, (0, 0, 0, 0), bias=False, act=False)

@@ -62,6 +62,9 @@ SIGNATURES = {
     "unflow_tc_wgrad_plan": (_i, [_i] * 10 + [ctypes.POINTER(_i)]),
     "unflow_tc_wgrad": (_i, [_vp, _i, _i, _i, _i, ctypes.c_longlong, _vp, _i, _i, _i, ctypes.c_longlong, _vp,
                              ctypes.c_longlong, ctypes.c_longlong] + [_i] * 5 + [_vp]),
+    "unflow_tc_conv_window": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, ctypes.c_longlong, _vp,
+                                   ctypes.c_float, _i, _i, _i, _i, _vp]),
+    "unflow_tc_wgrad_window": (_i, [_vp, _i, _i, _i, _i, ctypes.c_longlong, _vp, _i, _i, _i, _vp, _i, _i, _i, _vp]),
     "unflow_tc_conv": (_i, [_vp, _i, _i, _i, _i, ctypes.c_longlong, _vp, _vp, _vp, _i, _i, _i,
                             ctypes.c_longlong, _vp, ctypes.c_float, _i, _i] + [_i] * 6 + [_vp]),
 }

@@ -60,7 +60,7 @@ struct ConvParams {
   int N, Hit, Wit;            // images; iteration rows / columns of one class
   int TW, TH, TN;             // tile box, TW*TH*TN <= 128
   int tiles_x, tiles_y, tiles_n, n_blocks, n_classes;
-  int s_in, s_out;
+  int s_in_x, s_in_y, s_out;    // input strides per axis (the row-window form folds the x stride into the tensor map)
   int Cin, Cout, kblocks;
   float *out;
   long long out_pitch;        // floats between consecutive output pixels
@@ -152,7 +152,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       const unsigned a_box_bytes = (unsigned)(p.TW * p.TH * p.TN) * BK * 4u;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const TileCoord t = decode_tile(p, tile);
-        const int x0 = p.s_in * t.ix0, y0 = p.s_in * t.iy0;
+        const int x0 = p.s_in_x * t.ix0, y0 = p.s_in_y * t.iy0;
         for (int ti = p.class_start[t.cls]; ti < p.class_start[t.cls + 1]; ++ti) {
           const Tap tap = p.taps[ti];
           for (int kc = 0; kc < p.kblocks; ++kc) {
@@ -397,7 +397,7 @@ static int make_plan(tc::ConvParams &p, int &BN, int N, int Hin, int Win, int Ci
   p.Hout = Hout; p.Wout = Wout;
   int nt = 0;
   if (mode == 0) {
-    p.n_classes = 1; p.s_in = stride; p.s_out = 1; p.Hit = Hout; p.Wit = Wout;
+    p.n_classes = 1; p.s_in_x = p.s_in_y = stride; p.s_out = 1; p.Hit = Hout; p.Wit = Wout;
     p.class_px[0] = p.class_py[0] = 0;
     p.class_start[0] = 0;
     for (int ky = 0; ky < kh; ++ky)
@@ -405,7 +405,7 @@ static int make_plan(tc::ConvParams &p, int &BN, int N, int Hin, int Win, int Ci
     p.class_start[1] = nt;
   } else {
     UNFLOW_REQUIRE(Hout % stride == 0 && Wout % stride == 0, "tc_conv: transposed output extents must be multiples of the stride");
-    p.n_classes = stride * stride; p.s_in = 1; p.s_out = stride; p.Hit = Hout / stride; p.Wit = Wout / stride;
+    p.n_classes = stride * stride; p.s_in_x = p.s_in_y = 1; p.s_out = stride; p.Hit = Hout / stride; p.Wit = Wout / stride;
     int c = 0;
     for (int py = 0; py < stride; ++py)
       for (int px = 0; px < stride; ++px, ++c) {
@@ -456,7 +456,7 @@ extern "C" int unflow_tc_conv_plan(int N, int Hin, int Win, int Cin, int Hout, i
   const int need = 15 + 5 + 8 + 3 * nt;
   if (!out || cap < need) return -need;
   int i = 0;
-  const int head[15] = {p.n_classes, p.s_in, p.s_out, p.Hit, p.Wit, p.TW, p.TH, p.TN, p.tiles_x, p.tiles_y,
+  const int head[15] = {p.n_classes, p.s_in_y, p.s_out, p.Hit, p.Wit, p.TW, p.TH, p.TN, p.tiles_x, p.tiles_y,
                         p.tiles_n, p.n_blocks, BN, p.kblocks, nt};
   for (int k = 0; k < 15; ++k) out[i++] = head[k];
   for (int k = 0; k < 5; ++k) out[i++] = p.class_start[k];
@@ -489,8 +489,8 @@ extern "C" int unflow_tc_conv(const float *x, int N, int Hin, int Win, int Cin, 
   {
     cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)Win, (cuuint64_t)Hin, (cuuint64_t)N};
     cuuint64_t strides[3] = {(cuuint64_t)x_pitch * 4, (cuuint64_t)x_pitch * 4 * Win, (cuuint64_t)x_pitch * 4 * Win * Hin};
-    cuuint32_t box[4] = {(cuuint32_t)tc::BK, (cuuint32_t)(p.TW * p.s_in), (cuuint32_t)(p.TH * p.s_in), (cuuint32_t)p.TN};
-    cuuint32_t estr[4] = {1, (cuuint32_t)p.s_in, (cuuint32_t)p.s_in, 1};
+    cuuint32_t box[4] = {(cuuint32_t)tc::BK, (cuuint32_t)(p.TW * p.s_in_x), (cuuint32_t)(p.TH * p.s_in_y), (cuuint32_t)p.TN};
+    cuuint32_t estr[4] = {1, (cuuint32_t)p.s_in_x, (cuuint32_t)p.s_in_y, 1};
     int rc = tc::encode(&mA, x, 4, dims, strides, box, estr);
     if (rc) return rc;
   }
@@ -498,6 +498,59 @@ extern "C" int unflow_tc_conv(const float *x, int N, int Hin, int Win, int Cin, 
     const int Cp = (Cin + 3) / 4 * 4;
     cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)Cout, (cuuint64_t)(kh * kw)};
     cuuint64_t strides[2] = {(cuuint64_t)Cp * 4, (cuuint64_t)Cp * 4 * Cout};
+    cuuint32_t box[3] = {(cuuint32_t)tc::BK, (cuuint32_t)BN, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    int rc = tc::encode(&mBh, w_hi, 3, dims, strides, box, estr);
+    if (rc) return rc;
+    rc = tc::encode(&mBl, w_lo, 3, dims, strides, box, estr);
+    if (rc) return rc;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (BN == 128) return tc::launch<128>(mA, mBh, mBl, p, (int)total, st);
+  if (BN == 64) return tc::launch<64>(mA, mBh, mBl, p, (int)total, st);
+  return tc::launch<32>(mA, mBh, mBl, p, (int)total, st);
+}
+
+// First layers (7x7, stride 2, 3 / 6 / 14 input channels): with so few channels a K block of 32
+// channels per filter tap would be 90 % zeros.  In a channel-padded image (Cp = 4 / 8 / 16 floats per
+// pixel) the kw taps of one filter ROW are contiguous in memory -- 8 pixels x Cp floats -- so the layer
+// is run as a convolution with kh "taps" (the filter rows) whose contraction dimension is that
+// 8*Cp-float window: the tensor map's x axis counts OUTPUT columns with a stride of `stride` pixels
+// (overlapping windows), y keeps the element stride.  The image must be physically zero-padded in x
+// (pad_l pixels on the left, enough on the right for the last window) -- out-of-image ROWS are TMA
+// zero fill.  Weight planes: [kh][Cout][8*Cp] with column kx*Cp + c (zero for kx >= kw, c >= Cin).
+extern "C" int unflow_tc_conv_window(const float *xp, int N, int H, int Wp, int Cp, const float *w_hi,
+                                     const float *w_lo, float *y, int Hout, int Wout, int Cout, long long y_pitch,
+                                     const float *bias, float slope, int act, int kh, int stride, int pad_t,
+                                     void *stream) {
+  UNFLOW_REQUIRE(xp && w_hi && w_lo && y, "tc_conv_window: null pointer");
+  UNFLOW_REQUIRE(Cp == 4 || Cp == 8 || Cp == 16, "tc_conv_window: padded channel count must be 4, 8 or 16");
+  UNFLOW_REQUIRE(y_pitch % 4 == 0 && y_pitch >= Cout, "tc_conv_window: bad output pitch");
+  UNFLOW_REQUIRE(((uintptr_t)xp & 15) == 0 && ((uintptr_t)y & 15) == 0 && ((uintptr_t)w_hi & 15) == 0 &&
+                 ((uintptr_t)w_lo & 15) == 0, "tc_conv_window: pointers must be 16-byte aligned");
+  const int win = 8 * Cp;                              // floats per window = contraction length per filter row
+  UNFLOW_REQUIRE(N > 0 && H > 0 && Hout > 0 && Wout > 0 && Wp >= stride * (Wout - 1) + 8,
+                 "tc_conv_window: the padded row must hold the last 8-pixel window");
+  tc::ConvParams p{};
+  int BN = 0;
+  int rc0 = make_plan(p, BN, N, H, Wout, win, Hout, Wout, Cout, 0, stride, kh, 1, pad_t, 0);
+  if (rc0) return rc0;
+  p.s_in_x = 1;                                        // the x stride lives in the tensor map
+  p.out = y; p.out_pitch = y_pitch;
+  p.bias = bias; p.slope = slope; p.act = act; p.accumulate = 0;
+  const long long total = (long long)p.n_classes * p.tiles_n * p.tiles_y * p.tiles_x * p.n_blocks;
+  CUtensorMap mA, mBh, mBl;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)win, (cuuint64_t)Wout, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)stride * Cp * 4, (cuuint64_t)Wp * Cp * 4, (cuuint64_t)Wp * Cp * 4 * H};
+    cuuint32_t box[4] = {(cuuint32_t)tc::BK, (cuuint32_t)p.TW, (cuuint32_t)(p.TH * stride), (cuuint32_t)p.TN};
+    cuuint32_t estr[4] = {1, 1, (cuuint32_t)stride, 1};
+    int rc = tc::encode(&mA, xp, 4, dims, strides, box, estr);
+    if (rc) return rc;
+  }
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)win, (cuuint64_t)Cout, (cuuint64_t)kh};
+    cuuint64_t strides[2] = {(cuuint64_t)win * 4, (cuuint64_t)win * 4 * Cout};
     cuuint32_t box[3] = {(cuuint32_t)tc::BK, (cuuint32_t)BN, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     int rc = tc::encode(&mBh, w_hi, 3, dims, strides, box, estr);

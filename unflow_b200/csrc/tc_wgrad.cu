@@ -47,7 +47,7 @@ struct WgradParams {
   int R, C;                         // rows (channels of P) / columns (channels of G) of dW
   int cgroups, vgroups;             // 32-channel groups of G per tap; (tap, group) pairs = "virtual" column groups
   int r_blocks, c_blocks, taps, kw;  // c_blocks: blocks of BN/32 consecutive virtual groups
-  int stride, pad_t, pad_l;
+  int stride, stride_x, pad_t, pad_l;   // stride_x = 1 in the row-window form (x stride inside the tensor map)
   float *dw;
   long long pitch_r, pitch_t;       // dW[r * pitch_r + t * pitch_t + c]
 };
@@ -153,7 +153,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant_
             tma_4d(st + j * 4096, &mapP, full_raw(s), w.rb * BM + 32 * j, px, py, pn);
 #pragma unroll
           for (int j = 0; j < BN / 32; ++j)
-            tma_4d(st + 2 * A_BYTES + j * 4096, &mapG, full_raw(s), gch[j], p.stride * px + gdx[j],
+            tma_4d(st + 2 * A_BYTES + j * 4096, &mapG, full_raw(s), gch[j], p.stride_x * px + gdx[j],
                    p.stride * py + gdy[j], pn);
           if (++s == C::STAGES) { s = 0; ph ^= 1u; }
         }
@@ -323,7 +323,7 @@ static int make_plan(WgradParams &p, int &BN, int N, int Hp, int Wp, int R, int 
   UNFLOW_REQUIRE(stride == 1 || stride == 2, "tc_wgrad: stride must be 1 or 2");
   UNFLOW_REQUIRE(kh > 0 && kw > 0 && kh * kw <= 64, "tc_wgrad: at most 64 taps");
   p.N = N; p.Hp = Hp; p.Wp = Wp; p.R = R; p.C = C;
-  p.taps = kh * kw; p.kw = kw; p.stride = stride; p.pad_t = pad_t; p.pad_l = pad_l;
+  p.taps = kh * kw; p.kw = kw; p.stride = p.stride_x = stride; p.pad_t = pad_t; p.pad_l = pad_l;
   choose_box(p);
   p.cgroups = (C + 31) / 32; p.vgroups = p.taps * p.cgroups;
   BN = p.vgroups >= 4 ? 128 : (p.vgroups >= 2 ? 64 : 32);
@@ -386,6 +386,47 @@ extern "C" int unflow_tc_wgrad(const float *P, int N, int Hp, int Wp, int R, lon
     cuuint32_t box[4] = {32, (cuuint32_t)(p.TW * stride), (cuuint32_t)(p.TH * stride), (cuuint32_t)p.TN};
     cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
     rc = tc::encode(&mG, G, 4, dims, strides, box, estr, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    if (rc) return rc;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (BN == 128) return tcw::launch<128>(mP, mG, p, (int)total, st);
+  if (BN == 64) return tcw::launch<64>(mP, mG, p, (int)total, st);
+  return tcw::launch<32>(mP, mG, p, (int)total, st);
+}
+
+// Weight gradient of the row-window form of the first layers (see unflow_tc_conv_window):
+//     dw[co][ky][kx*Cp + c] += sum_p gpre[p][co] * xp[n, stride*y + ky - pad_t, window of output column x][kx*Cp + c]
+extern "C" int unflow_tc_wgrad_window(const float *P, int N, int Ho, int Wo, int R, long long p_pitch,
+                                      const float *xp, int H, int Wp, int Cp, float *dw, int kh, int stride,
+                                      int pad_t, void *stream) {
+  UNFLOW_REQUIRE(P && xp && dw, "tc_wgrad_window: null pointer");
+  UNFLOW_REQUIRE(Cp == 4 || Cp == 8 || Cp == 16, "tc_wgrad_window: padded channel count must be 4, 8 or 16");
+  UNFLOW_REQUIRE(p_pitch % 4 == 0 && p_pitch >= R, "tc_wgrad_window: bad pitch");
+  UNFLOW_REQUIRE(((uintptr_t)P & 15) == 0 && ((uintptr_t)xp & 15) == 0, "tc_wgrad_window: pointers must be 16-byte aligned");
+  UNFLOW_REQUIRE(H > 0 && Wp >= stride * (Wo - 1) + 8, "tc_wgrad_window: the padded row must hold the last 8-pixel window");
+  const int win = 8 * Cp;
+  tcw::WgradParams p{};
+  int BN = 0;
+  int rc = tcw::make_plan(p, BN, N, Ho, Wo, R, win, stride, kh, 1, pad_t, 0);
+  if (rc) return rc;
+  p.stride_x = 1;
+  p.dw = dw; p.pitch_r = (long long)kh * win; p.pitch_t = win;
+  const long long total = (long long)p.n_chunks * p.r_blocks * p.c_blocks;
+  CUtensorMap mP, mG;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)R, (cuuint64_t)Wo, (cuuint64_t)Ho, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)p_pitch * 4, (cuuint64_t)p_pitch * 4 * Wo, (cuuint64_t)p_pitch * 4 * Wo * Ho};
+    cuuint32_t box[4] = {32, (cuuint32_t)p.TW, (cuuint32_t)p.TH, (cuuint32_t)p.TN};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    rc = tc::encode(&mP, P, 4, dims, strides, box, estr, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    if (rc) return rc;
+  }
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)win, (cuuint64_t)Wo, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)stride * Cp * 4, (cuuint64_t)Wp * Cp * 4, (cuuint64_t)Wp * Cp * 4 * H};
+    cuuint32_t box[4] = {32, (cuuint32_t)p.TW, (cuuint32_t)(p.TH * stride), (cuuint32_t)p.TN};
+    cuuint32_t estr[4] = {1, 1, (cuuint32_t)stride, 1};
+    rc = tc::encode(&mG, xp, 4, dims, strides, box, estr, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     if (rc) return rc;
   }
   cudaStream_t st = (cudaStream_t)stream;

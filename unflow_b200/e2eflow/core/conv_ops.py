@@ -320,6 +320,58 @@ class _ConvTC(torch.autograd.Function):
         return gx, gw, gb, None, None, None
 
 
+class _ConvWindow(torch.autograd.Function):
+    """The first layers (7x7, stride 2, 3 / 6 / 14 input channels) in the row-window form of
+    csrc/tc_conv.cu / tc_wgrad.cu: the kw taps of a filter row are one contiguous window of the
+    channel-padded image, so the layer is a convolution with kh taps and an 8*Cp-wide contraction.
+    ``w_rw`` is the variable in that form (tc_conv.window_weights, differentiable); the input gets no
+    gradient (images / detached inputs)."""
+
+    @staticmethod
+    def forward(ctx, x, w_rw, b, kh, stride, pads, act):
+        from . import tc_conv
+        Co = w_rw.shape[0]
+        N, _, H, W = x.shape
+        pt, pb, pl, pr = pads
+        Ho, Wo = (H + pt + pb - kh) // stride + 1, (W + pl + pr - kh) // stride + 1
+        xp = tc_conv.window_input(x, pl, stride, Wo)
+        buf = torch.empty((N, Ho, Wo, _round4(Co)), device=x.device, dtype=torch.float32)
+        y = buf[..., :Co].permute(0, 3, 1, 2)
+        tc_conv.run_window(xp, tc_conv.split_weights(_khwc(w_rw)), y, kh=kh, stride=stride, pad_t=pt, bias=b,
+                           act=bool(act))
+        ctx.save_for_backward(xp, w_rw, y if act else None)
+        ctx.cfg = (kh, stride, pt, b is not None, bool(act))
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        from . import tc_conv
+        xp, w_rw, a = ctx.saved_tensors
+        kh, stride, pt, has_b, act = ctx.cfg
+        Co = w_rw.shape[0]
+        gw = gb = None
+        a_dense = a
+        if act and (tc_conv.nhwc_geometry(a)[4] != Co):
+            a_dense = a.contiguous(memory_format=torch.channels_last)
+        gpre, gb_all = _lrelu_bwd_bias(g, a_dense if act else None, has_b and ctx.needs_input_grad[2])
+        if has_b and ctx.needs_input_grad[2]:
+            gb = gb_all
+        if ctx.needs_input_grad[1]:
+            A, B, k1, k2 = w_rw.shape
+            gw = torch.zeros((A, k1, k2, B), device=w_rw.device, dtype=torch.float32).permute(0, 3, 1, 2)
+            tc_conv.wgrad_window(gpre, xp, gw, kh=kh, stride=stride, pad_t=pt)
+        return None, gw, gb, None, None, None, None
+
+
+_WINDOW = __import__('os').environ.get('UNFLOW_CONV1_WINDOW', '1') != '0'
+
+
+def _use_window(x, w, stride):
+    return (_WINDOW and _TC and _TC_WGRAD and _MODE == '3xtf32' and x.is_cuda and stride in (2, (2, 2))
+            and w.shape[2] == w.shape[3] and 5 <= w.shape[2] <= 8 and w.shape[1] <= 16 and w.shape[0] % 4 == 0
+            and not x.requires_grad)
+
+
 class _DeconvTC(torch.autograd.Function):
     """slim.conv2d_transpose(k=4, stride=2, SAME) on the same kernel (four output-parity classes)."""
 
@@ -492,6 +544,10 @@ def conv2d(x, w, b, stride, pads, act=False):
     if _MODE == '3xtf32' and x.is_cuda:
         if not act and _use_narrow(x, w, stride, pads):
             return _NarrowConv3x3.apply(x, w, b)
+        if _use_window(x, w, stride):
+            from . import tc_conv
+            w_rw = tc_conv.window_weights(w, tc_conv.window_channels(w.shape[1]))
+            return _ConvWindow.apply(x, w_rw, b, w.shape[2], 2, tuple(pads), bool(act))
         if _use_space_to_depth(x, w, stride):
             xs, ws = space_to_depth_operands(x, w, pads)
             return conv2d(xs, ws, b, 1, (0, 0, 0, 0), act=act)

@@ -115,3 +115,58 @@ def wgrad(P, G, dw, *, stride, kh, kw, pad_t, pad_l):
                                             dw.data_ptr(), kh * kw * C, C, stride, kh, kw, pad_t, pad_l,
                                             _stream()), "tc_wgrad")
     return dw
+
+
+# ---- first layers in the row-window form (unflow_tc_conv_window / unflow_tc_wgrad_window) ----------
+def window_channels(c):
+    """Padded channel count (floats per pixel) of the row-window input: 4, 8 or 16; None if c > 16."""
+    for cp in (4, 8, 16):
+        if c <= cp:
+            return cp
+    return None
+
+
+def window_input(x, pad_l, stride, wout):
+    """x: NCHW-shaped [N,C,H,W] (any strides) -> the zero-padded NHWC buffer [N,H,Wp,Cp] the window kernels
+    read: pad_l zero pixels on the left, zeros on the right up to the end of the last 8-pixel window."""
+    N, C, H, W = x.shape
+    cp = window_channels(C)
+    wp = max(W + pad_l, stride * (wout - 1) + 8)
+    buf = torch.zeros((N, H, wp, cp), device=x.device, dtype=torch.float32)
+    buf[:, :, pad_l:pad_l + W, :C].copy_(x.permute(0, 2, 3, 1))
+    return buf
+
+
+def window_weights(w, cp):
+    """[Co, Ci, kh, kw] variable (memory [Co][kh][kw][Ci]) -> the differentiable row-window form
+    [Co, 8*cp, kh, 1] (memory [Co][kh][1][8*cp], column kx*cp + c; zero for kx >= kw, c >= Ci)."""
+    Co, Ci, kh, kw = w.shape
+    assert kw <= 8 and Ci <= cp
+    wn = torch.nn.functional.pad(w.permute(0, 2, 3, 1), (0, cp - Ci, 0, 8 - kw))       # [Co, kh, 8, cp]
+    return wn.reshape(Co, kh, 1, 8 * cp).permute(0, 3, 1, 2)
+
+
+def run_window(xp, planes, out, *, kh, stride, pad_t, bias=None, act=False, slope=0.1):
+    N, H, Wp, Cp = xp.shape
+    go = nhwc_geometry(out)
+    No, Hout, Wout, Cout, yp = go
+    assert No == N and planes.rows == Cout and planes.cols == 8 * Cp and planes.taps == kh and xp.is_contiguous()
+    with torch.cuda.device(xp.device):
+        check(_native.lib().unflow_tc_conv_window(
+            xp.data_ptr(), N, H, Wp, Cp, planes.hi.data_ptr(), planes.lo.data_ptr(), out.data_ptr(), Hout, Wout,
+            Cout, yp, bias.data_ptr() if bias is not None else None, float(slope), 1 if act else 0, kh, stride,
+            pad_t, _stream()), "tc_conv_window")
+    return out
+
+
+def wgrad_window(P, xp, dw, *, kh, stride, pad_t):
+    """dw [Co, 8*Cp, kh, 1] (memory [Co][kh][1][8*Cp], zeroed) += the row-window weight gradient."""
+    N, Ho, Wo, R, pp = nhwc_geometry(P)
+    Nx, H, Wp, Cp = xp.shape
+    assert Nx == N and tuple(dw.shape) == (R, 8 * Cp, kh, 1) and xp.is_contiguous()
+    want = (kh * 8 * Cp, 1, 8 * Cp, 8 * Cp)
+    assert all(n == 1 or s == t for n, s, t in zip(dw.shape, dw.stride(), want))
+    with torch.cuda.device(P.device):
+        check(_native.lib().unflow_tc_wgrad_window(P.data_ptr(), N, Ho, Wo, R, pp, xp.data_ptr(), H, Wp, Cp,
+                                                   dw.data_ptr(), kh, stride, pad_t, _stream()), "tc_wgrad_window")
+    return dw
