@@ -83,6 +83,21 @@ int unflow_correlation_bwd(const float *gout, const float *in0, const float *in1
  * 0 = generic kernel, 1 = tiled TMA kernel (the FlowNetC path). */
 int unflow_correlation_fwd_path(int C, int H, int W, int kernel_size, int max_displacement,
                                 int pad, int stride_1, int stride_2);
+/* Both cost volumes of the bidirectional pass (reference call site src/e2eflow/core/flownet.py:34-44:
+ * flownet_c(conv3_a, conv3_b, ..) and flownet_c(conv3_b, conv3_a, ..)) in ONE launch:
+ *   out = Correlation(in0, in1),  out_rev = Correlation(in1, in0)
+ * using corr(in1,in0)[(-p,-o)](y+s2*p, x+s2*o) == corr(in0,in1)[(p,o)](y,x): the second volume is a
+ * second store of the first one's accumulators (zero where the displaced pixel leaves the image) and is
+ * bit-identical to a second launch.  unflow_correlation_fold_grad adds the re-indexed gradient of the
+ * reverse volume to the forward one's, so unflow_correlation_bwd(gout_eff, in0, in1) yields the
+ * gradients of BOTH volumes.  Served for the attribute / shape set of the tiled kernel only
+ * (unflow_correlation_fwd_path == 1), UNFLOW_EINVAL otherwise. */
+int unflow_correlation_fwd_bidir(const float *in0, const float *in1, float *out, float *out_rev, int B,
+                                 int C, int H, int W, int kernel_size, int max_displacement, int pad,
+                                 int stride_1, int stride_2, void *stream);
+int unflow_correlation_fold_grad(const float *gout, const float *gout_rev, float *gout_eff, int B, int C,
+                                 int H, int W, int kernel_size, int max_displacement, int pad,
+                                 int stride_1, int stride_2, void *stream);
 
 /* ------------------------------------------------------------------------
  * BackwardWarp / image_warp
@@ -203,10 +218,12 @@ int unflow_conv_operand_tf32(const float *x, float *out, int N, int C, int H, in
 int unflow_bias_lrelu(float *y, const float *bias, long long pixels, int C, float slope, void *stream);
 /* unflow_lrelu_bwd_bias: unflow_bias_grad_lrelu that also writes gpre = g * lrelu'(act) as dense
  * NHWC [N,H,W,C] (NULL: skip) -- the gradient w.r.t. the pre-activation output, the operand of the
- * tensor-core input / weight gradient kernels (one pass over g instead of two). */
+ * tensor-core input / weight gradient kernels (one pass over g instead of two).  Here `act` may be a
+ * channel slice of a concat buffer: `act_pitch` floats between pixels; gpre is written with
+ * `gpre_pitch` floats between pixels (>= C; a multiple of 4 for the tensor-core kernels). */
 int unflow_lrelu_bwd_bias(const float *g, long long sN, long long sC, long long sH, long long sW,
-                          const float *act, float *gpre, float *gb, int N, int C, int H, int W,
-                          float slope, void *stream);
+                          const float *act, long long act_pitch, float *gpre, long long gpre_pitch,
+                          float *gb, int N, int C, int H, int W, float slope, void *stream);
 int unflow_bias_grad_lrelu(const float *g, long long sN, long long sC, long long sH, long long sW,
                            const float *act, float *gb, int N, int C, int H, int W, float slope,
                            void *stream);
@@ -218,13 +235,13 @@ int unflow_bias_grad_lrelu(const float *g, long long sN, long long sC, long long
  *   x    NHWC [N,H,W,C] with `x_pitch` floats between pixels (>= C: a channel slice of a concat
  *        buffer is allowed), C even
  *   w    [2][3][3][C]  (OIHW weights stored channels-last = TF's HWIO with O moved to the front)
- *   bias [2] or NULL;  y dense NHWC [N,H,W,2], 8-byte aligned
+ *   bias [2] or NULL;  y NHWC [N,H,W,2] with `y_pitch` (even) floats between pixels, 8-byte aligned
  *   g    gradient w.r.t. y as a logical [N,2,H,W] tensor read through strides (floats)
  *   gw   [2][3][3][C], written (not accumulated); deterministic two-pass reduction through
  *        ``workspace`` (unflow_conv3x3_narrow_wgrad_workspace_bytes bytes).
  * UNFLOW_EINVAL unless C_out == 2 and C is even. */
 int unflow_conv3x3_narrow_fwd(const float *x, long long x_pitch, const float *w, const float *bias, float *y,
-                              int N, int H, int W, int C, int C_out, void *stream);
+                              long long y_pitch, int N, int H, int W, int C, int C_out, void *stream);
 size_t unflow_conv3x3_narrow_wgrad_workspace_bytes(int N, int H, int W, int C);
 int unflow_conv3x3_narrow_wgrad(const float *x, long long x_pitch, const float *g, long long gsN, long long gsC,
                                 long long gsH, long long gsW, float *gw, void *workspace, int N, int H,

@@ -42,8 +42,17 @@ def _worker(rank, world, port, out):
     loss = tr.loss(im1[sl], im2[sl])
     loss.backward()
     scale = tr.reduce_gradients()
+    single = tr.flat_grad * scale
+    # the same step with the bucketed all-reduce launched from the backward checkpoints (core/train.py
+    # _backward_overlapped): decoder slice, trunk slice, head -- must give the identical mean
+    tr.flat_grad.zero_()
+    plan = tr._bucket_plan()
+    assert plan is not None and len(plan[0]) == 2 and 0 < plan[1] < tr.flat_grad.numel()
+    tr._backward_overlapped(tr.loss(im1[sl], im2[sl]))
+    overlapped = tr.flat_grad * scale
     if rank == 0:
-        torch.save({"grad": tr.flat_grad * scale, "param": tr.flat_param.clone(), "n": tr.num_params}, out)
+        torch.save({"grad": single, "grad_overlapped": overlapped, "param": tr.flat_param.clone(),
+                    "n": tr.num_params}, out)
     with pytest.raises(RuntimeError):
         tr.apply_update(1e-4, scale)                # the optimiser kernel is CUDA only: loud failure
     dist.destroy_process_group()
@@ -63,6 +72,8 @@ def test_two_rank_gradient_mean_equals_single_rank_on_concatenated_batch(tmp_pat
     loss.backward()
     err = float((tr.flat_grad - got["grad"]).norm() / tr.flat_grad.norm())
     assert err < 1e-5, err
+    # the bucketed, backward-overlapped all-reduce reduces the same numbers in the same order per element
+    assert torch.equal(got["grad_overlapped"], got["grad"])
 
 
 def test_flat_views_alias_parameters():

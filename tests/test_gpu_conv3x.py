@@ -170,13 +170,13 @@ def test_narrow_flow_head_matches_float64(mode3x, N, C, H, W):
     wc = w.cuda().contiguous(memory_format=torch.channels_last).requires_grad_(True)
     bc = b.cuda().requires_grad_(True)
     y = conv_ops._NarrowConv3x3.apply(xc, wc, bc)
-    assert y.shape == (N, 2, H, W) and y.is_contiguous(memory_format=torch.channels_last)
+    assert y.shape == (N, 2, H, W) and y.stride() == (H * W * 4, 1, W * 4, 4)   # NHWC, 4 floats per pixel (TMA-readable)
     gc = gwide.cuda().permute(0, 3, 1, 2)[:, 1:3]
     y.backward(gc)
     assert rel(y.detach().cpu(), yd.detach()) < 2e-6
     assert rel(wc.grad.cpu(), wd.grad) < 2e-6
     assert rel(bc.grad.cpu(), bd.grad) < 2e-6
-    assert rel(xc.grad.cpu(), xd.grad) < 3e-5                    # 3xTF32 library path
+    assert rel(xc.grad.cpu(), xd.grad) < 3e-5                    # input gradient on the tensor-core kernel
     # deterministic: a second evaluation gives the same bits
     wc2 = wc.detach().clone().requires_grad_(True)
     y2 = conv_ops._NarrowConv3x3.apply(xc.detach(), wc2, bc.detach())
@@ -197,10 +197,11 @@ def test_narrow_conv_rejects_other_shapes():
     w = torch.zeros(2, 3, 3, 6, device="cuda")
     s = torch.cuda.current_stream().cuda_stream
     lib = _native.lib()
-    assert lib.unflow_conv3x3_narrow_fwd(x.data_ptr(), 6, w.data_ptr(), None, y.data_ptr(), 1, 4, 4, 6, 4, s) == 1
+    assert lib.unflow_conv3x3_narrow_fwd(x.data_ptr(), 6, w.data_ptr(), None, y.data_ptr(), 2, 1, 4, 4, 6, 4, s) == 1
     assert "2 output channels" in _native.lib().unflow_last_error().decode()
-    assert lib.unflow_conv3x3_narrow_fwd(x.data_ptr(), 6, w.data_ptr(), None, y.data_ptr(), 1, 4, 4, 5, 2, s) == 1
-    assert lib.unflow_conv3x3_narrow_fwd(x.data_ptr(), 4, w.data_ptr(), None, y.data_ptr(), 1, 4, 4, 6, 2, s) == 1   # pitch < C
+    assert lib.unflow_conv3x3_narrow_fwd(x.data_ptr(), 6, w.data_ptr(), None, y.data_ptr(), 2, 1, 4, 4, 5, 2, s) == 1
+    assert lib.unflow_conv3x3_narrow_fwd(x.data_ptr(), 4, w.data_ptr(), None, y.data_ptr(), 2, 1, 4, 4, 6, 2, s) == 1   # pitch < C
+    assert lib.unflow_conv3x3_narrow_fwd(x.data_ptr(), 6, w.data_ptr(), None, y.data_ptr(), 3, 1, 4, 4, 6, 2, s) == 1   # odd y pitch
     assert lib.unflow_conv3x3_narrow_wgrad_workspace_bytes(2, 16, 32, 6) == 2 * 18 * 6 * 4
     assert lib.unflow_conv3x3_narrow_wgrad_workspace_bytes(2, 17, 33, 6) == 8 * 18 * 6 * 4
 

@@ -154,6 +154,34 @@ def test_correlation_forward_variants_bit_identical():
     assert lib.unflow_set_int_option(b"corr_fwd_variant", 2) == 1
 
 
+@pytest.mark.parametrize("shape,md", [((2, 48, 20, 56), 20), ((1, 24, 12, 32), 8), ((4, 256, 48, 160), 20)])
+def test_correlation_bidirectional_one_pass(shape, md):
+    """Both cost volumes of the bidirectional pass from ONE forward launch (the reverse volume is a
+    re-indexing of the forward accumulators, flownet.py:34-44 / SURVEY.md H1b): forward bit-identical to
+    two launches, gradients equal to the sum autograd forms from the two separate ops."""
+    ops = _ops()
+    kw = dict(pad=md, kernel_size=1, max_displacement=md, stride_1=1, stride_2=2)
+    a, b = rnd(shape, 41).cuda().requires_grad_(True), rnd(shape, 42).cuda().requires_grad_(True)
+    ab, ba = ops.correlation_bidir(a, b, **kw)
+    a2, b2 = a.detach().clone().requires_grad_(True), b.detach().clone().requires_grad_(True)
+    ab2, ba2 = ops.correlation(a2, b2, **kw), ops.correlation(b2, a2, **kw)
+    assert torch.equal(ab, ab2) and torch.equal(ba, ba2)
+    gab, gba = rnd(tuple(ab.shape), 43).cuda(), rnd(tuple(ab.shape), 44).cuda()
+    (ab * gab).sum().add((ba * gba).sum()).backward()
+    (ab2 * gab).sum().add((ba2 * gba).sum()).backward()
+    for got, want in ((a.grad, a2.grad), (b.grad, b2.grad)):
+        scale = float(want.abs().max())
+        assert float((got - want).abs().max()) <= 2e-6 * scale
+
+
+def test_correlation_bidir_falls_back_for_other_attributes():
+    ops = _ops()
+    a, b = rnd((1, 8, 10, 14), 1).cuda(), rnd((1, 8, 10, 14), 2).cuda()
+    kw = dict(pad=4, kernel_size=3, max_displacement=3, stride_1=2, stride_2=1)      # generic kernel
+    ab, ba = ops.correlation_bidir(a, b, **kw)
+    assert torch.equal(ab, ops.correlation(a, b, **kw)) and torch.equal(ba, ops.correlation(b, a, **kw))
+
+
 def test_correlation_errors():
     ops = _ops()
     a = rnd((1, 2, 4, 4), 1).cuda()

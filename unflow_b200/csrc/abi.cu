@@ -15,6 +15,7 @@ void set_error(const char *fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+int set_tc_a_tmem(int v);       // tc_conv.cu
 void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 }  // namespace unflow
 
@@ -28,6 +29,7 @@ int unflow_set_int_option(const char *name, int value) {
     unflow::g_corr_fwd_variant = value;
     return UNFLOW_OK;
   }
+  if (name && !strcmp(name, "tc_a_tmem") && unflow::set_tc_a_tmem(value)) return UNFLOW_OK;
   unflow::set_error("unknown option or value: %s=%d", name ? name : "(null)", value);
   return UNFLOW_EINVAL;
 }

@@ -174,8 +174,39 @@ extern "C" int unflow_correlation_fwd(const float *in0, const float *in1, float 
   if (rc != UNFLOW_OK) return rc;
   if (B == 0) return UNFLOW_OK;
   UNFLOW_REQUIRE(in0 && in1 && out, "correlation: null pointer");
-  if (corr_tiled_supported(g)) return corr_fwd_tiled(in0, in1, out, g, (cudaStream_t)stream);
+  if (corr_tiled_supported(g)) return corr_fwd_tiled(in0, in1, out, nullptr, g, (cudaStream_t)stream);
   return corr_fwd_generic(in0, in1, out, g, (cudaStream_t)stream);
+}
+
+// Both cost volumes of the bidirectional pass (flownet.py:34-44) in ONE launch: out = corr(in0, in1),
+// out_rev = corr(in1, in0), the second obtained by re-indexing the accumulators of the first
+// (corr(in1,in0)[(-p,-o)](y+2p, x+2o) == corr(in0,in1)[(p,o)](y,x)); bit-identical to two launches.
+// Only the FlowNetC geometry of the tiled kernel (unflow_correlation_fwd_path == 1); UNFLOW_EINVAL else.
+extern "C" int unflow_correlation_fwd_bidir(const float *in0, const float *in1, float *out, float *out_rev,
+                                            int B, int C, int H, int W, int kernel_size, int max_displacement,
+                                            int pad, int stride_1, int stride_2, void *stream) {
+  CorrGeom g;
+  int rc = make_corr_geom(g, B, C, H, W, kernel_size, max_displacement, pad, stride_1, stride_2);
+  if (rc != UNFLOW_OK) return rc;
+  if (B == 0) return UNFLOW_OK;
+  UNFLOW_REQUIRE(in0 && in1 && out && out_rev, "correlation_bidir: null pointer");
+  UNFLOW_REQUIRE(corr_tiled_supported(g), "correlation_bidir: attributes / shape not served by the tiled kernel");
+  return corr_fwd_tiled(in0, in1, out, out_rev, g, (cudaStream_t)stream);
+}
+
+// gout_eff = gout + re-indexed gout_rev: the gradient of both cost volumes w.r.t. (in0, in1) is then
+// unflow_correlation_bwd(gout_eff, in0, in1).
+extern "C" int unflow_correlation_fold_grad(const float *gout, const float *gout_rev, float *gout_eff, int B,
+                                            int C, int H, int W, int kernel_size, int max_displacement, int pad,
+                                            int stride_1, int stride_2, void *stream) {
+  CorrGeom g;
+  int rc = make_corr_geom(g, B, C, H, W, kernel_size, max_displacement, pad, stride_1, stride_2);
+  if (rc != UNFLOW_OK) return rc;
+  if (B == 0) return UNFLOW_OK;
+  UNFLOW_REQUIRE(gout && gout_rev && gout_eff, "correlation_fold_grad: null pointer");
+  UNFLOW_REQUIRE(corr_tiled_supported(g), "correlation_fold_grad: attributes / shape not served by the tiled kernel");
+  UNFLOW_REQUIRE((((uintptr_t)gout | (uintptr_t)gout_rev | (uintptr_t)gout_eff) & 7) == 0, "correlation_fold_grad: pointers must be 8-byte aligned");
+  return corr_fold_grad(gout, gout_rev, gout_eff, g, (cudaStream_t)stream);
 }
 
 extern "C" int unflow_correlation_bwd(const float *gout, const float *in0, const float *in1,

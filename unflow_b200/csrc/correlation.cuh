@@ -21,7 +21,9 @@ int corr_bwd_generic(const float *gout, const float *in0, const float *in1, floa
 // correlation_tiled.cu
 extern int g_corr_fwd_variant;
 bool corr_tiled_supported(const CorrGeom &g);
-int corr_fwd_tiled(const float *in0, const float *in1, float *out, const CorrGeom &g, cudaStream_t s);
+int corr_fwd_tiled(const float *in0, const float *in1, float *out, float *out_rev, const CorrGeom &g,
+                   cudaStream_t s);
+int corr_fold_grad(const float *gout, const float *gout_rev, float *geff, const CorrGeom &g, cudaStream_t s);
 int corr_bwd_tiled(const float *gout, const float *in0, const float *in1, float *g0, float *g1,
                    const CorrGeom &g, cudaStream_t s);
 

@@ -122,7 +122,8 @@ __device__ __forceinline__ void tma_load_5d(void *dst, const CUtensorMap *map, u
 __global__ void __launch_bounds__(ct::NTHREADS, 1)
 corr_fwd_tiled_kernel(const __grid_constant__ CUtensorMap map0,  // in0 as [B][C][H/2][2][W]
                       const __grid_constant__ CUtensorMap map1,  // in1 as [B][C][H][W]
-                      float *__restrict__ out, int C, int H, int W, int r, int y2_first) {
+                      float *__restrict__ out, float *__restrict__ out_rev, int C, int H, int W, int r,
+                      int y2_first) {
   using namespace ct;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
@@ -284,7 +285,47 @@ corr_fwd_tiled_kernel(const __grid_constant__ CUtensorMap map0,  // in0 as [B][C
       if (x + 4 < W)
         *reinterpret_cast<float4 *>(dst + 4) =
             make_float4(acc[t][4] / denom, acc[t][5] / denom, acc[t][6] / denom, acc[t][7] / denom);
+      if (out_rev) {
+        // The cost volume of the OTHER direction is a re-indexing of this one:
+        //   corr(in1,in0)[(-p,-o)](y2, x+2o) == corr(in0,in1)[(p,o)](y, x),   y2 = y + 2p
+        // (same products, same summation order over the channels -> bit-identical to a second launch
+        // with swapped inputs).  Elements of the reverse volume whose displaced pixel is outside the
+        // image are never produced here: the launcher zero-fills the volume first.
+        float *rev = out_rev + (size_t)b * D * D * plane_out +
+                     ((size_t)((2 * r - pidx) * D + (r - o))) * plane_out + (size_t)(Y2 + y2r) * W;
+#pragma unroll
+        for (int j = 0; j < PX / 2; ++j) {
+          const int xs = x + 2 * j, xr = xs + S2 * o;      // source column, reverse-volume column (both even)
+          if (xs < W && xr >= 0 && xr < W)
+            *reinterpret_cast<float2 *>(rev + xr) = make_float2(acc[t][2 * j] / denom, acc[t][2 * j + 1] / denom);
+        }
+      }
     }
+  }
+}
+
+// gout_eff[(p,o)](y,x) = gout[(p,o)](y,x) + gout_rev[(-p,-o)](y+2p, x+2o): folds the gradient of the
+// reverse cost volume into the forward one, so ONE pair of backward launches serves both directions.
+__global__ void __launch_bounds__(256)
+corr_fold_grad_kernel(const float *__restrict__ g, const float *__restrict__ grev, float *__restrict__ geff,
+                      int D, int H, int W, long long total2) {
+  const int r = D / 2, W2 = W / 2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total2;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long t = i;
+    const int x = (int)(t % W2) * 2; t /= W2;
+    const int y = (int)(t % H); t /= H;
+    const int ch = (int)(t % (D * D));
+    const long long b = t / (D * D);
+    const int p = ch / D - r, o = ch % D - r;
+    float2 v = *reinterpret_cast<const float2 *>(g + 2 * i);
+    const int yr = y + ct::S2 * p, xr = x + ct::S2 * o;
+    if (yr >= 0 && yr < H && xr >= 0 && xr < W) {
+      const float2 w = *reinterpret_cast<const float2 *>(
+          grev + ((b * D * D + (long long)((r - p) * D + (r - o))) * H + yr) * W + xr);
+      v.x += w.x; v.y += w.y;
+    }
+    *reinterpret_cast<float2 *>(geff + 2 * i) = v;
   }
 }
 
@@ -532,8 +573,23 @@ bool corr_tiled_supported(const CorrGeom &g) {
          g.H % 2 == 0 && g.W % 4 == 0 && g.W >= ct::TX && g.H >= 2 && g.B <= 65535;
 }
 
-int corr_fwd_tiled(const float *in0, const float *in1, float *out, const CorrGeom &g, cudaStream_t s) {
+int corr_fold_grad(const float *gout, const float *gout_rev, float *geff, const CorrGeom &g, cudaStream_t s) {
+  const int D = 2 * g.ngr + 1;
+  const long long total2 = (long long)g.B * D * D * g.H * (g.W / 2);
+  corr_fold_grad_kernel<<<grid_for(total2, 256, 16), 256, 0, s>>>(gout, gout_rev, geff, D, g.H, g.W, total2);
+  count_launch();
+  return check_launch("correlation_fold_grad");
+}
+
+int corr_fwd_tiled(const float *in0, const float *in1, float *out, float *out_rev, const CorrGeom &g,
+                   cudaStream_t s) {
   using namespace ct;
+  if (out_rev) {
+    if ((uintptr_t)out_rev & 15) { set_error("correlation: pointers must be 16-byte aligned"); return UNFLOW_EINVAL; }
+    const int D = 2 * g.ngr + 1;
+    cudaError_t e = cudaMemsetAsync(out_rev, 0, sizeof(float) * (size_t)g.B * D * D * g.H * g.W, s);
+    if (e != cudaSuccess) { set_error("correlation memset: %s", cudaGetErrorString(e)); return UNFLOW_ECUDA; }
+  }
   if (((uintptr_t)in0 | (uintptr_t)in1 | (uintptr_t)out) & 15) {
     set_error("correlation: pointers must be 16-byte aligned");
     return UNFLOW_EINVAL;
@@ -557,7 +613,7 @@ int corr_fwd_tiled(const float *in0, const float *in1, float *out, const CorrGeo
   }
   static bool attr_set = false;
   const int smem_bytes = (int)sizeof(Smem), smem_bytes2 = (int)sizeof(ct2::Smem2);
-  const int variant = g_corr_fwd_variant;   // 1: pair per thread, 3: trio per thread (default)
+  const int variant = out_rev ? 1 : g_corr_fwd_variant;   // 1: pair per thread (default; the bidirectional form), 3: trio per thread
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(corr_fwd_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          smem_bytes);
@@ -571,7 +627,7 @@ int corr_fwd_tiled(const float *in0, const float *in1, float *out, const CorrGeo
   const int y2_end = g.H + S2 * r;  // exclusive
   dim3 grid(ceil_div(g.W, TX), ceil_div(y2_end - y2_first, NY2), g.B);
   if (variant == 1)
-    corr_fwd_tiled_kernel<<<grid, NTHREADS, smem_bytes, s>>>(map0, map1, out, g.C, g.H, g.W, r, y2_first);
+    corr_fwd_tiled_kernel<<<grid, NTHREADS, smem_bytes, s>>>(map0, map1, out, out_rev, g.C, g.H, g.W, r, y2_first);
   else
     corr_fwd_tiled3_kernel<<<grid, ct2::NTHREADS2, smem_bytes2, s>>>(map0, map1, out, g.C, g.H, g.W, r, y2_first);
   count_launch();

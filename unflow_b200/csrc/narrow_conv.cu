@@ -86,7 +86,7 @@ __device__ __forceinline__ void stage(float *xs, const float *__restrict__ x, in
 
 __global__ void __launch_bounds__(THREADS, 4)
 narrow_fwd_kernel(const float *__restrict__ x, const float *__restrict__ w, const float *__restrict__ bias,
-                  float *__restrict__ y, int H, int W, int C, long long XP) {
+                  float *__restrict__ y, int H, int W, int C, long long XP, long long YP) {
   // rows 38 floats apart: a half-warp's 8-byte reads (two tile rows) fall on disjoint banks;
   // channels 706 = 2 (mod 32) floats apart: the staging stores are conflict-free
   constexpr int CHS = FWD_CHS, FP = FWD_PITCH;
@@ -137,11 +137,11 @@ narrow_fwd_kernel(const float *__restrict__ x, const float *__restrict__ w, cons
   const int gy = y0 + row;
   if (gy < H) {
     const float b0 = bias ? bias[0] : 0.f, b1 = bias ? bias[1] : 0.f;
-    float2 *out = reinterpret_cast<float2 *>(y) + ((long long)n * H + gy) * W;
+    float *out = y + ((long long)n * H + gy) * W * YP;          // YP floats between output pixels (even)
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int gx = x0 + 4 * cg + j;
-      if (gx < W) out[gx] = make_float2(acc0[j] + b0, acc1[j] + b1);
+      if (gx < W) *reinterpret_cast<float2 *>(out + gx * YP) = make_float2(acc0[j] + b0, acc1[j] + b1);
     }
   }
 }
@@ -265,17 +265,19 @@ static int narrow_check(const char *what, int N, int H, int W, int C, int Co) {
 }
 
 extern "C" int unflow_conv3x3_narrow_fwd(const float *x, long long x_pitch, const float *w, const float *bias,
-                                         float *y, int N, int H, int W, int C, int Co, void *stream) {
+                                         float *y, long long y_pitch, int N, int H, int W, int C, int Co,
+                                         void *stream) {
   using namespace unflow;
   if (int rc = narrow_check("conv3x3_narrow_fwd", N, H, W, C, Co)) return rc;
   if (N == 0) return UNFLOW_OK;
   UNFLOW_REQUIRE(x && w && y, "conv3x3_narrow_fwd: null pointer");
   UNFLOW_REQUIRE(((uintptr_t)y & 7) == 0, "conv3x3_narrow_fwd: y must be 8-byte aligned");
   UNFLOW_REQUIRE(x_pitch >= C, "conv3x3_narrow_fwd: pixel pitch smaller than C");
+  UNFLOW_REQUIRE(y_pitch >= 2 && y_pitch % 2 == 0, "conv3x3_narrow_fwd: output pitch must be even and >= 2");
   const dim3 grid(ceil_div(W, nc::TW), ceil_div(H, nc::TH), N);
   const size_t smem = (size_t)(nc::KC * nc::FWD_CHS + nc::KC * 24) * sizeof(float);
   cudaStream_t st = (cudaStream_t)stream;
-  nc::narrow_fwd_kernel<<<grid, nc::THREADS, smem, st>>>(x, w, bias, y, H, W, C, x_pitch);
+  nc::narrow_fwd_kernel<<<grid, nc::THREADS, smem, st>>>(x, w, bias, y, H, W, C, x_pitch, y_pitch);
   count_launch();
   return check_launch("conv3x3_narrow_fwd");
 }

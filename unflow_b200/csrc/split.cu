@@ -110,7 +110,7 @@ template <bool LINEAR>
 __global__ void __launch_bounds__(256)
 bias_grad_lrelu_kernel(const float *__restrict__ g, long long sN, long long sC, long long sH, long long sW,
                        const float *__restrict__ act, float *__restrict__ gb, int N, int C, int H, int W,
-                       float slope, int pix_per_cta, float *__restrict__ gpre) {
+                       float slope, int pix_per_cta, float *__restrict__ gpre, long long AP, long long GP) {
   __shared__ float red[8][32];
   const int lane = threadIdx.x & 31, row = threadIdx.x >> 5;
   const int c = blockIdx.y * 32 + lane;
@@ -126,16 +126,16 @@ bias_grad_lrelu_kernel(const float *__restrict__ g, long long sN, long long sC, 
       for (; p + 8 < p1; p += 16) {           // two independent loads in flight per thread
         float v0 = __ldg(gp + p * sW), v1 = __ldg(gp + (p + 8) * sW);
         if (ap) {
-          if (__ldg(ap + p * C) <= 0.0f) v0 *= slope;
-          if (__ldg(ap + (p + 8) * C) <= 0.0f) v1 *= slope;
+          if (__ldg(ap + p * AP) <= 0.0f) v0 *= slope;
+          if (__ldg(ap + (p + 8) * AP) <= 0.0f) v1 *= slope;
         }
-        if (gpre) { gpre[p * C + c] = v0; gpre[(p + 8) * C + c] = v1; }
+        if (gpre) { gpre[p * GP + c] = v0; gpre[(p + 8) * GP + c] = v1; }
         s0 += v0; s1 += v1;
       }
       for (; p < p1; p += 8) {
         float v = __ldg(gp + p * sW);
-        if (ap && __ldg(ap + p * C) <= 0.0f) v *= slope;
-        if (gpre) gpre[p * C + c] = v;
+        if (ap && __ldg(ap + p * AP) <= 0.0f) v *= slope;
+        if (gpre) gpre[p * GP + c] = v;
         s0 += v;
       }
     } else {
@@ -144,8 +144,8 @@ bias_grad_lrelu_kernel(const float *__restrict__ g, long long sN, long long sC, 
         const int y = (int)((p / W) % H);
         const long long n = p / ((long long)W * H);
         float v = __ldg(g + n * sN + y * sH + x * sW + c * sC);
-        if (act && __ldg(act + p * C + c) <= 0.0f) v *= slope;
-        if (gpre) gpre[p * C + c] = v;
+        if (act && __ldg(act + p * AP + c) <= 0.0f) v *= slope;
+        if (gpre) gpre[p * GP + c] = v;
         s0 += v;
       }
     }
@@ -176,19 +176,21 @@ extern "C" int unflow_bias_lrelu(float *y, const float *bias, long long pixels, 
 }
 
 extern "C" int unflow_lrelu_bwd_bias(const float *g, long long sN, long long sC, long long sH, long long sW,
-                                     const float *act, float *gpre, float *gb, int N, int C, int H, int W,
-                                     float slope, void *stream);
+                                     const float *act, long long act_pitch, float *gpre, long long gpre_pitch,
+                                     float *gb, int N, int C, int H, int W, float slope, void *stream);
 
 extern "C" int unflow_bias_grad_lrelu(const float *g, long long sN, long long sC, long long sH,
                                       long long sW, const float *act, float *gb, int N, int C, int H,
                                       int W, float slope, void *stream) {
-  return unflow_lrelu_bwd_bias(g, sN, sC, sH, sW, act, nullptr, gb, N, C, H, W, slope, stream);
+  return unflow_lrelu_bwd_bias(g, sN, sC, sH, sW, act, C, nullptr, C, gb, N, C, H, W, slope, stream);
 }
 
 extern "C" int unflow_lrelu_bwd_bias(const float *g, long long sN, long long sC, long long sH, long long sW,
-                                     const float *act, float *gpre, float *gb, int N, int C, int H, int W,
-                                     float slope, void *stream) {
+                                     const float *act, long long act_pitch, float *gpre, long long gpre_pitch,
+                                     float *gb, int N, int C, int H, int W, float slope, void *stream) {
   using namespace unflow;
+  UNFLOW_REQUIRE(!gpre || gpre_pitch >= C, "lrelu_bwd_bias: gpre pitch smaller than C");
+  UNFLOW_REQUIRE(!act || act_pitch >= C, "lrelu_bwd_bias: activation pitch smaller than C");
   UNFLOW_REQUIRE(N >= 0 && C >= 1 && H >= 1 && W >= 1, "bias_grad: bad shape");
   UNFLOW_REQUIRE(g && gb, "bias_grad: null pointer");
   cudaStream_t s = (cudaStream_t)stream;
@@ -203,8 +205,8 @@ extern "C" int unflow_lrelu_bwd_bias(const float *g, long long sN, long long sC,
   if (pix_per_cta < 64) pix_per_cta = 64;
   dim3 grid(ceil_div(npix, pix_per_cta), cblocks);
   const bool linear = sH == (long long)W * sW && sN == (long long)H * sH;
-  if (linear) bias_grad_lrelu_kernel<true><<<grid, 256, 0, s>>>(g, sN, sC, sH, sW, act, gb, N, C, H, W, slope, pix_per_cta, gpre);
-  else bias_grad_lrelu_kernel<false><<<grid, 256, 0, s>>>(g, sN, sC, sH, sW, act, gb, N, C, H, W, slope, pix_per_cta, gpre);
+  if (linear) bias_grad_lrelu_kernel<true><<<grid, 256, 0, s>>>(g, sN, sC, sH, sW, act, gb, N, C, H, W, slope, pix_per_cta, gpre, act_pitch, gpre_pitch);
+  else bias_grad_lrelu_kernel<false><<<grid, 256, 0, s>>>(g, sN, sC, sH, sW, act, gb, N, C, H, W, slope, pix_per_cta, gpre, act_pitch, gpre_pitch);
   count_launch();
   return check_launch("bias_grad_lrelu");
 }

@@ -73,13 +73,24 @@ struct ConvParams {
   Tap taps[MAX_TAPS];
 };
 
-template <int BN>
+// AT = true (default): the split activation tile (hi, lo) goes to TENSOR MEMORY and the MMAs read their A
+// operand from there.  ncu on the shared-memory variant (profiles/r2_ncu_tc_conv.md) shows the kernel
+// bound by shared-memory bandwidth: LSU wavefronts (the split: read 16 KB, write 32 KB per K block) 48 % +
+// tensor-core operand reads (12 MMAs x (4 KB A + 4 KB B)) 53 % of the peak, tensor pipe 52 % busy.  With
+// A in TMEM the split writes nothing to shared memory and the MMAs fetch only B from it: 64 KB instead of
+// 144 KB of shared-memory traffic per K block, and a stage shrinks from 64 to 48 KB (4 stages).
+template <int BN, bool AT>
 struct Cfg {
   static constexpr int B_BYTES = BN * BK * 4;
-  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-  static constexpr int STAGES = (200 * 1024 / STAGE_BYTES) < 6 ? (200 * 1024 / STAGE_BYTES) : 6;
+  static constexpr int STAGE_BYTES = (AT ? 1 : 2) * A_BYTES + 2 * B_BYTES;
+  static constexpr int B_OFF = (AT ? 1 : 2) * A_BYTES;          // offset of the weight planes inside a stage
+  static constexpr int STAGES = (200 * 1024 / STAGE_BYTES) < (AT ? 4 : 6) ? (200 * 1024 / STAGE_BYTES) : (AT ? 4 : 6);
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
-  static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;   // two accumulator buffers
+  static constexpr int ACC_COLS = 2 * BN;                        // two accumulator buffers
+  static constexpr int A_COLS = AT ? STAGES * 2 * BK : 0;        // per stage: 32 columns hi + 32 columns lo
+  static constexpr int NEED = ACC_COLS + A_COLS;
+  static constexpr int TMEM_COLS = NEED <= 32 ? 32 : NEED <= 64 ? 64 : NEED <= 128 ? 128 : NEED <= 256 ? 256 : 512;
+  static_assert(NEED <= 512, "tensor memory has 512 columns");
 };
 
 struct TileCoord {
@@ -98,15 +109,15 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvParams &p, int tile) 
 // ------------------------------------------------------------------------------------------
 // The kernel
 // ------------------------------------------------------------------------------------------
-template <int BN>
+template <int BN, bool AT>
 __global__ void __launch_bounds__(NTHREADS, 1)
 tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapBhi,
                const __grid_constant__ CUtensorMap mapBlo, const __grid_constant__ ConvParams p) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, AT>;
   extern __shared__ unsigned char smem_raw[];
   const unsigned base = (s32(smem_raw) + 1023u) & ~1023u;          // 128B swizzle atoms need 1024 B alignment
   unsigned char *gbase = smem_raw + (base - s32(smem_raw));
-  // stage layout: [A hi (raw)] [A lo] [B hi] [B lo]
+  // stage layout: [A raw (= hi after the split when !AT)] [A lo, only when !AT] [B hi] [B lo]
   const unsigned bars = base + C::STAGES * C::STAGE_BYTES;
   auto full_raw = [&](int s) { return bars + 8u * s; };
   auto full_cvt = [&](int s) { return bars + 8u * (C::STAGES + s); };
@@ -160,8 +171,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             const unsigned st = base + s * C::STAGE_BYTES;
             mbar_expect_tx(full_raw(s), a_box_bytes + 2u * C::B_BYTES);
             tma_4d(st, &mapA, full_raw(s), kc * BK, x0 + tap.dx, y0 + tap.dy, t.n0);
-            tma_3d(st + 2 * A_BYTES, &mapBhi, full_raw(s), kc * BK, t.nb * BN, tap.widx);
-            tma_3d(st + 2 * A_BYTES + C::B_BYTES, &mapBlo, full_raw(s), kc * BK, t.nb * BN, tap.widx);
+            tma_3d(st + C::B_OFF, &mapBhi, full_raw(s), kc * BK, t.nb * BN, tap.widx);
+            tma_3d(st + C::B_OFF + C::B_BYTES, &mapBlo, full_raw(s), kc * BK, t.nb * BN, tap.widx);
             if (++s == C::STAGES) { s = 0; ph ^= 1u; }
           }
         }
@@ -188,15 +199,26 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           mbar_wait(full_cvt(s), ph);        // activations split (converter warps)
           tc_fence_after();
           const unsigned st = base + s * C::STAGE_BYTES;
-          const unsigned long long a_hi = umma_desc_k128(st), a_lo = umma_desc_k128(st + A_BYTES);
-          const unsigned long long b_hi = umma_desc_k128(st + 2 * A_BYTES);
-          const unsigned long long b_lo = umma_desc_k128(st + 2 * A_BYTES + C::B_BYTES);
+          const unsigned long long b_hi = umma_desc_k128(st + C::B_OFF);
+          const unsigned long long b_lo = umma_desc_k128(st + C::B_OFF + C::B_BYTES);
+          if (AT) {
+            const unsigned ta_hi = tmem_base + (unsigned)(C::ACC_COLS + s * 2 * BK), ta_lo = ta_hi + BK;
 #pragma unroll
-          for (int k = 0; k < BK / 8; ++k) {            // UMMA K = 8 tf32 = 32 bytes: +2 in 16-byte units
-            const unsigned long long adv = (unsigned long long)(2 * k);
-            umma_tf32(d, a_lo + adv, b_hi + adv, idesc, (in_chunk | k) != 0);
-            umma_tf32(d, a_hi + adv, b_lo + adv, idesc, 1u);
-            umma_tf32(d, a_hi + adv, b_hi + adv, idesc, 1u);
+            for (int k = 0; k < BK / 8; ++k) {          // A: 8 TMEM columns per K step; B: +32 bytes
+              const unsigned long long adv = (unsigned long long)(2 * k);
+              umma_tf32_ts(d, ta_lo + 8 * k, b_hi + adv, idesc, (in_chunk | k) != 0);
+              umma_tf32_ts(d, ta_hi + 8 * k, b_lo + adv, idesc, 1u);
+              umma_tf32_ts(d, ta_hi + 8 * k, b_hi + adv, idesc, 1u);
+            }
+          } else {
+            const unsigned long long a_hi = umma_desc_k128(st), a_lo = umma_desc_k128(st + A_BYTES);
+#pragma unroll
+            for (int k = 0; k < BK / 8; ++k) {          // UMMA K = 8 tf32 = 32 bytes: +2 in 16-byte units
+              const unsigned long long adv = (unsigned long long)(2 * k);
+              umma_tf32(d, a_lo + adv, b_hi + adv, idesc, (in_chunk | k) != 0);
+              umma_tf32(d, a_hi + adv, b_lo + adv, idesc, 1u);
+              umma_tf32(d, a_hi + adv, b_hi + adv, idesc, 1u);
+            }
           }
           umma_commit(empty(s));             // frees the stage when these MMAs have read it
           if (++s == C::STAGES) { s = 0; ph ^= 1u; }
@@ -208,7 +230,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       }
     }
   } else if (warp >= 4 && warp < 8) {
-    // ===================== activation split: hi in place, lo beside it =====================
+    // ===================== activation split =====================
     const int tid = threadIdx.x - 128;
     int s = 0;
     unsigned ph = 0;
@@ -217,19 +239,43 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       const int iters = (p.class_start[t.cls + 1] - p.class_start[t.cls]) * p.kblocks;
       for (int it = 0; it < iters; ++it) {
         mbar_wait(full_raw(s), ph);
-        float4 *a = reinterpret_cast<float4 *>(gbase + s * C::STAGE_BYTES);
-        float4 *l = reinterpret_cast<float4 *>(gbase + s * C::STAGE_BYTES + A_BYTES);
+        if (AT) {
+          // thread = tile row: read the row's 32 channels (8 x 16 bytes; the 128-byte swizzle stores logical
+          // chunk j of row r at chunk j ^ (r & 7) -- a quarter warp hits all 32 banks), split, and store
+          // hi / lo into this stage's tensor-memory columns (lane = row, one column per channel)
+          const float4 *rowp = reinterpret_cast<const float4 *>(gbase + s * C::STAGE_BYTES + tid * 128);
+          unsigned hi[BK], lo[BK];
 #pragma unroll
-        for (int j = 0; j < A_BYTES / 16 / 128; ++j) {
-          const int i = tid + 128 * j;
-          const float4 v = a[i];
-          float4 h, r;
-          h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
-          r.x = v.x - h.x; r.y = v.y - h.y; r.z = v.z - h.z; r.w = v.w - h.w;
-          a[i] = h;
-          l[i] = r;
+          for (int j = 0; j < 8; ++j) {
+            const float4 v = rowp[j ^ (tid & 7)];
+            const float x4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float h = tf32_rna(x4[e]);
+              hi[4 * j + e] = __float_as_uint(h);
+              lo[4 * j + e] = __float_as_uint(x4[e] - h);
+            }
+          }
+          const unsigned ta = tmem_base + ((unsigned)((warp & 3) * 32) << 16) + (unsigned)(C::ACC_COLS + s * 2 * BK);
+          tmem_st32(ta, hi);
+          tmem_st32(ta + BK, lo);
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+          tc_fence_before();
+        } else {
+          float4 *a = reinterpret_cast<float4 *>(gbase + s * C::STAGE_BYTES);
+          float4 *l = reinterpret_cast<float4 *>(gbase + s * C::STAGE_BYTES + A_BYTES);
+#pragma unroll
+          for (int j = 0; j < A_BYTES / 16 / 128; ++j) {
+            const int i = tid + 128 * j;
+            const float4 v = a[i];
+            float4 h, r;
+            h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
+            r.x = v.x - h.x; r.y = v.y - h.y; r.z = v.z - h.z; r.w = v.w - h.w;
+            a[i] = h;
+            l[i] = r;
+          }
+          fence_proxy_async();                 // generic-proxy writes -> visible to the tensor core
         }
-        fence_proxy_async();                 // generic-proxy writes -> visible to the tensor core
         __syncwarp();
         if (lane == 0) mbar_arrive(full_cvt(s));
         if (++s == C::STAGES) { s = 0; ph ^= 1u; }
@@ -352,23 +398,33 @@ wsplit_kernel(const float *__restrict__ w, float *__restrict__ hi, float *__rest
 // ------------------------------------------------------------------------------------------
 static int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
 
-template <int BN>
-static int launch(const CUtensorMap &mA, const CUtensorMap &mBh, const CUtensorMap &mBl, const ConvParams &p,
-                  int total_tiles, cudaStream_t stream) {
-  using C = Cfg<BN>;
+int g_a_in_tmem = 0;     // unflow_set_int_option("tc_a_tmem"): 1 = A operand in tensor memory (default), 0 = in shared memory
+
+template <int BN, bool AT>
+static int launch_v(const CUtensorMap &mA, const CUtensorMap &mBh, const CUtensorMap &mBl, const ConvParams &p,
+                    int total_tiles, cudaStream_t stream) {
+  using C = Cfg<BN, AT>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tc_conv_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(tc_conv_kernel<BN, AT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e != cudaSuccess) { set_error("tc_conv: cannot opt in to %d bytes of shared memory: %s", C::SMEM_BYTES, cudaGetErrorString(e)); return UNFLOW_ECUDA; }
     attr_set = true;
   }
   const int grid = total_tiles < kNumSMs ? total_tiles : kNumSMs;
-  tc_conv_kernel<BN><<<grid, NTHREADS, C::SMEM_BYTES, stream>>>(mA, mBh, mBl, p);
+  tc_conv_kernel<BN, AT><<<grid, NTHREADS, C::SMEM_BYTES, stream>>>(mA, mBh, mBl, p);
   count_launch();
   return check_launch("tc_conv_kernel");
 }
 
+template <int BN>
+static int launch(const CUtensorMap &mA, const CUtensorMap &mBh, const CUtensorMap &mBl, const ConvParams &p,
+                  int total_tiles, cudaStream_t stream) {
+  return g_a_in_tmem ? launch_v<BN, true>(mA, mBh, mBl, p, total_tiles, stream)
+                     : launch_v<BN, false>(mA, mBh, mBl, p, total_tiles, stream);
+}
+
 }  // namespace tc
+int set_tc_a_tmem(int v) { if (v != 0 && v != 1) return 0; tc::g_a_in_tmem = v; return 1; }
 }  // namespace unflow
 
 using namespace unflow;

@@ -52,13 +52,22 @@ struct WgradParams {
   long long pitch_r, pitch_t;       // dW[r * pitch_r + t * pitch_t + c]
 };
 
-template <int BN>
+// AT: the split P tile (the MMA's A operand) lives in TENSOR MEMORY (see tc_conv.cu, Cfg): the converter
+// warps read it from a plain (unswizzled) staging tile -- lane = channel, one LDS.32 per pixel, which is also
+// the transpose the K-major TMEM operand needs -- and store hi / lo with tcgen05.st; only G stays in
+// shared memory for the MMAs.
+template <int BN, bool AT>
 struct Cfg {
   static constexpr int B_BYTES = BN * KP * 4;
-  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-  static constexpr int STAGES = (200 * 1024 / STAGE_BYTES) < 6 ? (200 * 1024 / STAGE_BYTES) : 6;
+  static constexpr int STAGE_BYTES = (AT ? 1 : 2) * A_BYTES + 2 * B_BYTES;
+  static constexpr int B_OFF = (AT ? 1 : 2) * A_BYTES;
+  static constexpr int STAGES = (200 * 1024 / STAGE_BYTES) < (AT ? 4 : 6) ? (200 * 1024 / STAGE_BYTES) : (AT ? 4 : 6);
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
-  static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+  static constexpr int ACC_COLS = 2 * BN;
+  static constexpr int A_COLS = AT ? STAGES * 2 * KP : 0;
+  static constexpr int NEED = ACC_COLS + A_COLS;
+  static constexpr int TMEM_COLS = NEED <= 32 ? 32 : NEED <= 64 ? 64 : NEED <= 128 ? 128 : NEED <= 256 ? 256 : 512;
+  static_assert(NEED <= 512, "tensor memory has 512 columns");
 };
 
 struct Item {
@@ -76,11 +85,11 @@ __device__ __forceinline__ int chunk_len(const WgradParams &p, int chunk) {
   return (k0 + p.kc <= p.n_ptiles) ? p.kc : p.n_ptiles - k0;
 }
 
-template <int BN>
+template <int BN, bool AT>
 __global__ void __launch_bounds__(NTHREADS, 1)
 tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ CUtensorMap mapG,
                 const __grid_constant__ WgradParams p) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, AT>;
   extern __shared__ unsigned char smem_raw[];
   const unsigned base = (s32(smem_raw) + 1023u) & ~1023u;
   unsigned char *gbase = smem_raw + (base - s32(smem_raw));
@@ -153,7 +162,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant_
             tma_4d(st + j * 4096, &mapP, full_raw(s), w.rb * BM + 32 * j, px, py, pn);
 #pragma unroll
           for (int j = 0; j < BN / 32; ++j)
-            tma_4d(st + 2 * A_BYTES + j * 4096, &mapG, full_raw(s), gch[j], p.stride_x * px + gdx[j],
+            tma_4d(st + C::B_OFF + j * 4096, &mapG, full_raw(s), gch[j], p.stride_x * px + gdx[j],
                    p.stride * py + gdy[j], pn);
           if (++s == C::STAGES) { s = 0; ph ^= 1u; }
         }
@@ -163,7 +172,8 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant_
     // ===================== MMA issuer =====================
     if (lane == 0) {
       // D fp32, A / B tf32, both MN-major (bits 15, 16), N = BN, M = 128
-      const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
+      // (with A in tensor memory the A operand is K-major by construction: lane = row, column = K)
+      const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | (AT ? 0u : (1u << 15)) | (1u << 16) |
                              ((unsigned)(BN >> 3) << 17) | ((unsigned)(BM >> 4) << 24);
       int s = 0, acc = 0;
       unsigned ph = 0, aph = 0;
@@ -181,15 +191,26 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant_
           mbar_wait(full_cvt(s), ph);
           tc_fence_after();
           const unsigned st = base + s * C::STAGE_BYTES;
-          const unsigned long long a_hi = umma_desc_mn128(st, 4096), a_lo = umma_desc_mn128(st + A_BYTES, 4096);
-          const unsigned long long b_hi = umma_desc_mn128(st + 2 * A_BYTES, 4096);
-          const unsigned long long b_lo = umma_desc_mn128(st + 2 * A_BYTES + C::B_BYTES, 4096);
+          const unsigned long long b_hi = umma_desc_mn128(st + C::B_OFF, 4096);
+          const unsigned long long b_lo = umma_desc_mn128(st + C::B_OFF + C::B_BYTES, 4096);
+          if (AT) {
+            const unsigned ta_hi = tmem_base + (unsigned)(C::ACC_COLS + s * 2 * KP), ta_lo = ta_hi + KP;
 #pragma unroll
-          for (int k = 0; k < KP / 8; ++k) {            // 8 pixels = 8 rows of 128 B = 1024 B: +64 in 16-byte units
-            const unsigned long long adv = (unsigned long long)(64 * k);
-            umma_tf32(d, a_lo + adv, b_hi + adv, idesc, (in_chunk | k) != 0);
-            umma_tf32(d, a_hi + adv, b_lo + adv, idesc, 1u);
-            umma_tf32(d, a_hi + adv, b_hi + adv, idesc, 1u);
+            for (int k = 0; k < KP / 8; ++k) {          // A: 8 TMEM columns (pixels) per K step; B: 8 rows = 1024 B
+              const unsigned long long adv = (unsigned long long)(64 * k);
+              umma_tf32_ts(d, ta_lo + 8 * k, b_hi + adv, idesc, (in_chunk | k) != 0);
+              umma_tf32_ts(d, ta_hi + 8 * k, b_lo + adv, idesc, 1u);
+              umma_tf32_ts(d, ta_hi + 8 * k, b_hi + adv, idesc, 1u);
+            }
+          } else {
+            const unsigned long long a_hi = umma_desc_mn128(st, 4096), a_lo = umma_desc_mn128(st + A_BYTES, 4096);
+#pragma unroll
+            for (int k = 0; k < KP / 8; ++k) {          // 8 pixels = 8 rows of 128 B = 1024 B: +64 in 16-byte units
+              const unsigned long long adv = (unsigned long long)(64 * k);
+              umma_tf32(d, a_lo + adv, b_hi + adv, idesc, (in_chunk | k) != 0);
+              umma_tf32(d, a_hi + adv, b_lo + adv, idesc, 1u);
+              umma_tf32(d, a_hi + adv, b_hi + adv, idesc, 1u);
+            }
           }
           umma_commit(empty(s));
           if (++s == C::STAGES) { s = 0; ph ^= 1u; }
@@ -211,10 +232,25 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant_
       for (int it = 0; it < iters; ++it) {
         mbar_wait(full_raw(s), ph);
         unsigned char *stp = gbase + s * C::STAGE_BYTES;
+        if (AT) {
+          // P: warp = 32-channel group = TMEM lane quarter, lane = channel; column k of the operand = pixel k
+          const float *grp = reinterpret_cast<const float *>(stp + (warp & 3) * 4096) + lane;
+          unsigned hi[KP], lo[KP];
 #pragma unroll
-        for (int part = 0; part < 2; ++part) {
-          float4 *a = reinterpret_cast<float4 *>(stp + (part ? 2 * A_BYTES : 0));
-          float4 *l = reinterpret_cast<float4 *>(stp + (part ? 2 * A_BYTES + C::B_BYTES : A_BYTES));
+          for (int k = 0; k < KP; ++k) {
+            const float v = grp[k * 32];
+            const float h = tf32_rna(v);
+            hi[k] = __float_as_uint(h);
+            lo[k] = __float_as_uint(v - h);
+          }
+          const unsigned ta = tmem_base + ((unsigned)((warp & 3) * 32) << 16) + (unsigned)(C::ACC_COLS + s * 2 * KP);
+          tmem_st32(ta, hi);
+          tmem_st32(ta + KP, lo);
+        }
+#pragma unroll
+        for (int part = (AT ? 1 : 0); part < 2; ++part) {
+          float4 *a = reinterpret_cast<float4 *>(stp + (part ? C::B_OFF : 0));
+          float4 *l = reinterpret_cast<float4 *>(stp + (part ? C::B_OFF + C::B_BYTES : A_BYTES));
           const int n16 = (part ? C::B_BYTES : A_BYTES) / 16;
 #pragma unroll
           for (int i = tid; i < n16; i += 128) {
@@ -225,6 +261,10 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant_
             a[i] = h;
             l[i] = r;
           }
+        }
+        if (AT) {
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+          tc_fence_before();
         }
         fence_proxy_async();
         __syncwarp();
@@ -287,19 +327,24 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant_
   }
 }
 
-template <int BN>
-static int launch(const CUtensorMap &mP, const CUtensorMap &mG, const WgradParams &p, int total, cudaStream_t stream) {
-  using C = Cfg<BN>;
+template <int BN, bool AT>
+static int launch_v(const CUtensorMap &mP, const CUtensorMap &mG, const WgradParams &p, int total, cudaStream_t stream) {
+  using C = Cfg<BN, AT>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tc_wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(tc_wgrad_kernel<BN, AT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e != cudaSuccess) { set_error("tc_wgrad: cannot opt in to %d bytes of shared memory: %s", C::SMEM_BYTES, cudaGetErrorString(e)); return UNFLOW_ECUDA; }
     attr_set = true;
   }
   const int grid = total < kNumSMs ? total : kNumSMs;
-  tc_wgrad_kernel<BN><<<grid, NTHREADS, C::SMEM_BYTES, stream>>>(mP, mG, p);
+  tc_wgrad_kernel<BN, AT><<<grid, NTHREADS, C::SMEM_BYTES, stream>>>(mP, mG, p);
   count_launch();
   return check_launch("tc_wgrad_kernel");
+}
+
+template <int BN>
+static int launch(const CUtensorMap &mP, const CUtensorMap &mG, const WgradParams &p, int total, cudaStream_t stream) {
+  return tc::g_a_in_tmem ? launch_v<BN, true>(mP, mG, p, total, stream) : launch_v<BN, false>(mP, mG, p, total, stream);
 }
 
 // the K-block pixel box: TW*TH*TN == 32 exactly (rows past the tensor are TMA zero fill), fewest boxes
@@ -377,7 +422,8 @@ extern "C" int unflow_tc_wgrad(const float *P, int N, int Hp, int Wp, int R, lon
     cuuint64_t strides[3] = {(cuuint64_t)p_pitch * 4, (cuuint64_t)p_pitch * 4 * Wp, (cuuint64_t)p_pitch * 4 * Wp * Hp};
     cuuint32_t box[4] = {32, (cuuint32_t)p.TW, (cuuint32_t)p.TH, (cuuint32_t)p.TN};
     cuuint32_t estr[4] = {1, 1, 1, 1};
-    rc = tc::encode(&mP, P, 4, dims, strides, box, estr, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    rc = tc::encode(&mP, P, 4, dims, strides, box, estr,
+                    tc::g_a_in_tmem ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     if (rc) return rc;
   }
   {
@@ -418,7 +464,8 @@ extern "C" int unflow_tc_wgrad_window(const float *P, int N, int Ho, int Wo, int
     cuuint64_t strides[3] = {(cuuint64_t)p_pitch * 4, (cuuint64_t)p_pitch * 4 * Wo, (cuuint64_t)p_pitch * 4 * Wo * Ho};
     cuuint32_t box[4] = {32, (cuuint32_t)p.TW, (cuuint32_t)p.TH, (cuuint32_t)p.TN};
     cuuint32_t estr[4] = {1, 1, 1, 1};
-    rc = tc::encode(&mP, P, 4, dims, strides, box, estr, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    rc = tc::encode(&mP, P, 4, dims, strides, box, estr,
+                    tc::g_a_in_tmem ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     if (rc) return rc;
   }
   {

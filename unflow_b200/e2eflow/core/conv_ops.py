@@ -39,6 +39,42 @@ def get_mode():
 LRELU_SLOPE = 0.1   # _leaky_relu: tf.maximum(0.1 * x, x)  (reference flownet.py:84-86)
 
 
+# ---------------------------------------------------------------------------------------------
+# Backward checkpoints: the network marks a few activations ("everything created after this point
+# has finished its backward pass once the gradient arrives here"); the data-parallel trainer hangs
+# the all-reduce of the corresponding slice of the flat gradient buffer on them, so the reduction
+# of the decoder / encoder gradients overlaps the rest of the backward pass (core/train.py).
+# ---------------------------------------------------------------------------------------------
+_backward_point_cb = None
+
+
+def set_backward_point_callback(fn):
+    """fn(name) is called from inside the backward pass; None removes it."""
+    global _backward_point_cb
+    _backward_point_cb = fn
+
+
+class _BackwardPoint(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, name):
+        ctx.name = name
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        if _backward_point_cb is not None:
+            _backward_point_cb(ctx.name)
+        return g, None
+
+
+def backward_point(x, name):
+    """Identity; with a callback installed and a differentiable ``x`` it reports when the backward pass
+    comes back through this activation."""
+    if _backward_point_cb is None or not x.requires_grad:
+        return x
+    return _BackwardPoint.apply(x, name)
+
+
 def _bias_act_(y, b):
     """y = leaky_relu(y + b) in place (one pass instead of bias add + activation)."""
     N, C, H, W = y.shape
@@ -227,10 +263,29 @@ _TC = __import__('os').environ.get('UNFLOW_TC_CONV', '1') != '0'
 _TC_WGRAD = __import__('os').environ.get('UNFLOW_TC_WGRAD', '1') != '0'
 
 
+def _grad_slot(w):
+    """The variable's own gradient buffer when the weight-gradient kernel may accumulate into it directly:
+    a leaf whose ``.grad`` already exists in the variable's memory order (the Trainer's views into its flat
+    gradient buffer, zeroed by the fused Adam kernel).  The split-K kernel ADDS its partial sums with atomics,
+    which is exactly autograd's accumulate semantics -- returning None for that input then saves the zero
+    fill of a temporary and the ``grad += temporary`` pass over all 39 M parameters."""
+    g = w.grad if (w.is_leaf and w.requires_grad) else None
+    if g is None or g.shape != w.shape or g.stride() != w.stride() or g.dtype != torch.float32:
+        return None
+    return g
+
+
 def _tc_weight_grad(P, G, w, stride, pad_t, pad_l):
-    """dL/dw on csrc/tc_wgrad.cu: a zeroed tensor in the variable's memory order, accumulated by the kernel."""
+    """dL/dw on csrc/tc_wgrad.cu.  Returns the gradient tensor for autograd, or None when it has been
+    accumulated into ``w.grad`` in place (see _grad_slot)."""
     from . import tc_conv
     A, B, kh, kw = w.shape
+    want = (kh * kw * B, 1, kw * B, B)
+    in_order = all(n == 1 or s_ == t for n, s_, t in zip(w.shape, w.stride(), want))
+    slot = _grad_slot(w) if in_order else None
+    if slot is not None:
+        tc_conv.wgrad(P, G, slot, stride=stride, kh=kh, kw=kw, pad_t=pad_t, pad_l=pad_l)
+        return None
     gw = torch.zeros((A, kh, kw, B), device=w.device, dtype=torch.float32).permute(0, 3, 1, 2)
     return tc_conv.wgrad(P, G, gw, stride=stride, kh=kh, kw=kw, pad_t=pad_t, pad_l=pad_l)
 
@@ -253,36 +308,61 @@ def _khwc(w):
 
 def _lrelu_bwd_bias(g, act, want_bias):
     """One pass over the incoming gradient: gpre = g * lrelu'(act) as a dense NHWC tensor and the bias
-    gradient sum_pixels gpre.  ``act`` None: no activation (gpre is g made dense)."""
+    gradient sum_pixels gpre.  ``act`` (the layer's output, possibly a channel slice of a concat buffer)
+    None: no activation (gpre is g made dense)."""
     from . import tc_conv
     N, C, H, W = g.shape
     dense = tc_conv.nhwc_geometry(g)
     if act is None and not want_bias and dense is not None and dense[4] % 4 == 0 and g.data_ptr() % 16 == 0:
         return g, None
-    gpre = tc_conv.empty_nhwc(N, C, H, W, g.device)
+    ap = 0
+    if act is not None:
+        ga = tc_conv.nhwc_geometry(act)
+        if ga is None:
+            act = act.contiguous(memory_format=torch.channels_last)
+            ga = tc_conv.nhwc_geometry(act)
+        ap = ga[4]
+    gp = _round4(C)
+    gpre = torch.empty((N, H, W, gp), device=g.device, dtype=torch.float32)[..., :C].permute(0, 3, 1, 2)
     gb = torch.empty(C, device=g.device, dtype=torch.float32)
     sN, sC, sH, sW = g.stride()
     with torch.cuda.device(g.device):
         check(_native.lib().unflow_lrelu_bwd_bias(g.data_ptr(), sN, sC, sH, sW,
-                                                  act.data_ptr() if act is not None else None,
-                                                  gpre.data_ptr(), gb.data_ptr(), N, C, H, W, LRELU_SLOPE,
+                                                  act.data_ptr() if act is not None else None, ap,
+                                                  gpre.data_ptr(), gp, gb.data_ptr(), N, C, H, W, LRELU_SLOPE,
                                                   torch.cuda.current_stream().cuda_stream), "lrelu_bwd_bias")
     return gpre, gb
+
+
+def _dest(out, N, C, H, W, device):
+    """Where a tensor-core layer writes its output: the caller's slot (a channel slice of a pre-allocated
+    concat buffer -- the epilogue stores straight into it, no concat copy later) or a fresh NHWC tensor.
+    Returns (tensor to write, tensor to hand to autograd): the latter is a new tensor object over the same
+    memory, so autograd never sees it as a view of the buffer."""
+    if out is not None:
+        assert tuple(out.shape) == (N, C, H, W), (tuple(out.shape), (N, C, H, W))
+        # a NEW tensor over the same memory (own version counter -- ``detach()`` would share the buffer's,
+        # and the later in-place fill of a neighbouring slot would make autograd reject the saved output)
+        alias = torch.empty(0, device=out.device, dtype=out.dtype).set_(
+            out.untyped_storage(), out.storage_offset(), out.shape, out.stride())
+        return out, alias
+    buf = torch.empty((N, H, W, _round4(C)), device=device, dtype=torch.float32)
+    y = buf[..., :C].permute(0, 3, 1, 2)
+    return y, y
 
 
 class _ConvTC(torch.autograd.Function):
     """slim.conv2d on the hand-written tcgen05 kernel: y = act(conv(x, w; stride, TF SAME) + b)."""
 
     @staticmethod
-    def forward(ctx, x, w, b, stride, pads, act):
+    def forward(ctx, x, w, b, stride, pads, act, out=None):
         from . import tc_conv
         Co, Ci, k = w.shape[0], w.shape[1], w.shape[2]
         N, _, H, W = x.shape
         pt, pb, pl, pr = pads
         Ho, Wo = (H + pt + pb - k) // stride + 1, (W + pl + pr - k) // stride + 1
-        buf = torch.empty((N, Ho, Wo, _round4(Co)), device=x.device, dtype=torch.float32)
-        y = buf[..., :Co].permute(0, 3, 1, 2)
-        tc_conv.run(x, tc_conv.split_weights(_khwc(w)), y, mode=0, stride=stride, kh=k, kw=k, pad_t=pt, pad_l=pl,
+        dst, y = _dest(out, N, Co, Ho, Wo, x.device)
+        tc_conv.run(x, tc_conv.split_weights(_khwc(w)), dst, mode=0, stride=stride, kh=k, kw=k, pad_t=pt, pad_l=pl,
                     bias=b, act=bool(act))
         ctx.save_for_backward(x, w, y if act else None)
         ctx.cfg = (stride, tuple(pads), b is not None, bool(act))
@@ -297,10 +377,7 @@ class _ConvTC(torch.autograd.Function):
         N, _, H, W = x.shape
         pt, pb, pl, pr = pads
         gx = gw = gb = None
-        a_dense = a
-        if act and (tc_conv.nhwc_geometry(a)[4] != Co):
-            a_dense = a.contiguous(memory_format=torch.channels_last)       # C_out % 4 != 0 only
-        gpre, gb_all = _lrelu_bwd_bias(g, a_dense if act else None, has_b and ctx.needs_input_grad[2])
+        gpre, gb_all = _lrelu_bwd_bias(g, a if act else None, has_b and ctx.needs_input_grad[2])
         if has_b and ctx.needs_input_grad[2]:
             gb = gb_all
         if ctx.needs_input_grad[0]:
@@ -317,7 +394,7 @@ class _ConvTC(torch.autograd.Function):
                 xb = _operand(x, 0, concat_batch=True, c_pad=ci_p, pads=pads)      # [3N, Ci_p, Hp, Wp]
                 gb3 = _operand(gpre, 1, concat_batch=True, c_pad=co_p)             # [3N, Co_p, ..]
                 gw = nngrad.conv2d_weight(xb, (co_p, ci_p, k, k), gb3, stride=stride, padding=0)[:Co, :Ci]
-        return gx, gw, gb, None, None, None
+        return gx, gw, gb, None, None, None, None
 
 
 class _ConvWindow(torch.autograd.Function):
@@ -350,10 +427,7 @@ class _ConvWindow(torch.autograd.Function):
         kh, stride, pt, has_b, act = ctx.cfg
         Co = w_rw.shape[0]
         gw = gb = None
-        a_dense = a
-        if act and (tc_conv.nhwc_geometry(a)[4] != Co):
-            a_dense = a.contiguous(memory_format=torch.channels_last)
-        gpre, gb_all = _lrelu_bwd_bias(g, a_dense if act else None, has_b and ctx.needs_input_grad[2])
+        gpre, gb_all = _lrelu_bwd_bias(g, a if act else None, has_b and ctx.needs_input_grad[2])
         if has_b and ctx.needs_input_grad[2]:
             gb = gb_all
         if ctx.needs_input_grad[1]:
@@ -376,13 +450,12 @@ class _DeconvTC(torch.autograd.Function):
     """slim.conv2d_transpose(k=4, stride=2, SAME) on the same kernel (four output-parity classes)."""
 
     @staticmethod
-    def forward(ctx, x, w, b, act):
+    def forward(ctx, x, w, b, act, out=None):
         from . import tc_conv
         Ci, Co = w.shape[0], w.shape[1]
         N, _, H, W = x.shape
-        buf = torch.empty((N, 2 * H, 2 * W, _round4(Co)), device=x.device, dtype=torch.float32)
-        y = buf[..., :Co].permute(0, 3, 1, 2)
-        tc_conv.run(x, tc_conv.split_weights(_khwc(w), transpose=True), y, mode=1, stride=2, kh=4, kw=4, pad_t=1,
+        dst, y = _dest(out, N, Co, 2 * H, 2 * W, x.device)
+        tc_conv.run(x, tc_conv.split_weights(_khwc(w), transpose=True), dst, mode=1, stride=2, kh=4, kw=4, pad_t=1,
                     pad_l=1, bias=b, act=bool(act))
         ctx.save_for_backward(x, w, y if act else None)
         ctx.cfg = (b is not None, bool(act))
@@ -396,10 +469,7 @@ class _DeconvTC(torch.autograd.Function):
         Ci, Co = w.shape[0], w.shape[1]
         N, _, H, W = x.shape
         gx = gw = gb = None
-        a_dense = a
-        if act and (tc_conv.nhwc_geometry(a)[4] != Co):
-            a_dense = a.contiguous(memory_format=torch.channels_last)
-        gpre, gb_all = _lrelu_bwd_bias(g, a_dense if act else None, has_b and ctx.needs_input_grad[2])
+        gpre, gb_all = _lrelu_bwd_bias(g, a if act else None, has_b and ctx.needs_input_grad[2])
         if has_b and ctx.needs_input_grad[2]:
             gb = gb_all
         if ctx.needs_input_grad[0]:
@@ -415,7 +485,7 @@ class _DeconvTC(torch.autograd.Function):
                 gb3 = _operand(gpre, 0, concat_batch=True, c_pad=co_p)
                 xb = _operand(x, 1, concat_batch=True, c_pad=ci_p)
                 gw = nngrad.conv2d_weight(gb3, (ci_p, co_p, 4, 4), xb, stride=2, padding=1)[:Ci, :Co]
-        return gx, gw, gb, None
+        return gx, gw, gb, None, None
 
 
 # The narrow kernels pay off where the layer is large enough to fill the GPU with 16x32-pixel
@@ -455,13 +525,13 @@ class _NarrowConv3x3(torch.autograd.Function):
         N, C, H, W = x.shape
         wl = w if w.is_contiguous(memory_format=torch.channels_last) else \
             w.contiguous(memory_format=torch.channels_last)
-        y = torch.empty((N, 2, H, W), device=x.device, dtype=torch.float32,
-                        memory_format=torch.channels_last)
+        # 4 floats per pixel: the up-sampling deconv that consumes the flow reads it through a TMA tensor map
+        y = torch.empty((N, H, W, 4), device=x.device, dtype=torch.float32)[..., :2].permute(0, 3, 1, 2)
         from ..ops import kernel_timer
         with torch.cuda.device(x.device), kernel_timer.span("narrow_conv_fwd", 4 * x.numel() + 4 * y.numel()):
             check(_narrow_lib().unflow_conv3x3_narrow_fwd(
                 x.data_ptr(), _pixel_pitch(x), wl.data_ptr(), b.data_ptr() if b is not None else None, y.data_ptr(),
-                N, H, W, C, 2, torch.cuda.current_stream().cuda_stream), "conv3x3_narrow_fwd")
+                4, N, H, W, C, 2, torch.cuda.current_stream().cuda_stream), "conv3x3_narrow_fwd")
         ctx.save_for_backward(x, w)
         ctx.has_b = b is not None
         return y
@@ -472,10 +542,19 @@ class _NarrowConv3x3(torch.autograd.Function):
         N, C, H, W = x.shape
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
-            ci_p = _round4(C)
-            gs = _operand(g, 0, c_pad=4)                                          # [N, 12, H, W]
-            wt = _operand(w, 1, concat_batch=True, c_pad=ci_p, n_out=4)           # [12, Ci_p, 3, 3]
-            gx = _conv_input_grad((H + 2, W + 2), wt, gs, 1)[:, :C, 1:1 + H, 1:1 + W]
+            from . import tc_conv
+            if _TC and tc_conv.supported(x):
+                # input gradient (C_in wide) on the tensor-core kernel: contraction over the 2 flow channels
+                gd, _ = _lrelu_bwd_bias(g, None, False)
+                buf = torch.empty((N, H, W, _round4(C)), device=x.device, dtype=torch.float32)
+                gx = buf[..., :C].permute(0, 3, 1, 2)
+                tc_conv.run(gd, tc_conv.split_weights(_khwc(w), transpose=True), gx, mode=1, stride=1, kh=3, kw=3,
+                            pad_t=1, pad_l=1)
+            else:
+                ci_p = _round4(C)
+                gs = _operand(g, 0, c_pad=4)                                          # [N, 12, H, W]
+                wt = _operand(w, 1, concat_batch=True, c_pad=ci_p, n_out=4)           # [12, Ci_p, 3, 3]
+                gx = _conv_input_grad((H + 2, W + 2), wt, gs, 1)[:, :C, 1:1 + H, 1:1 + W]
         if ctx.needs_input_grad[1]:
             lib = _narrow_lib()
             ws = torch.empty(lib.unflow_conv3x3_narrow_wgrad_workspace_bytes(N, H, W, C) // 4,
@@ -539,8 +618,16 @@ def network_input(x_nhwc):
     return x if channels_last_active(x_nhwc) else x.contiguous()
 
 
-def conv2d(x, w, b, stride, pads, act=False):
-    """pads = (top, bottom, left, right) TF-SAME padding; act: apply the leaky ReLU."""
+def direct_write_ok(x):
+    """True when the tensor-core layers are active, i.e. when a caller may hand ``out=`` slots (channel
+    slices of pre-allocated concat buffers) to conv2d / conv_transpose2d."""
+    return _TC and _MODE == '3xtf32' and x.is_cuda
+
+
+def conv2d(x, w, b, stride, pads, act=False, out=None):
+    """pads = (top, bottom, left, right) TF-SAME padding; act: apply the leaky ReLU.  ``out``: optional
+    destination (NCHW-shaped view with NHWC memory); honoured by the tensor-core path -- the result then
+    aliases it -- and ignored by the others (the caller's concat copies as before)."""
     if _MODE == '3xtf32' and x.is_cuda:
         if not act and _use_narrow(x, w, stride, pads):
             return _NarrowConv3x3.apply(x, w, b)
@@ -551,9 +638,8 @@ def conv2d(x, w, b, stride, pads, act=False):
         if _use_space_to_depth(x, w, stride):
             xs, ws = space_to_depth_operands(x, w, pads)
             return conv2d(xs, ws, b, 1, (0, 0, 0, 0), act=act)
-        if (_tc_ok(x, stride) and w.shape[2] == w.shape[3] and w.shape[2] * w.shape[3] <= 64
-                and w.shape[0] % 4 == 0):       # (the 2-channel flow heads keep their own kernels / the library)
-            return _ConvTC.apply(x, w, b, stride, tuple(pads), bool(act))
+        if _tc_ok(x, stride) and w.shape[2] == w.shape[3] and w.shape[2] * w.shape[3] <= 64:
+            return _ConvTC.apply(x, w, b, stride, tuple(pads), bool(act), out)
         fuse = act and b is not None and w.shape[0] % 4 == 0
         y = _Conv3x.apply(x, w, b, stride, tuple(pads), fuse)
         return F.leaky_relu(y, LRELU_SLOPE) if (act and not fuse) else y
@@ -569,10 +655,10 @@ def conv2d(x, w, b, stride, pads, act=False):
     return F.leaky_relu(y, LRELU_SLOPE) if act else y
 
 
-def conv_transpose2d(x, w, b, act=False):
+def conv_transpose2d(x, w, b, act=False, out=None):
     if _MODE == '3xtf32' and x.is_cuda:
-        if _tc_ok(x, 1) and w.shape[1] % 4 == 0:
-            return _DeconvTC.apply(x, w, b, bool(act))
+        if _tc_ok(x, 1):
+            return _DeconvTC.apply(x, w, b, bool(act), out)
         fuse = act and b is not None and w.shape[1] % 4 == 0
         y = _Deconv3x.apply(x, w, b, fuse)
         return F.leaky_relu(y, LRELU_SLOPE) if (act and not fuse) else y

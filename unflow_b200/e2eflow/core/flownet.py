@@ -20,7 +20,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from ..ops import correlation
+from ..ops import correlation, correlation_bidir
 from .image_warp import image_warp
 from . import tf_image
 from . import conv_ops
@@ -252,39 +252,76 @@ class _Scope:
     def sub(self, name):
         return _Scope(self.v, self.p + name + '/')
 
-    def conv(self, x, name, stride=1, act=True):
+    def conv(self, x, name, stride=1, act=True, out=None):
         w, b = self.v.weights(self.p + name)
         k = w.shape[2]
         # TF SAME padding: asymmetric for the stride-2 layers at even sizes
         pads = _same_pad(x.shape[2], k, stride) + _same_pad(x.shape[3], k, stride)
-        return conv_ops.conv2d(x, w, b, stride, pads, act=act)
+        return conv_ops.conv2d(x, w, b, stride, pads, act=act, out=out)
 
-    def deconv(self, x, name, act=True):
+    def deconv(self, x, name, act=True, out=None):
         w, b = self.v.weights(self.p + name)
-        return conv_ops.conv_transpose2d(x, w, b, act=act)  # slim.conv2d_transpose(k=4, s=2, SAME)
+        return conv_ops.conv_transpose2d(x, w, b, act=act, out=out)  # slim.conv2d_transpose(k=4, s=2, SAME)
+
+    def cout(self, name):
+        w, _ = self.v.weights(self.p + name)
+        return w.shape[0] if self.v.kinds[self.p + name] == 'conv' else w.shape[1]
+
+
+class _Cat:
+    """A pre-allocated NHWC concat buffer (pixel pitch rounded up to 4 floats) and the NCHW-shaped views of
+    its members: the tensor-core layers store their outputs straight into their slot, so the concat
+    itself copies only what was produced elsewhere (the 2-channel up-sampled flow)."""
+
+    def __init__(self, n, h, w, channels, device):
+        c = sum(channels)
+        self.buf = torch.empty((n, h, w, (c + 3) // 4 * 4), device=device, dtype=torch.float32)
+        self.slots, off = [], 0
+        for ci in channels:
+            self.slots.append(self.buf[..., off:off + ci].permute(0, 3, 1, 2))
+            off += ci
+
+
+def _decoder_cats(s, like, n, hw3, hw2, c2):
+    """Concat buffers of _flownet_upconv for a trunk whose conv3_1 is ``hw3`` and whose conv2 (``c2``
+    channels) is ``hw2`` in size; None when the tensor-core path is not active for ``like``."""
+    if not conv_ops.direct_write_ok(like):
+        return None
+    half = lambda v: -(-v // 2)
+    (h3, w3), (h2, w2) = hw3, hw2
+    h4, w4 = half(h3), half(w3)
+    h5, w5 = half(h4), half(w4)
+    dev = like.device
+    return {2: _Cat(n, h2, w2, [c2, s.cout('deconv2'), 2], dev),
+            3: _Cat(n, h3, w3, [s.cout('conv3_1'), s.cout('deconv3'), 2], dev),
+            4: _Cat(n, h4, w4, [s.cout('conv4_1'), s.cout('deconv4'), 2], dev),
+            5: _Cat(n, h5, w5, [s.cout('conv5_1'), s.cout('deconv5'), 2], dev)}
 
 
 def _flownet_upconv(s, conv6_1, conv5_1, conv4_1, conv3_1, conv2, conv1=None, inputs=None,
-                    channel_mult=1, full_res=False, channels=2):
+                    channel_mult=1, full_res=False, channels=2, cats=None):
+    slot = (lambda lvl: cats[lvl].slots[1]) if cats else (lambda lvl: None)
+    buf = (lambda lvl: cats[lvl].buf) if cats else (lambda lvl: None)
+    conv6_1 = conv_ops.backward_point(conv6_1, s.p + 'decoder')     # decoder gradients complete behind this point
     flow6 = s.conv(conv6_1, 'flow6', act=False)
-    deconv5 = s.deconv(conv6_1, 'deconv5')
+    deconv5 = s.deconv(conv6_1, 'deconv5', out=slot(5))
     flow6_up5 = s.deconv(flow6, 'flow6_up5', act=False)
-    concat5 = _cat_c([conv5_1, deconv5, flow6_up5])
+    concat5 = _cat_c([conv5_1, deconv5, flow6_up5], buf(5))
     flow5 = s.conv(concat5, 'flow5', act=False)
 
-    deconv4 = s.deconv(concat5, 'deconv4')
+    deconv4 = s.deconv(concat5, 'deconv4', out=slot(4))
     flow5_up4 = s.deconv(flow5, 'flow5_up4', act=False)
-    concat4 = _cat_c([conv4_1, deconv4, flow5_up4])
+    concat4 = _cat_c([conv4_1, deconv4, flow5_up4], buf(4))
     flow4 = s.conv(concat4, 'flow4', act=False)
 
-    deconv3 = s.deconv(concat4, 'deconv3')
+    deconv3 = s.deconv(concat4, 'deconv3', out=slot(3))
     flow4_up3 = s.deconv(flow4, 'flow4_up3', act=False)
-    concat3 = _cat_c([conv3_1, deconv3, flow4_up3])
+    concat3 = _cat_c([conv3_1, deconv3, flow4_up3], buf(3))
     flow3 = s.conv(concat3, 'flow3', act=False)
 
-    deconv2 = s.deconv(concat3, 'deconv2')
+    deconv2 = s.deconv(concat3, 'deconv2', out=slot(2))
     flow3_up2 = s.deconv(flow3, 'flow3_up2', act=False)
-    concat2 = _cat_c([conv2, deconv2, flow3_up2])
+    concat2 = _cat_c([conv2, deconv2, flow3_up2], buf(2))
     flow2 = s.conv(concat2, 'flow2', act=False)
 
     flows = [flow2, flow3, flow4, flow5, flow6]
@@ -317,17 +354,22 @@ def flownet_s(inputs, channel_mult=1, full_res=False, _scope=None):
     s = _scope
     x = conv_ops.network_input(inputs)
     conv1 = s.conv(x, 'conv1', 2)
-    conv2 = s.conv(conv1, 'conv2', 2)
+    half = lambda v: -(-v // 2)
+    h2, w2 = half(conv1.shape[2]), half(conv1.shape[3])
+    cats = _decoder_cats(s, x, x.shape[0], (half(h2), half(w2)), (h2, w2), s.cout('conv2'))
+    first = (lambda lvl: cats[lvl].slots[0]) if cats else (lambda lvl: None)
+    conv2 = s.conv(conv1, 'conv2', 2, out=first(2))
     conv3 = s.conv(conv2, 'conv3', 2)
-    conv3_1 = s.conv(conv3, 'conv3_1')
+    conv3 = conv_ops.backward_point(conv3, s.p + 'trunk')
+    conv3_1 = s.conv(conv3, 'conv3_1', out=first(3))
     conv4 = s.conv(conv3_1, 'conv4', 2)
-    conv4_1 = s.conv(conv4, 'conv4_1')
+    conv4_1 = s.conv(conv4, 'conv4_1', out=first(4))
     conv5 = s.conv(conv4_1, 'conv5', 2)
-    conv5_1 = s.conv(conv5, 'conv5_1')
+    conv5_1 = s.conv(conv5, 'conv5_1', out=first(5))
     conv6 = s.conv(conv5_1, 'conv6', 2)
     conv6_1 = s.conv(conv6, 'conv6_1')
     res = _flownet_upconv(s, conv6_1, conv5_1, conv4_1, conv3_1, conv2, conv1, x,
-                          channel_mult=channel_mult, full_res=full_res)
+                          channel_mult=channel_mult, full_res=full_res, cats=cats)
     return nchw_to_nhwc(res)
 
 
@@ -341,15 +383,19 @@ def flownet_c_features(im, channel_mult=1, reuse=None, _scope=None):
 
 
 def _flownet_c_trunk(s, conv_redir_and_corr, conv2_a, channel_mult, full_res):
-    conv3_1 = s.conv(conv_redir_and_corr, 'conv3_1')
+    x = conv_ops.backward_point(conv_redir_and_corr, s.p + 'trunk')   # conv3_1 .. conv6_1 complete behind this point
+    cats = _decoder_cats(s, x, x.shape[0], (x.shape[2], x.shape[3]), (conv2_a.shape[2], conv2_a.shape[3]),
+                         conv2_a.shape[1])
+    first = (lambda lvl: cats[lvl].slots[0]) if cats else (lambda lvl: None)
+    conv3_1 = s.conv(x, 'conv3_1', out=first(3))
     conv4 = s.conv(conv3_1, 'conv4', 2)
-    conv4_1 = s.conv(conv4, 'conv4_1')
+    conv4_1 = s.conv(conv4, 'conv4_1', out=first(4))
     conv5 = s.conv(conv4_1, 'conv5', 2)
-    conv5_1 = s.conv(conv5, 'conv5_1')
+    conv5_1 = s.conv(conv5, 'conv5_1', out=first(5))
     conv6 = s.conv(conv5_1, 'conv6', 2)
     conv6_1 = s.conv(conv6, 'conv6_1')
     res = _flownet_upconv(s, conv6_1, conv5_1, conv4_1, conv3_1, conv2_a,
-                          channel_mult=channel_mult, full_res=full_res)
+                          channel_mult=channel_mult, full_res=full_res, cats=cats)
     return nchw_to_nhwc(res)
 
 
@@ -366,19 +412,25 @@ class _ConcatCL(torch.autograd.Function):
     concatenated along N and appended along C (the two correlation directions of FlowNetC)."""
 
     @staticmethod
-    def forward(ctx, n_first, *tensors):
+    def forward(ctx, n_first, buf, *tensors):
         first, second = tensors[:n_first], tensors[n_first:]
         n = first[0].shape[0]
         c = sum(t.shape[1] for t in first) + (second[0].shape[1] if second else 0)
         h, w = first[0].shape[2], first[0].shape[3]
         # NHWC buffer whose pixel pitch is a multiple of 4 floats (16 bytes): the tensor-core conv
         # kernels read channel slices of it in place through TMA tensor maps (csrc/tc_conv.cu); the
-        # returned tensor is the [:, :c] view (the 1..3 slack channels are never read)
-        buf = torch.empty((n, h, w, (c + 3) // 4 * 4), device=first[0].device, dtype=first[0].dtype)
+        # returned tensor is the [:, :c] view (the 1..3 slack channels are never read).  ``buf``: the
+        # buffer was allocated up front and some members already live in their slot (written there by
+        # the producing kernel's epilogue) -- those are not copied.
+        if buf is None:
+            buf = torch.empty((n, h, w, (c + 3) // 4 * 4), device=first[0].device, dtype=first[0].dtype)
+        assert tuple(buf.shape) == (n, h, w, (c + 3) // 4 * 4)
         out = buf[..., :c].permute(0, 3, 1, 2)
         spans, off = [], 0
         for t in first:
-            out[:, off:off + t.shape[1]].copy_(t)
+            slot = out[:, off:off + t.shape[1]]
+            if not (t.data_ptr() == slot.data_ptr() and t.stride() == slot.stride()):
+                slot.copy_(t)
             spans.append((0, n, off, off + t.shape[1]))
             off += t.shape[1]
         b0 = 0
@@ -391,17 +443,17 @@ class _ConcatCL(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
-        return (None,) + tuple(g[b0:b1, c0:c1] for (b0, b1, c0, c1) in ctx.spans)
+        return (None, None) + tuple(g[b0:b1, c0:c1] for (b0, b1, c0, c1) in ctx.spans)
 
 
-def _concat_channels_last(first, second_batch_parts=None):
-    return _ConcatCL.apply(len(first), *(list(first) + list(second_batch_parts or [])))
+def _concat_channels_last(first, second_batch_parts=None, buf=None):
+    return _ConcatCL.apply(len(first), buf, *(list(first) + list(second_batch_parts or [])))
 
 
-def _cat_c(tensors):
-    """tf.concat(tensors, 1) of NCHW-shaped tensors."""
+def _cat_c(tensors, buf=None):
+    """tf.concat(tensors, 1) of NCHW-shaped tensors (``buf``: pre-allocated NHWC destination, see _Cat)."""
     if conv_ops.channels_last_active(tensors[0]):
-        return _concat_channels_last(list(tensors))
+        return _concat_channels_last(list(tensors), buf=buf)
     return torch.cat(tensors, 1)
 
 
@@ -448,8 +500,8 @@ def flownet(im1, im2, flownet_spec='S', full_resolution=False, train_all=False,
                                                            channel_mult=channel_mult, _scope=fs)
                 conv3_a, conv3_b = conv3_ab[:B], conv3_ab[B:]
                 kw = dict(pad=20, kernel_size=1, max_displacement=20, stride_1=1, stride_2=2)
-                corr_ab = correlation(conv3_a, conv3_b, **kw)
-                corr_ba = correlation(conv3_b, conv3_a, **kw)
+                # both cost volumes from one pass over the features (the reverse one is a re-indexing)
+                corr_ab, corr_ba = correlation_bidir(conv3_a, conv3_b, **kw)
                 conv_redir = cs.conv(conv3_ab, 'conv_redir')
                 if conv_ops.channels_last_active(conv_redir):
                     trunk_in = _concat_channels_last([conv_redir], [corr_ab, corr_ba])

@@ -84,7 +84,10 @@ def run(x, planes, out, *, mode, stride, kh, kw, pad_t, pad_l, bias=None, act=Fa
     N, Hin, Win, Cin, xp = gx
     No, Hout, Wout, Cout, yp = go
     assert No == N and planes.rows == Cout and planes.cols == Cin and planes.taps == kh * kw
-    with torch.cuda.device(x.device):
+    from ..ops import kernel_timer
+    pix = N * (Hin * Win if mode == 1 else Hout * Wout)       # positions each tap is applied to
+    flops = 2 * pix * Cout * Cin * kh * kw            # nominal fp32 multiply-adds x 2 (executed as 3 TF32 MMAs each)
+    with torch.cuda.device(x.device), kernel_timer.span("tc_conv", flops):
         check(_native.lib().unflow_tc_conv(
             x.data_ptr(), N, Hin, Win, Cin, xp, planes.hi.data_ptr(), planes.lo.data_ptr(),
             out.data_ptr(), Hout, Wout, Cout, yp, bias.data_ptr() if bias is not None else None,
@@ -110,7 +113,8 @@ def wgrad(P, G, dw, *, stride, kh, kw, pad_t, pad_l):
     assert (A, B, k1, k2) == (R, C, kh, kw) and Ng == N
     want = (kh * kw * C, 1, kw * C, C)
     assert all(n == 1 or s == t for n, s, t in zip(dw.shape, dw.stride(), want)), "dw must be stored [rows][kh][kw][cols]"
-    with torch.cuda.device(P.device):
+    from ..ops import kernel_timer
+    with torch.cuda.device(P.device), kernel_timer.span("tc_wgrad", 2 * N * Hp * Wp * R * C * kh * kw):
         check(_native.lib().unflow_tc_wgrad(P.data_ptr(), N, Hp, Wp, R, pp, G.data_ptr(), Hg, Wg, C, gpitch,
                                             dw.data_ptr(), kh * kw * C, C, stride, kh, kw, pad_t, pad_l,
                                             _stream()), "tc_wgrad")
@@ -151,7 +155,8 @@ def run_window(xp, planes, out, *, kh, stride, pad_t, bias=None, act=False, slop
     go = nhwc_geometry(out)
     No, Hout, Wout, Cout, yp = go
     assert No == N and planes.rows == Cout and planes.cols == 8 * Cp and planes.taps == kh and xp.is_contiguous()
-    with torch.cuda.device(xp.device):
+    from ..ops import kernel_timer
+    with torch.cuda.device(xp.device), kernel_timer.span("tc_conv", 2 * N * Hout * Wout * Cout * 8 * Cp * kh):
         check(_native.lib().unflow_tc_conv_window(
             xp.data_ptr(), N, H, Wp, Cp, planes.hi.data_ptr(), planes.lo.data_ptr(), out.data_ptr(), Hout, Wout,
             Cout, yp, bias.data_ptr() if bias is not None else None, float(slope), 1 if act else 0, kh, stride,
@@ -166,7 +171,8 @@ def wgrad_window(P, xp, dw, *, kh, stride, pad_t):
     assert Nx == N and tuple(dw.shape) == (R, 8 * Cp, kh, 1) and xp.is_contiguous()
     want = (kh * 8 * Cp, 1, 8 * Cp, 8 * Cp)
     assert all(n == 1 or s == t for n, s, t in zip(dw.shape, dw.stride(), want))
-    with torch.cuda.device(P.device):
+    from ..ops import kernel_timer
+    with torch.cuda.device(P.device), kernel_timer.span("tc_wgrad", 2 * N * Ho * Wo * R * 8 * Cp * kh):
         check(_native.lib().unflow_tc_wgrad_window(P.data_ptr(), N, Ho, Wo, R, pp, xp.data_ptr(), H, Wp, Cp,
                                                    dw.data_ptr(), kh, stride, pad_t, _stream()), "tc_wgrad_window")
     return dw

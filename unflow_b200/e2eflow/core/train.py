@@ -60,6 +60,7 @@ class Trainer:
         train.py:160,169).  run.py trains with it on; bench.py and the parity tests keep it off
         (random draws cannot be parity-pinned).  The draws come from the device generator so the
         step stays capturable in a CUDA graph."""
+        self.overlap_allreduce = __import__('os').environ.get('UNFLOW_OVERLAP_ALLREDUCE', '1') != '0'
         self.augment = bool(augment)
         if self.augment:
             from . import augment as _aug
@@ -165,6 +166,62 @@ class Trainer:
             return 1.0 / self.world_size
         return 1.0
 
+    # -- gradient all-reduce overlapped with the backward pass ---------------------------------------
+    def _bucket_plan(self):
+        """Cut the flat gradient buffer where the network's backward checkpoints (conv_ops.backward_point)
+        say a suffix of it is final: the variables are laid out in forward order, the backward pass
+        finishes them from the back -- first the decoder (flow6 .. flow2, deconv5 .. deconv2), then
+        conv3_1 .. conv6_1, last the feature layers.  {checkpoint name: (start, end)} in floats; the
+        head of the buffer [0, first start) is reduced after the backward pass."""
+        n_nets = len(self.params.get('flownet', 'S'))
+        if not (n_nets == 1 or not self.params.get('train_all')):
+            return None                                   # several trained networks: keep the single all-reduce
+        names, offs = self.trainable_names, self._offsets
+        scope = names[0].rsplit('/', 2)[0] + '/' if names else ''
+
+        def first(pred):
+            for nm, off in zip(names, offs):
+                if pred(nm):
+                    return off
+            return None
+        dec = first(lambda nm: '/flow6/' in nm)
+        trunk = first(lambda nm: '/conv3_1/' in nm)
+        if dec is None or trunk is None or not trunk < dec:
+            return None
+        net = [nm for nm in names if '/conv3_1/' in nm][0].split('conv3_1/')[0]      # e.g. 'flownet_c/'
+        end = self.flat_grad.numel()
+        return {net + 'decoder': (dec, end), net + 'trunk': (trunk, dec)}, trunk
+
+    def _backward_overlapped(self, loss):
+        """loss.backward() with the all-reduce of each finished slice of the flat gradient buffer launched
+        from the backward checkpoints (NCCL runs on its own stream; the compute stream only waits for the
+        handles before Adam)."""
+        from . import conv_ops
+        plan = self._bucket_plan()
+        if plan is None:
+            loss.backward()
+            self.reduce_gradients()
+            return
+        buckets, head_end = plan
+        works, done = [], set()
+
+        def on_point(name):
+            if name in buckets and name not in done:
+                done.add(name)
+                a, b = buckets[name]
+                works.append(dist.all_reduce(self.flat_grad[a:b], op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
+        conv_ops.set_backward_point_callback(on_point)
+        try:
+            loss.backward()
+        finally:
+            conv_ops.set_backward_point_callback(None)
+        for name, (a, b) in buckets.items():               # a checkpoint that never fired: reduce its slice now
+            if name not in done:
+                works.append(dist.all_reduce(self.flat_grad[a:b], op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
+        works.append(dist.all_reduce(self.flat_grad[:head_end], op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
+        for w in works:
+            w.wait()
+
     def apply_update(self, lr, grad_scale=1.0):
         if self.flat_param.device.type != "cuda":
             raise RuntimeError("the Adam update is a CUDA kernel (csrc/adam.cu); no CPU fallback")
@@ -186,8 +243,11 @@ class Trainer:
     def _step_impl(self, im1, im2):
         """forward + loss + backward + gradient mean + Adam, hyper-parameters from device memory."""
         loss = self.loss(im1, im2)
-        loss.backward()
-        self.reduce_gradients()
+        if self.world_size > 1 and self.overlap_allreduce:
+            self._backward_overlapped(loss)
+        else:
+            loss.backward()
+            self.reduce_gradients()
         from ..ops import kernel_timer
         with torch.cuda.device(self.device), kernel_timer.span("adam", 32 * self.flat_param.numel()):
             check(_native.lib().unflow_adam_step_dev(
@@ -278,8 +338,12 @@ class Trainer:
             self.graph_replays += 1
             return self._static_loss
         loss = self.loss(im1, im2)
-        loss.backward()   # accumulates into the flat gradient views
-        scale = self.reduce_gradients()
+        if self.world_size > 1 and self.overlap_allreduce:
+            self._backward_overlapped(loss)
+            scale = 1.0 / self.world_size
+        else:
+            loss.backward()   # accumulates into the flat gradient views
+            scale = self.reduce_gradients()
         self.apply_update(lr, scale)
         return loss.detach()
 

@@ -144,6 +144,61 @@ def correlation(first, second, **kwargs):
     return _Correlation.apply(first, second, _corr_attrs(kwargs))
 
 
+class _CorrelationBidir(torch.autograd.Function):
+    """(correlation(a, b), correlation(b, a)) in one forward launch and one pair of backward launches:
+    the reverse cost volume is a re-indexing of the forward one (include/unflow.h,
+    unflow_correlation_fwd_bidir).  The reference builds the two volumes with two op instances
+    (flownet.py:34-44); the values are bit-identical."""
+
+    @staticmethod
+    def forward(ctx, in0, in1, attrs):
+        in0 = _prep(in0, "input_0")
+        in1 = _prep(in1, "input_1")
+        if in0.shape != in1.shape:
+            raise ValueError("Input shapes have to be the same")
+        B, C, H, W = in0.shape
+        import ctypes
+        oc, oh, ow = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        lib = _native.lib()
+        check(lib.unflow_correlation_out_shape(H, W, *attrs, ctypes.byref(oc), ctypes.byref(oh),
+                                               ctypes.byref(ow)), "correlation")
+        out = torch.empty(B, oc.value, oh.value, ow.value, device=in0.device, dtype=torch.float32)
+        rev = torch.empty_like(out)
+        with torch.cuda.device(in0.device), kernel_timer.span("correlation_fwd_bidir"):
+            check(lib.unflow_correlation_fwd_bidir(in0.data_ptr(), in1.data_ptr(), out.data_ptr(), rev.data_ptr(),
+                                                   B, C, H, W, *attrs, _stream()), "correlation_bidir")
+        ctx.save_for_backward(in0, in1)
+        ctx.attrs = attrs
+        return out, rev
+
+    @staticmethod
+    def backward(ctx, gout, grev):
+        in0, in1 = ctx.saved_tensors
+        B, C, H, W = in0.shape
+        gout, grev = gout.contiguous(), grev.contiguous()
+        geff = torch.empty_like(gout)
+        g0 = torch.empty_like(in0)
+        g1 = torch.empty_like(in1)
+        lib = _native.lib()
+        with torch.cuda.device(in0.device), kernel_timer.span("correlation_bwd_bidir"):
+            check(lib.unflow_correlation_fold_grad(gout.data_ptr(), grev.data_ptr(), geff.data_ptr(), B, C, H, W,
+                                                   *ctx.attrs, _stream()), "correlation_fold_grad")
+            check(lib.unflow_correlation_bwd(geff.data_ptr(), in0.data_ptr(), in1.data_ptr(),
+                                             g0.data_ptr(), g1.data_ptr(), B, C, H, W, *ctx.attrs, _stream()),
+                  "correlation_grad")
+        return g0, g1, None
+
+
+def correlation_bidir(first, second, **kwargs):
+    """(correlation(first, second), correlation(second, first)); one pass where the tiled kernel serves the
+    attributes and shape, two ordinary calls otherwise."""
+    attrs = _corr_attrs(kwargs)
+    B, C, H, W = first.shape
+    if first.is_cuda and first.dim() == 4 and _native.lib().unflow_correlation_fwd_path(C, H, W, *attrs) == 1:
+        return _CorrelationBidir.apply(first, second, attrs)
+    return _Correlation.apply(first, second, attrs), _Correlation.apply(second, first, attrs)
+
+
 class _Warp(torch.autograd.Function):
     """Bilinear gather; ``mode`` selects the op semantics (zero) or image_warp (clamp)."""
 
