@@ -141,7 +141,9 @@ def run_ours(args):
     conv_ops.set_mode(args.conv)
     torch.backends.cudnn.benchmark = bool(args.cudnn_benchmark)
 
-    params = dict(synth.KITTI_PARAMS, learning_rate=1.0e-5)
+    global PER_GPU_BATCH
+    PER_GPU_BATCH = args.batch
+    params = dict(synth.KITTI_PARAMS, learning_rate=1.0e-5, flownet=args.spec)
     trainer = Trainer(params, synth.KITTI_NORMALIZATION, dev, seed=1234)
     trainer.broadcast_variables(0)
     h_im1, h_im2 = make_batch(rank, pinned=True)
@@ -290,6 +292,11 @@ def run_ours(args):
 
     roofs = [tensor_roof("tc_conv", "tc_conv_kernel (tcgen05 3xTF32 conv / deconv forward + input gradient, all launches)"),
              tensor_roof("tc_wgrad", "tc_wgrad_kernel (tcgen05 3xTF32 weight gradient, all launches)"),
+             # one-pass bidirectional correlation: inputs read once, both volumes written (+ the zero fill of the
+             # reverse volume); flops = the ONE set of products both volumes share
+             roof("correlation_fwd_bidir", 4 * Bc * hc * wc * (2 * C + 3 * D2), corr_flops),
+             # gradient fold (read 2 volumes, write 1) + the two gradient launches on the folded volume
+             roof("correlation_bwd_bidir", 4 * Bc * hc * wc * (3 * D2 + D2 + 4 * C), 2 * corr_flops),
              roof("correlation_fwd", corr_bytes, corr_flops),
              roof("correlation_bwd", 4 * Bc * hc * wc * (D2 + 4 * C), 2 * corr_flops),
              roof("level_loss_fwd_%dx%d" % (H // 4, W // 4), (44 + 16) * npx0),
@@ -301,9 +308,13 @@ def run_ours(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / steps_timed, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic (seeded smooth images + smooth <=8px flow + noise; random-init weights)",
-        "config": {"workload": "BASELINE configs[2]/[3]: FlowNetC full unsupervised training step "
-                               "(bidir forward, corr d=20, 5-level census/fb/2nd-order loss, backward, "
-                               "grad all-reduce, Adam), 384x1280, batch 4 per GPU",
+        "config": {"workload": ("BASELINE configs[2]/[3]: FlowNetC full unsupervised training step "
+                                "(bidir forward, corr d=20, 5-level census/fb/2nd-order loss, backward, "
+                                "grad all-reduce, Adam), 384x1280, batch 4 per GPU") if (args.spec == "C" and args.batch == 4)
+                   else ("BASELINE configs[4] geometry: stacked %s unsupervised training step (forward of every "
+                         "network + loss; backward / Adam of the last network, config.ini:55-58), 384x1280, batch %d per GPU"
+                         % (args.spec, args.batch)),
+                   "flownet": args.spec,
                    "global_batch": PER_GPU_BATCH * world, "parallelism": "dp%d" % world,
                    "l2": "inputs+activations per step >> 126 MB L2 (no flush needed)",
                    "conv_precision": ("fp32 (cuDNN, TF32 disabled)" if args.conv == "fp32" else
@@ -451,6 +462,8 @@ def main():
     ap.add_argument("--graph", type=int, default=int(os.environ.get("UNFLOW_CUDA_GRAPH", "1")),
                     help="1: replay the whole training step as one CUDA graph (value and e2e); the "
                          "per-kernel roofline timings always come from an eager pass")
+    ap.add_argument("--spec", default="C", help="network stack (reference `flownet` parameter): C (headline), CSS = BASELINE configs[4]")
+    ap.add_argument("--batch", type=int, default=4, help="image pairs per GPU (4 = BASELINE configs[2]/[3]; configs[4] uses 2)")
     ap.add_argument("--also-fp32", type=int, nargs="?", const=1, default=1,
                     help="1 (default, N=1 only): additionally time the exact-fp32 conv mode (no tensor "
                          "cores) for a few steps and report it as fp32_exact next to the 3xTF32 headline")

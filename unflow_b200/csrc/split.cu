@@ -160,6 +160,58 @@ bias_grad_lrelu_kernel(const float *__restrict__ g, long long sN, long long sC, 
   }
 }
 
+// Vector form of the LINEAR case (NHWC gradient, channels contiguous, everything 16-byte aligned):
+// a lane owns 4 channels (one 128-bit load per tensor and pixel), a warp 128 channels, the 8 warps of a
+// CTA walk the pixel strip with two pixels in flight each.  The scalar kernel above reaches 39 % of the
+// HBM roofline (one 4-byte load per lane in flight); this one moves 4x the bytes per instruction.
+__global__ void __launch_bounds__(256)
+bias_grad_lrelu_vec_kernel(const float *__restrict__ g, long long GS, const float *__restrict__ act, long long AP,
+                           float *__restrict__ gpre, long long GP, float *__restrict__ gb, int C, long long npix,
+                           float slope, int pix_per_cta) {
+  __shared__ float4 red[8][32];
+  const int lane = threadIdx.x & 31, row = threadIdx.x >> 5;
+  const int c = blockIdx.y * 128 + lane * 4;
+  const long long p0 = (long long)blockIdx.x * pix_per_cta;
+  const long long p1 = p0 + pix_per_cta < npix ? p0 + pix_per_cta : npix;
+  float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
+  if (c < C) {                                   // C % 4 == 0: a lane's four channels are all inside or all outside
+    long long p = p0 + row;
+    for (; p + 8 < p1; p += 16) {
+      float4 v0 = __ldg(reinterpret_cast<const float4 *>(g + p * GS + c));
+      float4 v1 = __ldg(reinterpret_cast<const float4 *>(g + (p + 8) * GS + c));
+      if (act) {
+        const float4 a0 = __ldg(reinterpret_cast<const float4 *>(act + p * AP + c));
+        const float4 a1 = __ldg(reinterpret_cast<const float4 *>(act + (p + 8) * AP + c));
+        if (a0.x <= 0.f) v0.x *= slope; if (a0.y <= 0.f) v0.y *= slope; if (a0.z <= 0.f) v0.z *= slope; if (a0.w <= 0.f) v0.w *= slope;
+        if (a1.x <= 0.f) v1.x *= slope; if (a1.y <= 0.f) v1.y *= slope; if (a1.z <= 0.f) v1.z *= slope; if (a1.w <= 0.f) v1.w *= slope;
+      }
+      if (gpre) {
+        *reinterpret_cast<float4 *>(gpre + p * GP + c) = v0;
+        *reinterpret_cast<float4 *>(gpre + (p + 8) * GP + c) = v1;
+      }
+      s0.x += v0.x; s0.y += v0.y; s0.z += v0.z; s0.w += v0.w;
+      s1.x += v1.x; s1.y += v1.y; s1.z += v1.z; s1.w += v1.w;
+    }
+    for (; p < p1; p += 8) {
+      float4 v = __ldg(reinterpret_cast<const float4 *>(g + p * GS + c));
+      if (act) {
+        const float4 a = __ldg(reinterpret_cast<const float4 *>(act + p * AP + c));
+        if (a.x <= 0.f) v.x *= slope; if (a.y <= 0.f) v.y *= slope; if (a.z <= 0.f) v.z *= slope; if (a.w <= 0.f) v.w *= slope;
+      }
+      if (gpre) *reinterpret_cast<float4 *>(gpre + p * GP + c) = v;
+      s0.x += v.x; s0.y += v.y; s0.z += v.z; s0.w += v.w;
+    }
+  }
+  red[row][lane] = make_float4(s0.x + s1.x, s0.y + s1.y, s0.z + s1.z, s0.w + s1.w);
+  __syncthreads();
+  if (row == 0 && c < C) {
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { const float4 r = red[k][lane]; t.x += r.x; t.y += r.y; t.z += r.z; t.w += r.w; }
+    atomicAdd(gb + c, t.x); atomicAdd(gb + c + 1, t.y); atomicAdd(gb + c + 2, t.z); atomicAdd(gb + c + 3, t.w);
+  }
+}
+
 }  // namespace unflow
 
 extern "C" int unflow_bias_lrelu(float *y, const float *bias, long long pixels, int C, float slope,
@@ -205,6 +257,20 @@ extern "C" int unflow_lrelu_bwd_bias(const float *g, long long sN, long long sC,
   if (pix_per_cta < 64) pix_per_cta = 64;
   dim3 grid(ceil_div(npix, pix_per_cta), cblocks);
   const bool linear = sH == (long long)W * sW && sN == (long long)H * sH;
+  const bool vec = linear && sC == 1 && C % 4 == 0 && sW % 4 == 0 && ((uintptr_t)g & 15) == 0 &&
+                   (!act || (act_pitch % 4 == 0 && ((uintptr_t)act & 15) == 0)) &&
+                   (!gpre || (gpre_pitch % 4 == 0 && ((uintptr_t)gpre & 15) == 0));
+  if (vec) {
+    const int cb = ceil_div(C, 128);
+    long long st = (long long)kNumSMs * 8 / cb;
+    if (st < 1) st = 1;
+    int ppc = (int)((npix + st - 1) / st);
+    if (ppc < 64) ppc = 64;
+    dim3 vgrid(ceil_div(npix, ppc), cb);
+    bias_grad_lrelu_vec_kernel<<<vgrid, 256, 0, s>>>(g, sW, act, act_pitch, gpre, gpre_pitch, gb, C, npix, slope, ppc);
+    count_launch();
+    return check_launch("bias_grad_lrelu(vec)");
+  }
   if (linear) bias_grad_lrelu_kernel<true><<<grid, 256, 0, s>>>(g, sN, sC, sH, sW, act, gb, N, C, H, W, slope, pix_per_cta, gpre, act_pitch, gpre_pitch);
   else bias_grad_lrelu_kernel<false><<<grid, 256, 0, s>>>(g, sN, sC, sH, sW, act, gb, N, C, H, W, slope, pix_per_cta, gpre, act_pitch, gpre_pitch);
   count_launch();

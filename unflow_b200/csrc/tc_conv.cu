@@ -398,7 +398,7 @@ wsplit_kernel(const float *__restrict__ w, float *__restrict__ hi, float *__rest
 // ------------------------------------------------------------------------------------------
 static int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
 
-int g_a_in_tmem = 0;     // unflow_set_int_option("tc_a_tmem"): 1 = A operand in tensor memory (default), 0 = in shared memory
+int g_a_in_tmem = 1;     // unflow_set_int_option("tc_a_tmem"): 1 = A operand in tensor memory (default), 0 = in shared memory
 
 template <int BN, bool AT>
 static int launch_v(const CUtensorMap &mA, const CUtensorMap &mBh, const CUtensorMap &mBl, const ConvParams &p,

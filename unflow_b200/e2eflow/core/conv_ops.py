@@ -47,6 +47,42 @@ LRELU_SLOPE = 0.1   # _leaky_relu: tf.maximum(0.1 * x, x)  (reference flownet.py
 # ---------------------------------------------------------------------------------------------
 _backward_point_cb = None
 
+# ---------------------------------------------------------------------------------------------
+# Gradient slots: an activation with several consumers (conv5_1 feeds conv6 AND concat5; a concat buffer
+# feeds the next deconv AND a flow head) receives one gradient per consumer, and autograd adds them with a
+# generic strided elementwise kernel (0.5 ms per step in the CUPTI table).  The tensor-core input-gradient
+# kernels can ADD into an existing buffer in their epilogue, so the first producer of a gradient for an
+# activation registers its buffer here and later producers accumulate into it and hand autograd None
+# ("no further contribution").  Keys are (forward generation, data pointer, shape): the generation counter
+# advances with every forward pass of the network, so buffers of an older graph are never picked up.
+# ---------------------------------------------------------------------------------------------
+_generation = 0
+_grad_slots = {}
+_GRAD_SLOTS = __import__('os').environ.get('UNFLOW_GRAD_SLOTS', '1') != '0'
+
+
+def new_forward_generation():
+    """Called at the start of every network forward pass."""
+    global _generation
+    _generation += 1
+    for g in [g for g in _grad_slots if g < _generation - 1]:
+        del _grad_slots[g]
+    return _generation
+
+
+def _slot_key(x):
+    return (x.data_ptr(), tuple(x.shape))
+
+
+def grad_slot_get(gen, x):
+    return _grad_slots.get(gen, {}).get(_slot_key(x)) if _GRAD_SLOTS else None
+
+
+def grad_slot_put(gen, key_or_tensor, g):
+    if _GRAD_SLOTS:
+        key = key_or_tensor if isinstance(key_or_tensor, tuple) else _slot_key(key_or_tensor)
+        _grad_slots.setdefault(gen, {})[key] = g
+
 
 def set_backward_point_callback(fn):
     """fn(name) is called from inside the backward pass; None removes it."""
@@ -351,6 +387,23 @@ def _dest(out, N, C, H, W, device):
     return y, y
 
 
+def _input_grad_into_slot(gen, x, launch):
+    """Run an input-gradient kernel for activation ``x``: into the gradient buffer another consumer of ``x``
+    already registered (epilogue adds; autograd gets None) or into a fresh NHWC buffer that is registered for
+    the consumers still to come.  ``launch(dst, accumulate)``."""
+    from . import tc_conv
+    N, C, H, W = x.shape
+    slot = grad_slot_get(gen, x)
+    if slot is not None and tuple(slot.shape) == (N, C, H, W) and tc_conv.supported(slot):
+        launch(slot, True)
+        return None
+    buf = torch.empty((N, H, W, _round4(C)), device=x.device, dtype=torch.float32)
+    gx = buf[..., :C].permute(0, 3, 1, 2)
+    launch(gx, False)
+    grad_slot_put(gen, x, gx)
+    return gx
+
+
 class _ConvTC(torch.autograd.Function):
     """slim.conv2d on the hand-written tcgen05 kernel: y = act(conv(x, w; stride, TF SAME) + b)."""
 
@@ -366,6 +419,7 @@ class _ConvTC(torch.autograd.Function):
                     bias=b, act=bool(act))
         ctx.save_for_backward(x, w, y if act else None)
         ctx.cfg = (stride, tuple(pads), b is not None, bool(act))
+        ctx.gen = _generation
         return y
 
     @staticmethod
@@ -382,10 +436,9 @@ class _ConvTC(torch.autograd.Function):
             gb = gb_all
         if ctx.needs_input_grad[0]:
             # dx = conv_transpose(gpre, w): rows of the GEMM = C_in, contraction = C_out
-            buf = torch.empty((N, H, W, _round4(Ci)), device=x.device, dtype=torch.float32)
-            gx = buf[..., :Ci].permute(0, 3, 1, 2)
-            tc_conv.run(gpre, tc_conv.split_weights(_khwc(w), transpose=True), gx, mode=1, stride=stride, kh=k, kw=k,
-                        pad_t=pt, pad_l=pl)
+            gx = _input_grad_into_slot(ctx.gen, x, lambda dst, acc: tc_conv.run(
+                gpre, tc_conv.split_weights(_khwc(w), transpose=True), dst, mode=1, stride=stride, kh=k, kw=k,
+                pad_t=pt, pad_l=pl, accumulate=acc))
         if ctx.needs_input_grad[1]:
             if _TC_WGRAD and tc_conv.supported(gpre):
                 gw = _tc_weight_grad(gpre, x, w, stride, pt, pl)                   # rows C_out, columns C_in
@@ -459,6 +512,7 @@ class _DeconvTC(torch.autograd.Function):
                     pad_l=1, bias=b, act=bool(act))
         ctx.save_for_backward(x, w, y if act else None)
         ctx.cfg = (b is not None, bool(act))
+        ctx.gen = _generation
         return y
 
     @staticmethod
@@ -474,9 +528,9 @@ class _DeconvTC(torch.autograd.Function):
             gb = gb_all
         if ctx.needs_input_grad[0]:
             # dx = conv(gpre, w; stride 2, pad 1): rows = C_in (dim 0 of the IOHW variable), contraction = C_out
-            buf = torch.empty((N, H, W, _round4(Ci)), device=x.device, dtype=torch.float32)
-            gx = buf[..., :Ci].permute(0, 3, 1, 2)
-            tc_conv.run(gpre, tc_conv.split_weights(_khwc(w)), gx, mode=0, stride=2, kh=4, kw=4, pad_t=1, pad_l=1)
+            gx = _input_grad_into_slot(ctx.gen, x, lambda dst, acc: tc_conv.run(
+                gpre, tc_conv.split_weights(_khwc(w)), dst, mode=0, stride=2, kh=4, kw=4, pad_t=1, pad_l=1,
+                accumulate=acc))
         if ctx.needs_input_grad[1]:
             if _TC_WGRAD and tc_conv.supported(gpre):
                 gw = _tc_weight_grad(x, gpre, w, 2, 1, 1)                          # rows C_in, columns C_out
@@ -534,6 +588,7 @@ class _NarrowConv3x3(torch.autograd.Function):
                 4, N, H, W, C, 2, torch.cuda.current_stream().cuda_stream), "conv3x3_narrow_fwd")
         ctx.save_for_backward(x, w)
         ctx.has_b = b is not None
+        ctx.gen = _generation
         return y
 
     @staticmethod
@@ -546,10 +601,9 @@ class _NarrowConv3x3(torch.autograd.Function):
             if _TC and tc_conv.supported(x):
                 # input gradient (C_in wide) on the tensor-core kernel: contraction over the 2 flow channels
                 gd, _ = _lrelu_bwd_bias(g, None, False)
-                buf = torch.empty((N, H, W, _round4(C)), device=x.device, dtype=torch.float32)
-                gx = buf[..., :C].permute(0, 3, 1, 2)
-                tc_conv.run(gd, tc_conv.split_weights(_khwc(w), transpose=True), gx, mode=1, stride=1, kh=3, kw=3,
-                            pad_t=1, pad_l=1)
+                gx = _input_grad_into_slot(ctx.gen, x, lambda dst, acc: tc_conv.run(
+                    gd, tc_conv.split_weights(_khwc(w), transpose=True), dst, mode=1, stride=1, kh=3, kw=3,
+                    pad_t=1, pad_l=1, accumulate=acc))
             else:
                 ci_p = _round4(C)
                 gs = _operand(g, 0, c_pad=4)                                          # [N, 12, H, W]

@@ -439,11 +439,19 @@ class _ConcatCL(torch.autograd.Function):
             spans.append((b0, b0 + t.shape[0], off, c))
             b0 += t.shape[0]
         ctx.spans = spans
+        ctx.gen = conv_ops._generation
+        # keys of the members as their other consumers see them (pointer + shape), for the gradient slots
+        ctx.member_keys = [(t.data_ptr(), tuple(t.shape)) for t in tensors]
         return out
 
     @staticmethod
     def backward(ctx, g):
-        return (None, None) + tuple(g[b0:b1, c0:c1] for (b0, b1, c0, c1) in ctx.spans)
+        views = tuple(g[b0:b1, c0:c1] for (b0, b1, c0, c1) in ctx.spans)
+        # a member's other consumers (conv5_1 also feeds conv6) add their input gradient into this view
+        # instead of handing autograd a second tensor to sum (conv_ops: gradient slots)
+        for key, v in zip(ctx.member_keys, views):
+            conv_ops.grad_slot_put(ctx.gen, key, v)
+        return (None, None) + views
 
 
 def _concat_channels_last(first, second_batch_parts=None, buf=None):
@@ -480,6 +488,7 @@ def flownet(im1, im2, flownet_spec='S', full_resolution=False, train_all=False,
     B, height, width, _ = im1.shape
     flownet_num = len(flownet_spec)
     assert flownet_num > 0
+    conv_ops.new_forward_generation()
     if variables is None:
         variables = get_variables(flownet_spec, full_resolution, device=im1.device)
     flows_fw = []
@@ -501,7 +510,10 @@ def flownet(im1, im2, flownet_spec='S', full_resolution=False, train_all=False,
                 conv3_a, conv3_b = conv3_ab[:B], conv3_ab[B:]
                 kw = dict(pad=20, kernel_size=1, max_displacement=20, stride_1=1, stride_2=2)
                 # both cost volumes from one pass over the features (the reverse one is a re-indexing)
-                corr_ab, corr_ba = correlation_bidir(conv3_a, conv3_b, **kw)
+                if conv3_a.is_cuda:
+                    corr_ab, corr_ba = correlation_bidir(conv3_a, conv3_b, **kw)
+                else:       # (CPU: only reachable with the op swapped for a stand-in, as the host-logic tests do)
+                    corr_ab, corr_ba = correlation(conv3_a, conv3_b, **kw), correlation(conv3_b, conv3_a, **kw)
                 conv_redir = cs.conv(conv3_ab, 'conv_redir')
                 if conv_ops.channels_last_active(conv_redir):
                     trunk_in = _concat_channels_last([conv_redir], [corr_ab, corr_ba])
