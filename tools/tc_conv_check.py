@@ -229,6 +229,9 @@ def main():
         for v in (1, 0, 1):
             _native.check(_native.lib().unflow_set_int_option(b"tc_a_tmem", v), "tc_a_tmem")
             say(phase="tc_a_tmem=%d" % v)
+            case_conv("1x1 one tile", 1, 32, 32, 8, 16, 1, 1, (0, 0, 0, 0), bias=False, act=False)
+            case_conv("3x3 s1 odd tiles", 3, 64, 128, 16, 24, 3, 1, (1, 1, 1, 1))
+            case_deconv("dgrad of 5x5 s2", 2, 128, 64, 8, 12, 5, 2, 1, bias=False, act=False, out_hw=(16, 24))
             case_conv("3x3 s1 small", 2, 64, 128, 16, 24, 3, 1, (1, 1, 1, 1))
             case_conv("3x3 s1 ragged", 2, 70, 50, 13, 21, 3, 1, (1, 1, 1, 1), pitch=80)
             case_deconv("deconv small", 2, 130, 64, 6, 20, 4, 2, 1, pitch=132)

@@ -251,7 +251,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             const float x4[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              const float h = tf32_rna(x4[e]);
+              const float h = tf32_rna_fast(x4[e]);
               hi[4 * j + e] = __float_as_uint(h);
               lo[4 * j + e] = __float_as_uint(x4[e] - h);
             }
@@ -269,7 +269,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             const int i = tid + 128 * j;
             const float4 v = a[i];
             float4 h, r;
-            h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
+            h.x = tf32_rna_fast(v.x); h.y = tf32_rna_fast(v.y); h.z = tf32_rna_fast(v.z); h.w = tf32_rna_fast(v.w);
             r.x = v.x - h.x; r.y = v.y - h.y; r.z = v.z - h.z; r.w = v.w - h.w;
             a[i] = h;
             l[i] = r;

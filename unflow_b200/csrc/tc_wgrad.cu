@@ -109,7 +109,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant_
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
       mbar_init(full_raw(s), 1);
-      mbar_init(full_cvt(s), 4);
+      mbar_init(full_cvt(s), AT ? 6 : 4);       // AT: 4 warps (P -> tensor memory) + 2 warps (G in shared memory)
       mbar_init(empty(s), 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -223,6 +223,10 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant_
     }
   } else if (warp >= 4 && warp < 8) {
     // ===================== split both tiles =====================
+    // AT: warps 4-7 put P into tensor memory (warp = 32-channel group = TMEM lane quarter), warps 2-3 split G
+    // in shared memory -- one warp per scheduler could not keep up with both tiles (ncu: the weight-gradient
+    // kernel sat at 45 % of the tensor pipe with the ALU pipe of the converter warps saturated).
+    // !AT: warps 4-7 split both tiles in shared memory.
     const int tid = threadIdx.x - 128;
     int s = 0;
     unsigned ph = 0;
@@ -233,38 +237,65 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant_
         mbar_wait(full_raw(s), ph);
         unsigned char *stp = gbase + s * C::STAGE_BYTES;
         if (AT) {
-          // P: warp = 32-channel group = TMEM lane quarter, lane = channel; column k of the operand = pixel k
+          // P: lane = channel; column k of the operand = pixel k
           const float *grp = reinterpret_cast<const float *>(stp + (warp & 3) * 4096) + lane;
           unsigned hi[KP], lo[KP];
 #pragma unroll
           for (int k = 0; k < KP; ++k) {
             const float v = grp[k * 32];
-            const float h = tf32_rna(v);
+            const float h = tf32_rna_fast(v);
             hi[k] = __float_as_uint(h);
             lo[k] = __float_as_uint(v - h);
           }
           const unsigned ta = tmem_base + ((unsigned)((warp & 3) * 32) << 16) + (unsigned)(C::ACC_COLS + s * 2 * KP);
           tmem_st32(ta, hi);
           tmem_st32(ta + KP, lo);
-        }
-#pragma unroll
-        for (int part = (AT ? 1 : 0); part < 2; ++part) {
-          float4 *a = reinterpret_cast<float4 *>(stp + (part ? C::B_OFF : 0));
-          float4 *l = reinterpret_cast<float4 *>(stp + (part ? C::B_OFF + C::B_BYTES : A_BYTES));
-          const int n16 = (part ? C::B_BYTES : A_BYTES) / 16;
-#pragma unroll
-          for (int i = tid; i < n16; i += 128) {
-            const float4 v = a[i];
-            float4 h, r;
-            h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
-            r.x = v.x - h.x; r.y = v.y - h.y; r.z = v.z - h.z; r.w = v.w - h.w;
-            a[i] = h;
-            l[i] = r;
-          }
-        }
-        if (AT) {
           asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
           tc_fence_before();
+        } else {
+#pragma unroll
+          for (int part = 0; part < 2; ++part) {
+            float4 *a = reinterpret_cast<float4 *>(stp + (part ? C::B_OFF : 0));
+            float4 *l = reinterpret_cast<float4 *>(stp + (part ? C::B_OFF + C::B_BYTES : A_BYTES));
+            const int n16 = (part ? C::B_BYTES : A_BYTES) / 16;
+#pragma unroll
+            for (int i = tid; i < n16; i += 128) {
+              const float4 v = a[i];
+              float4 h, r;
+              h.x = tf32_rna_fast(v.x); h.y = tf32_rna_fast(v.y); h.z = tf32_rna_fast(v.z); h.w = tf32_rna_fast(v.w);
+              r.x = v.x - h.x; r.y = v.y - h.y; r.z = v.z - h.z; r.w = v.w - h.w;
+              a[i] = h;
+              l[i] = r;
+            }
+          }
+          fence_proxy_async();
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(full_cvt(s));
+        if (++s == C::STAGES) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else if (AT && (warp == 2 || warp == 3)) {
+    // ===================== G split (shared memory, in place + lo plane), AT variant =====================
+    const int tid = threadIdx.x - 64;                 // 0..63
+    int s = 0;
+    unsigned ph = 0;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+      const Item w = decode_item(p, item);
+      const int iters = chunk_len(p, w.chunk);
+      for (int it = 0; it < iters; ++it) {
+        mbar_wait(full_raw(s), ph);
+        unsigned char *stp = gbase + s * C::STAGE_BYTES;
+        float4 *a = reinterpret_cast<float4 *>(stp + C::B_OFF);
+        float4 *l = reinterpret_cast<float4 *>(stp + C::B_OFF + C::B_BYTES);
+#pragma unroll
+        for (int i = tid; i < C::B_BYTES / 16; i += 64) {
+          const float4 v = a[i];
+          float4 h, r;
+          h.x = tf32_rna_fast(v.x); h.y = tf32_rna_fast(v.y); h.z = tf32_rna_fast(v.z); h.w = tf32_rna_fast(v.w);
+          r.x = v.x - h.x; r.y = v.y - h.y; r.z = v.z - h.z; r.w = v.w - h.w;
+          a[i] = h;
+          l[i] = r;
         }
         fence_proxy_async();
         __syncwarp();
