@@ -223,33 +223,30 @@ def main():
     quick = "--quick" in sys.argv
     torch.backends.cudnn.benchmark = True
     t0 = time.time()
-    if "--ab-tmem" in sys.argv:          # A operand in tensor memory (1) against in shared memory (0)
-        from unflow_b200 import _native
+    if "--timing" in sys.argv:           # the FlowNetC layer shapes, all three kernels
         B = 8
-        for v in (1, 0, 1):
-            _native.check(_native.lib().unflow_set_int_option(b"tc_a_tmem", v), "tc_a_tmem")
-            say(phase="tc_a_tmem=%d" % v)
-            case_conv("1x1 one tile", 1, 32, 32, 8, 16, 1, 1, (0, 0, 0, 0), bias=False, act=False)
-            case_conv("3x3 s1 odd tiles", 3, 64, 128, 16, 24, 3, 1, (1, 1, 1, 1))
-            case_deconv("dgrad of 5x5 s2", 2, 128, 64, 8, 12, 5, 2, 1, bias=False, act=False, out_hw=(16, 24))
-            case_conv("3x3 s1 small", 2, 64, 128, 16, 24, 3, 1, (1, 1, 1, 1))
-            case_conv("3x3 s1 ragged", 2, 70, 50, 13, 21, 3, 1, (1, 1, 1, 1), pitch=80)
-            case_deconv("deconv small", 2, 130, 64, 6, 20, 4, 2, 1, pitch=132)
-            case_conv("conv3_1", B, 473, 256, 48, 160, 3, 1, (1, 1, 1, 1), pitch=476, time_it=True)
-            case_conv("conv4_1", B, 512, 512, 24, 80, 3, 1, (1, 1, 1, 1), time_it=True)
-            case_conv("conv6_1", B, 1024, 1024, 6, 20, 3, 1, (1, 1, 1, 1), time_it=True)
-            case_conv("conv2 (5x5 s2)", B, 64, 128, 192, 640, 5, 2, (1, 2, 1, 2), time_it=True)
-            case_deconv("deconv3", B, 770, 128, 24, 80, 4, 2, 1, pitch=772, time_it=True)
-            case_deconv("deconv2", B, 386, 64, 48, 160, 4, 2, 1, pitch=388, time_it=True)
-            case_deconv("dgrad conv3_1", B, 256, 473, 48, 160, 3, 1, 1, bias=False, act=False, time_it=True)
-            case_wgrad("wgrad 3x3 s1 ragged", 2, 70, 50, 13, 21, 3, 1, (1, 1, 1, 1), pitch_x=80)
-            case_wgrad("wgrad 5x5 s2", 2, 24, 64, 16, 24, 5, 2, (1, 2, 1, 2))
-            case_wgrad("wgrad deconv k4 s2", 2, 130, 64, 6, 10, 4, 2, None, pitch_x=132, deconv=True)
-            case_wgrad("wgrad conv3_1", B, 473, 256, 48, 160, 3, 1, (1, 1, 1, 1), pitch_x=476, time_it=True)
-            case_wgrad("wgrad conv4_1", B, 512, 512, 24, 80, 3, 1, (1, 1, 1, 1), time_it=True)
-            case_wgrad("wgrad conv2 (5x5 s2)", B, 64, 128, 192, 640, 5, 2, (1, 2, 1, 2), time_it=True)
-            case_wgrad("wgrad deconv2", B, 386, 64, 48, 160, 4, 2, None, pitch_x=388, time_it=True, deconv=True)
-            case_window("window conv1 FlowNetC", B, 3, 384, 1280)
+        case_conv("3x3 s1 small", 2, 64, 128, 16, 24, 3, 1, (1, 1, 1, 1))
+        case_conv("3x3 s1 ragged", 2, 70, 50, 13, 21, 3, 1, (1, 1, 1, 1), pitch=80)
+        case_deconv("deconv small", 2, 130, 64, 6, 20, 4, 2, 1, pitch=132)
+        case_conv("conv3_1", B, 473, 256, 48, 160, 3, 1, (1, 1, 1, 1), pitch=476, time_it=True)
+        case_conv("conv4_1", B, 512, 512, 24, 80, 3, 1, (1, 1, 1, 1), time_it=True)
+        case_conv("conv5_1", B, 512, 512, 12, 40, 3, 1, (1, 1, 1, 1), time_it=True)
+        case_conv("conv6_1", B, 1024, 1024, 6, 20, 3, 1, (1, 1, 1, 1), time_it=True)
+        case_conv("conv2 (5x5 s2)", B, 64, 128, 192, 640, 5, 2, (1, 2, 1, 2), time_it=True)
+        case_conv("conv4 (s2)", B, 256, 512, 48, 160, 3, 2, (0, 1, 0, 1), time_it=True)
+        case_deconv("deconv5", B, 1024, 512, 6, 20, 4, 2, 1, time_it=True)
+        case_deconv("deconv3", B, 770, 128, 24, 80, 4, 2, 1, pitch=772, time_it=True)
+        case_deconv("deconv2", B, 386, 64, 48, 160, 4, 2, 1, pitch=388, time_it=True)
+        case_deconv("dgrad conv3_1", B, 256, 473, 48, 160, 3, 1, 1, bias=False, act=False, time_it=True)
+        case_wgrad("wgrad 3x3 s1 ragged", 2, 70, 50, 13, 21, 3, 1, (1, 1, 1, 1), pitch_x=80)
+        case_wgrad("wgrad deconv k4 s2", 2, 130, 64, 6, 10, 4, 2, None, pitch_x=132, deconv=True)
+        case_wgrad("wgrad conv3_1", B, 473, 256, 48, 160, 3, 1, (1, 1, 1, 1), pitch_x=476, time_it=True)
+        case_wgrad("wgrad conv4_1", B, 512, 512, 24, 80, 3, 1, (1, 1, 1, 1), time_it=True)
+        case_wgrad("wgrad conv6_1", B, 1024, 1024, 6, 20, 3, 1, (1, 1, 1, 1), time_it=True)
+        case_wgrad("wgrad conv2 (5x5 s2)", B, 64, 128, 192, 640, 5, 2, (1, 2, 1, 2), time_it=True)
+        case_wgrad("wgrad deconv2", B, 386, 64, 48, 160, 4, 2, None, pitch_x=388, time_it=True, deconv=True)
+        case_wgrad("wgrad deconv5", B, 1024, 512, 6, 20, 4, 2, None, time_it=True, deconv=True)
+        case_window("window conv1 FlowNetC", B, 3, 384, 1280)
         return
     if "--profile" in sys.argv:          # one launch of each big kernel, for ncu
         B = 8

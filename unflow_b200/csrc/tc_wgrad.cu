@@ -10,11 +10,11 @@
 //   convolution   y = conv(x, W):     P = dL/dy (rows r = C_out), G = x   (cols c = C_in),  d_t = k - pad
 //   transposed    y = deconv(x, W):   P = x     (rows r = C_in),  G = dL/dy (cols c = C_out), stride 2
 //
-// GEMM view per work item: M = 128 rows of P's channels, N = BN channels of G, K = pixels.  Both
-// operands are "MN-major" for the tensor core: NHWC memory has the channels contiguous and the
-// contraction index (pixels) across rows, which is exactly what a TMA box of 32 pixels x 32 channels
-// (one 128-byte row per pixel, written in the 32-byte-atom swizzle the tensor core requires of MN-major
-// tf32 operands) delivers -- no transposed copy of any activation exists.
+// GEMM view per work item: M = 128 rows of P's channels, N = BN channels of G, K = pixels.  NHWC
+// memory has the channels contiguous and the contraction index (pixels) across rows: G is used as an
+// "MN-major" shared-memory operand -- exactly what a TMA box of 32 pixels x 32 channels (one 128-byte row
+// per pixel, in the 32-byte-atom swizzle the tensor core requires of MN-major tf32 operands) delivers --
+// and P is transposed for free on its way into tensor memory.  No transposed copy of any activation exists.
 //
 // Work item = (pixel chunk, 128-row block, BN-column block); the BN columns are BN/32 consecutive
 // (tap, 32-channel group) pairs, so a layer with few input channels fills the 128-wide MMA with
@@ -23,8 +23,10 @@
 // schedule, so the chunk's activations are read from HBM once and re-read from L2.
 //   warp 0      TMA: per K block 4 boxes of P (32 px x 32 ch each) and BN/32 boxes of G (element
 //               stride = the conv stride, tap offset in the start coordinate, zero fill outside)
-//   warps 4-7   split both tiles: hi = tf32(v) in place, lo = v - hi beside it
-//   warp 1      tcgen05.mma kind::tf32, A and B MN-major: lo*hi + hi*lo + hi*hi per 8-pixel K step
+//   warps 4-7   P tile -> hi / lo in TENSOR MEMORY (lane = channel: the transposing read is free)
+//   warps 2-3   G tile: hi = tf32(v) in place, lo = v - hi beside it (shared memory)
+//   warp 1      tcgen05.mma kind::tf32, A from tensor memory, B MN-major from shared memory:
+//               lo*hi + hi*lo + hi*hi per 8-pixel K step
 //   warps 8-15  every 4 K blocks: tcgen05.ld the TMEM accumulator and add it to fp32 registers (see
 //               tc_conv.cu, "Accuracy"); at the end of the item: red.global.add into dW
 // dW is accumulated with fp32 atomics (split-K partial sums from several CTAs): the caller zeroes
@@ -52,19 +54,19 @@ struct WgradParams {
   long long pitch_r, pitch_t;       // dW[r * pitch_r + t * pitch_t + c]
 };
 
-// AT: the split P tile (the MMA's A operand) lives in TENSOR MEMORY (see tc_conv.cu, Cfg): the converter
-// warps read it from a plain (unswizzled) staging tile -- lane = channel, one LDS.32 per pixel, which is also
-// the transpose the K-major TMEM operand needs -- and store hi / lo with tcgen05.st; only G stays in
-// shared memory for the MMAs.
-template <int BN, bool AT>
+// The split P tile (the MMA's A operand) lives in TENSOR MEMORY (see tc_conv.cu, Cfg): converter warps read
+// it from a plain (unswizzled) staging tile -- lane = channel, one LDS.32 per pixel, which is also the
+// transpose the K-major TMEM operand needs -- and store hi / lo with tcgen05.st; only G is split in shared
+// memory (hi in place, lo beside it) for the MMAs.
+template <int BN>
 struct Cfg {
   static constexpr int B_BYTES = BN * KP * 4;
-  static constexpr int STAGE_BYTES = (AT ? 1 : 2) * A_BYTES + 2 * B_BYTES;
-  static constexpr int B_OFF = (AT ? 1 : 2) * A_BYTES;
-  static constexpr int STAGES = (200 * 1024 / STAGE_BYTES) < (AT ? 4 : 6) ? (200 * 1024 / STAGE_BYTES) : (AT ? 4 : 6);
+  static constexpr int STAGE_BYTES = A_BYTES + 2 * B_BYTES;
+  static constexpr int B_OFF = A_BYTES;
+  static constexpr int STAGES = (200 * 1024 / STAGE_BYTES) < 4 ? (200 * 1024 / STAGE_BYTES) : 4;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
   static constexpr int ACC_COLS = 2 * BN;
-  static constexpr int A_COLS = AT ? STAGES * 2 * KP : 0;
+  static constexpr int A_COLS = STAGES * 2 * KP;
   static constexpr int NEED = ACC_COLS + A_COLS;
   static constexpr int TMEM_COLS = NEED <= 32 ? 32 : NEED <= 64 ? 64 : NEED <= 128 ? 128 : NEED <= 256 ? 256 : 512;
   static_assert(NEED <= 512, "tensor memory has 512 columns");
@@ -85,11 +87,11 @@ __device__ __forceinline__ int chunk_len(const WgradParams &p, int chunk) {
   return (k0 + p.kc <= p.n_ptiles) ? p.kc : p.n_ptiles - k0;
 }
 
-template <int BN, bool AT>
+template <int BN>
 __global__ void __launch_bounds__(NTHREADS, 1)
 tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ CUtensorMap mapG,
                 const __grid_constant__ WgradParams p) {
-  using C = Cfg<BN, AT>;
+  using C = Cfg<BN>;
   extern __shared__ unsigned char smem_raw[];
   const unsigned base = (s32(smem_raw) + 1023u) & ~1023u;
   unsigned char *gbase = smem_raw + (base - s32(smem_raw));
@@ -109,7 +111,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant_
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
       mbar_init(full_raw(s), 1);
-      mbar_init(full_cvt(s), AT ? 6 : 4);       // AT: 4 warps (P -> tensor memory) + 2 warps (G in shared memory)
+      mbar_init(full_cvt(s), 6);                // 4 warps (P -> tensor memory) + 2 warps (G in shared memory)
       mbar_init(empty(s), 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -172,8 +174,8 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant_
     // ===================== MMA issuer =====================
     if (lane == 0) {
       // D fp32, A / B tf32, both MN-major (bits 15, 16), N = BN, M = 128
-      // (with A in tensor memory the A operand is K-major by construction: lane = row, column = K)
-      const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | (AT ? 0u : (1u << 15)) | (1u << 16) |
+      // (A lives in tensor memory: K-major by construction -- lane = row, column = K; B is MN-major, bit 16)
+      const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) |
                              ((unsigned)(BN >> 3) << 17) | ((unsigned)(BM >> 4) << 24);
       int s = 0, acc = 0;
       unsigned ph = 0, aph = 0;
@@ -193,24 +195,13 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant_
           const unsigned st = base + s * C::STAGE_BYTES;
           const unsigned long long b_hi = umma_desc_mn128(st + C::B_OFF, 4096);
           const unsigned long long b_lo = umma_desc_mn128(st + C::B_OFF + C::B_BYTES, 4096);
-          if (AT) {
-            const unsigned ta_hi = tmem_base + (unsigned)(C::ACC_COLS + s * 2 * KP), ta_lo = ta_hi + KP;
+          const unsigned ta_hi = tmem_base + (unsigned)(C::ACC_COLS + s * 2 * KP), ta_lo = ta_hi + KP;
 #pragma unroll
-            for (int k = 0; k < KP / 8; ++k) {          // A: 8 TMEM columns (pixels) per K step; B: 8 rows = 1024 B
-              const unsigned long long adv = (unsigned long long)(64 * k);
-              umma_tf32_ts(d, ta_lo + 8 * k, b_hi + adv, idesc, (in_chunk | k) != 0);
-              umma_tf32_ts(d, ta_hi + 8 * k, b_lo + adv, idesc, 1u);
-              umma_tf32_ts(d, ta_hi + 8 * k, b_hi + adv, idesc, 1u);
-            }
-          } else {
-            const unsigned long long a_hi = umma_desc_mn128(st, 4096), a_lo = umma_desc_mn128(st + A_BYTES, 4096);
-#pragma unroll
-            for (int k = 0; k < KP / 8; ++k) {          // 8 pixels = 8 rows of 128 B = 1024 B: +64 in 16-byte units
-              const unsigned long long adv = (unsigned long long)(64 * k);
-              umma_tf32(d, a_lo + adv, b_hi + adv, idesc, (in_chunk | k) != 0);
-              umma_tf32(d, a_hi + adv, b_lo + adv, idesc, 1u);
-              umma_tf32(d, a_hi + adv, b_hi + adv, idesc, 1u);
-            }
+          for (int k = 0; k < KP / 8; ++k) {            // A: 8 TMEM columns (pixels) per K step; B: 8 rows = 1024 B
+            const unsigned long long adv = (unsigned long long)(64 * k);
+            umma_tf32_ts(d, ta_lo + 8 * k, b_hi + adv, idesc, (in_chunk | k) != 0);
+            umma_tf32_ts(d, ta_hi + 8 * k, b_lo + adv, idesc, 1u);
+            umma_tf32_ts(d, ta_hi + 8 * k, b_hi + adv, idesc, 1u);
           }
           umma_commit(empty(s));
           if (++s == C::STAGES) { s = 0; ph ^= 1u; }
@@ -222,12 +213,10 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant_
       }
     }
   } else if (warp >= 4 && warp < 8) {
-    // ===================== split both tiles =====================
-    // AT: warps 4-7 put P into tensor memory (warp = 32-channel group = TMEM lane quarter), warps 2-3 split G
-    // in shared memory -- one warp per scheduler could not keep up with both tiles (ncu: the weight-gradient
-    // kernel sat at 45 % of the tensor pipe with the ALU pipe of the converter warps saturated).
-    // !AT: warps 4-7 split both tiles in shared memory.
-    const int tid = threadIdx.x - 128;
+    // ===================== P -> tensor memory =====================
+    // warp = 32-channel group = TMEM lane quarter, lane = channel; column k of the operand = pixel k.
+    // (G is split by warps 2-3: one warp per scheduler could not keep up with both tiles -- ncu: 45 % of the
+    // tensor pipe with the ALU pipe of the converter warps saturated.)
     int s = 0;
     unsigned ph = 0;
     for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
@@ -235,48 +224,27 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant_
       const int iters = chunk_len(p, w.chunk);
       for (int it = 0; it < iters; ++it) {
         mbar_wait(full_raw(s), ph);
-        unsigned char *stp = gbase + s * C::STAGE_BYTES;
-        if (AT) {
-          // P: lane = channel; column k of the operand = pixel k
-          const float *grp = reinterpret_cast<const float *>(stp + (warp & 3) * 4096) + lane;
-          unsigned hi[KP], lo[KP];
+        const float *grp = reinterpret_cast<const float *>(gbase + s * C::STAGE_BYTES + (warp & 3) * 4096) + lane;
+        unsigned hi[KP], lo[KP];
 #pragma unroll
-          for (int k = 0; k < KP; ++k) {
-            const float v = grp[k * 32];
-            const float h = tf32_rna_fast(v);
-            hi[k] = __float_as_uint(h);
-            lo[k] = __float_as_uint(v - h);
-          }
-          const unsigned ta = tmem_base + ((unsigned)((warp & 3) * 32) << 16) + (unsigned)(C::ACC_COLS + s * 2 * KP);
-          tmem_st32(ta, hi);
-          tmem_st32(ta + KP, lo);
-          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-          tc_fence_before();
-        } else {
-#pragma unroll
-          for (int part = 0; part < 2; ++part) {
-            float4 *a = reinterpret_cast<float4 *>(stp + (part ? C::B_OFF : 0));
-            float4 *l = reinterpret_cast<float4 *>(stp + (part ? C::B_OFF + C::B_BYTES : A_BYTES));
-            const int n16 = (part ? C::B_BYTES : A_BYTES) / 16;
-#pragma unroll
-            for (int i = tid; i < n16; i += 128) {
-              const float4 v = a[i];
-              float4 h, r;
-              h.x = tf32_rna_fast(v.x); h.y = tf32_rna_fast(v.y); h.z = tf32_rna_fast(v.z); h.w = tf32_rna_fast(v.w);
-              r.x = v.x - h.x; r.y = v.y - h.y; r.z = v.z - h.z; r.w = v.w - h.w;
-              a[i] = h;
-              l[i] = r;
-            }
-          }
-          fence_proxy_async();
+        for (int k = 0; k < KP; ++k) {
+          const float v = grp[k * 32];
+          const float h = tf32_rna_fast(v);
+          hi[k] = __float_as_uint(h);
+          lo[k] = __float_as_uint(v - h);
         }
+        const unsigned ta = tmem_base + ((unsigned)((warp & 3) * 32) << 16) + (unsigned)(C::ACC_COLS + s * 2 * KP);
+        tmem_st32(ta, hi);
+        tmem_st32(ta + KP, lo);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(full_cvt(s));
         if (++s == C::STAGES) { s = 0; ph ^= 1u; }
       }
     }
-  } else if (AT && (warp == 2 || warp == 3)) {
-    // ===================== G split (shared memory, in place + lo plane), AT variant =====================
+  } else if (warp == 2 || warp == 3) {
+    // ===================== G split in shared memory: hi in place, lo beside it =====================
     const int tid = threadIdx.x - 64;                 // 0..63
     int s = 0;
     unsigned ph = 0;
@@ -358,24 +326,19 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant_
   }
 }
 
-template <int BN, bool AT>
-static int launch_v(const CUtensorMap &mP, const CUtensorMap &mG, const WgradParams &p, int total, cudaStream_t stream) {
-  using C = Cfg<BN, AT>;
+template <int BN>
+static int launch(const CUtensorMap &mP, const CUtensorMap &mG, const WgradParams &p, int total, cudaStream_t stream) {
+  using C = Cfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tc_wgrad_kernel<BN, AT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(tc_wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e != cudaSuccess) { set_error("tc_wgrad: cannot opt in to %d bytes of shared memory: %s", C::SMEM_BYTES, cudaGetErrorString(e)); return UNFLOW_ECUDA; }
     attr_set = true;
   }
   const int grid = total < kNumSMs ? total : kNumSMs;
-  tc_wgrad_kernel<BN, AT><<<grid, NTHREADS, C::SMEM_BYTES, stream>>>(mP, mG, p);
+  tc_wgrad_kernel<BN><<<grid, NTHREADS, C::SMEM_BYTES, stream>>>(mP, mG, p);
   count_launch();
   return check_launch("tc_wgrad_kernel");
-}
-
-template <int BN>
-static int launch(const CUtensorMap &mP, const CUtensorMap &mG, const WgradParams &p, int total, cudaStream_t stream) {
-  return tc::g_a_in_tmem ? launch_v<BN, true>(mP, mG, p, total, stream) : launch_v<BN, false>(mP, mG, p, total, stream);
 }
 
 // the K-block pixel box: TW*TH*TN == 32 exactly (rows past the tensor are TMA zero fill), fewest boxes
@@ -453,8 +416,7 @@ extern "C" int unflow_tc_wgrad(const float *P, int N, int Hp, int Wp, int R, lon
     cuuint64_t strides[3] = {(cuuint64_t)p_pitch * 4, (cuuint64_t)p_pitch * 4 * Wp, (cuuint64_t)p_pitch * 4 * Wp * Hp};
     cuuint32_t box[4] = {32, (cuuint32_t)p.TW, (cuuint32_t)p.TH, (cuuint32_t)p.TN};
     cuuint32_t estr[4] = {1, 1, 1, 1};
-    rc = tc::encode(&mP, P, 4, dims, strides, box, estr,
-                    tc::g_a_in_tmem ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    rc = tc::encode(&mP, P, 4, dims, strides, box, estr, CU_TENSOR_MAP_SWIZZLE_NONE);   // read by the converter warps only
     if (rc) return rc;
   }
   {
@@ -495,8 +457,7 @@ extern "C" int unflow_tc_wgrad_window(const float *P, int N, int Ho, int Wo, int
     cuuint64_t strides[3] = {(cuuint64_t)p_pitch * 4, (cuuint64_t)p_pitch * 4 * Wo, (cuuint64_t)p_pitch * 4 * Wo * Ho};
     cuuint32_t box[4] = {32, (cuuint32_t)p.TW, (cuuint32_t)p.TH, (cuuint32_t)p.TN};
     cuuint32_t estr[4] = {1, 1, 1, 1};
-    rc = tc::encode(&mP, P, 4, dims, strides, box, estr,
-                    tc::g_a_in_tmem ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    rc = tc::encode(&mP, P, 4, dims, strides, box, estr, CU_TENSOR_MAP_SWIZZLE_NONE);   // read by the converter warps only
     if (rc) return rc;
   }
   {
