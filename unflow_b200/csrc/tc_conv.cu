@@ -82,8 +82,10 @@ struct ConvParams {
 // What limits the AT kernel is the SM's ingress from L2: 48 KB per K block (16 KB activations + 32 KB
 // hi / lo weight planes) at ~43 B/clk -- ncu: 10.4 TB/s chip-wide, the fabric limit -- for 768 clk of MMA
 // work.  Two ways to cut it were tried on B200 and measured slower / equal, and removed again: (1) fetching
-// the fp32 weights once and splitting them in the kernel too (32 KB per K block; the two spare warps cannot
-// split 16 KB per K block fast enough: conv3_1 forward 756 us instead of 680 us); (2) TMA multicast of the
+// the fp32 weights once and splitting them in the kernel too (32 KB per K block): 756 us instead of 680 us
+// for conv3_1 forward with the two spare warps doing the split, 680 instead of 617 us with the work spread
+// over all six converter warps -- the extra shared-memory round trip of the weight tile costs more than the
+// saved ingress; (2) TMA multicast of the
 // weight tiles to CTA pairs (the ingress per SM is unchanged, and L2 already merges the concurrent reads:
 // 679 us vs 680 us).  A cta_group::2 MMA (each SM holds half of B) is the remaining lever.
 template <int BN, bool AT>
