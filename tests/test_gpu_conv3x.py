@@ -177,11 +177,17 @@ def test_narrow_flow_head_matches_float64(mode3x, N, C, H, W):
     assert rel(wc.grad.cpu(), wd.grad) < 2e-6
     assert rel(bc.grad.cpu(), bd.grad) < 2e-6
     assert rel(xc.grad.cpu(), xd.grad) < 3e-5                    # input gradient on the tensor-core kernel
-    # deterministic: a second evaluation gives the same bits
+    # the weight gradient is a fixed-order two-pass reduction: a second evaluation gives the same bits; the
+    # forward is bit-repeatable when one CTA owns a tile (the full-size heads), while small images split the
+    # channels over CTAs whose partial sums meet through atomics (order free, values within rounding)
     wc2 = wc.detach().clone().requires_grad_(True)
     y2 = conv_ops._NarrowConv3x3.apply(xc.detach(), wc2, bc.detach())
     y2.backward(gc)
-    assert torch.equal(y2, y) and torch.equal(wc2.grad, wc.grad)
+    assert torch.equal(wc2.grad, wc.grad)
+    if N * ((H + 15) // 16) * ((W + 31) // 32) >= 2 * 148:
+        assert torch.equal(y2, y)
+    else:
+        assert rel(y2.detach().cpu(), y.detach().cpu()) < 1e-6
     # no bias, and the dispatch rule of conv2d
     y3 = conv_ops._NarrowConv3x3.apply(xc.detach(), wc.detach(), None)
     assert rel((y3 + bc.detach().view(1, 2, 1, 1)).cpu(), yd.detach()) < 2e-6
@@ -208,7 +214,7 @@ def test_narrow_conv_rejects_other_shapes():
 
 def test_narrow_conv_on_a_channel_slice_of_a_wider_buffer(mode3x):
     """The flow heads read their input in place from the (pitch-padded) concat buffers: a channel slice
-    with a larger pixel pitch must give bit-identical results to the dense copy."""
+    with a larger pixel pitch must give the same results as the dense copy."""
     from unflow_b200.e2eflow.core import conv_ops
     gen = torch.Generator().manual_seed(3)
     buf = torch.randn(2, 37, 70, 200, generator=gen).cuda()
@@ -223,7 +229,10 @@ def test_narrow_conv_on_a_channel_slice_of_a_wider_buffer(mode3x):
         y = conv_ops._NarrowConv3x3.apply(x, wr, b)
         y.backward(g)
         outs.append((y.detach().clone(), wr.grad.clone()))
-    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    # 18 tiles < 2 x 148 SMs: the forward splits the channels over several CTAs that add their parts with
+    # atomics (order not fixed), the weight gradient splits them into disjoint ranges (bit-identical)
+    assert torch.equal(outs[0][1], outs[1][1])
+    assert (outs[0][0] - outs[1][0]).abs().max().item() < 1e-5 * outs[0][0].abs().max().item()
 
 
 @pytest.mark.parametrize("cin,hw", [(3, (20, 28)), (14, (22, 26)), (6, (21, 27))])

@@ -1,24 +1,24 @@
 #!/bin/bash
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-timeout 300 python tools/tc_conv_check.py --timing > gpurun_out/tc_timing_v3.jsonl 2> gpurun_out/tc_timing_v3.err
+timeout 300 python tools/tc_conv_check.py --timing > gpurun_out/tc_timing_v5.jsonl 2> gpurun_out/tc_timing_v5.err
 echo "timing rc=$?"; python - <<'PY'
 import json
-for ln in open('gpurun_out/tc_timing_v3.jsonl'):
+for ln in open('gpurun_out/tc_timing_v5.jsonl'):
     d=json.loads(ln)
     if 'case' in d: print('%-28s err %.2e %s us=%s us_wgrad=%s tf=%s'%(d['case'], d['err'], d.get('err_wgrad',''), d.get('us'), d.get('us_wgrad'), d.get('tflops_fp32_equiv')))
 PY
-tail -5 gpurun_out/tc_timing_v3.err
-timeout 900 python -m pytest tests -m gpu -q --timeout 600 > gpurun_out/r2_pytest17.log 2>&1
-echo "pytest rc=$?"; grep -E "passed|failed|FAILED|Error" gpurun_out/r2_pytest17.log | tail -12
+tail -5 gpurun_out/tc_timing_v5.err
+timeout 900 python -m pytest tests -m gpu -q --timeout 600 > gpurun_out/r2_pytest20.log 2>&1
+echo "pytest rc=$?"; grep -E "passed|failed|FAILED|Error" gpurun_out/r2_pytest20.log | tail -12
 B="timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --also-fp32 0"
-$B > gpurun_out/r2_tc_v11.json 2> gpurun_out/r2_tc_v11.err; tail -3 gpurun_out/r2_tc_v11.err
+$B > gpurun_out/r2_tc_v13.json 2> gpurun_out/r2_tc_v13.err; tail -3 gpurun_out/r2_tc_v13.err
 python - <<'PY'
 import json
 try:
-    d=json.loads(open('gpurun_out/r2_tc_v11.json').read().strip().splitlines()[-1])
+    d=json.loads(open('gpurun_out/r2_tc_v13.json').read().strip().splitlines()[-1])
     print('v10', d['ms_per_step'], d['e2e']['ms_per_step'], d['final_loss'])
     print(json.dumps(d['roofline'])[:400]); print(json.dumps(d['rooflines_other'][0])[:400])
 except Exception as e: print('FAILED',e)
 PY
-timeout 300 python tools/kernel_time_table.py > gpurun_out/r2_kernel_table_v11.md 2> gpurun_out/r2_kernel_table_v11.err; head -26 gpurun_out/r2_kernel_table_v11.md
+timeout 300 python tools/kernel_time_table.py > gpurun_out/r2_kernel_table_v13.md 2> gpurun_out/r2_kernel_table_v13.err; head -26 gpurun_out/r2_kernel_table_v13.md

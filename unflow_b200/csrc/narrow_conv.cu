@@ -86,18 +86,23 @@ __device__ __forceinline__ void stage(float *xs, const float *__restrict__ x, in
 
 __global__ void __launch_bounds__(THREADS, 4)
 narrow_fwd_kernel(const float *__restrict__ x, const float *__restrict__ w, const float *__restrict__ bias,
-                  float *__restrict__ y, int H, int W, int C, long long XP, long long YP) {
+                  float *__restrict__ y, int H, int W, int C, long long XP, long long YP, int csplit) {
   // rows 38 floats apart: a half-warp's 8-byte reads (two tile rows) fall on disjoint banks;
   // channels 706 = 2 (mod 32) floats apart: the staging stores are conflict-free
   constexpr int CHS = FWD_CHS, FP = FWD_PITCH;
   extern __shared__ __align__(16) float smem[];
   float *xs = smem;                           // [KC][CHS]
   float *ws = smem + KC * CHS;                // [KC][3][8]: co0 kx0..2, co1 kx0..2, 0, 0
-  const int tid = threadIdx.x, n = blockIdx.z, y0 = blockIdx.y * TH, x0 = blockIdx.x * TW;
+  // csplit > 1 (small images: flow4..flow6 have 8..48 tiles for 148 SMs): blockIdx.z also selects a slice of
+  // the input channels; the slices' partial sums meet in y (zeroed by the launcher) through atomics
+  const int tid = threadIdx.x, n = blockIdx.z / csplit, split = blockIdx.z - n * csplit;
+  const int y0 = blockIdx.y * TH, x0 = blockIdx.x * TW;
   const int row = tid >> 3, cg = tid & 7;     // 16 rows x 8 groups of 4 pixels
   float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f};
+  const int chunks = (C + KC - 1) / KC, per = (chunks + csplit - 1) / csplit;
+  const int c_begin = split * per * KC, c_end = (split + 1) * per * KC < C ? (split + 1) * per * KC : C;
 
-  for (int c0 = 0; c0 < C; c0 += KC) {
+  for (int c0 = c_begin; c0 < c_end; c0 += KC) {
     __syncthreads();                          // the previous chunk has been consumed
     stage<CHS, FP>(xs, x, n, y0, x0, c0, H, W, C, XP, tid);
     for (int idx = tid; idx < KC * 24; idx += THREADS) {
@@ -136,25 +141,37 @@ narrow_fwd_kernel(const float *__restrict__ x, const float *__restrict__ w, cons
 
   const int gy = y0 + row;
   if (gy < H) {
-    const float b0 = bias ? bias[0] : 0.f, b1 = bias ? bias[1] : 0.f;
+    const float b0 = (bias && split == 0) ? bias[0] : 0.f, b1 = (bias && split == 0) ? bias[1] : 0.f;
     float *out = y + ((long long)n * H + gy) * W * YP;          // YP floats between output pixels (even)
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int gx = x0 + 4 * cg + j;
-      if (gx < W) *reinterpret_cast<float2 *>(out + gx * YP) = make_float2(acc0[j] + b0, acc1[j] + b1);
+      if (gx < W) {
+        if (csplit == 1) {
+          *reinterpret_cast<float2 *>(out + gx * YP) = make_float2(acc0[j] + b0, acc1[j] + b1);
+        } else {
+          atomicAdd(out + gx * YP, acc0[j] + b0);
+          atomicAdd(out + gx * YP + 1, acc1[j] + b1);
+        }
+      }
     }
   }
 }
 
 __global__ void __launch_bounds__(THREADS, 4)
 narrow_wgrad_kernel(const float *__restrict__ x, const float *__restrict__ g, long long gsN, long long gsC,
-                    long long gsH, long long gsW, float *__restrict__ partial, int H, int W, int C, long long XP) {
+                    long long gsH, long long gsW, float *__restrict__ partial, int H, int W, int C, long long XP,
+                    int csplit) {
   constexpr int CHS = SR * PITCH + 1;         // 649: odd -> lanes on consecutive channels hit distinct banks
   extern __shared__ __align__(16) float smem[];
   float *xs = smem;                           // [KC][CHS]; reused as red[8][KC][NOUT] after the arithmetic
   float *gs = smem + KC * CHS;                // [TH][GPITCH] (even offset: 8-byte aligned float2 reads)
-  const int tid = threadIdx.x, n = blockIdx.z, y0 = blockIdx.y * TH, x0 = blockIdx.x * TW;
-  const long long bid = ((long long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+  // csplit > 1: several CTAs per tile, each with its own slice of the input channels (disjoint outputs)
+  const int tid = threadIdx.x, n = blockIdx.z / csplit, split = blockIdx.z - n * csplit;
+  const int y0 = blockIdx.y * TH, x0 = blockIdx.x * TW;
+  const long long bid = ((long long)n * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+  const int chunks = (C + KC - 1) / KC, per = (chunks + csplit - 1) / csplit;
+  const int c_begin = split * per * KC, c_end = (split + 1) * per * KC < C ? (split + 1) * per * KC : C;
   const int ch = tid & 15, h = tid >> 4;      // channel, row group (0..7)
   // rows {base, base + 8}; the two row groups of a warp sit 4 rows apart (bank offset 16)
   const int base = (h >> 1) + 4 * (h & 1);
@@ -167,7 +184,7 @@ narrow_wgrad_kernel(const float *__restrict__ x, const float *__restrict__ g, lo
     gs[r * GPITCH + 2 * c + co] = v;
   }
 
-  for (int c0 = 0; c0 < C; c0 += KC) {
+  for (int c0 = c_begin; c0 < c_end; c0 += KC) {
     __syncthreads();                          // red (aliasing xs) has been read; gs is complete
     stage<CHS, PITCH>(xs, x, n, y0, x0, c0, H, W, C, XP, tid);
     __syncthreads();
@@ -274,10 +291,23 @@ extern "C" int unflow_conv3x3_narrow_fwd(const float *x, long long x_pitch, cons
   UNFLOW_REQUIRE(((uintptr_t)y & 7) == 0, "conv3x3_narrow_fwd: y must be 8-byte aligned");
   UNFLOW_REQUIRE(x_pitch >= C, "conv3x3_narrow_fwd: pixel pitch smaller than C");
   UNFLOW_REQUIRE(y_pitch >= 2 && y_pitch % 2 == 0, "conv3x3_narrow_fwd: output pitch must be even and >= 2");
-  const dim3 grid(ceil_div(W, nc::TW), ceil_div(H, nc::TH), N);
-  const size_t smem = (size_t)(nc::KC * nc::FWD_CHS + nc::KC * 24) * sizeof(float);
+  // few tiles (the coarse pyramid levels): split the channel range over several CTAs per tile
+  const long long tiles = nc::tiles(N, H, W);
+  const int chunks = ceil_div(C, nc::KC);
+  int csplit = 1;
+  if (tiles < 2 * kNumSMs) {
+    csplit = (int)((2ll * kNumSMs + tiles - 1) / tiles);
+    if (csplit > chunks / 2) csplit = chunks / 2 > 0 ? chunks / 2 : 1;
+    if ((long long)N * csplit > 65535) csplit = 65535 / N;
+  }
   cudaStream_t st = (cudaStream_t)stream;
-  nc::narrow_fwd_kernel<<<grid, nc::THREADS, smem, st>>>(x, w, bias, y, H, W, C, x_pitch, y_pitch);
+  if (csplit > 1) {
+    cudaError_t e = cudaMemsetAsync(y, 0, sizeof(float) * (size_t)N * H * W * y_pitch, st);
+    if (e != cudaSuccess) { set_error("conv3x3_narrow_fwd memset: %s", cudaGetErrorString(e)); return UNFLOW_ECUDA; }
+  }
+  const dim3 grid(ceil_div(W, nc::TW), ceil_div(H, nc::TH), N * csplit);
+  const size_t smem = (size_t)(nc::KC * nc::FWD_CHS + nc::KC * 24) * sizeof(float);
+  nc::narrow_fwd_kernel<<<grid, nc::THREADS, smem, st>>>(x, w, bias, y, H, W, C, x_pitch, y_pitch, csplit);
   count_launch();
   return check_launch("conv3x3_narrow_fwd");
 }
@@ -296,11 +326,18 @@ extern "C" int unflow_conv3x3_narrow_wgrad(const float *x, long long x_pitch, co
   }
   UNFLOW_REQUIRE(x && g && workspace, "conv3x3_narrow_wgrad: null pointer");
   UNFLOW_REQUIRE(x_pitch >= C, "conv3x3_narrow_wgrad: pixel pitch smaller than C");
-  const dim3 grid(ceil_div(W, nc::TW), ceil_div(H, nc::TH), N);
   const int nblocks = (int)nc::tiles(N, H, W);
+  const int chunks = ceil_div(C, nc::KC);
+  int csplit = 1;
+  if (nblocks < 2 * kNumSMs) {
+    csplit = (2 * kNumSMs + nblocks - 1) / nblocks;
+    if (csplit > chunks / 2) csplit = chunks / 2 > 0 ? chunks / 2 : 1;
+    if ((long long)N * csplit > 65535) csplit = 65535 / N;
+  }
+  const dim3 grid(ceil_div(W, nc::TW), ceil_div(H, nc::TH), N * csplit);
   const size_t smem = (size_t)(nc::KC * (nc::SR * nc::PITCH + 1) + nc::TH * nc::GPITCH) * sizeof(float);
   float *part = (float *)workspace;
-  nc::narrow_wgrad_kernel<<<grid, nc::THREADS, smem, s>>>(x, g, gsN, gsC, gsH, gsW, part, H, W, C, x_pitch);
+  nc::narrow_wgrad_kernel<<<grid, nc::THREADS, smem, s>>>(x, g, gsN, gsC, gsH, gsW, part, H, W, C, x_pitch, csplit);
   count_launch();
   if (int rc = check_launch("conv3x3_narrow_wgrad")) return rc;
   const int total = nc::NOUT * C;

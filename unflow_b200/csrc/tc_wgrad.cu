@@ -215,8 +215,9 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant_
   } else if (warp >= 4 && warp < 8) {
     // ===================== P -> tensor memory =====================
     // warp = 32-channel group = TMEM lane quarter, lane = channel; column k of the operand = pixel k.
-    // (G is split by warps 2-3: one warp per scheduler could not keep up with both tiles -- ncu: 45 % of the
-    // tensor pipe with the ALU pipe of the converter warps saturated.)
+    // (The G tile is split by all six converter warps, half here and half in warps 2-3: one warp per scheduler
+    // could not keep up with both tiles -- ncu: 45 % of the tensor pipe with the ALU pipe of the converter warps
+    // saturated -- and two warps alone cannot split 16 KB per K block in time either.)
     int s = 0;
     unsigned ph = 0;
     for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
@@ -236,6 +237,20 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant_
         const unsigned ta = tmem_base + ((unsigned)((warp & 3) * 32) << 16) + (unsigned)(C::ACC_COLS + s * 2 * KP);
         tmem_st32(ta, hi);
         tmem_st32(ta + KP, lo);
+        {                                    // ... and the first half of G (warps 2-3 take the second half)
+          float4 *a = reinterpret_cast<float4 *>(gbase + s * C::STAGE_BYTES + C::B_OFF);
+          float4 *l = reinterpret_cast<float4 *>(gbase + s * C::STAGE_BYTES + C::B_OFF + C::B_BYTES);
+#pragma unroll
+          for (int i = threadIdx.x - 128; i < C::B_BYTES / 32; i += 128) {
+            const float4 v = a[i];
+            float4 h, r;
+            h.x = tf32_rna_fast(v.x); h.y = tf32_rna_fast(v.y); h.z = tf32_rna_fast(v.z); h.w = tf32_rna_fast(v.w);
+            r.x = v.x - h.x; r.y = v.y - h.y; r.z = v.z - h.z; r.w = v.w - h.w;
+            a[i] = h;
+            l[i] = r;
+          }
+          fence_proxy_async();
+        }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         tc_fence_before();
         __syncwarp();
@@ -257,7 +272,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant_
         float4 *a = reinterpret_cast<float4 *>(stp + C::B_OFF);
         float4 *l = reinterpret_cast<float4 *>(stp + C::B_OFF + C::B_BYTES);
 #pragma unroll
-        for (int i = tid; i < C::B_BYTES / 16; i += 64) {
+        for (int i = C::B_BYTES / 32 + tid; i < C::B_BYTES / 16; i += 64) {
           const float4 v = a[i];
           float4 h, r;
           h.x = tf32_rna_fast(v.x); h.y = tf32_rna_fast(v.y); h.z = tf32_rna_fast(v.z); h.w = tf32_rna_fast(v.w);

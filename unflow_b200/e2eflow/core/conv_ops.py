@@ -542,9 +542,11 @@ class _DeconvTC(torch.autograd.Function):
         return gx, gw, gb, None, None
 
 
-# The narrow kernels pay off where the layer is large enough to fill the GPU with 16x32-pixel
-# tiles (the flow2 / flow3 heads of a training batch); smaller heads stay on the library path.
-NARROW_MIN_TILES = 96
+# The narrow kernels serve every 2-channel 3x3 head: the large ones (flow2 / flow3 of a training batch)
+# fill the GPU with 16x32-pixel tiles, the coarse ones (flow4 .. flow6: 8 .. 48 tiles) split the input
+# channels over several CTAs per tile (csrc/narrow_conv.cu, csplit).  On the tensor-core kernel a head is
+# one 32-wide N block with 2 useful columns and a K of 9 x 1026 walked by a handful of CTAs: 0.5 ms per step.
+NARROW_MIN_TILES = 1
 _NARROW = __import__('os').environ.get('UNFLOW_NARROW_CONV', '1') != '0'
 
 
