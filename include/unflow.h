@@ -98,6 +98,19 @@ int unflow_correlation_fwd_bidir(const float *in0, const float *in1, float *out,
 int unflow_correlation_fold_grad(const float *gout, const float *gout_rev, float *gout_eff, int B, int C,
                                  int H, int W, int kernel_size, int max_displacement, int pad,
                                  int stride_1, int stride_2, void *stream);
+/* Layout bridge around the correlation op.  The op keeps the reference's tensor layout -- inputs and cost
+ * volume are [B, C, H, W] (ops/correlation_op.cc:15-27, ops/correlation_op.cu.cc:250-315) -- while the conv
+ * stack keeps activations NHWC inside pitch-padded concat buffers (src/e2eflow/core/flownet.py:34-44 is the
+ * call site: conv3 features in, concat([conv_redir, corr]) out).  These two tiled transposes replace the
+ * strided library copies at that border:
+ *   planar_to_interleaved: dst[b][p][c] (+)= src[b][c][p]     src dense [C][P] per image (P = H*W)
+ *   interleaved_to_planar: dst[b][c][p]  =  src[b][p][c]      interleaved side: pixel pitch >= C floats
+ * `*_batch` = floats between consecutive images on that side (lets the interleaved side be a channel and
+ * batch slice of a larger buffer); accumulate != 0 adds into dst. */
+int unflow_planar_to_interleaved(const float *src, long long src_batch, float *dst, long long dst_batch,
+                                 long long pitch, int B, int C, int P, int accumulate, void *stream);
+int unflow_interleaved_to_planar(const float *src, long long src_batch, long long pitch, float *dst,
+                                 long long dst_batch, int B, int C, int P, void *stream);
 
 /* ------------------------------------------------------------------------
  * BackwardWarp / image_warp

@@ -174,6 +174,59 @@ def test_correlation_bidirectional_one_pass(shape, md):
         assert float((got - want).abs().max()) <= 2e-6 * scale
 
 
+@pytest.mark.parametrize("B,C,P,pitch,c0", [(2, 5, 37, 12, 3), (3, 441, 48 * 160, 476, 32), (2, 256, 24 * 20, 256, 0)])
+def test_relayout_planar_interleaved(B, C, P, pitch, c0):
+    """csrc/relayout.cu: the tiled transposes between the correlation op's NCHW tensors and channel slices of
+    the NHWC concat buffers -- exact copies, accumulate adds, the slack channels stay untouched."""
+    from unflow_b200 import _native
+    lib = _native.lib()
+    st = torch.cuda.current_stream().cuda_stream
+    src = rnd((B, C, P), 7).cuda()
+    buf = torch.full((B + 1, P, pitch), -3.5, device="cuda")
+    dst = buf[1:]                                       # a batch slice too
+    assert lib.unflow_planar_to_interleaved(src.data_ptr(), C * P, dst.data_ptr() + 4 * c0, P * pitch, pitch,
+                                            B, C, P, 0, st) == 0
+    assert torch.equal(dst[:, :, c0:c0 + C], src.permute(0, 2, 1))
+    untouched = torch.ones(pitch, dtype=torch.bool); untouched[c0:c0 + C] = False
+    assert bool((dst[:, :, untouched.cuda()] == -3.5).all()) and bool((buf[0] == -3.5).all())
+    assert lib.unflow_planar_to_interleaved(src.data_ptr(), C * P, dst.data_ptr() + 4 * c0, P * pitch, pitch,
+                                            B, C, P, 1, st) == 0
+    assert torch.equal(dst[:, :, c0:c0 + C], 2 * src.permute(0, 2, 1))
+    back = torch.empty_like(src)
+    assert lib.unflow_interleaved_to_planar(dst.data_ptr() + 4 * c0, P * pitch, pitch, back.data_ptr(), C * P,
+                                            B, C, P, st) == 0
+    assert torch.equal(back, 2 * src)
+    assert lib.unflow_planar_to_interleaved(src.data_ptr(), C * P, dst.data_ptr(), P * pitch, C - 1, B, C, P, 0, st) == 1
+
+
+def test_flownetc_fused_trunk_input_matches_unfused():
+    """concat([conv_redir, corr]) of both directions written into one NHWC buffer (ops.
+    _CorrelationBidirConcat) against the unfused correlation_bidir + concat: same flows, same gradients."""
+    from unflow_b200.e2eflow.core import flownet as F
+    v = F.FlowNetVariables('C', False, seed=3).cuda()
+    g = torch.Generator().manual_seed(5)
+    im1 = (torch.rand(2, 128, 192, 3, generator=g) - 0.5).cuda()
+    im2 = (torch.rand(2, 128, 192, 3, generator=g) - 0.5).cuda()
+    res = {}
+    try:
+        for fused in (True, False):
+            F.FUSED_TRUNK_INPUT = fused
+            for p in v.parameters():
+                p.grad = None
+            fw, bw = F.flownet(im1, im2, 'C', backward_flow=True, variables=v)
+            loss = sum((f * f).sum() * (i + 1) for i, f in enumerate(fw[0] + bw[0]))
+            loss.backward()
+            res[fused] = ([f.detach().clone() for f in fw[0] + bw[0]],
+                          {k: p.grad.detach().clone() for k, p in v.named_parameters()})
+    finally:
+        F.FUSED_TRUNK_INPUT = True
+    for a, b in zip(res[True][0], res[False][0]):
+        assert float((a - b).abs().max()) <= 1e-6 * float(b.abs().max())
+    for k, want in res[False][1].items():
+        got = res[True][1][k]
+        assert float((got - want).abs().max()) <= 2e-5 * float(want.abs().max()) + 1e-12, k
+
+
 def test_correlation_bidir_falls_back_for_other_attributes():
     ops = _ops()
     a, b = rnd((1, 8, 10, 14), 1).cuda(), rnd((1, 8, 10, 14), 2).cuda()

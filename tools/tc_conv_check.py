@@ -219,10 +219,83 @@ def bench(fn, iters=10, warmup=3):
     return round(ts[len(ts) // 2], 2)
 
 
+def conv_layer_cases(time_it=True):
+    B = 8
+    case_conv("conv3_1", B, 473, 256, 48, 160, 3, 1, (1, 1, 1, 1), pitch=476, time_it=time_it)
+    case_conv("conv4_1", B, 512, 512, 24, 80, 3, 1, (1, 1, 1, 1), time_it=time_it)
+    case_conv("conv5_1", B, 512, 512, 12, 40, 3, 1, (1, 1, 1, 1), time_it=time_it)
+    case_conv("conv6_1", B, 1024, 1024, 6, 20, 3, 1, (1, 1, 1, 1), time_it=time_it)
+    case_conv("conv2 (5x5 s2)", B, 64, 128, 192, 640, 5, 2, (1, 2, 1, 2), time_it=time_it)
+    case_conv("conv4 (s2)", B, 256, 512, 48, 160, 3, 2, (0, 1, 0, 1), time_it=time_it)
+    case_deconv("deconv5", B, 1024, 512, 6, 20, 4, 2, 1, time_it=time_it)
+    case_deconv("deconv3", B, 770, 128, 24, 80, 4, 2, 1, pitch=772, time_it=time_it)
+    case_deconv("deconv2", B, 386, 64, 48, 160, 4, 2, 1, pitch=388, time_it=time_it)
+    case_deconv("dgrad conv3_1", B, 256, 473, 48, 160, 3, 1, 1, bias=False, act=False, time_it=time_it)
+    case_deconv("dgrad conv2 (5x5 s2)", B, 128, 64, 96, 320, 5, 2, 1, bias=False, act=False, out_hw=(192, 640),
+                time_it=time_it)
+
+
+def wgrad_layer_cases():
+    B = 8
+    case_wgrad("wgrad conv3_1", B, 473, 256, 48, 160, 3, 1, (1, 1, 1, 1), pitch_x=476, time_it=True)
+    case_wgrad("wgrad conv4_1", B, 512, 512, 24, 80, 3, 1, (1, 1, 1, 1), time_it=True)
+    case_wgrad("wgrad conv6_1", B, 1024, 1024, 6, 20, 3, 1, (1, 1, 1, 1), time_it=True)
+    case_wgrad("wgrad conv4 (s2)", B, 256, 512, 48, 160, 3, 2, (0, 1, 0, 1), time_it=True)
+    case_wgrad("wgrad conv3 (5x5 s2)", B, 128, 256, 96, 320, 5, 2, (1, 2, 1, 2), time_it=True)
+    case_wgrad("wgrad deconv2", B, 386, 64, 48, 160, 4, 2, None, pitch_x=388, time_it=True, deconv=True)
+    case_wgrad("wgrad deconv5", B, 1024, 512, 6, 20, 4, 2, None, time_it=True, deconv=True)
+
+
+def set_pair(v):
+    from unflow_b200 import _native
+    assert _native.lib().unflow_set_int_option(b"tc_pair", v) == 0
+    say(option="tc_pair", value=v)
+
+
 def main():
     quick = "--quick" in sys.argv
     torch.backends.cudnn.benchmark = True
     t0 = time.time()
+    if "--chunk-test" in sys.argv:       # K blocks per tensor-memory accumulation: accuracy and time
+        from unflow_b200 import _native
+        for ck in (4, 8, 16, 32):
+            assert _native.lib().unflow_set_int_option(b"tc_chunk", ck) == 0
+            say(option="tc_chunk", value=ck)
+            B = 8
+            case_conv("conv3_1", B, 473, 256, 48, 160, 3, 1, (1, 1, 1, 1), pitch=476, time_it=True)
+            case_conv("conv4_1", B, 512, 512, 24, 80, 3, 1, (1, 1, 1, 1), time_it=True)
+            case_conv("conv6_1", B, 1024, 1024, 6, 20, 3, 1, (1, 1, 1, 1), time_it=True)
+            case_conv("conv2 (5x5 s2)", B, 64, 128, 192, 640, 5, 2, (1, 2, 1, 2), time_it=True)
+            case_deconv("deconv2", B, 386, 64, 48, 160, 4, 2, 1, pitch=388, time_it=True)
+            case_wgrad("wgrad conv3_1", B, 473, 256, 48, 160, 3, 1, (1, 1, 1, 1), pitch_x=476, time_it=True)
+            case_wgrad("wgrad conv4_1", B, 512, 512, 24, 80, 3, 1, (1, 1, 1, 1), time_it=True)
+        _native.lib().unflow_set_int_option(b"tc_chunk", 4)
+        return
+    if "--pair-test" in sys.argv:        # CTA pairs (cta_group::2) forced on: small cases of every mode, then the layers
+        set_pair(2)
+        case_conv("1x1 two tiles", 1, 32, 64, 16, 16, 1, 1, (0, 0, 0, 0), bias=False, act=False)
+        case_conv("1x1 K=64 N=128", 1, 64, 128, 16, 16, 1, 1, (0, 0, 0, 0), bias=False, act=False)
+        case_conv("3x3 s1", 2, 64, 128, 16, 24, 3, 1, (1, 1, 1, 1))
+        case_conv("3x3 s1 ragged channels + pitch, odd tile count", 3, 70, 64, 13, 21, 3, 1, (1, 1, 1, 1), pitch=80)
+        case_conv("3x3 s1 C_out tail 70", 1, 32, 70, 19, 21, 3, 1, (1, 1, 1, 1))
+        case_conv("3x3 s1 accumulate, no act", 2, 64, 96, 12, 20, 3, 1, (1, 1, 1, 1), bias=False, act=False, accumulate=True)
+        case_conv("3x3 s2 SAME(0,1)", 2, 64, 128, 16, 24, 3, 2, (0, 1, 0, 1))
+        case_conv("5x5 s2 SAME(1,2)", 2, 64, 128, 16, 24, 5, 2, (1, 2, 1, 2))
+        case_deconv("deconv k4 s2 p1", 2, 64, 128, 6, 10, 4, 2, 1)
+        case_deconv("deconv k4 s2 p1 ragged", 2, 130, 64, 6, 20, 4, 2, 1, pitch=132)
+        case_deconv("dgrad of 3x3 s2 SAME(0,1)", 2, 128, 64, 8, 12, 3, 2, 0, bias=False, act=False, out_hw=(16, 24))
+        case_deconv("dgrad of 3x3 s1", 2, 128, 64, 9, 14, 3, 1, 1, bias=False, act=False)
+        case_wgrad("wgrad 3x3 s1, 2 row blocks", 2, 64, 256, 16, 24, 3, 1, (1, 1, 1, 1))
+        case_wgrad("wgrad 3x3 s1 ragged, 3 row blocks", 2, 70, 300, 13, 21, 3, 1, (1, 1, 1, 1), pitch_x=80)
+        case_wgrad("wgrad 3x3 s2 SAME(0,1)", 2, 64, 256, 16, 24, 3, 2, (0, 1, 0, 1))
+        case_wgrad("wgrad deconv k4 s2", 2, 260, 64, 6, 10, 4, 2, None, pitch_x=264, deconv=True)
+        say(phase="small pair cases done", seconds=round(time.time() - t0, 1))
+        for v in (2, 0, 1):
+            set_pair(v)
+            conv_layer_cases()
+            if v != 2:
+                wgrad_layer_cases()
+        return
     if "--timing" in sys.argv:           # the FlowNetC layer shapes, all three kernels
         B = 8
         case_conv("3x3 s1 small", 2, 64, 128, 16, 24, 3, 1, (1, 1, 1, 1))
@@ -247,6 +320,12 @@ def main():
         case_wgrad("wgrad deconv2", B, 386, 64, 48, 160, 4, 2, None, pitch_x=388, time_it=True, deconv=True)
         case_wgrad("wgrad deconv5", B, 1024, 512, 6, 20, 4, 2, None, time_it=True, deconv=True)
         case_window("window conv1 FlowNetC", B, 3, 384, 1280)
+        return
+    if "--profile2" in sys.argv:         # the half-width (BN = 64) layers and the pair kernels, for ncu
+        B = 8
+        case_deconv("deconv2", B, 386, 64, 48, 160, 4, 2, 1, pitch=388)
+        case_deconv("dgrad conv2 (5x5 s2)", B, 128, 64, 96, 320, 5, 2, 1, bias=False, act=False, out_hw=(192, 640))
+        case_wgrad("wgrad conv4_1", B, 512, 512, 24, 80, 3, 1, (1, 1, 1, 1))
         return
     if "--profile" in sys.argv:          # one launch of each big kernel, for ncu
         B = 8

@@ -13,6 +13,8 @@ constexpr int BK = 32;           // fp32 elements per K block = 128 bytes = one 
 constexpr int CHUNK = 4;         // K blocks accumulated inside the tensor core before the fp32 register add
 constexpr int A_BYTES = BM * BK * 4;   // 16 KB
 extern int g_a_in_tmem;                // tc_conv.cu: A operand of the MMAs in tensor memory (1) or shared memory (0)
+extern int g_chunk;                    // tc_conv.cu: K blocks accumulated in tensor memory between register adds (default CHUNK)
+extern int g_pair;                     // tc_conv.cu: CTA pairs (cta_group::2): 0 never, 1 where the model says so, 2 wherever possible
 
 // ------------------------------------------------------------------------------------------
 // PTX helpers
@@ -78,6 +80,42 @@ __device__ __forceinline__ void umma_tf32_ts(unsigned d_tmem, unsigned a_tmem, u
       "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n"
       " tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n}\n"
       ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// ---- CTA pairs (cta_group::2): two CTAs of a cluster on the two SMs of a TPC run ONE MMA of M = 256: each
+// supplies its own 128 rows of A (tensor memory) and HALF of the B tile (shared memory), the leader issues ----
+__device__ __forceinline__ unsigned cluster_ctarank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {       // every thread of every CTA of the cluster
+  asm volatile("barrier.cluster.arrive.release.aligned;\n barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier that sits at the same shared-memory offset in CTA `cta` of the cluster.  Plain arrive
+// (release at CTA scope): what the leader consumes after it -- tensor-memory stores fenced with
+// tcgen05.fence::before_thread_sync, TMA data whose own barrier this thread has waited on, shared-memory writes
+// behind fence.proxy.async -- is complete when the arrive is sent; `.release.cluster` would put a GPU-scope
+// MEMBAR in front of every arrive (measured: 1900 instead of 770 clk per K block).
+__device__ __forceinline__ void mbar_arrive_cta(unsigned bar, unsigned cta) {
+  unsigned r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(bar), "r"(cta));
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(r) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(unsigned bar, unsigned parity) {     // pairs with mbar_arrive_cta
+  mbar_wait(bar, parity);
+}
+__device__ __forceinline__ void umma_tf32_ts_pair(unsigned d_tmem, unsigned a_tmem, unsigned long long bdesc,
+                                                  unsigned idesc, unsigned accumulate) {
+  asm volatile(
+      "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n"
+      " tcgen05.mma.cta_group::2.kind::tf32 [%0], [%1], %2, %3, p;\n}\n"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrives (once the MMAs issued so far have completed) on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(unsigned bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(bar), "h"((unsigned short)3) : "memory");
 }
 __device__ __forceinline__ void tmem_st32(unsigned taddr, const unsigned (&r)[32]) {
   asm volatile(

@@ -43,6 +43,8 @@
 // over all of K and cuDNN's TF32 kernels alike: max error / max|y| = 6.8e-9 * K, i.e. 6e-5 at
 // K = 9216 where an fp32 FMA loop has 2e-5; profiles/r2_tc_conv.md).  Cutting K into chunks of
 // 128 and summing the chunks in fp32 registers (round to nearest) removes that term.
+#include <algorithm>
+
 #include "tc_common.cuh"
 
 namespace unflow {
@@ -68,6 +70,7 @@ struct ConvParams {
   const float *bias;          // [Cout] or nullptr
   float slope;                // leaky-ReLU slope when act != 0
   int act, accumulate;
+  int chunk;                  // K blocks accumulated in tensor memory between two register adds (g_chunk)
   int class_start[5];
   short class_px[4], class_py[4];
   Tap taps[MAX_TAPS];
@@ -88,12 +91,19 @@ struct ConvParams {
 // saved ingress; (2) TMA multicast of the
 // weight tiles to CTA pairs (the ingress per SM is unchanged, and L2 already merges the concurrent reads:
 // 679 us vs 680 us).  A cta_group::2 MMA (each SM holds half of B) is the remaining lever.
-template <int BN, bool AT>
+//
+// CG = 2 (CTA pair, cta_group::2): the two CTAs of a cluster take two M tiles of the SAME column block; each
+// loads its own activation box and HALF of the weight tile (BN/2 rows of the hi and lo planes), the leader's
+// MMAs (M = 256) read both halves.  Per SM and K block that is 16 + 16 KB of ingress instead of 16 + 32 KB
+// (BN = 128) -- below the 768 clk of MMA work -- and 16 + 8 instead of 16 + 16 KB for BN = 64.
+template <int BN, bool AT, int CG = 1>
 struct Cfg {
-  static constexpr int B_BYTES = BN * BK * 4;
+  static_assert(CG == 1 || (CG == 2 && AT && BN >= 64), "CTA pairs: tensor-memory A operand, BN 64 / 128");
+  static constexpr int B_BYTES = BN / CG * BK * 4;               // this CTA's part of one weight plane
   static constexpr int STAGE_BYTES = (AT ? 1 : 2) * A_BYTES + 2 * B_BYTES;
   static constexpr int B_OFF = (AT ? 1 : 2) * A_BYTES;          // offset of the weight planes inside a stage
-  static constexpr int STAGES = (200 * 1024 / STAGE_BYTES) < (AT ? 4 : 6) ? (200 * 1024 / STAGE_BYTES) : (AT ? 4 : 6);
+  static constexpr int MAX_STAGES = CG == 2 ? (512 - 2 * BN) / (2 * BK) : (AT ? 4 : 6);
+  static constexpr int STAGES = (200 * 1024 / STAGE_BYTES) < MAX_STAGES ? (200 * 1024 / STAGE_BYTES) : MAX_STAGES;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
   static constexpr int ACC_COLS = 2 * BN;                        // two accumulator buffers
   static constexpr int A_COLS = AT ? STAGES * 2 * BK : 0;        // per stage: 32 columns hi + 32 columns lo
@@ -105,24 +115,35 @@ struct Cfg {
 struct TileCoord {
   int cls, n0, iy0, ix0, nb;
 };
-__device__ __forceinline__ TileCoord decode_tile(const ConvParams &p, int tile) {
+// Tile order, fastest first: column block, output-parity class, M tile (CG = 2: PAIR of M tiles; CTA `rank`
+// takes M tile 2 * pair + rank; past the last M tile the box lies behind the last image: TMA zero fill, no
+// stores).  The classes of a transposed layer all read the same input box: next to each other in the schedule
+// they run at the same time on neighbouring SMs and share it in L2 -- with the class outermost every class
+// swept the whole input again (ncu on deconv2 / the input gradient of conv2: 4x the input in DRAM reads, 82 %
+// L2 read hit rate, the TMA ring starved).
+template <int CG>
+__device__ __forceinline__ TileCoord decode_tile(const ConvParams &p, int tile, int rank) {
   TileCoord t;
   t.nb = tile % p.n_blocks; tile /= p.n_blocks;
+  t.cls = tile % p.n_classes; tile /= p.n_classes;
+  if (CG == 2) {
+    tile = 2 * tile + rank;
+    if (tile >= p.tiles_n * p.tiles_y * p.tiles_x) { t.ix0 = t.iy0 = 0; t.n0 = p.tiles_n * p.TN; return t; }
+  }
   t.ix0 = (tile % p.tiles_x) * p.TW; tile /= p.tiles_x;
   t.iy0 = (tile % p.tiles_y) * p.TH; tile /= p.tiles_y;
-  t.n0 = (tile % p.tiles_n) * p.TN; tile /= p.tiles_n;
-  t.cls = tile;
+  t.n0 = tile * p.TN;
   return t;
 }
 
 // ------------------------------------------------------------------------------------------
 // The kernel
 // ------------------------------------------------------------------------------------------
-template <int BN, bool AT>
+template <int BN, bool AT, int CG>
 __global__ void __launch_bounds__(NTHREADS, 1)
 tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapBhi,
                const __grid_constant__ CUtensorMap mapBlo, const __grid_constant__ ConvParams p) {
-  using C = Cfg<BN, AT>;
+  using C = Cfg<BN, AT, CG>;
   extern __shared__ unsigned char smem_raw[];
   const unsigned base = (s32(smem_raw) + 1023u) & ~1023u;          // 128B swizzle atoms need 1024 B alignment
   unsigned char *gbase = smem_raw + (base - s32(smem_raw));
@@ -137,17 +158,23 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   volatile unsigned *tmem_slot_ptr = (volatile unsigned *)(gbase + C::STAGES * C::STAGE_BYTES + 8 * (3 * C::STAGES + 4));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int total_tiles = p.n_classes * p.tiles_n * p.tiles_y * p.tiles_x * p.n_blocks;
+  const int m_tiles = p.tiles_n * p.tiles_y * p.tiles_x;
+  const int total_tiles = p.n_classes * (CG == 2 ? (m_tiles + 1) / 2 : m_tiles) * p.n_blocks;
+  // CG = 2: the two CTAs of a cluster walk the same tile sequence; rank 0 (the leader) issues the MMAs and owns
+  // the barriers both CTAs arrive on (full_cvt, tmem_empty); full_raw / empty / tmem_full stay per CTA
+  const int rank = CG == 2 ? (int)cluster_ctarank() : 0;
+  const int first_tile = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tile_step = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
       mbar_init(full_raw(s), 1);
-      mbar_init(full_cvt(s), 4);
+      mbar_init(full_cvt(s), 4 * CG);
       mbar_init(empty(s), 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tmem_full(a), 1);
-      mbar_init(tmem_empty(a), 8);
+      mbar_init(tmem_empty(a), 8 * CG);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
@@ -155,12 +182,18 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapBlo) : "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
-                 "r"((unsigned)C::TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (CG == 2) {       // one warp of EACH CTA of the pair, same warp id, same destination offset
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                   "r"((unsigned)C::TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                   "r"((unsigned)C::TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();     // pair: the peer's barriers are initialised too
   tc_fence_after();
   const unsigned tmem_base = *tmem_slot_ptr;
 
@@ -170,9 +203,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       int s = 0;
       unsigned ph = 0;
       const unsigned a_box_bytes = (unsigned)(p.TW * p.TH * p.TN) * BK * 4u;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const TileCoord t = decode_tile(p, tile);
+      for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
+        const TileCoord t = decode_tile<CG>(p, tile, rank);
         const int x0 = p.s_in_x * t.ix0, y0 = p.s_in_y * t.iy0;
+        const int brow = t.nb * BN + rank * (BN / CG);      // pair: this CTA's half of the weight rows
         for (int ti = p.class_start[t.cls]; ti < p.class_start[t.cls + 1]; ++ti) {
           const Tap tap = p.taps[ti];
           for (int kc = 0; kc < p.kblocks; ++kc) {
@@ -180,8 +214,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             const unsigned st = base + s * C::STAGE_BYTES;
             mbar_expect_tx(full_raw(s), a_box_bytes + 2u * C::B_BYTES);
             tma_4d(st, &mapA, full_raw(s), kc * BK, x0 + tap.dx, y0 + tap.dy, t.n0);
-            tma_3d(st + C::B_OFF, &mapBhi, full_raw(s), kc * BK, t.nb * BN, tap.widx);
-            tma_3d(st + C::B_OFF + C::B_BYTES, &mapBlo, full_raw(s), kc * BK, t.nb * BN, tap.widx);
+            tma_3d(st + C::B_OFF, &mapBhi, full_raw(s), kc * BK, brow, tap.widx);
+            tma_3d(st + C::B_OFF + C::B_BYTES, &mapBlo, full_raw(s), kc * BK, brow, tap.widx);
             if (++s == C::STAGES) { s = 0; ph ^= 1u; }
           }
         }
@@ -189,28 +223,43 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      // instruction descriptor: D fp32, A/B tf32, both K-major, N = BN, M = 128
-      const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(BN >> 3) << 17) | ((unsigned)(BM >> 4) << 24);
+    if (lane == 0 && rank == 0) {
+      // instruction descriptor: D fp32, A/B tf32, both K-major, N = BN, M = 128 (256 over a CTA pair)
+      const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(BN >> 3) << 17) | ((unsigned)((CG * BM) >> 4) << 24);
       int s = 0, acc = 0;
       unsigned ph = 0, aph = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const TileCoord t = decode_tile(p, tile);
+      for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
+        const TileCoord t = decode_tile<CG>(p, tile, rank);
         const int iters = (p.class_start[t.cls + 1] - p.class_start[t.cls]) * p.kblocks;
         for (int it = 0; it < iters; ++it) {
-          const int in_chunk = it % CHUNK;
+          const int in_chunk = it % p.chunk;
           if (in_chunk == 0) {               // a fresh TMEM accumulator for every chunk of K
-            mbar_wait(tmem_empty(acc), aph ^ 1u);
+            if (CG == 2) mbar_wait_cluster(tmem_empty(acc), aph ^ 1u); else mbar_wait(tmem_empty(acc), aph ^ 1u);
             tc_fence_after();
           }
           const unsigned d = tmem_base + (unsigned)(acc * BN);
-          mbar_wait(full_raw(s), ph);        // weights landed (TMA)
-          mbar_wait(full_cvt(s), ph);        // activations split (converter warps)
+          if (CG == 2) {
+            // the converter warps of BOTH CTAs arrive here after their own TMA barrier: activations split and
+            // both halves of the weight tile landed
+            mbar_wait_cluster(full_cvt(s), ph);
+          } else {
+            mbar_wait(full_raw(s), ph);        // weights landed (TMA)
+            mbar_wait(full_cvt(s), ph);        // activations split (converter warps)
+          }
           tc_fence_after();
           const unsigned st = base + s * C::STAGE_BYTES;
           const unsigned long long b_hi = umma_desc_k128(st + C::B_OFF);
           const unsigned long long b_lo = umma_desc_k128(st + C::B_OFF + C::B_BYTES);
-          if (AT) {
+          if (CG == 2) {
+            const unsigned ta_hi = tmem_base + (unsigned)(C::ACC_COLS + s * 2 * BK), ta_lo = ta_hi + BK;
+#pragma unroll
+            for (int k = 0; k < BK / 8; ++k) {
+              const unsigned long long adv = (unsigned long long)(2 * k);
+              umma_tf32_ts_pair(d, ta_lo + 8 * k, b_hi + adv, idesc, (in_chunk | k) != 0);
+              umma_tf32_ts_pair(d, ta_hi + 8 * k, b_lo + adv, idesc, 1u);
+              umma_tf32_ts_pair(d, ta_hi + 8 * k, b_hi + adv, idesc, 1u);
+            }
+          } else if (AT) {
             const unsigned ta_hi = tmem_base + (unsigned)(C::ACC_COLS + s * 2 * BK), ta_lo = ta_hi + BK;
 #pragma unroll
             for (int k = 0; k < BK / 8; ++k) {          // A: 8 TMEM columns per K step; B: +32 bytes
@@ -229,10 +278,12 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
               umma_tf32(d, a_hi + adv, b_hi + adv, idesc, 1u);
             }
           }
-          umma_commit(empty(s));             // frees the stage when these MMAs have read it
+          // frees the stage when these MMAs have read it (pair: in both CTAs)
+          if (CG == 2) umma_commit_pair(empty(s)); else umma_commit(empty(s));
           if (++s == C::STAGES) { s = 0; ph ^= 1u; }
-          if (in_chunk == CHUNK - 1 || it == iters - 1) {
-            umma_commit(tmem_full(acc));     // chunk complete -> epilogue warps add it to their registers
+          if (in_chunk == p.chunk - 1 || it == iters - 1) {
+            // chunk complete -> epilogue warps (of both CTAs) add it to their registers
+            if (CG == 2) umma_commit_pair(tmem_full(acc)); else umma_commit(tmem_full(acc));
             if (++acc == 2) { acc = 0; aph ^= 1u; }
           }
         }
@@ -243,8 +294,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const int tid = threadIdx.x - 128;
     int s = 0;
     unsigned ph = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const TileCoord t = decode_tile(p, tile);
+    for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
+      const TileCoord t = decode_tile<CG>(p, tile, rank);
       const int iters = (p.class_start[t.cls + 1] - p.class_start[t.cls]) * p.kblocks;
       for (int it = 0; it < iters; ++it) {
         mbar_wait(full_raw(s), ph);
@@ -286,7 +337,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           fence_proxy_async();                 // generic-proxy writes -> visible to the tensor core
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(full_cvt(s));
+        if (lane == 0) {
+          if (CG == 2) mbar_arrive_cta(full_cvt(s), 0); else mbar_arrive(full_cvt(s));
+        }
         if (++s == C::STAGES) { s = 0; ph ^= 1u; }
       }
     }
@@ -301,10 +354,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const int ty = rem / p.TW, tx = rem - ty * p.TW;
     int acc = 0;
     unsigned aph = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const TileCoord t = decode_tile(p, tile);
+    for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
+      const TileCoord t = decode_tile<CG>(p, tile, rank);
       const int iters = (p.class_start[t.cls + 1] - p.class_start[t.cls]) * p.kblocks;
-      const int chunks = (iters + CHUNK - 1) / CHUNK;
+      const int chunks = (iters + p.chunk - 1) / p.chunk;
       float sum[COLS];
 #pragma unroll
       for (int c = 0; c < COLS; ++c) sum[c] = 0.f;
@@ -321,7 +374,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tmem_empty(acc));
+        if (lane == 0) {
+          if (CG == 2) mbar_arrive_cta(tmem_empty(acc), 0); else mbar_arrive(tmem_empty(acc));
+        }
         if (++acc == 2) { acc = 0; aph ^= 1u; }
       }
       const int n = t.n0 + tn, iy = t.iy0 + ty, ix = t.ix0 + tx;
@@ -362,9 +417,12 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();      // pair: the peer may still be reading / being read
   if (warp == 2) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((unsigned)C::TMEM_COLS) : "memory");
+    if (CG == 2)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((unsigned)C::TMEM_COLS) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((unsigned)C::TMEM_COLS) : "memory");
   }
 }
 
@@ -408,32 +466,84 @@ wsplit_kernel(const float *__restrict__ w, float *__restrict__ hi, float *__rest
 static int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
 
 int g_a_in_tmem = 1;     // unflow_set_int_option("tc_a_tmem"): 1 = A operand in tensor memory (default), 0 = in shared memory
+int g_chunk = CHUNK;     // unflow_set_int_option("tc_chunk"): K blocks per tensor-memory accumulation
+int g_pair = 1;          // unflow_set_int_option("tc_pair"): 0 = single CTAs only, 1 = CTA pairs where the model below says so, 2 = wherever possible
 
-template <int BN, bool AT>
+template <int BN, bool AT, int CG>
 static int launch_v(const CUtensorMap &mA, const CUtensorMap &mBh, const CUtensorMap &mBl, const ConvParams &p,
                     int total_tiles, cudaStream_t stream) {
-  using C = Cfg<BN, AT>;
+  using C = Cfg<BN, AT, CG>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tc_conv_kernel<BN, AT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(tc_conv_kernel<BN, AT, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e != cudaSuccess) { set_error("tc_conv: cannot opt in to %d bytes of shared memory: %s", C::SMEM_BYTES, cudaGetErrorString(e)); return UNFLOW_ECUDA; }
     attr_set = true;
   }
-  const int grid = total_tiles < kNumSMs ? total_tiles : kNumSMs;
-  tc_conv_kernel<BN, AT><<<grid, NTHREADS, C::SMEM_BYTES, stream>>>(mA, mBh, mBl, p);
+  if (CG == 2) {                       // clusters of two CTAs: the pair sits on the two SMs of one TPC
+    const int pairs = total_tiles < kNumSMs / 2 ? total_tiles : kNumSMs / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = C::SMEM_BYTES; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, tc_conv_kernel<BN, AT, CG>, mA, mBh, mBl, p);
+    if (e != cudaSuccess) { set_error("tc_conv: cluster launch failed: %s", cudaGetErrorString(e)); return UNFLOW_ECUDA; }
+  } else {
+    const int grid = total_tiles < kNumSMs ? total_tiles : kNumSMs;
+    tc_conv_kernel<BN, AT, CG><<<grid, NTHREADS, C::SMEM_BYTES, stream>>>(mA, mBh, mBl, p);
+  }
   count_launch();
   return check_launch("tc_conv_kernel");
 }
 
+// Single CTAs or pairs?  Time model per K block and CTA, in clocks: the MMAs (768 at BN = 128) against the SM's
+// ingress from L2 (~43 B/clk) of the activation box plus this CTA's share of the two weight planes; times the
+// number of waves the tiles need on 148 SMs / 74 pairs.
+inline int pick_cta_group(const ConvParams &p, int BN) {
+  if (!g_a_in_tmem || g_pair == 0 || BN < 64) return 1;
+  const long long m_tiles = (long long)p.tiles_n * p.tiles_y * p.tiles_x;
+  if (m_tiles < 2) return 1;
+  if (g_pair == 2) return 2;
+  const double mma = 768.0 * BN / 128.0;
+  const double t1 = std::max(mma, (16384.0 + 2.0 * BN * 128.0) / 43.0), t2 = std::max(mma, (16384.0 + BN * 128.0) / 43.0);
+  const long long tiles1 = p.n_classes * m_tiles * p.n_blocks, tiles2 = p.n_classes * ((m_tiles + 1) / 2) * p.n_blocks;
+  const double w1 = (double)((tiles1 + kNumSMs - 1) / kNumSMs) * t1, w2 = (double)((tiles2 + kNumSMs / 2 - 1) / (kNumSMs / 2)) * t2;
+  return w2 < w1 ? 2 : 1;
+}
+
 template <int BN>
 static int launch(const CUtensorMap &mA, const CUtensorMap &mBh, const CUtensorMap &mBl, const ConvParams &p,
-                  int total_tiles, cudaStream_t stream) {
-  return g_a_in_tmem ? launch_v<BN, true>(mA, mBh, mBl, p, total_tiles, stream)
-                     : launch_v<BN, false>(mA, mBh, mBl, p, total_tiles, stream);
+                  int cta_group, cudaStream_t stream) {
+  const int m_tiles = p.tiles_n * p.tiles_y * p.tiles_x;
+  const int total = p.n_classes * (cta_group == 2 ? (m_tiles + 1) / 2 : m_tiles) * p.n_blocks;
+  if constexpr (BN >= 64) {
+    if (cta_group == 2) return launch_v<BN, true, 2>(mA, mBh, mBl, p, total, stream);
+  }
+  return g_a_in_tmem ? launch_v<BN, true, 1>(mA, mBh, mBl, p, total, stream)
+                     : launch_v<BN, false, 1>(mA, mBh, mBl, p, total, stream);
+}
+
+// tile -> kernel: encodes the two weight-plane maps (box = this CTA's rows) and launches
+static int launch_bn(int BN, const CUtensorMap &mA, const float *w_hi, const float *w_lo, const cuuint64_t *wdims,
+                     const cuuint64_t *wstrides, const ConvParams &p, cudaStream_t stream) {
+  const int cg = pick_cta_group(p, BN);
+  CUtensorMap mBh, mBl;
+  cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)(BN / cg), 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  int rc = encode(&mBh, w_hi, 3, wdims, wstrides, box, estr);
+  if (rc) return rc;
+  rc = encode(&mBl, w_lo, 3, wdims, wstrides, box, estr);
+  if (rc) return rc;
+  if (BN == 128) return launch<128>(mA, mBh, mBl, p, cg, stream);
+  if (BN == 64) return launch<64>(mA, mBh, mBl, p, cg, stream);
+  return launch<32>(mA, mBh, mBl, p, cg, stream);
 }
 
 }  // namespace tc
 int set_tc_a_tmem(int v) { if (v != 0 && v != 1) return 0; tc::g_a_in_tmem = v; return 1; }
+int set_tc_pair(int v) { if (v < 0 || v > 2) return 0; tc::g_pair = v; return 1; }
+int set_tc_chunk(int v) { if (v < 1 || v > 64) return 0; tc::g_chunk = v; return 1; }
 }  // namespace unflow
 
 using namespace unflow;
@@ -458,7 +568,7 @@ static int make_plan(tc::ConvParams &p, int &BN, int N, int Hin, int Win, int Ci
   UNFLOW_REQUIRE(mode == 0 || mode == 1, "tc_conv: mode must be 0 (conv) or 1 (transposed)");
   UNFLOW_REQUIRE(stride == 1 || stride == 2, "tc_conv: stride must be 1 or 2");
   UNFLOW_REQUIRE(kh > 0 && kw > 0 && kh * kw <= tc::MAX_TAPS, "tc_conv: at most %d taps", tc::MAX_TAPS);
-  p.N = N; p.Cin = Cin; p.Cout = Cout; p.kblocks = (Cin + tc::BK - 1) / tc::BK;
+  p.N = N; p.Cin = Cin; p.Cout = Cout; p.kblocks = (Cin + tc::BK - 1) / tc::BK; p.chunk = tc::g_chunk;
   p.Hout = Hout; p.Wout = Wout;
   int nt = 0;
   if (mode == 0) {
@@ -548,9 +658,8 @@ extern "C" int unflow_tc_conv(const float *x, int N, int Hin, int Win, int Cin, 
   if (rc0) return rc0;
   p.out = y; p.out_pitch = y_pitch;
   p.bias = bias; p.slope = slope; p.act = act; p.accumulate = accumulate;
-  const long long total = (long long)p.n_classes * p.tiles_n * p.tiles_y * p.tiles_x * p.n_blocks;
 
-  CUtensorMap mA, mBh, mBl;
+  CUtensorMap mA;
   {
     cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)Win, (cuuint64_t)Hin, (cuuint64_t)N};
     cuuint64_t strides[3] = {(cuuint64_t)x_pitch * 4, (cuuint64_t)x_pitch * 4 * Win, (cuuint64_t)x_pitch * 4 * Win * Hin};
@@ -559,21 +668,10 @@ extern "C" int unflow_tc_conv(const float *x, int N, int Hin, int Win, int Cin, 
     int rc = tc::encode(&mA, x, 4, dims, strides, box, estr);
     if (rc) return rc;
   }
-  {
-    const int Cp = (Cin + 3) / 4 * 4;
-    cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)Cout, (cuuint64_t)(kh * kw)};
-    cuuint64_t strides[2] = {(cuuint64_t)Cp * 4, (cuuint64_t)Cp * 4 * Cout};
-    cuuint32_t box[3] = {(cuuint32_t)tc::BK, (cuuint32_t)BN, 1};
-    cuuint32_t estr[3] = {1, 1, 1};
-    int rc = tc::encode(&mBh, w_hi, 3, dims, strides, box, estr);
-    if (rc) return rc;
-    rc = tc::encode(&mBl, w_lo, 3, dims, strides, box, estr);
-    if (rc) return rc;
-  }
-  cudaStream_t st = (cudaStream_t)stream;
-  if (BN == 128) return tc::launch<128>(mA, mBh, mBl, p, (int)total, st);
-  if (BN == 64) return tc::launch<64>(mA, mBh, mBl, p, (int)total, st);
-  return tc::launch<32>(mA, mBh, mBl, p, (int)total, st);
+  const int Cp = (Cin + 3) / 4 * 4;
+  cuuint64_t wdims[3] = {(cuuint64_t)Cin, (cuuint64_t)Cout, (cuuint64_t)(kh * kw)};
+  cuuint64_t wstrides[2] = {(cuuint64_t)Cp * 4, (cuuint64_t)Cp * 4 * Cout};
+  return tc::launch_bn(BN, mA, w_hi, w_lo, wdims, wstrides, p, (cudaStream_t)stream);
 }
 
 // First layers (7x7, stride 2, 3 / 6 / 14 input channels): with so few channels a K block of 32
@@ -603,8 +701,7 @@ extern "C" int unflow_tc_conv_window(const float *xp, int N, int H, int Wp, int 
   p.s_in_x = 1;                                        // the x stride lives in the tensor map
   p.out = y; p.out_pitch = y_pitch;
   p.bias = bias; p.slope = slope; p.act = act; p.accumulate = 0;
-  const long long total = (long long)p.n_classes * p.tiles_n * p.tiles_y * p.tiles_x * p.n_blocks;
-  CUtensorMap mA, mBh, mBl;
+  CUtensorMap mA;
   {
     cuuint64_t dims[4] = {(cuuint64_t)win, (cuuint64_t)Wout, (cuuint64_t)H, (cuuint64_t)N};
     cuuint64_t strides[3] = {(cuuint64_t)stride * Cp * 4, (cuuint64_t)Wp * Cp * 4, (cuuint64_t)Wp * Cp * 4 * H};
@@ -613,18 +710,7 @@ extern "C" int unflow_tc_conv_window(const float *xp, int N, int H, int Wp, int 
     int rc = tc::encode(&mA, xp, 4, dims, strides, box, estr);
     if (rc) return rc;
   }
-  {
-    cuuint64_t dims[3] = {(cuuint64_t)win, (cuuint64_t)Cout, (cuuint64_t)kh};
-    cuuint64_t strides[2] = {(cuuint64_t)win * 4, (cuuint64_t)win * 4 * Cout};
-    cuuint32_t box[3] = {(cuuint32_t)tc::BK, (cuuint32_t)BN, 1};
-    cuuint32_t estr[3] = {1, 1, 1};
-    int rc = tc::encode(&mBh, w_hi, 3, dims, strides, box, estr);
-    if (rc) return rc;
-    rc = tc::encode(&mBl, w_lo, 3, dims, strides, box, estr);
-    if (rc) return rc;
-  }
-  cudaStream_t st = (cudaStream_t)stream;
-  if (BN == 128) return tc::launch<128>(mA, mBh, mBl, p, (int)total, st);
-  if (BN == 64) return tc::launch<64>(mA, mBh, mBl, p, (int)total, st);
-  return tc::launch<32>(mA, mBh, mBl, p, (int)total, st);
+  cuuint64_t wdims[3] = {(cuuint64_t)win, (cuuint64_t)Cout, (cuuint64_t)kh};
+  cuuint64_t wstrides[2] = {(cuuint64_t)win * 4, (cuuint64_t)win * 4 * Cout};
+  return tc::launch_bn(BN, mA, w_hi, w_lo, wdims, wstrides, p, (cudaStream_t)stream);
 }

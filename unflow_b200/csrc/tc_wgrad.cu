@@ -49,6 +49,7 @@ struct WgradParams {
   int R, C;                         // rows (channels of P) / columns (channels of G) of dW
   int cgroups, vgroups;             // 32-channel groups of G per tap; (tap, group) pairs = "virtual" column groups
   int r_blocks, c_blocks, taps, kw;  // c_blocks: blocks of BN/32 consecutive virtual groups
+  int chunk;                        // K blocks per tensor-memory accumulation (tc::g_chunk)
   int stride, stride_x, pad_t, pad_l;   // stride_x = 1 in the row-window form (x stride inside the tensor map)
   float *dw;
   long long pitch_r, pitch_t;       // dW[r * pitch_r + t * pitch_t + c]
@@ -58,9 +59,16 @@ struct WgradParams {
 // it from a plain (unswizzled) staging tile -- lane = channel, one LDS.32 per pixel, which is also the
 // transpose the K-major TMEM operand needs -- and store hi / lo with tcgen05.st; only G is split in shared
 // memory (hi in place, lo beside it) for the MMAs.
-template <int BN>
+//
+// CG = 2 (CTA pair, cta_group::2, see tc_conv.cu): the two CTAs take two ROW blocks of the same (chunk, column
+// block) item; each converts its own P tile and loads + splits HALF of the G tile (BN/64 of the 32-channel
+// groups), the leader's MMAs (M = 256) read both halves.  The single-CTA kernel is bound by shared-memory
+// bandwidth -- per K block 32 KB written by TMA, 16 + 16 KB read and 32 KB written by the converter warps, 48 KB
+// read by the MMAs: 144 KB against 128 B/clk x 768 clk -- the pair moves 88 KB per CTA.
+template <int BN, int CG = 1>
 struct Cfg {
-  static constexpr int B_BYTES = BN * KP * 4;
+  static_assert(CG == 1 || (CG == 2 && BN == 128), "CTA pairs: BN = 128");
+  static constexpr int B_BYTES = BN / CG * KP * 4;               // this CTA's part of the G tile
   static constexpr int STAGE_BYTES = A_BYTES + 2 * B_BYTES;
   static constexpr int B_OFF = A_BYTES;
   static constexpr int STAGES = (200 * 1024 / STAGE_BYTES) < 4 ? (200 * 1024 / STAGE_BYTES) : 4;
@@ -75,10 +83,16 @@ struct Cfg {
 struct Item {
   int chunk, rb, cb;
 };
-__device__ __forceinline__ Item decode_item(const WgradParams &p, int it) {
+template <int CG>
+__device__ __forceinline__ Item decode_item(const WgradParams &p, int it, int rank) {
   Item w;
   w.cb = it % p.c_blocks; it /= p.c_blocks;
-  w.rb = it % p.r_blocks; it /= p.r_blocks;
+  if (CG == 2) {                 // pair: row blocks 2i and 2i + 1 (past the last one: rows >= R, zero fill, no stores)
+    const int rp = (p.r_blocks + 1) / 2;
+    w.rb = 2 * (it % rp) + rank; it /= rp;
+  } else {
+    w.rb = it % p.r_blocks; it /= p.r_blocks;
+  }
   w.chunk = it;
   return w;
 }
@@ -87,11 +101,12 @@ __device__ __forceinline__ int chunk_len(const WgradParams &p, int chunk) {
   return (k0 + p.kc <= p.n_ptiles) ? p.kc : p.n_ptiles - k0;
 }
 
-template <int BN>
+template <int BN, int CG>
 __global__ void __launch_bounds__(NTHREADS, 1)
 tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ CUtensorMap mapG,
                 const __grid_constant__ WgradParams p) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, CG>;
+  constexpr int GROUPS = BN / 32 / CG;        // 32-channel groups of G this CTA loads and splits
   extern __shared__ unsigned char smem_raw[];
   const unsigned base = (s32(smem_raw) + 1023u) & ~1023u;
   unsigned char *gbase = smem_raw + (base - s32(smem_raw));
@@ -106,29 +121,39 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant_
   volatile unsigned *tmem_slot_ptr = (volatile unsigned *)(gbase + C::STAGES * C::STAGE_BYTES + 8 * (3 * C::STAGES + 4));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int total_items = p.n_chunks * p.r_blocks * p.c_blocks;
+  const int total_items = p.n_chunks * (CG == 2 ? (p.r_blocks + 1) / 2 : p.r_blocks) * p.c_blocks;
+  // CG = 2: both CTAs of the cluster walk the same items; rank 0 issues the MMAs and owns full_cvt / tmem_empty
+  const int rank = CG == 2 ? (int)cluster_ctarank() : 0;
+  const int first_item = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int item_step = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
       mbar_init(full_raw(s), 1);
-      mbar_init(full_cvt(s), 6);                // 4 warps (P -> tensor memory) + 2 warps (G in shared memory)
+      mbar_init(full_cvt(s), 6 * CG);           // 4 warps (P -> tensor memory) + 2 warps (G in shared memory), per CTA
       mbar_init(empty(s), 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tmem_full(a), 1);
-      mbar_init(tmem_empty(a), 8);
+      mbar_init(tmem_empty(a), 8 * CG);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapP) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapG) : "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
-                 "r"((unsigned)C::TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (CG == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                   "r"((unsigned)C::TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                   "r"((unsigned)C::TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const unsigned tmem_base = *tmem_slot_ptr;
 
@@ -137,12 +162,12 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant_
     if (lane == 0) {
       int s = 0;
       unsigned ph = 0;
-      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-        const Item w = decode_item(p, item);
-        int gch[BN / 32], gdx[BN / 32], gdy[BN / 32];        // per column group: channel, tap offset
+      for (int item = first_item; item < total_items; item += item_step) {
+        const Item w = decode_item<CG>(p, item, rank);
+        int gch[GROUPS], gdx[GROUPS], gdy[GROUPS];           // per column group of this CTA: channel, tap offset
 #pragma unroll
-        for (int j = 0; j < BN / 32; ++j) {
-          const int v = w.cb * (BN / 32) + j;
+        for (int j = 0; j < GROUPS; ++j) {
+          const int v = w.cb * (BN / 32) + rank * GROUPS + j;
           if (v < p.vgroups) {
             const int tap = v / p.cgroups, ky = tap / p.kw;
             gch[j] = (v - tap * p.cgroups) * 32; gdy[j] = ky - p.pad_t; gdx[j] = tap - ky * p.kw - p.pad_l;
@@ -163,7 +188,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant_
           for (int j = 0; j < BM / 32; ++j)       // channels past R are TMA zero fill
             tma_4d(st + j * 4096, &mapP, full_raw(s), w.rb * BM + 32 * j, px, py, pn);
 #pragma unroll
-          for (int j = 0; j < BN / 32; ++j)
+          for (int j = 0; j < GROUPS; ++j)
             tma_4d(st + C::B_OFF + j * 4096, &mapG, full_raw(s), gch[j], p.stride_x * px + gdx[j],
                    p.stride * py + gdy[j], pn);
           if (++s == C::STAGES) { s = 0; ph ^= 1u; }
@@ -172,25 +197,29 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant_
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      // D fp32, A / B tf32, both MN-major (bits 15, 16), N = BN, M = 128
+    if (lane == 0 && rank == 0) {
+      // D fp32, A / B tf32, N = BN, M = 128 (256 over a CTA pair)
       // (A lives in tensor memory: K-major by construction -- lane = row, column = K; B is MN-major, bit 16)
       const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) |
-                             ((unsigned)(BN >> 3) << 17) | ((unsigned)(BM >> 4) << 24);
+                             ((unsigned)(BN >> 3) << 17) | ((unsigned)((CG * BM) >> 4) << 24);
       int s = 0, acc = 0;
       unsigned ph = 0, aph = 0;
-      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-        const Item w = decode_item(p, item);
+      for (int item = first_item; item < total_items; item += item_step) {
+        const Item w = decode_item<CG>(p, item, rank);
         const int iters = chunk_len(p, w.chunk);
         for (int it = 0; it < iters; ++it) {
-          const int in_chunk = it % CHUNK;
+          const int in_chunk = it % p.chunk;
           if (in_chunk == 0) {
-            mbar_wait(tmem_empty(acc), aph ^ 1u);
+            if (CG == 2) mbar_wait_cluster(tmem_empty(acc), aph ^ 1u); else mbar_wait(tmem_empty(acc), aph ^ 1u);
             tc_fence_after();
           }
           const unsigned d = tmem_base + (unsigned)(acc * BN);
-          mbar_wait(full_raw(s), ph);
-          mbar_wait(full_cvt(s), ph);
+          if (CG == 2) {
+            mbar_wait_cluster(full_cvt(s), ph);      // the converter warps of both CTAs, each behind its own TMA barrier
+          } else {
+            mbar_wait(full_raw(s), ph);
+            mbar_wait(full_cvt(s), ph);
+          }
           tc_fence_after();
           const unsigned st = base + s * C::STAGE_BYTES;
           const unsigned long long b_hi = umma_desc_mn128(st + C::B_OFF, 4096);
@@ -199,14 +228,20 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant_
 #pragma unroll
           for (int k = 0; k < KP / 8; ++k) {            // A: 8 TMEM columns (pixels) per K step; B: 8 rows = 1024 B
             const unsigned long long adv = (unsigned long long)(64 * k);
-            umma_tf32_ts(d, ta_lo + 8 * k, b_hi + adv, idesc, (in_chunk | k) != 0);
-            umma_tf32_ts(d, ta_hi + 8 * k, b_lo + adv, idesc, 1u);
-            umma_tf32_ts(d, ta_hi + 8 * k, b_hi + adv, idesc, 1u);
+            if (CG == 2) {
+              umma_tf32_ts_pair(d, ta_lo + 8 * k, b_hi + adv, idesc, (in_chunk | k) != 0);
+              umma_tf32_ts_pair(d, ta_hi + 8 * k, b_lo + adv, idesc, 1u);
+              umma_tf32_ts_pair(d, ta_hi + 8 * k, b_hi + adv, idesc, 1u);
+            } else {
+              umma_tf32_ts(d, ta_lo + 8 * k, b_hi + adv, idesc, (in_chunk | k) != 0);
+              umma_tf32_ts(d, ta_hi + 8 * k, b_lo + adv, idesc, 1u);
+              umma_tf32_ts(d, ta_hi + 8 * k, b_hi + adv, idesc, 1u);
+            }
           }
-          umma_commit(empty(s));
+          if (CG == 2) umma_commit_pair(empty(s)); else umma_commit(empty(s));
           if (++s == C::STAGES) { s = 0; ph ^= 1u; }
-          if (in_chunk == CHUNK - 1 || it == iters - 1) {
-            umma_commit(tmem_full(acc));
+          if (in_chunk == p.chunk - 1 || it == iters - 1) {
+            if (CG == 2) umma_commit_pair(tmem_full(acc)); else umma_commit(tmem_full(acc));
             if (++acc == 2) { acc = 0; aph ^= 1u; }
           }
         }
@@ -220,8 +255,8 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant_
     // saturated -- and two warps alone cannot split 16 KB per K block in time either.)
     int s = 0;
     unsigned ph = 0;
-    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-      const Item w = decode_item(p, item);
+    for (int item = first_item; item < total_items; item += item_step) {
+      const Item w = decode_item<CG>(p, item, rank);
       const int iters = chunk_len(p, w.chunk);
       for (int it = 0; it < iters; ++it) {
         mbar_wait(full_raw(s), ph);
@@ -254,7 +289,9 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant_
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(full_cvt(s));
+        if (lane == 0) {
+          if (CG == 2) mbar_arrive_cta(full_cvt(s), 0); else mbar_arrive(full_cvt(s));
+        }
         if (++s == C::STAGES) { s = 0; ph ^= 1u; }
       }
     }
@@ -263,8 +300,8 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant_
     const int tid = threadIdx.x - 64;                 // 0..63
     int s = 0;
     unsigned ph = 0;
-    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-      const Item w = decode_item(p, item);
+    for (int item = first_item; item < total_items; item += item_step) {
+      const Item w = decode_item<CG>(p, item, rank);
       const int iters = chunk_len(p, w.chunk);
       for (int it = 0; it < iters; ++it) {
         mbar_wait(full_raw(s), ph);
@@ -282,7 +319,9 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant_
         }
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0) mbar_arrive(full_cvt(s));
+        if (lane == 0) {
+          if (CG == 2) mbar_arrive_cta(full_cvt(s), 0); else mbar_arrive(full_cvt(s));
+        }
         if (++s == C::STAGES) { s = 0; ph ^= 1u; }
       }
     }
@@ -294,10 +333,10 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant_
     const int row = q * 32 + lane;
     int acc = 0;
     unsigned aph = 0;
-    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-      const Item w = decode_item(p, item);
+    for (int item = first_item; item < total_items; item += item_step) {
+      const Item w = decode_item<CG>(p, item, rank);
       const int iters = chunk_len(p, w.chunk);
-      const int chunks = (iters + CHUNK - 1) / CHUNK;
+      const int chunks = (iters + p.chunk - 1) / p.chunk;
       float sum[COLS];
 #pragma unroll
       for (int c = 0; c < COLS; ++c) sum[c] = 0.f;
@@ -314,7 +353,9 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant_
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tmem_empty(acc));
+        if (lane == 0) {
+          if (CG == 2) mbar_arrive_cta(tmem_empty(acc), 0); else mbar_arrive(tmem_empty(acc));
+        }
         if (++acc == 2) { acc = 0; aph ^= 1u; }
       }
       const int r = w.rb * BM + row;
@@ -335,25 +376,50 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant_
     }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 2) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((unsigned)C::TMEM_COLS) : "memory");
+    if (CG == 2)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((unsigned)C::TMEM_COLS) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((unsigned)C::TMEM_COLS) : "memory");
   }
 }
 
-template <int BN>
-static int launch(const CUtensorMap &mP, const CUtensorMap &mG, const WgradParams &p, int total, cudaStream_t stream) {
-  using C = Cfg<BN>;
+template <int BN, int CG>
+static int launch_v(const CUtensorMap &mP, const CUtensorMap &mG, const WgradParams &p, cudaStream_t stream) {
+  using C = Cfg<BN, CG>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tc_wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(tc_wgrad_kernel<BN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e != cudaSuccess) { set_error("tc_wgrad: cannot opt in to %d bytes of shared memory: %s", C::SMEM_BYTES, cudaGetErrorString(e)); return UNFLOW_ECUDA; }
     attr_set = true;
   }
-  const int grid = total < kNumSMs ? total : kNumSMs;
-  tc_wgrad_kernel<BN><<<grid, NTHREADS, C::SMEM_BYTES, stream>>>(mP, mG, p);
+  const long long total = (long long)p.n_chunks * (CG == 2 ? (p.r_blocks + 1) / 2 : p.r_blocks) * p.c_blocks;
+  if (CG == 2) {
+    const int pairs = total < kNumSMs / 2 ? (int)total : kNumSMs / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = C::SMEM_BYTES; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, tc_wgrad_kernel<BN, CG>, mP, mG, p);
+    if (e != cudaSuccess) { set_error("tc_wgrad: cluster launch failed: %s", cudaGetErrorString(e)); return UNFLOW_ECUDA; }
+  } else {
+    const int grid = total < kNumSMs ? (int)total : kNumSMs;
+    tc_wgrad_kernel<BN, CG><<<grid, NTHREADS, C::SMEM_BYTES, stream>>>(mP, mG, p);
+  }
   count_launch();
   return check_launch("tc_wgrad_kernel");
+}
+
+// CTA pairs (see Cfg) whenever there are at least two row blocks to pair and the full-width tile
+// (unflow_set_int_option("tc_pair", 0) switches them off)
+static int launch_bn(int BN, const CUtensorMap &mP, const CUtensorMap &mG, const WgradParams &p, cudaStream_t stream) {
+  if (BN == 128 && p.r_blocks >= 2 && g_pair != 0) return launch_v<128, 2>(mP, mG, p, stream);
+  if (BN == 128) return launch_v<128, 1>(mP, mG, p, stream);
+  if (BN == 64) return launch_v<64, 1>(mP, mG, p, stream);
+  return launch_v<32, 1>(mP, mG, p, stream);
 }
 
 // the K-block pixel box: TW*TH*TN == 32 exactly (rows past the tensor are TMA zero fill), fewest boxes
@@ -376,7 +442,7 @@ static int make_plan(WgradParams &p, int &BN, int N, int Hp, int Wp, int R, int 
   UNFLOW_REQUIRE(N > 0 && Hp > 0 && Wp > 0 && R > 0 && C > 0, "tc_wgrad: bad extents");
   UNFLOW_REQUIRE(stride == 1 || stride == 2, "tc_wgrad: stride must be 1 or 2");
   UNFLOW_REQUIRE(kh > 0 && kw > 0 && kh * kw <= 64, "tc_wgrad: at most 64 taps");
-  p.N = N; p.Hp = Hp; p.Wp = Wp; p.R = R; p.C = C;
+  p.N = N; p.Hp = Hp; p.Wp = Wp; p.R = R; p.C = C; p.chunk = g_chunk;
   p.taps = kh * kw; p.kw = kw; p.stride = p.stride_x = stride; p.pad_t = pad_t; p.pad_l = pad_l;
   choose_box(p);
   p.cgroups = (C + 31) / 32; p.vgroups = p.taps * p.cgroups;
@@ -424,7 +490,6 @@ extern "C" int unflow_tc_wgrad(const float *P, int N, int Hp, int Wp, int R, lon
   int rc = tcw::make_plan(p, BN, N, Hp, Wp, R, C, stride, kh, kw, pad_t, pad_l);
   if (rc) return rc;
   p.dw = dw; p.pitch_r = pitch_r; p.pitch_t = pitch_t;
-  const long long total = (long long)p.n_chunks * p.r_blocks * p.c_blocks;
   CUtensorMap mP, mG;
   {
     cuuint64_t dims[4] = {(cuuint64_t)R, (cuuint64_t)Wp, (cuuint64_t)Hp, (cuuint64_t)N};
@@ -442,10 +507,7 @@ extern "C" int unflow_tc_wgrad(const float *P, int N, int Hp, int Wp, int R, lon
     rc = tc::encode(&mG, G, 4, dims, strides, box, estr, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     if (rc) return rc;
   }
-  cudaStream_t st = (cudaStream_t)stream;
-  if (BN == 128) return tcw::launch<128>(mP, mG, p, (int)total, st);
-  if (BN == 64) return tcw::launch<64>(mP, mG, p, (int)total, st);
-  return tcw::launch<32>(mP, mG, p, (int)total, st);
+  return tcw::launch_bn(BN, mP, mG, p, (cudaStream_t)stream);
 }
 
 // Weight gradient of the row-window form of the first layers (see unflow_tc_conv_window):
@@ -465,7 +527,6 @@ extern "C" int unflow_tc_wgrad_window(const float *P, int N, int Ho, int Wo, int
   if (rc) return rc;
   p.stride_x = 1;
   p.dw = dw; p.pitch_r = (long long)kh * win; p.pitch_t = win;
-  const long long total = (long long)p.n_chunks * p.r_blocks * p.c_blocks;
   CUtensorMap mP, mG;
   {
     cuuint64_t dims[4] = {(cuuint64_t)R, (cuuint64_t)Wo, (cuuint64_t)Ho, (cuuint64_t)N};
@@ -483,8 +544,5 @@ extern "C" int unflow_tc_wgrad_window(const float *P, int N, int Ho, int Wo, int
     rc = tc::encode(&mG, xp, 4, dims, strides, box, estr, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     if (rc) return rc;
   }
-  cudaStream_t st = (cudaStream_t)stream;
-  if (BN == 128) return tcw::launch<128>(mP, mG, p, (int)total, st);
-  if (BN == 64) return tcw::launch<64>(mP, mG, p, (int)total, st);
-  return tcw::launch<32>(mP, mG, p, (int)total, st);
+  return tcw::launch_bn(BN, mP, mG, p, (cudaStream_t)stream);
 }

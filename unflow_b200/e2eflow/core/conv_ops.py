@@ -74,8 +74,8 @@ def _slot_key(x):
     return (x.data_ptr(), tuple(x.shape))
 
 
-def grad_slot_get(gen, x):
-    return _grad_slots.get(gen, {}).get(_slot_key(x)) if _GRAD_SLOTS else None
+def grad_slot_get(gen, x, key=None):
+    return _grad_slots.get(gen, {}).get(key if key is not None else _slot_key(x)) if _GRAD_SLOTS else None
 
 
 def grad_slot_put(gen, key_or_tensor, g):

@@ -373,19 +373,20 @@ def flownet_s(inputs, channel_mult=1, full_res=False, _scope=None):
     return nchw_to_nhwc(res)
 
 
-def flownet_c_features(im, channel_mult=1, reuse=None, _scope=None):
+def flownet_c_features(im, channel_mult=1, reuse=None, _scope=None, _conv2_out=None):
     s = _scope
     x = conv_ops.network_input(im)
     conv1 = s.conv(x, 'conv1', 2)
-    conv2 = s.conv(conv1, 'conv2', 2)
+    conv2 = s.conv(conv1, 'conv2', 2, out=_conv2_out)       # (its slot in the decoder's concat2 buffer, if any)
     conv3 = s.conv(conv2, 'conv3', 2)
     return conv1, conv2, conv3
 
 
-def _flownet_c_trunk(s, conv_redir_and_corr, conv2_a, channel_mult, full_res):
+def _flownet_c_trunk(s, conv_redir_and_corr, conv2_a, channel_mult, full_res, cats=None):
     x = conv_ops.backward_point(conv_redir_and_corr, s.p + 'trunk')   # conv3_1 .. conv6_1 complete behind this point
-    cats = _decoder_cats(s, x, x.shape[0], (x.shape[2], x.shape[3]), (conv2_a.shape[2], conv2_a.shape[3]),
-                         conv2_a.shape[1])
+    if cats is None:
+        cats = _decoder_cats(s, x, x.shape[0], (x.shape[2], x.shape[3]), (conv2_a.shape[2], conv2_a.shape[3]),
+                             conv2_a.shape[1])
     first = (lambda lvl: cats[lvl].slots[0]) if cats else (lambda lvl: None)
     conv3_1 = s.conv(x, 'conv3_1', out=first(3))
     conv4 = s.conv(conv3_1, 'conv4', 2)
@@ -465,6 +466,29 @@ def _cat_c(tensors, buf=None):
     return torch.cat(tensors, 1)
 
 
+FUSED_TRUNK_INPUT = True      # tests switch it off to compare with the unfused correlation + concat
+
+
+def _trunk_input_bidir(cs, conv3_ab, kw):
+    """concat([conv_redir(conv3), correlation]) of both directions (batch [a|b] against [b|a]) in one NHWC
+    buffer: conv_redir's epilogue writes its channel slice, the two cost volumes follow it (ops.
+    correlation_bidir_concat).  None when the tiled correlation kernel does not serve the shape."""
+    from ..ops import correlation_bidir_concat, _corr_attrs
+    from ... import _native
+    n2, C, H, W = conv3_ab.shape
+    attrs = _corr_attrs(kw)
+    if n2 % 2 or _native.lib().unflow_correlation_fwd_path(C, H, W, *attrs) != 1 or not conv_ops._tc_ok(conv3_ab, 1):
+        return None
+    md, s2 = attrs[1], attrs[4]
+    D = (2 * (md // s2) + 1) ** 2
+    c0 = cs.cout('conv_redir')
+    buf = torch.empty((n2, H, W, (c0 + D + 3) // 4 * 4), device=conv3_ab.device, dtype=torch.float32)
+    conv_redir = cs.conv(conv3_ab, 'conv_redir', out=buf[..., :c0].permute(0, 3, 1, 2))
+    if conv_redir.data_ptr() != buf.data_ptr():
+        raise RuntimeError("conv_redir did not write into its concat slot")
+    return correlation_bidir_concat(buf, c0, conv3_ab, [conv_redir], **kw)
+
+
 def flownet_c(conv3_a, conv3_b, conv2_a, channel_mult=1, full_res=False, _scope=None):
     """Given two feature maps, returns flow predictions in decreasing resolution (FlowNetCorr)."""
     s = _scope
@@ -504,22 +528,32 @@ def flownet(im1, im2, flownet_spec='S', full_resolution=False, train_all=False,
             fs = root.sub('flownet_c_features')
             cs = root.sub('flownet_c')
             if backward_flow:
-                # both images through the shared feature extractor as one 2B batch
+                # both images through the shared feature extractor as one 2B batch; the decoder's concat
+                # buffers exist up front so that conv2 is born in its concat2 slot (no 126 MB copy later)
+                half = lambda v: -(-v // 2)
+                hw2 = (half(half(height)), half(half(width)))
+                cats = _decoder_cats(cs, im1, 2 * B, (half(hw2[0]), half(hw2[1])), hw2, fs.cout('conv2'))
                 _, conv2_ab, conv3_ab = flownet_c_features(torch.cat([im1, im2], 0),
-                                                           channel_mult=channel_mult, _scope=fs)
+                                                           channel_mult=channel_mult, _scope=fs,
+                                                           _conv2_out=cats[2].slots[0] if cats else None)
                 conv3_a, conv3_b = conv3_ab[:B], conv3_ab[B:]
                 kw = dict(pad=20, kernel_size=1, max_displacement=20, stride_1=1, stride_2=2)
-                # both cost volumes from one pass over the features (the reverse one is a re-indexing)
-                if conv3_a.is_cuda:
-                    corr_ab, corr_ba = correlation_bidir(conv3_a, conv3_b, **kw)
-                else:       # (CPU: only reachable with the op swapped for a stand-in, as the host-logic tests do)
-                    corr_ab, corr_ba = correlation(conv3_a, conv3_b, **kw), correlation(conv3_b, conv3_a, **kw)
-                conv_redir = cs.conv(conv3_ab, 'conv_redir')
-                if conv_ops.channels_last_active(conv_redir):
-                    trunk_in = _concat_channels_last([conv_redir], [corr_ab, corr_ba])
+                trunk_in = (_trunk_input_bidir(cs, conv3_ab, kw)
+                            if FUSED_TRUNK_INPUT and conv_ops.direct_write_ok(conv3_ab) else None)
+                if trunk_in is not None:
+                    pass        # conv_redir and both cost volumes written into one NHWC buffer (ops.py)
                 else:
-                    trunk_in = torch.cat([conv_redir, torch.cat([corr_ab, corr_ba], 0)], 1)
-                flows = _flownet_c_trunk(cs, trunk_in, conv2_ab, channel_mult, full_res)
+                    # both cost volumes from one pass over the features (the reverse one is a re-indexing)
+                    if conv3_a.is_cuda:
+                        corr_ab, corr_ba = correlation_bidir(conv3_a, conv3_b, **kw)
+                    else:   # (CPU: only reachable with the op swapped for a stand-in, as the host-logic tests do)
+                        corr_ab, corr_ba = correlation(conv3_a, conv3_b, **kw), correlation(conv3_b, conv3_a, **kw)
+                    conv_redir = cs.conv(conv3_ab, 'conv_redir')
+                    if conv_ops.channels_last_active(conv_redir):
+                        trunk_in = _concat_channels_last([conv_redir], [corr_ab, corr_ba])
+                    else:
+                        trunk_in = torch.cat([conv_redir, torch.cat([corr_ab, corr_ba], 0)], 1)
+                flows = _flownet_c_trunk(cs, trunk_in, conv2_ab, channel_mult, full_res, cats=cats)
                 flows_fw.append([f[:B] for f in flows])
                 flows_bw.append([f[B:] for f in flows])
             else:

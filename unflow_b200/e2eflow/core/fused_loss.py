@@ -82,6 +82,9 @@ class _LevelLoss(torch.autograd.Function):
         return (dfw, dbw) + (None,) * 9
 
 
+VECTOR_KEY = '_vector'
+
+
 def compute_losses_fused(im1, im2, flow_fw, flow_bw, border_mask=None, mask_occlusion='',
                          data_max_distance=1, terms=None, return_masks=False):
     terms = list(_ALL_FUSED if terms is None else terms)
@@ -109,6 +112,7 @@ def compute_losses_fused(im1, im2, flow_fw, flow_bw, border_mask=None, mask_occl
     zero = torch.zeros((), device=im1.device, dtype=torch.float32)
     parts = vec.unbind(0)
     losses = {name: (parts[i] if name in terms else zero) for i, name in enumerate(TERM_ORDER)}
+    losses[VECTOR_KEY] = vec        # the terms as ONE tensor (TERM_ORDER): lets the caller weight them with one dot product
     if return_masks:
         return losses, masks[0], masks[1]
     return losses

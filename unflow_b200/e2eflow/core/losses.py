@@ -57,6 +57,7 @@ def compute_losses(im1, im2, flow_fw, flow_bw,
         return_masks=True)
     losses['grad'] = (gradient_loss(im1, image_warp(im2, flow_fw), mask_fw) +
                       gradient_loss(im2, image_warp(im1, flow_bw), mask_bw))
+    losses.pop(fused_loss.VECTOR_KEY, None)       # the kernel's vector does not hold this term
     return losses
 
 

@@ -16,7 +16,7 @@ backward kernel pair.
 """
 import torch
 
-from . import tf_image
+from . import fused_loss, tf_image
 from .flownet import FLOW_SCALE, flownet, get_variables
 from .losses import compute_losses, create_border_mask
 from .util import downsample
@@ -110,6 +110,7 @@ def unsupervised_loss(batch, params, normalization=None, augment=True,
     assert mask_occlusion in ['fb', 'disocc', '']
 
     per_term = {t: 0.0 for t in LOSSES}
+    per_vec = None
     total = 0.0
     for lvl in range(n_levels):
         to_pixels = top_scale / (2 ** lvl)                 # network units -> pixels at this level
@@ -119,11 +120,23 @@ def unsupervised_loss(batch, params, normalization=None, augment=True,
                                mask_occlusion=mask_occlusion,
                                data_max_distance=distances[lvl],
                                _terms=active)
-        level_sum = 0.0
-        for t in active:
-            _track_loss(terms[t], t)
-            level_sum = level_sum + params[t + '_weight'] * terms[t]
-            per_term[t] = per_term[t] + weights[lvl] * terms[t]
+        vec = terms.get(fused_loss.VECTOR_KEY)
+        if vec is not None:
+            # fused kernel: the terms come as one vector -- weight them with one dot product instead of a
+            # scalar multiply + add per term and level (about 100 one-element kernels per step and as many
+            # again in the backward pass); same sum, order of the fp32 additions aside
+            for t in active:
+                _track_loss(terms[t], t)
+            wvec = _device_constant([(params.get(t + '_weight') or 0.0) if t in active else 0.0
+                                     for t in fused_loss.TERM_ORDER], vec.device)
+            level_sum = torch.dot(vec, wvec)
+            per_vec = (per_vec if per_vec is not None else 0.0) + weights[lvl] * vec.detach()
+        else:
+            level_sum = 0.0
+            for t in active:
+                _track_loss(terms[t], t)
+                level_sum = level_sum + params[t + '_weight'] * terms[t]
+                per_term[t] = per_term[t] + weights[lvl] * terms[t]
         total = total + weights[lvl] * level_sum
         if lvl + 1 < n_levels:      # (the reference also builds one level more, which TF prunes)
             level_im1, level_im2 = downsample(level_im1, 2), downsample(level_im2, 2)
@@ -131,6 +144,10 @@ def unsupervised_loss(batch, params, normalization=None, augment=True,
 
     final_loss = total + variables.regularization_loss()
 
+    if per_vec is not None:
+        for i, t in enumerate(fused_loss.TERM_ORDER):
+            if t in active:
+                per_term[t] = per_vec[i]
     _track_loss(final_loss, 'loss/combined')
     for t in LOSSES:
         _track_loss(per_term[t], 'loss/' + t)

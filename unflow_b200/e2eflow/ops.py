@@ -189,6 +189,123 @@ class _CorrelationBidir(torch.autograd.Function):
         return g0, g1, None
 
 
+def _nhwc_geometry(t):
+    """(batch stride, pixel pitch) of an NCHW-shaped tensor whose memory is NHWC (channels contiguous, rows and
+    pixels linear, any pitch / batch stride), or None."""
+    N, C, H, W = t.shape
+    sn, sc, sh, sw = t.stride()
+    if (sc == 1 or C == 1) and sw >= C and sh == W * sw and (N == 1 or sn >= H * sh):
+        return sn, sw
+    return None
+
+
+class _CorrelationBidirConcat(torch.autograd.Function):
+    """The FlowNetC trunk input of the bidirectional pass, concat([conv_redir, corr], channels) for both
+    directions at once (reference flownet.py:34-44 with the two directions batched), written into ONE
+    pre-allocated NHWC buffer:
+
+        buf[:B,  :, :, c0:c0+D] = correlation(feat[:B], feat[B:])        feat: [2B, C, H, W], NHWC memory
+        buf[B:,  :, :, c0:c0+D] = correlation(feat[B:], feat[:B])
+
+    The correlation kernels keep the reference op's NCHW layout; the tensors crossing into the NHWC conv stack
+    go through the tiled transposes of csrc/relayout.cu instead of strided library copies, and the gradient
+    of ``feat`` is produced as one NHWC buffer that the other consumer of ``feat`` (conv_redir's input-gradient
+    kernel) accumulates into (conv_ops gradient slots) -- no zero fill, slice copy or add.
+    ``members``: tensors already living in ``buf`` (conv_redir, written there by its conv's epilogue); their
+    gradient is the matching channel slice of the incoming gradient."""
+
+    @staticmethod
+    def forward(ctx, buf, c0, feat, attrs, *members):
+        from .core import conv_ops
+        n2, C, H, W = feat.shape
+        B = n2 // 2
+        geo = _nhwc_geometry(feat)
+        if geo is None:
+            feat = feat.contiguous(memory_format=torch.channels_last)
+            geo = _nhwc_geometry(feat)
+        import ctypes
+        oc, oh, ow = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        lib = _native.lib()
+        check(lib.unflow_correlation_out_shape(H, W, *attrs, ctypes.byref(oc), ctypes.byref(oh),
+                                               ctypes.byref(ow)), "correlation")
+        D = oc.value
+        assert (oh.value, ow.value) == (H, W) and tuple(buf.shape[:3]) == (n2, H, W) and buf.shape[3] >= c0 + D
+        P = H * W
+        planar = torch.empty(n2, C, H, W, device=feat.device, dtype=torch.float32)       # in0 | in1, NCHW
+        vol = torch.empty(n2, D, H, W, device=feat.device, dtype=torch.float32)          # corr_ab | corr_ba
+        pitch = buf.stride(2)
+        with torch.cuda.device(feat.device):
+            check(lib.unflow_interleaved_to_planar(feat.data_ptr(), geo[0], geo[1], planar.data_ptr(), C * P,
+                                                   n2, C, P, _stream()), "interleaved_to_planar")
+            with kernel_timer.span("correlation_fwd_bidir"):
+                check(lib.unflow_correlation_fwd_bidir(planar[:B].data_ptr(), planar[B:].data_ptr(),
+                                                       vol[:B].data_ptr(), vol[B:].data_ptr(),
+                                                       B, C, H, W, *attrs, _stream()), "correlation_bidir")
+            check(lib.unflow_planar_to_interleaved(vol.data_ptr(), D * P, buf.data_ptr() + 4 * c0, buf.stride(0),
+                                                   pitch, n2, D, P, 0, _stream()), "planar_to_interleaved")
+        ctx.save_for_backward(planar)
+        ctx.attrs, ctx.c0, ctx.D = attrs, c0, D
+        ctx.gen = conv_ops._generation
+        ctx.feat_key = (feat.data_ptr(), tuple(feat.shape))
+        ctx.member_spans = []
+        off = 0
+        for m in members:
+            assert m.data_ptr() == buf.data_ptr() + 4 * off and m.stride(3) == pitch, "member not in its slot"
+            ctx.member_spans.append((off, off + m.shape[1]))
+            off += m.shape[1]
+        assert off == c0
+        return buf[..., :c0 + D].permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, g):
+        from .core import conv_ops
+        planar, = ctx.saved_tensors
+        n2, C, H, W = planar.shape
+        B, P, D, c0 = n2 // 2, H * W, ctx.D, ctx.c0
+        geo = _nhwc_geometry(g)
+        if geo is None:
+            g = g.contiguous(memory_format=torch.channels_last)
+            geo = _nhwc_geometry(g)
+        lib = _native.lib()
+        gvol = torch.empty(n2, D, H, W, device=g.device, dtype=torch.float32)
+        geff = torch.empty(B, D, H, W, device=g.device, dtype=torch.float32)
+        gplanar = torch.empty_like(planar)
+        slot = conv_ops.grad_slot_get(ctx.gen, None, key=ctx.feat_key)
+        if slot is not None and _nhwc_geometry(slot) is None:
+            slot = None
+        if slot is None:
+            gbuf = torch.empty(n2, H, W, (C + 3) // 4 * 4, device=g.device, dtype=torch.float32)
+            gfeat = gbuf[..., :C].permute(0, 3, 1, 2)
+        else:
+            gfeat = slot
+        sgeo = _nhwc_geometry(gfeat)
+        with torch.cuda.device(g.device):
+            check(lib.unflow_interleaved_to_planar(g.data_ptr() + 4 * c0 * g.stride(1), geo[0], geo[1],
+                                                   gvol.data_ptr(), D * P, n2, D, P, _stream()),
+                  "interleaved_to_planar")
+            with kernel_timer.span("correlation_bwd_bidir"):
+                check(lib.unflow_correlation_fold_grad(gvol[:B].data_ptr(), gvol[B:].data_ptr(), geff.data_ptr(),
+                                                       B, C, H, W, *ctx.attrs, _stream()), "correlation_fold_grad")
+                check(lib.unflow_correlation_bwd(geff.data_ptr(), planar[:B].data_ptr(), planar[B:].data_ptr(),
+                                                 gplanar[:B].data_ptr(), gplanar[B:].data_ptr(), B, C, H, W,
+                                                 *ctx.attrs, _stream()), "correlation_grad")
+            check(lib.unflow_planar_to_interleaved(gplanar.data_ptr(), C * P, gfeat.data_ptr(), sgeo[0], sgeo[1],
+                                                   n2, C, P, 0 if slot is None else 1, _stream()),
+                  "planar_to_interleaved")
+        if slot is None:
+            conv_ops.grad_slot_put(ctx.gen, ctx.feat_key, gfeat)
+        return (None, None, gfeat if slot is None else None, None) + tuple(g[:, a:b] for a, b in ctx.member_spans)
+
+
+def correlation_bidir_concat(buf, c0, feat, members, **kwargs):
+    """See _CorrelationBidirConcat; None when the tiled kernel does not serve the attributes / shape."""
+    attrs = _corr_attrs(kwargs)
+    n2, C, H, W = feat.shape
+    if not (feat.is_cuda and n2 % 2 == 0 and _native.lib().unflow_correlation_fwd_path(C, H, W, *attrs) == 1):
+        return None
+    return _CorrelationBidirConcat.apply(buf, c0, feat, attrs, *members)
+
+
 def correlation_bidir(first, second, **kwargs):
     """(correlation(first, second), correlation(second, first)); one pass where the tiled kernel serves the
     attributes and shape, two ordinary calls otherwise."""
