@@ -280,6 +280,10 @@ int unflow_conv3x3_narrow_wgrad(const float *x, long long x_pitch, const float *
  *   mode 1  y[stride*iy - pad_t + ky, stride*ix - pad_l + kx] += x[iy,ix] W[ky*kw+kx]
  *           (slim.conv2d_transpose and the input gradient of mode 0; Hout, Wout % stride == 0)
  *   stride 1 or 2, kh*kw <= 64.  UNFLOW_EINVAL otherwise. */
+/* Debug hook (tools/tc_conv_check.py --roles): CTA 0 of every following tc_conv launch writes its role timers
+ * (clocks blocked on each pipeline barrier / in total, see csrc/tc_conv.cu) into `buf`, device memory for 16
+ * long longs; nullptr switches it off. */
+int unflow_tc_conv_debug(long long *buf);
 /* unflow_tc_conv_plan (host only, for the CPU tests): the tap / class / tile plan the launcher builds,
  * as integers (layout in csrc/tc_conv.cu); returns the count written, -needed when `cap` is too
  * small, -1 on invalid arguments. */

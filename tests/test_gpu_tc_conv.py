@@ -199,3 +199,22 @@ def test_conv_ops_layers_run_on_the_tensor_core_kernels():
             assert rel(got, want) < 2e-5
     finally:
         conv_ops.set_mode(prev)
+
+
+@pytest.mark.parametrize("C,hw,act_pitch", [(4, (5, 7), 8), (32, (9, 11), 36), (64, (13, 21), 196), (128, (6, 10), 128),
+                                            (200, (7, 9), 204), (2, (5, 6), 4)])
+def test_lrelu_bwd_bias_pass(C, hw, act_pitch):
+    """gpre = g * lrelu'(act) and the bias gradient in one pass (csrc/split.cu), for channel counts that fill
+    a quarter / half / whole warp of float4 lanes and for the scalar path (C = 2); act is a channel slice
+    of a wider NHWC buffer."""
+    from unflow_b200.e2eflow.core import conv_ops
+    N, (H, W) = 3, hw
+    gen = torch.Generator().manual_seed(C)
+    g = torch.randn(N, H, W, C, generator=gen).cuda().permute(0, 3, 1, 2)
+    abuf = torch.randn(N, H, W, act_pitch, generator=gen).cuda()
+    act = abuf[..., 1:1 + C].permute(0, 3, 1, 2) if act_pitch > C + 1 and C % 4 else abuf[..., :C].permute(0, 3, 1, 2)
+    gpre, gb = conv_ops._lrelu_bwd_bias(g, act, True)
+    want = g.double() * torch.where(act.double() > 0, 1.0, conv_ops.LRELU_SLOPE)
+    assert float((gpre.double() - want).abs().max()) <= 1e-6 * float(want.abs().max())
+    wb = want.sum((0, 2, 3))
+    assert float((gb.double() - wb).abs().max()) <= 2e-6 * float(want.abs().sum((0, 2, 3)).max())

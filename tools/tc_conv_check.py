@@ -256,6 +256,47 @@ def main():
     quick = "--quick" in sys.argv
     torch.backends.cudnn.benchmark = True
     t0 = time.time()
+    if "--roles" in sys.argv:            # where does each warp role of tc_conv_kernel wait? (CTA 0's timers)
+        from unflow_b200 import _native
+        lib = _native.lib()
+        buf = torch.zeros(16, dtype=torch.int64, device=dev)
+        names = ["producer: wait free stage", "producer: total", "mma: wait free accumulator", "mma: wait operands",
+                 "mma: total", "converter: wait TMA data", "converter: total", "epilogue: wait chunk", "epilogue: total"]
+
+        def roles(label, fn):
+            fn()                                   # warm
+            torch.cuda.synchronize()
+            assert lib.unflow_tc_conv_debug(buf.data_ptr()) == 0
+            buf.zero_()
+            fn()
+            torch.cuda.synchronize()
+            lib.unflow_tc_conv_debug(None)
+            v = buf.tolist()
+            say(case=label, **{n: int(x) for n, x in zip(names, v)})
+
+        B = 8
+        for pair in (0, 1):
+            set_pair(pair)
+            for (label, N, Cin, Cout, H, W, k, st, pads, pitch) in [
+                    ("conv3_1", B, 473, 256, 48, 160, 3, 1, (1, 1, 1, 1), 476),
+                    ("conv4_1", B, 512, 512, 24, 80, 3, 1, (1, 1, 1, 1), None),
+                    ("conv6_1", B, 1024, 1024, 6, 20, 3, 1, (1, 1, 1, 1), None)]:
+                x = make_x(N, Cin, H, W, pitch, seed=Cin + H)
+                g = torch.Generator().manual_seed(Cout + k)
+                w = cl((torch.randn(Cout, Cin, k, k, generator=g) * (2.0 / (Cin * k * k)) ** 0.5).to(dev))
+                planes = T.split_weights(w)
+                out, obuf = out_buf(N, Cout, H, W)
+                roles("%s pair=%d" % (label, pair),
+                      lambda: T.run(x, planes, out, mode=0, stride=st, kh=k, kw=k, pad_t=pads[0], pad_l=pads[2], bias=None, act=False))
+            x = make_x(B, 386, 48, 160, 388, seed=3)
+            g = torch.Generator().manual_seed(9)
+            w = cl((torch.randn(386, 64, 4, 4, generator=g) * 0.05).to(dev))
+            planes = T.split_weights(w, transpose=True)
+            out, obuf = out_buf(B, 64, 96, 320)
+            roles("deconv2 (BN=64) pair=%d" % pair,
+                  lambda: T.run(x, planes, out, mode=1, stride=2, kh=4, kw=4, pad_t=1, pad_l=1, bias=None, act=False))
+        set_pair(1)
+        return
     if "--chunk-test" in sys.argv:       # K blocks per tensor-memory accumulation: accuracy and time
         from unflow_b200 import _native
         for ck in (4, 8, 16, 32):

@@ -37,6 +37,7 @@ SIGNATURES = {
     "unflow_correlation_fwd_path": (_i, [_i] * 8),
     "unflow_correlation_fwd_bidir": (_i, [_vp] * 4 + [_i] * 9 + [_vp]),
     "unflow_correlation_fold_grad": (_i, [_vp] * 3 + [_i] * 9 + [_vp]),
+    "unflow_tc_conv_debug": (_i, [_vp]),
     "unflow_planar_to_interleaved": (_i, [_vp, ctypes.c_longlong, _vp, ctypes.c_longlong, ctypes.c_longlong] +
                                      [_i] * 4 + [_vp]),
     "unflow_interleaved_to_planar": (_i, [_vp, ctypes.c_longlong, ctypes.c_longlong, _vp, ctypes.c_longlong] +

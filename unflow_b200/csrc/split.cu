@@ -164,35 +164,40 @@ bias_grad_lrelu_kernel(const float *__restrict__ g, long long sN, long long sC, 
 // a lane owns 4 channels (one 128-bit load per tensor and pixel), a warp 128 channels, the 8 warps of a
 // CTA walk the pixel strip with two pixels in flight each.  The scalar kernel above reaches 39 % of the
 // HBM roofline (one 4-byte load per lane in flight); this one moves 4x the bytes per instruction.
+// Layers with fewer than 128 channels (conv1 / deconv2: 64, the largest tensors of the step) would leave
+// lanes without channels: `cl` = lanes per pixel (a power of two <= 32, cl * 4 >= min(C, 128)), the other
+// 32 / cl lane groups of a warp take the following pixels.
 __global__ void __launch_bounds__(256)
 bias_grad_lrelu_vec_kernel(const float *__restrict__ g, long long GS, const float *__restrict__ act, long long AP,
                            float *__restrict__ gpre, long long GP, float *__restrict__ gb, int C, long long npix,
-                           float slope, int pix_per_cta) {
+                           float slope, int pix_per_cta, int cl) {
   __shared__ float4 red[8][32];
   const int lane = threadIdx.x & 31, row = threadIdx.x >> 5;
-  const int c = blockIdx.y * 128 + lane * 4;
+  const int sub = 32 / cl;                        // pixels per warp and step
+  const int c = blockIdx.y * 128 + (lane & (cl - 1)) * 4;
   const long long p0 = (long long)blockIdx.x * pix_per_cta;
   const long long p1 = p0 + pix_per_cta < npix ? p0 + pix_per_cta : npix;
+  const int step = 8 * sub;
   float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
   if (c < C) {                                   // C % 4 == 0: a lane's four channels are all inside or all outside
-    long long p = p0 + row;
-    for (; p + 8 < p1; p += 16) {
+    long long p = p0 + row * sub + lane / cl;
+    for (; p + step < p1; p += 2 * step) {
       float4 v0 = __ldg(reinterpret_cast<const float4 *>(g + p * GS + c));
-      float4 v1 = __ldg(reinterpret_cast<const float4 *>(g + (p + 8) * GS + c));
+      float4 v1 = __ldg(reinterpret_cast<const float4 *>(g + (p + step) * GS + c));
       if (act) {
         const float4 a0 = __ldg(reinterpret_cast<const float4 *>(act + p * AP + c));
-        const float4 a1 = __ldg(reinterpret_cast<const float4 *>(act + (p + 8) * AP + c));
+        const float4 a1 = __ldg(reinterpret_cast<const float4 *>(act + (p + step) * AP + c));
         if (a0.x <= 0.f) v0.x *= slope; if (a0.y <= 0.f) v0.y *= slope; if (a0.z <= 0.f) v0.z *= slope; if (a0.w <= 0.f) v0.w *= slope;
         if (a1.x <= 0.f) v1.x *= slope; if (a1.y <= 0.f) v1.y *= slope; if (a1.z <= 0.f) v1.z *= slope; if (a1.w <= 0.f) v1.w *= slope;
       }
       if (gpre) {
         *reinterpret_cast<float4 *>(gpre + p * GP + c) = v0;
-        *reinterpret_cast<float4 *>(gpre + (p + 8) * GP + c) = v1;
+        *reinterpret_cast<float4 *>(gpre + (p + step) * GP + c) = v1;
       }
       s0.x += v0.x; s0.y += v0.y; s0.z += v0.z; s0.w += v0.w;
       s1.x += v1.x; s1.y += v1.y; s1.z += v1.z; s1.w += v1.w;
     }
-    for (; p < p1; p += 8) {
+    for (; p < p1; p += step) {
       float4 v = __ldg(reinterpret_cast<const float4 *>(g + p * GS + c));
       if (act) {
         const float4 a = __ldg(reinterpret_cast<const float4 *>(act + p * AP + c));
@@ -204,10 +209,10 @@ bias_grad_lrelu_vec_kernel(const float *__restrict__ g, long long GS, const floa
   }
   red[row][lane] = make_float4(s0.x + s1.x, s0.y + s1.y, s0.z + s1.z, s0.w + s1.w);
   __syncthreads();
-  if (row == 0 && c < C) {
+  if (row == 0 && lane < cl && c < C) {
     float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) { const float4 r = red[k][lane]; t.x += r.x; t.y += r.y; t.z += r.z; t.w += r.w; }
+    for (int k = 0; k < 8; ++k)
+      for (int u = 0; u < sub; ++u) { const float4 r = red[k][lane + u * cl]; t.x += r.x; t.y += r.y; t.z += r.z; t.w += r.w; }
     atomicAdd(gb + c, t.x); atomicAdd(gb + c + 1, t.y); atomicAdd(gb + c + 2, t.z); atomicAdd(gb + c + 3, t.w);
   }
 }
@@ -267,7 +272,9 @@ extern "C" int unflow_lrelu_bwd_bias(const float *g, long long sN, long long sC,
     int ppc = (int)((npix + st - 1) / st);
     if (ppc < 64) ppc = 64;
     dim3 vgrid(ceil_div(npix, ppc), cb);
-    bias_grad_lrelu_vec_kernel<<<vgrid, 256, 0, s>>>(g, sW, act, act_pitch, gpre, gpre_pitch, gb, C, npix, slope, ppc);
+    int cl = 32;                                  // lanes per pixel: the smallest power of two covering min(C, 128) / 4
+    while (cl > 1 && (cl / 2) * 4 >= (C < 128 ? C : 128)) cl /= 2;
+    bias_grad_lrelu_vec_kernel<<<vgrid, 256, 0, s>>>(g, sW, act, act_pitch, gpre, gpre_pitch, gb, C, npix, slope, ppc, cl);
     count_launch();
     return check_launch("bias_grad_lrelu(vec)");
   }

@@ -10,7 +10,10 @@ namespace tc {
 
 constexpr int BM = 128;          // UMMA M
 constexpr int BK = 32;           // fp32 elements per K block = 128 bytes = one swizzle row
-constexpr int CHUNK = 4;         // K blocks accumulated inside the tensor core before the fp32 register add
+// K blocks accumulated inside the tensor core before the fp32 register add (default of the "tc_chunk" option).
+// Measured on the FlowNetC layers (tools/tc_conv_check.py --chunk-test, error = max |y - y_f64| / max |y_f64|):
+//   4: 1.0e-6   8: 1.8e-6 (-2.5 % time)   16: 3.6e-6 (-3.7 %)   32: 7.1e-6 (-4.3 %)   all of K: 6.8e-9 * K
+constexpr int CHUNK = 8;
 constexpr int A_BYTES = BM * BK * 4;   // 16 KB
 extern int g_a_in_tmem;                // tc_conv.cu: A operand of the MMAs in tensor memory (1) or shared memory (0)
 extern int g_chunk;                    // tc_conv.cu: K blocks accumulated in tensor memory between register adds (default CHUNK)
@@ -38,6 +41,16 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
         " selp.u32 %0, 1, 0, p;\n}\n"
         : "=r"(done) : "r"(bar), "r"(parity) : "memory");
   } while (!done);
+}
+// One lane of a fully converged warp (elect.sync).  The MMA issuer runs its loop with ALL lanes converged and
+// issues tcgen05.mma / tcgen05.commit under this predicate: ptxas then emits the uniform-datapath instruction
+// once.  Under a plain `if (lane == 0)` it cannot prove that the region is entered by one thread only and wraps
+// EVERY UTCHMMA in an elect-and-branch loop -- the role timers (tools/tc_conv_check.py --roles) showed the issuing
+// thread busy 87 % of the time at ~100 clocks per MMA where the tensor core needs 64.
+__device__ __forceinline__ bool elect_one() {
+  unsigned pred = 0;
+  asm volatile("{\n .reg .pred p;\n elect.sync _|p, 0xFFFFFFFF;\n selp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void tma_4d(unsigned dst, const CUtensorMap *map, unsigned bar, int c0, int c1,
                                        int c2, int c3) {

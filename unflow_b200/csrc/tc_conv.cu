@@ -26,7 +26,7 @@
 //              into a second buffer (same swizzled layout: the split is element-wise).
 //   warp 1     one thread issues tcgen05.mma kind::tf32, three per K step:
 //              lo*hi' + hi*lo' + hi*hi' accumulate in fp32 in TENSOR MEMORY (double-buffered).
-//   warps 8-15 epilogue: the K loop is cut into CHUNKS of 4 K blocks; the tensor core accumulates one
+//   warps 8-15 epilogue: the K loop is cut into CHUNKS of 8 K blocks (tc_common.cuh: CHUNK); the tensor core accumulates one
 //              chunk in tensor memory, these warps read it back (tcgen05.ld) and add it to fp32
 //              REGISTER accumulators with round-to-nearest while the next chunk is being multiplied
 //              into the other TMEM buffer (see "Accuracy"); after the last chunk: bias + leaky ReLU
@@ -71,6 +71,7 @@ struct ConvParams {
   float slope;                // leaky-ReLU slope when act != 0
   int act, accumulate;
   int chunk;                  // K blocks accumulated in tensor memory between two register adds (g_chunk)
+  long long *dbg;             // role timers of CTA 0 (unflow_tc_conv_debug), or nullptr
   int class_start[5];
   short class_px[4], class_py[4];
   Tap taps[MAX_TAPS];
@@ -198,10 +199,11 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   const unsigned tmem_base = *tmem_slot_ptr;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (whole warp converged, one elected lane issues) =====================
+    {
       int s = 0;
       unsigned ph = 0;
+      long long t_wait = 0, t_all = clock64();          // role timers: cycles blocked on the barrier / in total
       const unsigned a_box_bytes = (unsigned)(p.TW * p.TH * p.TN) * BK * 4u;
       for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
         const TileCoord t = decode_tile<CG>(p, tile, rank);
@@ -210,33 +212,41 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         for (int ti = p.class_start[t.cls]; ti < p.class_start[t.cls + 1]; ++ti) {
           const Tap tap = p.taps[ti];
           for (int kc = 0; kc < p.kblocks; ++kc) {
-            mbar_wait(empty(s), ph ^ 1u);
+            { const long long t0 = clock64(); mbar_wait(empty(s), ph ^ 1u); t_wait += clock64() - t0; }
             const unsigned st = base + s * C::STAGE_BYTES;
-            mbar_expect_tx(full_raw(s), a_box_bytes + 2u * C::B_BYTES);
-            tma_4d(st, &mapA, full_raw(s), kc * BK, x0 + tap.dx, y0 + tap.dy, t.n0);
-            tma_3d(st + C::B_OFF, &mapBhi, full_raw(s), kc * BK, brow, tap.widx);
-            tma_3d(st + C::B_OFF + C::B_BYTES, &mapBlo, full_raw(s), kc * BK, brow, tap.widx);
+            if (elect_one()) {
+              mbar_expect_tx(full_raw(s), a_box_bytes + 2u * C::B_BYTES);
+              tma_4d(st, &mapA, full_raw(s), kc * BK, x0 + tap.dx, y0 + tap.dy, t.n0);
+              tma_3d(st + C::B_OFF, &mapBhi, full_raw(s), kc * BK, brow, tap.widx);
+              tma_3d(st + C::B_OFF + C::B_BYTES, &mapBlo, full_raw(s), kc * BK, brow, tap.widx);
+            }
+            __syncwarp();
             if (++s == C::STAGES) { s = 0; ph ^= 1u; }
           }
         }
       }
+      if (p.dbg && blockIdx.x == 0 && lane == 0) { p.dbg[0] = t_wait; p.dbg[1] = clock64() - t_all; }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0 && rank == 0) {
+    // ===================== MMA issuer (whole warp converged, one elected lane issues) =====================
+    if (rank == 0) {
       // instruction descriptor: D fp32, A/B tf32, both K-major, N = BN, M = 128 (256 over a CTA pair)
       const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(BN >> 3) << 17) | ((unsigned)((CG * BM) >> 4) << 24);
       int s = 0, acc = 0;
       unsigned ph = 0, aph = 0;
+      long long t_wait_acc = 0, t_wait_ops = 0, t_all = clock64();
       for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
         const TileCoord t = decode_tile<CG>(p, tile, rank);
         const int iters = (p.class_start[t.cls + 1] - p.class_start[t.cls]) * p.kblocks;
         for (int it = 0; it < iters; ++it) {
           const int in_chunk = it % p.chunk;
           if (in_chunk == 0) {               // a fresh TMEM accumulator for every chunk of K
+            const long long t0 = clock64();
             if (CG == 2) mbar_wait_cluster(tmem_empty(acc), aph ^ 1u); else mbar_wait(tmem_empty(acc), aph ^ 1u);
+            t_wait_acc += clock64() - t0;
             tc_fence_after();
           }
+          const long long t1 = clock64();
           const unsigned d = tmem_base + (unsigned)(acc * BN);
           if (CG == 2) {
             // the converter warps of BOTH CTAs arrive here after their own TMA barrier: activations split and
@@ -246,10 +256,12 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             mbar_wait(full_raw(s), ph);        // weights landed (TMA)
             mbar_wait(full_cvt(s), ph);        // activations split (converter warps)
           }
+          t_wait_ops += clock64() - t1;
           tc_fence_after();
           const unsigned st = base + s * C::STAGE_BYTES;
           const unsigned long long b_hi = umma_desc_k128(st + C::B_OFF);
           const unsigned long long b_lo = umma_desc_k128(st + C::B_OFF + C::B_BYTES);
+          if (elect_one()) {
           if (CG == 2) {
             const unsigned ta_hi = tmem_base + (unsigned)(C::ACC_COLS + s * 2 * BK), ta_lo = ta_hi + BK;
 #pragma unroll
@@ -280,25 +292,31 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           }
           // frees the stage when these MMAs have read it (pair: in both CTAs)
           if (CG == 2) umma_commit_pair(empty(s)); else umma_commit(empty(s));
-          if (++s == C::STAGES) { s = 0; ph ^= 1u; }
           if (in_chunk == p.chunk - 1 || it == iters - 1) {
             // chunk complete -> epilogue warps (of both CTAs) add it to their registers
             if (CG == 2) umma_commit_pair(tmem_full(acc)); else umma_commit(tmem_full(acc));
+          }
+          }     // elect_one
+          __syncwarp();
+          if (++s == C::STAGES) { s = 0; ph ^= 1u; }
+          if (in_chunk == p.chunk - 1 || it == iters - 1) {
             if (++acc == 2) { acc = 0; aph ^= 1u; }
           }
         }
       }
+      if (p.dbg && blockIdx.x == 0 && lane == 0) { p.dbg[2] = t_wait_acc; p.dbg[3] = t_wait_ops; p.dbg[4] = clock64() - t_all; }
     }
   } else if (warp >= 4 && warp < 8) {
     // ===================== activation split =====================
     const int tid = threadIdx.x - 128;
     int s = 0;
     unsigned ph = 0;
+    long long t_wait = 0, t_all = clock64();
     for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
       const TileCoord t = decode_tile<CG>(p, tile, rank);
       const int iters = (p.class_start[t.cls + 1] - p.class_start[t.cls]) * p.kblocks;
       for (int it = 0; it < iters; ++it) {
-        mbar_wait(full_raw(s), ph);
+        { const long long t0 = clock64(); mbar_wait(full_raw(s), ph); t_wait += clock64() - t0; }
         if (AT) {
           // thread = tile row: read the row's 32 channels (8 x 16 bytes; the 128-byte swizzle stores logical
           // chunk j of row r at chunk j ^ (r & 7) -- a quarter warp hits all 32 banks), split, and store
@@ -343,6 +361,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         if (++s == C::STAGES) { s = 0; ph ^= 1u; }
       }
     }
+    if (p.dbg && blockIdx.x == 0 && threadIdx.x == 128) { p.dbg[5] = t_wait; p.dbg[6] = clock64() - t_all; }
   } else if (warp >= 8) {
     // ===================== epilogue: fp32 register accumulation over the K chunks =====================
     constexpr int COLS = BN / 2;             // columns per thread: warps 8-11 take the low half, 12-15 the high half
@@ -354,6 +373,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const int ty = rem / p.TW, tx = rem - ty * p.TW;
     int acc = 0;
     unsigned aph = 0;
+    long long t_wait = 0, t_all = clock64();
     for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
       const TileCoord t = decode_tile<CG>(p, tile, rank);
       const int iters = (p.class_start[t.cls + 1] - p.class_start[t.cls]) * p.kblocks;
@@ -362,7 +382,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll
       for (int c = 0; c < COLS; ++c) sum[c] = 0.f;
       for (int ck = 0; ck < chunks; ++ck) {
-        mbar_wait(tmem_full(acc), aph);
+        { const long long t0 = clock64(); mbar_wait(tmem_full(acc), aph); t_wait += clock64() - t0; }
         tc_fence_after();
         const unsigned taddr = tmem_base + ((unsigned)(q * 32) << 16) + (unsigned)(acc * BN + half * COLS);
 #pragma unroll
@@ -415,6 +435,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         }
       }
     }
+    if (p.dbg && blockIdx.x == 0 && threadIdx.x == 256) { p.dbg[7] = t_wait; p.dbg[8] = clock64() - t_all; }
   }
   tc_fence_before();
   if (CG == 2) cluster_sync_all(); else __syncthreads();      // pair: the peer may still be reading / being read
@@ -467,6 +488,7 @@ static int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b
 
 int g_a_in_tmem = 1;     // unflow_set_int_option("tc_a_tmem"): 1 = A operand in tensor memory (default), 0 = in shared memory
 int g_chunk = CHUNK;     // unflow_set_int_option("tc_chunk"): K blocks per tensor-memory accumulation
+long long *g_dbg = nullptr;   // unflow_tc_conv_debug: device buffer of 16 long longs for the role timers of CTA 0
 int g_pair = 1;          // unflow_set_int_option("tc_pair"): 0 = single CTAs only, 1 = CTA pairs where the model below says so, 2 = wherever possible
 
 template <int BN, bool AT, int CG>
@@ -568,7 +590,7 @@ static int make_plan(tc::ConvParams &p, int &BN, int N, int Hin, int Win, int Ci
   UNFLOW_REQUIRE(mode == 0 || mode == 1, "tc_conv: mode must be 0 (conv) or 1 (transposed)");
   UNFLOW_REQUIRE(stride == 1 || stride == 2, "tc_conv: stride must be 1 or 2");
   UNFLOW_REQUIRE(kh > 0 && kw > 0 && kh * kw <= tc::MAX_TAPS, "tc_conv: at most %d taps", tc::MAX_TAPS);
-  p.N = N; p.Cin = Cin; p.Cout = Cout; p.kblocks = (Cin + tc::BK - 1) / tc::BK; p.chunk = tc::g_chunk;
+  p.N = N; p.Cin = Cin; p.Cout = Cout; p.kblocks = (Cin + tc::BK - 1) / tc::BK; p.chunk = tc::g_chunk; p.dbg = tc::g_dbg;
   p.Hout = Hout; p.Wout = Wout;
   int nt = 0;
   if (mode == 0) {
@@ -618,6 +640,12 @@ static int make_plan(tc::ConvParams &p, int &BN, int N, int Hin, int Win, int Ci
   UNFLOW_REQUIRE(total < (1ll << 30), "tc_conv: too many tiles");
   return UNFLOW_OK;
 }
+
+// Debug hook: role timers.  `buf` = device memory for 16 long longs (or nullptr to switch off); every following
+// tc_conv launch makes CTA 0 write, in clocks: [0] TMA producer blocked on a free stage, [1] its total; [2] MMA
+// issuer blocked on a free accumulator, [3] on the operands of a K block, [4] its total; [5] converter warp 4
+// blocked on the TMA data, [6] its total; [7] epilogue warp 8 blocked on a finished chunk, [8] its total.
+extern "C" int unflow_tc_conv_debug(long long *buf) { tc::g_dbg = buf; return UNFLOW_OK; }
 
 // Debug / test hook: the plan as integers --
 // [n_classes, s_in, s_out, Hit, Wit, TW, TH, TN, tiles_x, tiles_y, tiles_n, n_blocks, BN, kblocks, ntaps,

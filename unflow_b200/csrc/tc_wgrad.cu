@@ -27,7 +27,7 @@
 //   warps 2-3   G tile: hi = tf32(v) in place, lo = v - hi beside it (shared memory)
 //   warp 1      tcgen05.mma kind::tf32, A from tensor memory, B MN-major from shared memory:
 //               lo*hi + hi*lo + hi*hi per 8-pixel K step
-//   warps 8-15  every 4 K blocks: tcgen05.ld the TMEM accumulator and add it to fp32 registers (see
+//   warps 8-15  every 8 K blocks: tcgen05.ld the TMEM accumulator and add it to fp32 registers (see
 //               tc_conv.cu, "Accuracy"); at the end of the item: red.global.add into dW
 // dW is accumulated with fp32 atomics (split-K partial sums from several CTAs): the caller zeroes
 // it; the order of the additions, hence the last bits, vary from run to run.
@@ -158,8 +158,8 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant_
   const unsigned tmem_base = *tmem_slot_ptr;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (whole warp converged, one elected lane issues) =====================
+    {
       int s = 0;
       unsigned ph = 0;
       for (int item = first_item; item < total_items; item += item_step) {
@@ -183,21 +183,24 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant_
           const int pn = q * p.TN;
           mbar_wait(empty(s), ph ^ 1u);
           const unsigned st = base + s * C::STAGE_BYTES;
-          mbar_expect_tx(full_raw(s), (unsigned)(A_BYTES + C::B_BYTES));
+          if (elect_one()) {
+            mbar_expect_tx(full_raw(s), (unsigned)(A_BYTES + C::B_BYTES));
 #pragma unroll
-          for (int j = 0; j < BM / 32; ++j)       // channels past R are TMA zero fill
-            tma_4d(st + j * 4096, &mapP, full_raw(s), w.rb * BM + 32 * j, px, py, pn);
+            for (int j = 0; j < BM / 32; ++j)       // channels past R are TMA zero fill
+              tma_4d(st + j * 4096, &mapP, full_raw(s), w.rb * BM + 32 * j, px, py, pn);
 #pragma unroll
-          for (int j = 0; j < GROUPS; ++j)
-            tma_4d(st + C::B_OFF + j * 4096, &mapG, full_raw(s), gch[j], p.stride_x * px + gdx[j],
-                   p.stride * py + gdy[j], pn);
+            for (int j = 0; j < GROUPS; ++j)
+              tma_4d(st + C::B_OFF + j * 4096, &mapG, full_raw(s), gch[j], p.stride_x * px + gdx[j],
+                     p.stride * py + gdy[j], pn);
+          }
+          __syncwarp();
           if (++s == C::STAGES) { s = 0; ph ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0 && rank == 0) {
+    // ===================== MMA issuer (whole warp converged, one elected lane issues: tc_common.cuh) ==========
+    if (rank == 0) {
       // D fp32, A / B tf32, N = BN, M = 128 (256 over a CTA pair)
       // (A lives in tensor memory: K-major by construction -- lane = row, column = K; B is MN-major, bit 16)
       const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) |
@@ -225,6 +228,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant_
           const unsigned long long b_hi = umma_desc_mn128(st + C::B_OFF, 4096);
           const unsigned long long b_lo = umma_desc_mn128(st + C::B_OFF + C::B_BYTES, 4096);
           const unsigned ta_hi = tmem_base + (unsigned)(C::ACC_COLS + s * 2 * KP), ta_lo = ta_hi + KP;
+          if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < KP / 8; ++k) {            // A: 8 TMEM columns (pixels) per K step; B: 8 rows = 1024 B
             const unsigned long long adv = (unsigned long long)(64 * k);
@@ -239,9 +243,13 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant_
             }
           }
           if (CG == 2) umma_commit_pair(empty(s)); else umma_commit(empty(s));
-          if (++s == C::STAGES) { s = 0; ph ^= 1u; }
           if (in_chunk == p.chunk - 1 || it == iters - 1) {
             if (CG == 2) umma_commit_pair(tmem_full(acc)); else umma_commit(tmem_full(acc));
+          }
+          }     // elect_one
+          __syncwarp();
+          if (++s == C::STAGES) { s = 0; ph ^= 1u; }
+          if (in_chunk == p.chunk - 1 || it == iters - 1) {
             if (++acc == 2) { acc = 0; aph ^= 1u; }
           }
         }
