@@ -205,6 +205,16 @@ int unflow_adam_step(float *params, float *grads, float *m, float *v, long long 
  * of the whole training step be replayed without per-step host writes. */
 int unflow_adam_step_dev(float *params, float *grads, float *m, float *v, long long n,
                          float *hyper, int zero_grad, void *stream);
+/* The same two updates with the L2 regularisation gradient of slim.l2_regularizer (reference
+ * src/e2eflow/core/flownet.py:176,200,218: `weights` variables only) folded in: bit k of l2mask[i] marks
+ * element 4*i + k of the flat buffer as regularised; its gradient becomes grad * grad_scale + l2 * param.
+ * (l2mask == NULL: identical to the functions above.) */
+int unflow_adam_step_l2(float *params, float *grads, float *m, float *v, long long n, float lr,
+                        float beta1, float beta2, float eps, long long step, float grad_scale,
+                        int zero_grad, const unsigned char *l2mask, float l2, void *stream);
+int unflow_adam_step_dev_l2(float *params, float *grads, float *m, float *v, long long n,
+                            float *hyper, int zero_grad, const unsigned char *l2mask, float l2,
+                            void *stream);
 
 /* ------------------------------------------------------------------------
  * 3xTF32 operand preparation for the conv / deconv stacks (no reference counterpart: the

@@ -125,6 +125,29 @@ def test_adam_kernel_matches_tf_rule():
     np.testing.assert_allclose(pc.cpu().numpy(), pd.float().numpy(), rtol=1e-5, atol=1e-6)
 
 
+def test_adam_kernel_l2_mask():
+    """The regularisation gradient folded into the update: masked elements see grad * scale + l2 * p."""
+    from unflow_b200 import _native
+    n = 1024
+    g = torch.Generator().manual_seed(1)
+    p, gr = torch.randn(n, generator=g), torch.randn(n, generator=g)
+    bits = (torch.rand(n, generator=g) < 0.5)
+    q = bits.view(-1, 4).to(torch.uint8)
+    mask = (q[:, 0] | (q[:, 1] << 1) | (q[:, 2] << 2) | (q[:, 3] << 3)).contiguous().cuda()
+    l2, lr = 0.37, 1e-2
+    st = torch.cuda.current_stream().cuda_stream
+    out = []
+    for fused in (True, False):
+        pc, mc, vc = p.cuda(), torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+        gc = (gr if fused else gr + l2 * p * bits).cuda()
+        _native.check(_native.lib().unflow_adam_step_l2(pc.data_ptr(), gc.data_ptr(), mc.data_ptr(), vc.data_ptr(), n,
+                                                        lr, 0.9, 0.999, 1e-8, 1, 1.0, 1,
+                                                        mask.data_ptr() if fused else None, l2, st), "adam")
+        out.append((pc.cpu(), mc.cpu(), vc.cpu()))
+    for a, b in zip(*out):
+        np.testing.assert_allclose(a.numpy(), b.numpy(), rtol=2e-6, atol=1e-7)
+
+
 def test_trainer_step_applies_adam_to_the_flat_buffer():
     """One Trainer.step == Adam's first update on the gradient of the loss (the total loss itself
     need not decrease: the occlusion penalty is piecewise constant and grows as flows develop)."""
@@ -136,7 +159,8 @@ def test_trainer_step_applies_adam_to_the_flat_buffer():
     im1, im2, _ = synth.image_pair(2, 128, 256, seed=8)
     im1, im2 = im1.cuda(), im2.cuda()
     tr.loss(im1, im2).backward()
-    g = tr.flat_grad.clone()
+    g = tr.flat_grad.clone() + tr.l2_gradient()           # the L2 term is added inside the Adam kernel
+    assert tr.l2_mask is not None and float(tr.l2_gradient().abs().max()) > 0
     tr.flat_grad.zero_()
     p0 = tr.flat_param.clone()
     _native.reset_launch_count()

@@ -57,6 +57,9 @@ SIGNATURES = {
     "unflow_adam_step": (_i, [_vp] * 4 + [ctypes.c_longlong] + [ctypes.c_float] * 4 +
                          [ctypes.c_longlong, ctypes.c_float, _i, _vp]),
     "unflow_adam_step_dev": (_i, [_vp] * 4 + [ctypes.c_longlong, _vp, _i, _vp]),
+    "unflow_adam_step_l2": (_i, [_vp] * 4 + [ctypes.c_longlong] + [ctypes.c_float] * 4 +
+                            [ctypes.c_longlong, ctypes.c_float, _i, _vp, ctypes.c_float, _vp]),
+    "unflow_adam_step_dev_l2": (_i, [_vp] * 4 + [ctypes.c_longlong, _vp, _i, _vp, ctypes.c_float, _vp]),
     "unflow_level_loss_workspace_bytes": (ctypes.c_size_t, [_i] * 3),
     "unflow_level_loss_fwd": (_i, [_vp] * 11 + [_i] * 5 + [ctypes.c_uint, _vp]),
     "unflow_level_loss_bwd": (_i, [_vp] * 11 + [_i] * 5 + [ctypes.c_uint, _vp]),

@@ -192,10 +192,19 @@ class FlowNetVariables(nn.Module):
                     p.copy_(v)
         return self
 
-    def regularization_loss(self, scale=0.0004):
+    L2_SCALE = 0.0004
+
+    def regularization_loss(self, scale=L2_SCALE):
         """slim.l2_regularizer(0.0004) on every ``weights`` variable (flownet.py:176,200,218):
-        sum_v scale * sum(v^2) / 2  ==  tf.losses.get_regularization_loss()."""
+        sum_v scale * sum(v^2) / 2  ==  tf.losses.get_regularization_loss().
+
+        ``l2_in_optimizer`` (set by the Trainer on CUDA): only the VALUE is formed here; the gradient
+        ``scale * w`` is added to the weight gradients by the fused Adam kernel (csrc/adam.cu, l2mask), which
+        reads the weights anyway -- instead of 36 scaled copies that autograd adds to the gradients."""
         ws = [self.params[_key(n + '/weights')] for n in self.kinds]
+        if getattr(self, 'l2_in_optimizer', False):
+            with torch.no_grad():
+                return _L2Reg.apply(float(scale), *[w.detach() for w in ws])
         return _L2Reg.apply(float(scale), *ws)
 
 

@@ -97,6 +97,19 @@ class Trainer:
         self._flatten()
         self.iteration = 0
         self._graph = None
+        # L2 regularisation gradient inside the Adam kernel (CUDA only; UNFLOW_L2_IN_ADAM=0: autograd forms it).
+        # flat_grad then holds the gradient of the data terms only -- l2_gradient() is the missing part.
+        self.l2_mask = None
+        self.l2_scale = float(self.variables.L2_SCALE)
+        if self.device.type == 'cuda' and __import__('os').environ.get('UNFLOW_L2_IN_ADAM', '1') != '0':
+            isw = torch.zeros(self.flat_param.numel(), dtype=torch.uint8)
+            for off, p, name in zip(self._offsets, self.trainable, self.trainable_names):
+                if name.endswith('/weights'):
+                    isw[off:off + p.numel()] = 1
+            q = isw.view(-1, 4)
+            self.l2_mask = (q[:, 0] | (q[:, 1] << 1) | (q[:, 2] << 2) | (q[:, 3] << 3)).contiguous().to(self.device)
+            self._l2_elements = isw.to(self.device)
+            self.variables.l2_in_optimizer = True
 
     def _flatten(self):
         n = sum(p.numel() for p in self.trainable)
@@ -225,16 +238,23 @@ class Trainer:
         for w in works:
             w.wait()
 
+    def l2_gradient(self):
+        """The regularisation gradient the Adam kernel adds (zeros when autograd forms it instead)."""
+        if self.l2_mask is None:
+            return torch.zeros_like(self.flat_param)
+        return self.l2_scale * self.flat_param * self._l2_elements
+
     def apply_update(self, lr, grad_scale=1.0):
         if self.flat_param.device.type != "cuda":
             raise RuntimeError("the Adam update is a CUDA kernel (csrc/adam.cu); no CPU fallback")
         from ..ops import kernel_timer
         with torch.cuda.device(self.device), kernel_timer.span("adam", 32 * self.flat_param.numel()):
-            check(_native.lib().unflow_adam_step(
+            check(_native.lib().unflow_adam_step_l2(
                 self.flat_param.data_ptr(), self.flat_grad.data_ptr(), self.adam_m.data_ptr(),
                 self.adam_v.data_ptr(), self.flat_param.numel(), float(lr), 0.9, 0.999, 1e-8,
-                self.iteration, float(grad_scale), 1, torch.cuda.current_stream().cuda_stream),
-                "adam_step")
+                self.iteration, float(grad_scale), 1,
+                self.l2_mask.data_ptr() if self.l2_mask is not None else None, self.l2_scale,
+                torch.cuda.current_stream().cuda_stream), "adam_step")
 
     def _set_hyper(self, lr, step):
         """(rare, synchronous) host -> device update of [lr, beta1, beta2, eps, grad_scale, step]."""
@@ -253,9 +273,10 @@ class Trainer:
             self.reduce_gradients()
         from ..ops import kernel_timer
         with torch.cuda.device(self.device), kernel_timer.span("adam", 32 * self.flat_param.numel()):
-            check(_native.lib().unflow_adam_step_dev(
+            check(_native.lib().unflow_adam_step_dev_l2(
                 self.flat_param.data_ptr(), self.flat_grad.data_ptr(), self.adam_m.data_ptr(),
                 self.adam_v.data_ptr(), self.flat_param.numel(), self._hyper_dev.data_ptr(), 1,
+                self.l2_mask.data_ptr() if self.l2_mask is not None else None, self.l2_scale,
                 torch.cuda.current_stream().cuda_stream), "adam_step")
         return loss.detach()
 
