@@ -25,6 +25,10 @@
 #include "common.cuh"
 
 namespace unflow {
+int g_narrow_fwd_tma = 1;          // unflow_set_int_option("narrow_fwd_tma"): 1 = TMA-staged forward (default), 0 = cp.async version
+int set_narrow_fwd_tma(int v) { if (v != 0 && v != 1) return 0; g_narrow_fwd_tma = v; return 1; }
+int narrow_fwd_tma(const float *x, long long x_pitch, const float *w, const float *bias, float *y, long long y_pitch,
+                   int N, int H, int W, int C, int csplit, cudaStream_t st);     // narrow_conv_tma.cu
 namespace nc {
 
 constexpr int TH = 16, TW = 32;            // output tile
@@ -304,6 +308,10 @@ extern "C" int unflow_conv3x3_narrow_fwd(const float *x, long long x_pitch, cons
   if (csplit > 1) {
     cudaError_t e = cudaMemsetAsync(y, 0, sizeof(float) * (size_t)N * H * W * y_pitch, st);
     if (e != cudaSuccess) { set_error("conv3x3_narrow_fwd memset: %s", cudaGetErrorString(e)); return UNFLOW_ECUDA; }
+  }
+  if (g_narrow_fwd_tma) {            // TMA-staged version (narrow_conv_tma.cu); -1: arguments it cannot take
+    const int rc = narrow_fwd_tma(x, x_pitch, w, bias, y, y_pitch, N, H, W, C, csplit, st);
+    if (rc >= 0) return rc;
   }
   const dim3 grid(ceil_div(W, nc::TW), ceil_div(H, nc::TH), N * csplit);
   const size_t smem = (size_t)(nc::KC * nc::FWD_CHS + nc::KC * 24) * sizeof(float);
