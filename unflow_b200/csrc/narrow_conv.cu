@@ -29,6 +29,8 @@ int g_narrow_fwd_tma = 1;          // unflow_set_int_option("narrow_fwd_tma"): 1
 int set_narrow_fwd_tma(int v) { if (v != 0 && v != 1) return 0; g_narrow_fwd_tma = v; return 1; }
 int narrow_fwd_tma(const float *x, long long x_pitch, const float *w, const float *bias, float *y, long long y_pitch,
                    int N, int H, int W, int C, int csplit, cudaStream_t st);     // narrow_conv_tma.cu
+int narrow_wgrad_tma(const float *x, long long x_pitch, const float *g, long long gsN, long long gsC, long long gsH,
+                     long long gsW, float *partial, int N, int H, int W, int C, int csplit, cudaStream_t st);
 namespace nc {
 
 constexpr int TH = 16, TW = 32;            // output tile
@@ -345,9 +347,14 @@ extern "C" int unflow_conv3x3_narrow_wgrad(const float *x, long long x_pitch, co
   const dim3 grid(ceil_div(W, nc::TW), ceil_div(H, nc::TH), N * csplit);
   const size_t smem = (size_t)(nc::KC * (nc::SR * nc::PITCH + 1) + nc::TH * nc::GPITCH) * sizeof(float);
   float *part = (float *)workspace;
-  nc::narrow_wgrad_kernel<<<grid, nc::THREADS, smem, s>>>(x, g, gsN, gsC, gsH, gsW, part, H, W, C, x_pitch, csplit);
-  count_launch();
-  if (int rc = check_launch("conv3x3_narrow_wgrad")) return rc;
+  int rc_tma = -1;
+  if (g_narrow_fwd_tma) rc_tma = narrow_wgrad_tma(x, x_pitch, g, gsN, gsC, gsH, gsW, part, N, H, W, C, csplit, s);
+  if (rc_tma > 0) return rc_tma;
+  if (rc_tma < 0) {
+    nc::narrow_wgrad_kernel<<<grid, nc::THREADS, smem, s>>>(x, g, gsN, gsC, gsH, gsW, part, H, W, C, x_pitch, csplit);
+    count_launch();
+    if (int rc = check_launch("conv3x3_narrow_wgrad")) return rc;
+  }
   const int total = nc::NOUT * C;
   nc::narrow_wgrad_reduce_kernel<<<ceil_div(total, 32), 256, 0, s>>>((const float *)workspace, gw, nblocks, total);
   count_launch();
