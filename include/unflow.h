@@ -289,7 +289,10 @@ int unflow_conv3x3_narrow_wgrad(const float *x, long long x_pitch, const float *
  *           (slim.conv2d; TF SAME padding enters as the offsets pad_t / pad_l, zero outside)
  *   mode 1  y[stride*iy - pad_t + ky, stride*ix - pad_l + kx] += x[iy,ix] W[ky*kw+kx]
  *           (slim.conv2d_transpose and the input gradient of mode 0; Hout, Wout % stride == 0)
- *   stride 1 or 2, kh*kw <= 64.  UNFLOW_EINVAL otherwise. */
+ *   stride 1 or 2, kh*kw <= 64.  UNFLOW_EINVAL otherwise.
+ *   mode | 2: the weight planes are those of the layer's other direction, [taps][Cin][Cout_p] (contraction
+ *           outermost): the input gradient of a layer reuses the planes its forward pass split, no second,
+ *           transposed pair of planes is made (the kernel then reads B tiles MN-major). */
 /* Debug hook (tools/tc_conv_check.py --roles): CTA 0 of every following tc_conv launch writes its role timers
  * (clocks blocked on each pipeline barrier / in total, see csrc/tc_conv.cu) into `buf`, device memory for 16
  * long longs; nullptr switches it off. */

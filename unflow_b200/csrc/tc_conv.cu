@@ -72,6 +72,8 @@ struct ConvParams {
   int act, accumulate;
   int chunk;                  // K blocks accumulated in tensor memory between two register adds (g_chunk)
   long long *dbg;             // role timers of CTA 0 (unflow_tc_conv_debug), or nullptr
+  int b_mn;                   // weight planes given as [tap][contraction][rows] (the planes of the layer's OTHER direction):
+                              // B tiles are MN-major (32-row x 32-column boxes, 32-byte-atom swizzle) instead of K-major
   int class_start[5];
   short class_px[4], class_py[4];
   Tap taps[MAX_TAPS];
@@ -217,8 +219,16 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             if (elect_one()) {
               mbar_expect_tx(full_raw(s), a_box_bytes + 2u * C::B_BYTES);
               tma_4d(st, &mapA, full_raw(s), kc * BK, x0 + tap.dx, y0 + tap.dy, t.n0);
-              tma_3d(st + C::B_OFF, &mapBhi, full_raw(s), kc * BK, brow, tap.widx);
-              tma_3d(st + C::B_OFF + C::B_BYTES, &mapBlo, full_raw(s), kc * BK, brow, tap.widx);
+              if (p.b_mn) {        // 32 contraction rows x 32 output columns per box, BN / CG / 32 boxes per plane
+#pragma unroll
+                for (int j = 0; j < BN / CG / 32; ++j) {
+                  tma_3d(st + C::B_OFF + j * 4096, &mapBhi, full_raw(s), brow + 32 * j, kc * BK, tap.widx);
+                  tma_3d(st + C::B_OFF + C::B_BYTES + j * 4096, &mapBlo, full_raw(s), brow + 32 * j, kc * BK, tap.widx);
+                }
+              } else {
+                tma_3d(st + C::B_OFF, &mapBhi, full_raw(s), kc * BK, brow, tap.widx);
+                tma_3d(st + C::B_OFF + C::B_BYTES, &mapBlo, full_raw(s), kc * BK, brow, tap.widx);
+              }
             }
             __syncwarp();
             if (++s == C::STAGES) { s = 0; ph ^= 1u; }
@@ -231,7 +241,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     // ===================== MMA issuer (whole warp converged, one elected lane issues) =====================
     if (rank == 0) {
       // instruction descriptor: D fp32, A/B tf32, both K-major, N = BN, M = 128 (256 over a CTA pair)
-      const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(BN >> 3) << 17) | ((unsigned)((CG * BM) >> 4) << 24);
+      const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | (p.b_mn ? (1u << 16) : 0u) |
+                             ((unsigned)(BN >> 3) << 17) | ((unsigned)((CG * BM) >> 4) << 24);
+      const unsigned long long kstep = p.b_mn ? 64ull : 2ull;    // 8 contraction elements: 8 rows of 128 B / 32 bytes
       int s = 0, acc = 0;
       unsigned ph = 0, aph = 0;
       long long t_wait_acc = 0, t_wait_ops = 0, t_all = clock64();
@@ -259,14 +271,15 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           t_wait_ops += clock64() - t1;
           tc_fence_after();
           const unsigned st = base + s * C::STAGE_BYTES;
-          const unsigned long long b_hi = umma_desc_k128(st + C::B_OFF);
-          const unsigned long long b_lo = umma_desc_k128(st + C::B_OFF + C::B_BYTES);
+          const unsigned long long b_hi = p.b_mn ? umma_desc_mn128(st + C::B_OFF, 4096) : umma_desc_k128(st + C::B_OFF);
+          const unsigned long long b_lo = p.b_mn ? umma_desc_mn128(st + C::B_OFF + C::B_BYTES, 4096)
+                                                 : umma_desc_k128(st + C::B_OFF + C::B_BYTES);
           if (elect_one()) {
           if (CG == 2) {
             const unsigned ta_hi = tmem_base + (unsigned)(C::ACC_COLS + s * 2 * BK), ta_lo = ta_hi + BK;
 #pragma unroll
             for (int k = 0; k < BK / 8; ++k) {
-              const unsigned long long adv = (unsigned long long)(2 * k);
+              const unsigned long long adv = kstep * (unsigned long long)k;
               umma_tf32_ts_pair(d, ta_lo + 8 * k, b_hi + adv, idesc, (in_chunk | k) != 0);
               umma_tf32_ts_pair(d, ta_hi + 8 * k, b_lo + adv, idesc, 1u);
               umma_tf32_ts_pair(d, ta_hi + 8 * k, b_hi + adv, idesc, 1u);
@@ -275,7 +288,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             const unsigned ta_hi = tmem_base + (unsigned)(C::ACC_COLS + s * 2 * BK), ta_lo = ta_hi + BK;
 #pragma unroll
             for (int k = 0; k < BK / 8; ++k) {          // A: 8 TMEM columns per K step; B: +32 bytes
-              const unsigned long long adv = (unsigned long long)(2 * k);
+              const unsigned long long adv = kstep * (unsigned long long)k;
               umma_tf32_ts(d, ta_lo + 8 * k, b_hi + adv, idesc, (in_chunk | k) != 0);
               umma_tf32_ts(d, ta_hi + 8 * k, b_lo + adv, idesc, 1u);
               umma_tf32_ts(d, ta_hi + 8 * k, b_hi + adv, idesc, 1u);
@@ -284,10 +297,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             const unsigned long long a_hi = umma_desc_k128(st), a_lo = umma_desc_k128(st + A_BYTES);
 #pragma unroll
             for (int k = 0; k < BK / 8; ++k) {          // UMMA K = 8 tf32 = 32 bytes: +2 in 16-byte units
-              const unsigned long long adv = (unsigned long long)(2 * k);
-              umma_tf32(d, a_lo + adv, b_hi + adv, idesc, (in_chunk | k) != 0);
-              umma_tf32(d, a_hi + adv, b_lo + adv, idesc, 1u);
-              umma_tf32(d, a_hi + adv, b_hi + adv, idesc, 1u);
+              const unsigned long long adv = kstep * (unsigned long long)k, adva = (unsigned long long)(2 * k);
+              umma_tf32(d, a_lo + adva, b_hi + adv, idesc, (in_chunk | k) != 0);
+              umma_tf32(d, a_hi + adva, b_lo + adv, idesc, 1u);
+              umma_tf32(d, a_hi + adva, b_hi + adv, idesc, 1u);
             }
           }
           // frees the stage when these MMAs have read it (pair: in both CTAs)
@@ -552,10 +565,12 @@ static int launch_bn(int BN, const CUtensorMap &mA, const float *w_hi, const flo
   const int cg = pick_cta_group(p, BN);
   CUtensorMap mBh, mBl;
   cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)(BN / cg), 1};
+  if (p.b_mn) { box[0] = 32; box[1] = (cuuint32_t)BK; }      // planes [tap][contraction][rows]: 32 rows x 32 contraction
   cuuint32_t estr[3] = {1, 1, 1};
-  int rc = encode(&mBh, w_hi, 3, wdims, wstrides, box, estr);
+  const CUtensorMapSwizzle swz = p.b_mn ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B;
+  int rc = encode(&mBh, w_hi, 3, wdims, wstrides, box, estr, swz);
   if (rc) return rc;
-  rc = encode(&mBl, w_lo, 3, wdims, wstrides, box, estr);
+  rc = encode(&mBl, w_lo, 3, wdims, wstrides, box, estr, swz);
   if (rc) return rc;
   if (BN == 128) return launch<128>(mA, mBh, mBl, p, cg, stream);
   if (BN == 64) return launch<64>(mA, mBh, mBl, p, cg, stream);
@@ -676,6 +691,8 @@ extern "C" int unflow_tc_conv(const float *x, int N, int Hin, int Win, int Cin, 
                               long long y_pitch, const float *bias, float slope, int act, int accumulate,
                               int mode, int stride, int kh, int kw, int pad_t, int pad_l, void *stream) {
   UNFLOW_REQUIRE(x && w_hi && w_lo && y, "tc_conv: null pointer");
+  const int planes_t = (mode >> 1) & 1;          // bit 1: the planes are [taps][Cin][Cout_p] (see include/unflow.h)
+  mode &= 1;
   UNFLOW_REQUIRE(x_pitch % 4 == 0 && y_pitch % 4 == 0 && x_pitch >= Cin && y_pitch >= Cout,
                  "tc_conv: channel pitches must be multiples of 4 floats");
   UNFLOW_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0 && ((uintptr_t)w_hi & 15) == 0 &&
@@ -685,7 +702,7 @@ extern "C" int unflow_tc_conv(const float *x, int N, int Hin, int Win, int Cin, 
   int rc0 = make_plan(p, BN, N, Hin, Win, Cin, Hout, Wout, Cout, mode, stride, kh, kw, pad_t, pad_l);
   if (rc0) return rc0;
   p.out = y; p.out_pitch = y_pitch;
-  p.bias = bias; p.slope = slope; p.act = act; p.accumulate = accumulate;
+  p.bias = bias; p.slope = slope; p.act = act; p.accumulate = accumulate; p.b_mn = planes_t;
 
   CUtensorMap mA;
   {
@@ -695,6 +712,12 @@ extern "C" int unflow_tc_conv(const float *x, int N, int Hin, int Win, int Cin, 
     cuuint32_t estr[4] = {1, (cuuint32_t)p.s_in_x, (cuuint32_t)p.s_in_y, 1};
     int rc = tc::encode(&mA, x, 4, dims, strides, box, estr);
     if (rc) return rc;
+  }
+  if (planes_t) {
+    const int Cop = (Cout + 3) / 4 * 4;
+    cuuint64_t wdims[3] = {(cuuint64_t)Cout, (cuuint64_t)Cin, (cuuint64_t)(kh * kw)};
+    cuuint64_t wstrides[2] = {(cuuint64_t)Cop * 4, (cuuint64_t)Cop * 4 * Cin};
+    return tc::launch_bn(BN, mA, w_hi, w_lo, wdims, wstrides, p, (cudaStream_t)stream);
   }
   const int Cp = (Cin + 3) / 4 * 4;
   cuuint64_t wdims[3] = {(cuuint64_t)Cin, (cuuint64_t)Cout, (cuuint64_t)(kh * kw)};

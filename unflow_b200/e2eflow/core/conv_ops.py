@@ -415,8 +415,10 @@ class _ConvTC(torch.autograd.Function):
         pt, pb, pl, pr = pads
         Ho, Wo = (H + pt + pb - k) // stride + 1, (W + pl + pr - k) // stride + 1
         dst, y = _dest(out, N, Co, Ho, Wo, x.device)
-        tc_conv.run(x, tc_conv.split_weights(_khwc(w)), dst, mode=0, stride=stride, kh=k, kw=k, pad_t=pt, pad_l=pl,
+        planes = tc_conv.split_weights(_khwc(w))
+        tc_conv.run(x, planes, dst, mode=0, stride=stride, kh=k, kw=k, pad_t=pt, pad_l=pl,
                     bias=b, act=bool(act))
+        ctx.planes = planes if _REUSE_PLANES else None      # the input gradient reads the same planes (MN-major)
         ctx.save_for_backward(x, w, y if act else None)
         ctx.cfg = (stride, tuple(pads), b is not None, bool(act))
         ctx.gen = _generation
@@ -436,9 +438,10 @@ class _ConvTC(torch.autograd.Function):
             gb = gb_all
         if ctx.needs_input_grad[0]:
             # dx = conv_transpose(gpre, w): rows of the GEMM = C_in, contraction = C_out
+            planes, ctx.planes = getattr(ctx, 'planes', None), None
             gx = _input_grad_into_slot(ctx.gen, x, lambda dst, acc: tc_conv.run(
-                gpre, tc_conv.split_weights(_khwc(w), transpose=True), dst, mode=1, stride=stride, kh=k, kw=k,
-                pad_t=pt, pad_l=pl, accumulate=acc))
+                gpre, planes if planes is not None else tc_conv.split_weights(_khwc(w), transpose=True), dst, mode=1,
+                stride=stride, kh=k, kw=k, pad_t=pt, pad_l=pl, accumulate=acc, planes_t=planes is not None))
         if ctx.needs_input_grad[1]:
             if _TC_WGRAD and tc_conv.supported(gpre):
                 gw = _tc_weight_grad(gpre, x, w, stride, pt, pl)                   # rows C_out, columns C_in
@@ -491,6 +494,9 @@ class _ConvWindow(torch.autograd.Function):
 
 
 _WINDOW = __import__('os').environ.get('UNFLOW_CONV1_WINDOW', '1') != '0'
+# the input-gradient launch of a layer reads the hi / lo weight planes its forward launch split (as MN-major B
+# tiles) instead of splitting a transposed pair: half the wsplit launches of a step (UNFLOW_REUSE_PLANES=0: off)
+_REUSE_PLANES = __import__('os').environ.get('UNFLOW_REUSE_PLANES', '1') != '0'
 
 
 def _use_window(x, w, stride):
@@ -508,8 +514,9 @@ class _DeconvTC(torch.autograd.Function):
         Ci, Co = w.shape[0], w.shape[1]
         N, _, H, W = x.shape
         dst, y = _dest(out, N, Co, 2 * H, 2 * W, x.device)
-        tc_conv.run(x, tc_conv.split_weights(_khwc(w), transpose=True), dst, mode=1, stride=2, kh=4, kw=4, pad_t=1,
-                    pad_l=1, bias=b, act=bool(act))
+        planes = tc_conv.split_weights(_khwc(w), transpose=True)
+        tc_conv.run(x, planes, dst, mode=1, stride=2, kh=4, kw=4, pad_t=1, pad_l=1, bias=b, act=bool(act))
+        ctx.planes = planes if _REUSE_PLANES else None
         ctx.save_for_backward(x, w, y if act else None)
         ctx.cfg = (b is not None, bool(act))
         ctx.gen = _generation
@@ -528,9 +535,10 @@ class _DeconvTC(torch.autograd.Function):
             gb = gb_all
         if ctx.needs_input_grad[0]:
             # dx = conv(gpre, w; stride 2, pad 1): rows = C_in (dim 0 of the IOHW variable), contraction = C_out
+            planes, ctx.planes = getattr(ctx, 'planes', None), None
             gx = _input_grad_into_slot(ctx.gen, x, lambda dst, acc: tc_conv.run(
-                gpre, tc_conv.split_weights(_khwc(w)), dst, mode=0, stride=2, kh=4, kw=4, pad_t=1, pad_l=1,
-                accumulate=acc))
+                gpre, planes if planes is not None else tc_conv.split_weights(_khwc(w)), dst, mode=0, stride=2, kh=4,
+                kw=4, pad_t=1, pad_l=1, accumulate=acc, planes_t=planes is not None))
         if ctx.needs_input_grad[1]:
             if _TC_WGRAD and tc_conv.supported(gpre):
                 gw = _tc_weight_grad(x, gpre, w, 2, 1, 1)                          # rows C_in, columns C_out
