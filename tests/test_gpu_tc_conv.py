@@ -72,6 +72,43 @@ def test_conv_forward(N, Cin, Cout, H, W, k, stride, pads, xp, bias, act, accum)
     assert bool((obuf[..., Cout:] == -3.5).all())          # nothing written past C_out
 
 
+@pytest.mark.parametrize("bias_act,accum,dense", [(True, False, True), (False, True, False), (False, False, False)])
+def test_conv_k_slices(bias_act, accum, dense):
+    """Few tiles, long K loop (the conv6 / conv6_1 shape of the step): the K loop of a tile is cut into slices
+    on different CTAs whose partial sums meet in the output through atomics (zeroed first unless accumulating),
+    bias + leaky ReLU as a separate pass.  Same result as the float64 convolution; slack channels untouched."""
+    from unflow_b200 import _native
+    t = T()
+    N, Cin, Cout, H, W, k = 2, 1024, 256, 6, 20, 3
+    x, _ = pitched(N, Cin, H, W, Cin, seed=5)
+    g = torch.Generator().manual_seed(11)
+    w = cl((torch.randn(Cout, Cin, k, k, generator=g) * (2.0 / (Cin * k * k)) ** 0.5).cuda())
+    b = (torch.randn(Cout + 1, generator=g) * 0.1).cuda()[1:] if bias_act else None
+    ref = F.conv2d(F.pad(x.double(), (1, 1, 1, 1)), w.double(), b.double() if bias_act else None)
+    if bias_act:
+        ref = F.leaky_relu(ref, 0.1)
+    out, obuf = pitched(N, Cout, H, W, Cout if dense else Cout + 4, seed=1, fill=-3.5)
+    if accum:
+        ref = ref + out.double()
+    else:
+        out.fill_(float("nan"))
+    planes = t.split_weights(w)
+    res = {}
+    for ks in (1, 0):
+        assert _native.lib().unflow_set_int_option(b"tc_ksplit", ks) == 0
+        o2 = out.clone() if not dense else None
+        dst, dbuf = (out, obuf) if ks == 1 else pitched(N, Cout, H, W, Cout if dense else Cout + 4, seed=1, fill=-3.5)
+        if ks == 0 and not accum:
+            dst.fill_(float("nan"))
+        t.run(x, planes, dst, mode=0, stride=1, kh=k, kw=k, pad_t=1, pad_l=1, bias=b, act=bias_act, accumulate=accum)
+        res[ks] = dst.clone()
+        assert rel(dst, ref) < TOL, ks
+        if not dense:
+            assert bool((dbuf[..., Cout:] == -3.5).all())
+    _native.lib().unflow_set_int_option(b"tc_ksplit", 1)
+    assert rel(res[1], res[0].double()) < 1e-5
+
+
 DECONV = [  # N, Cin, Cout, H, W, k, stride, pad, out_hw, x pitch, bias+act
     (2, 64, 128, 6, 10, 4, 2, 1, None, 64, True),            # deconvN forward
     (2, 130, 64, 6, 20, 4, 2, 1, None, 132, True),

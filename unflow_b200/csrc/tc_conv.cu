@@ -72,6 +72,8 @@ struct ConvParams {
   int act, accumulate;
   int chunk;                  // K blocks accumulated in tensor memory between two register adds (g_chunk)
   long long *dbg;             // role timers of CTA 0 (unflow_tc_conv_debug), or nullptr
+  int ksplit;                 // > 1: the K loop of a tile is cut into ksplit work items whose partial sums meet in the
+                              // (zeroed) output through red.global.add; bias / activation run as a separate pass
   int b_mn;                   // weight planes given as [tap][contraction][rows] (the planes of the layer's OTHER direction):
                               // B tiles are MN-major (32-row x 32-column boxes, 32-byte-atom swizzle) instead of K-major
   int class_start[5];
@@ -139,6 +141,26 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvParams &p, int tile, 
   return t;
 }
 
+// Work item = (tile, K slice).  Layers with few tiles (conv6 / conv6_1 of the step: 32 pair tiles for 74 SM pairs,
+// 288 K blocks each) cut the K loop of a tile into p.ksplit slices that run at the same time on different CTAs
+// (adjacent in the schedule: the slice index is the fastest).
+struct Work {
+  TileCoord t;
+  int it0, iters;       // first K block (tap * kblocks + channel block) and count of this item
+};
+template <int CG>
+__device__ __forceinline__ Work decode_work(const ConvParams &p, int w, int rank) {
+  Work k;
+  const int tile = w / p.ksplit, ks = w - tile * p.ksplit;
+  k.t = decode_tile<CG>(p, tile, rank);
+  const int total = (p.class_start[k.t.cls + 1] - p.class_start[k.t.cls]) * p.kblocks;
+  const int per = (total + p.ksplit - 1) / p.ksplit;
+  k.it0 = ks * per;
+  k.iters = total - k.it0 < per ? total - k.it0 : per;
+  if (k.iters < 0) k.iters = 0;
+  return k;
+}
+
 // ------------------------------------------------------------------------------------------
 // The kernel
 // ------------------------------------------------------------------------------------------
@@ -162,7 +184,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = p.tiles_n * p.tiles_y * p.tiles_x;
-  const int total_tiles = p.n_classes * (CG == 2 ? (m_tiles + 1) / 2 : m_tiles) * p.n_blocks;
+  const int total_tiles = p.n_classes * (CG == 2 ? (m_tiles + 1) / 2 : m_tiles) * p.n_blocks * p.ksplit;   // work items
   // CG = 2: the two CTAs of a cluster walk the same tile sequence; rank 0 (the leader) issues the MMAs and owns
   // the barriers both CTAs arrive on (full_cvt, tmem_empty); full_raw / empty / tmem_full stay per CTA
   const int rank = CG == 2 ? (int)cluster_ctarank() : 0;
@@ -208,12 +230,14 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       long long t_wait = 0, t_all = clock64();          // role timers: cycles blocked on the barrier / in total
       const unsigned a_box_bytes = (unsigned)(p.TW * p.TH * p.TN) * BK * 4u;
       for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
-        const TileCoord t = decode_tile<CG>(p, tile, rank);
+        const Work wk = decode_work<CG>(p, tile, rank);
+        const TileCoord t = wk.t;
         const int x0 = p.s_in_x * t.ix0, y0 = p.s_in_y * t.iy0;
         const int brow = t.nb * BN + rank * (BN / CG);      // pair: this CTA's half of the weight rows
-        for (int ti = p.class_start[t.cls]; ti < p.class_start[t.cls + 1]; ++ti) {
-          const Tap tap = p.taps[ti];
-          for (int kc = 0; kc < p.kblocks; ++kc) {
+        int ti = p.class_start[t.cls] + wk.it0 / p.kblocks, kc = wk.it0 % p.kblocks;
+        {
+          for (int it = 0; it < wk.iters; ++it) {
+            const Tap tap = p.taps[ti];
             { const long long t0 = clock64(); mbar_wait(empty(s), ph ^ 1u); t_wait += clock64() - t0; }
             const unsigned st = base + s * C::STAGE_BYTES;
             if (elect_one()) {
@@ -232,6 +256,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             }
             __syncwarp();
             if (++s == C::STAGES) { s = 0; ph ^= 1u; }
+            if (++kc == p.kblocks) { kc = 0; ++ti; }
           }
         }
       }
@@ -248,8 +273,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       unsigned ph = 0, aph = 0;
       long long t_wait_acc = 0, t_wait_ops = 0, t_all = clock64();
       for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
-        const TileCoord t = decode_tile<CG>(p, tile, rank);
-        const int iters = (p.class_start[t.cls + 1] - p.class_start[t.cls]) * p.kblocks;
+        const int iters = decode_work<CG>(p, tile, rank).iters;
         for (int it = 0; it < iters; ++it) {
           const int in_chunk = it % p.chunk;
           if (in_chunk == 0) {               // a fresh TMEM accumulator for every chunk of K
@@ -326,8 +350,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     unsigned ph = 0;
     long long t_wait = 0, t_all = clock64();
     for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
-      const TileCoord t = decode_tile<CG>(p, tile, rank);
-      const int iters = (p.class_start[t.cls + 1] - p.class_start[t.cls]) * p.kblocks;
+      const int iters = decode_work<CG>(p, tile, rank).iters;
       for (int it = 0; it < iters; ++it) {
         { const long long t0 = clock64(); mbar_wait(full_raw(s), ph); t_wait += clock64() - t0; }
         if (AT) {
@@ -388,8 +411,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     unsigned aph = 0;
     long long t_wait = 0, t_all = clock64();
     for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
-      const TileCoord t = decode_tile<CG>(p, tile, rank);
-      const int iters = (p.class_start[t.cls + 1] - p.class_start[t.cls]) * p.kblocks;
+      const Work wk = decode_work<CG>(p, tile, rank);
+      const TileCoord t = wk.t;
+      const int iters = wk.iters;
       const int chunks = (iters + p.chunk - 1) / p.chunk;
       float sum[COLS];
 #pragma unroll
@@ -416,7 +440,15 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       const bool valid = tn < p.TN && n < p.N && iy < p.Hit && ix < p.Wit;
       const int oy = p.s_out * iy + p.class_py[t.cls], ox = p.s_out * ix + p.class_px[t.cls];
       const int cbase = t.nb * BN + half * COLS;          // first output channel of this thread
-      if (valid && cbase < p.Cout) {
+      if (valid && cbase < p.Cout && p.ksplit > 1) {
+        // K slice: add the raw partial sums (the launcher zeroed the output unless it accumulates anyway)
+        float *dst = p.out + (((long long)n * p.Hout + oy) * p.Wout + ox) * p.out_pitch + cbase;
+        if (chunks > 0) {
+#pragma unroll
+          for (int c = 0; c < COLS; ++c)
+            if (cbase + c < p.Cout) red_add_f32(dst + c, sum[c]);
+        }
+      } else if (valid && cbase < p.Cout) {
         float *dst = p.out + (((long long)n * p.Hout + oy) * p.Wout + ox) * p.out_pitch + cbase;
 #pragma unroll
         for (int j = 0; j < COLS / 4; ++j) {
@@ -501,6 +533,7 @@ static int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b
 
 int g_a_in_tmem = 1;     // unflow_set_int_option("tc_a_tmem"): 1 = A operand in tensor memory (default), 0 = in shared memory
 int g_chunk = CHUNK;     // unflow_set_int_option("tc_chunk"): K blocks per tensor-memory accumulation
+int g_ksplit = 1;        // unflow_set_int_option("tc_ksplit"): 1 = layers with few tiles cut their K loops into slices, 0 = never
 long long *g_dbg = nullptr;   // unflow_tc_conv_debug: device buffer of 16 long longs for the role timers of CTA 0
 int g_pair = 1;          // unflow_set_int_option("tc_pair"): 0 = single CTAs only, 1 = CTA pairs where the model below says so, 2 = wherever possible
 
@@ -551,12 +584,26 @@ template <int BN>
 static int launch(const CUtensorMap &mA, const CUtensorMap &mBh, const CUtensorMap &mBl, const ConvParams &p,
                   int cta_group, cudaStream_t stream) {
   const int m_tiles = p.tiles_n * p.tiles_y * p.tiles_x;
-  const int total = p.n_classes * (cta_group == 2 ? (m_tiles + 1) / 2 : m_tiles) * p.n_blocks;
+  const int total = p.n_classes * (cta_group == 2 ? (m_tiles + 1) / 2 : m_tiles) * p.n_blocks * p.ksplit;
   if constexpr (BN >= 64) {
     if (cta_group == 2) return launch_v<BN, true, 2>(mA, mBh, mBl, p, total, stream);
   }
   return g_a_in_tmem ? launch_v<BN, true, 1>(mA, mBh, mBl, p, total, stream)
                      : launch_v<BN, false, 1>(mA, mBh, mBl, p, total, stream);
+}
+
+// K slices for a layer with few tiles and long K loops (work items <= half of the SMs / SM pairs): how many
+inline int choose_ksplit(const ConvParams &p, int BN) {
+  if (!g_ksplit) return 1;
+  const int cg = pick_cta_group(p, BN);
+  const long long m_tiles = (long long)p.tiles_n * p.tiles_y * p.tiles_x;
+  const long long items = p.n_classes * (cg == 2 ? (m_tiles + 1) / 2 : m_tiles) * p.n_blocks;
+  const long long slots = cg == 2 ? kNumSMs / 2 : kNumSMs;
+  if (2 * items > slots) return 1;
+  int min_iters = 1 << 30;
+  for (int c = 0; c < p.n_classes; ++c) min_iters = std::min(min_iters, (p.class_start[c + 1] - p.class_start[c]) * p.kblocks);
+  const long long ks = std::min<long long>(std::min<long long>(slots / items, 4), std::max(1, min_iters / (4 * p.chunk)));
+  return ks < 1 ? 1 : (int)ks;
 }
 
 // tile -> kernel: encodes the two weight-plane maps (box = this CTA's rows) and launches
@@ -581,9 +628,12 @@ static int launch_bn(int BN, const CUtensorMap &mA, const float *w_hi, const flo
 int set_tc_a_tmem(int v) { if (v != 0 && v != 1) return 0; tc::g_a_in_tmem = v; return 1; }
 int set_tc_pair(int v) { if (v < 0 || v > 2) return 0; tc::g_pair = v; return 1; }
 int set_tc_chunk(int v) { if (v < 1 || v > 64) return 0; tc::g_chunk = v; return 1; }
+int set_tc_ksplit(int v) { if (v != 0 && v != 1) return 0; tc::g_ksplit = v; return 1; }
 }  // namespace unflow
 
 using namespace unflow;
+
+extern "C" int unflow_bias_lrelu(float *y, const float *bias, long long pixels, int C, float slope, void *stream);   // split.cu
 
 extern "C" int unflow_tc_wsplit(const float *w, float *w_hi, float *w_lo, int taps, int R, int C, long long s_t,
                                 long long s_r, long long s_c, void *stream) {
@@ -605,7 +655,7 @@ static int make_plan(tc::ConvParams &p, int &BN, int N, int Hin, int Win, int Ci
   UNFLOW_REQUIRE(mode == 0 || mode == 1, "tc_conv: mode must be 0 (conv) or 1 (transposed)");
   UNFLOW_REQUIRE(stride == 1 || stride == 2, "tc_conv: stride must be 1 or 2");
   UNFLOW_REQUIRE(kh > 0 && kw > 0 && kh * kw <= tc::MAX_TAPS, "tc_conv: at most %d taps", tc::MAX_TAPS);
-  p.N = N; p.Cin = Cin; p.Cout = Cout; p.kblocks = (Cin + tc::BK - 1) / tc::BK; p.chunk = tc::g_chunk; p.dbg = tc::g_dbg;
+  p.N = N; p.Cin = Cin; p.Cout = Cout; p.kblocks = (Cin + tc::BK - 1) / tc::BK; p.chunk = tc::g_chunk; p.dbg = tc::g_dbg; p.ksplit = 1;
   p.Hout = Hout; p.Wout = Wout;
   int nt = 0;
   if (mode == 0) {
@@ -703,6 +753,14 @@ extern "C" int unflow_tc_conv(const float *x, int N, int Hin, int Win, int Cin, 
   if (rc0) return rc0;
   p.out = y; p.out_pitch = y_pitch;
   p.bias = bias; p.slope = slope; p.act = act; p.accumulate = accumulate; p.b_mn = planes_t;
+  // K slices (few tiles, long K): partial sums are added into the output, which is zeroed first unless the call
+  // accumulates anyway; bias + leaky ReLU then run as unflow_bias_lrelu over the (dense) result
+  const bool post = bias && act;
+  if ((!bias && !act) || (post && y_pitch == Cout && Cout % 4 == 0)) p.ksplit = tc::choose_ksplit(p, BN);
+  if (p.ksplit > 1 && !accumulate) {
+    cudaError_t e = cudaMemset2DAsync(y, (size_t)y_pitch * 4, 0, (size_t)Cout * 4, (size_t)N * Hout * Wout, (cudaStream_t)stream);
+    if (e != cudaSuccess) { set_error("tc_conv: memset of the output: %s", cudaGetErrorString(e)); return UNFLOW_ECUDA; }
+  }
 
   CUtensorMap mA;
   {
@@ -713,16 +771,20 @@ extern "C" int unflow_tc_conv(const float *x, int N, int Hin, int Win, int Cin, 
     int rc = tc::encode(&mA, x, 4, dims, strides, box, estr);
     if (rc) return rc;
   }
+  int rc;
   if (planes_t) {
     const int Cop = (Cout + 3) / 4 * 4;
     cuuint64_t wdims[3] = {(cuuint64_t)Cout, (cuuint64_t)Cin, (cuuint64_t)(kh * kw)};
     cuuint64_t wstrides[2] = {(cuuint64_t)Cop * 4, (cuuint64_t)Cop * 4 * Cin};
-    return tc::launch_bn(BN, mA, w_hi, w_lo, wdims, wstrides, p, (cudaStream_t)stream);
+    rc = tc::launch_bn(BN, mA, w_hi, w_lo, wdims, wstrides, p, (cudaStream_t)stream);
+  } else {
+    const int Cp = (Cin + 3) / 4 * 4;
+    cuuint64_t wdims[3] = {(cuuint64_t)Cin, (cuuint64_t)Cout, (cuuint64_t)(kh * kw)};
+    cuuint64_t wstrides[2] = {(cuuint64_t)Cp * 4, (cuuint64_t)Cp * 4 * Cout};
+    rc = tc::launch_bn(BN, mA, w_hi, w_lo, wdims, wstrides, p, (cudaStream_t)stream);
   }
-  const int Cp = (Cin + 3) / 4 * 4;
-  cuuint64_t wdims[3] = {(cuuint64_t)Cin, (cuuint64_t)Cout, (cuuint64_t)(kh * kw)};
-  cuuint64_t wstrides[2] = {(cuuint64_t)Cp * 4, (cuuint64_t)Cp * 4 * Cout};
-  return tc::launch_bn(BN, mA, w_hi, w_lo, wdims, wstrides, p, (cudaStream_t)stream);
+  if (rc || p.ksplit == 1 || !post) return rc;
+  return unflow_bias_lrelu(y, bias, (long long)N * Hout * Wout, Cout, slope, stream);
 }
 
 // First layers (7x7, stride 2, 3 / 6 / 14 input channels): with so few channels a K block of 32
