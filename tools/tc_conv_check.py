@@ -293,8 +293,12 @@ def main():
             w = cl((torch.randn(386, 64, 4, 4, generator=g) * 0.05).to(dev))
             planes = T.split_weights(w, transpose=True)
             out, obuf = out_buf(B, 64, 96, 320)
-            roles("deconv2 (BN=64) pair=%d" % pair,
-                  lambda: T.run(x, planes, out, mode=1, stride=2, kh=4, kw=4, pad_t=1, pad_l=1, bias=None, act=False))
+            for ppx in (0, 1):
+                assert lib.unflow_set_int_option(b"tc_pair_px", ppx) == 0
+                fn = lambda: T.run(x, planes, out, mode=1, stride=2, kh=4, kw=4, pad_t=1, pad_l=1, bias=None, act=False)
+                roles("deconv2 (64 channels) pair=%d pair_px=%d" % (pair, ppx), fn)
+                say(case="deconv2 pair=%d pair_px=%d" % (pair, ppx), us=bench(fn))
+            lib.unflow_set_int_option(b"tc_pair_px", 1)
         set_pair(1)
         return
     if "--chunk-test" in sys.argv:       # K blocks per tensor-memory accumulation: accuracy and time

@@ -56,6 +56,7 @@ constexpr int NTHREADS = 512;    // 16 warps, see the role table above
 struct Tap {
   short dx, dy;
   int widx;
+  int widx2;                  // pair_px: the weight tap of the px = 1 class for this input offset (-1: none)
 };
 
 struct ConvParams {
@@ -72,6 +73,8 @@ struct ConvParams {
   int act, accumulate;
   int chunk;                  // K blocks accumulated in tensor memory between two register adds (g_chunk)
   long long *dbg;             // role timers of CTA 0 (unflow_tc_conv_debug), or nullptr
+  int pair_px;                // two output-parity classes (px = 0, 1) of a narrow transposed layer share one tile, see
+                              // pair_px_plan()
   int ksplit;                 // > 1: the K loop of a tile is cut into ksplit work items whose partial sums meet in the
                               // (zeroed) output through red.global.add; bias / activation run as a separate pass
   int b_mn;                   // weight planes given as [tap][contraction][rows] (the planes of the layer's OTHER direction):
@@ -233,11 +236,16 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         const Work wk = decode_work<CG>(p, tile, rank);
         const TileCoord t = wk.t;
         const int x0 = p.s_in_x * t.ix0, y0 = p.s_in_y * t.iy0;
-        const int brow = t.nb * BN + rank * (BN / CG);      // pair: this CTA's half of the weight rows
+        // pair: this CTA's half of the weight rows (pair_px: rows 0.. of its own class's tap)
+        const int brow = p.pair_px ? 0 : t.nb * BN + rank * (BN / CG);
         int ti = p.class_start[t.cls] + wk.it0 / p.kblocks, kc = wk.it0 % p.kblocks;
         {
           for (int it = 0; it < wk.iters; ++it) {
-            const Tap tap = p.taps[ti];
+            Tap tap = p.taps[ti];
+            if (p.pair_px) {         // rank 0 loads the weights of class px = 0, rank 1 those of px = 1; no tap: zero fill
+              const int wi = rank ? tap.widx2 : tap.widx;
+              tap.widx = wi < 0 ? (1 << 20) : wi;
+            }
             { const long long t0 = clock64(); mbar_wait(empty(s), ph ^ 1u); t_wait += clock64() - t0; }
             const unsigned st = base + s * C::STAGE_BYTES;
             if (elect_one()) {
@@ -438,8 +446,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       }
       const int n = t.n0 + tn, iy = t.iy0 + ty, ix = t.ix0 + tx;
       const bool valid = tn < p.TN && n < p.N && iy < p.Hit && ix < p.Wit;
-      const int oy = p.s_out * iy + p.class_py[t.cls], ox = p.s_out * ix + p.class_px[t.cls];
-      const int cbase = t.nb * BN + half * COLS;          // first output channel of this thread
+      // pair_px: the two column halves of the tile are the two px classes of the same (<= 64) output channels
+      const int oy = p.s_out * iy + p.class_py[t.cls], ox = p.s_out * ix + (p.pair_px ? half : p.class_px[t.cls]);
+      const int cbase = p.pair_px ? 0 : t.nb * BN + half * COLS;          // first output channel of this thread
       if (valid && cbase < p.Cout && p.ksplit > 1) {
         // K slice: add the raw partial sums (the launcher zeroed the output unless it accumulates anyway)
         float *dst = p.out + (((long long)n * p.Hout + oy) * p.Wout + ox) * p.out_pitch + cbase;
@@ -533,6 +542,7 @@ static int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b
 
 int g_a_in_tmem = 1;     // unflow_set_int_option("tc_a_tmem"): 1 = A operand in tensor memory (default), 0 = in shared memory
 int g_chunk = CHUNK;     // unflow_set_int_option("tc_chunk"): K blocks per tensor-memory accumulation
+int g_pair_px = 1;       // unflow_set_int_option("tc_pair_px"): 1 = narrow transposed layers compute two parity classes per tile
 int g_ksplit = 1;        // unflow_set_int_option("tc_ksplit"): 1 = layers with few tiles cut their K loops into slices, 0 = never
 long long *g_dbg = nullptr;   // unflow_tc_conv_debug: device buffer of 16 long longs for the role timers of CTA 0
 int g_pair = 1;          // unflow_set_int_option("tc_pair"): 0 = single CTAs only, 1 = CTA pairs where the model below says so, 2 = wherever possible
@@ -569,6 +579,7 @@ static int launch_v(const CUtensorMap &mA, const CUtensorMap &mBh, const CUtenso
 // ingress from L2 (~43 B/clk) of the activation box plus this CTA's share of the two weight planes; times the
 // number of waves the tiles need on 148 SMs / 74 pairs.
 inline int pick_cta_group(const ConvParams &p, int BN) {
+  if (p.pair_px) return 2;
   if (!g_a_in_tmem || g_pair == 0 || BN < 64) return 1;
   const long long m_tiles = (long long)p.tiles_n * p.tiles_y * p.tiles_x;
   if (m_tiles < 2) return 1;
@@ -629,6 +640,7 @@ int set_tc_a_tmem(int v) { if (v != 0 && v != 1) return 0; tc::g_a_in_tmem = v; 
 int set_tc_pair(int v) { if (v < 0 || v > 2) return 0; tc::g_pair = v; return 1; }
 int set_tc_chunk(int v) { if (v < 1 || v > 64) return 0; tc::g_chunk = v; return 1; }
 int set_tc_ksplit(int v) { if (v != 0 && v != 1) return 0; tc::g_ksplit = v; return 1; }
+int set_tc_pair_px(int v) { if (v != 0 && v != 1) return 0; tc::g_pair_px = v; return 1; }
 }  // namespace unflow
 
 using namespace unflow;
@@ -706,6 +718,47 @@ static int make_plan(tc::ConvParams &p, int &BN, int N, int Hin, int Win, int Ci
   return UNFLOW_OK;
 }
 
+// Narrow transposed layers (33..64 output channels: deconv2, the input gradient of conv2): the MMA costs the same
+// for N = 64 as for N = 128 (profiles/r2_mma_probe.md), so a 64-wide tile wastes half of the tensor core.  The
+// two output-parity classes px = 0 / 1 of a row class py read overlapping input offsets (k4 s2: dx {0,-1} and
+// {+1,0}; 5x5 s2: {0,-1} and {+1,0,-1}): ONE 128-wide tile computes both -- columns [0,64) = the channels of
+// px = 0, [64,128) = those of px = 1 -- over the union of the offsets; where only one class has a tap for an
+// offset the other half of the weight tile is TMA zero fill.  CTA pairs only: rank r loads the weights of class
+// px = r (its half of B).  K blocks per output tile: k4 s2 6 instead of 8, 5x5 s2 15 instead of 25.
+static bool pair_px_plan(tc::ConvParams &p, int &BN, int mode, int stride, int Cout) {
+  if (!tc::g_pair_px || !tc::g_pair || !tc::g_a_in_tmem || mode != 1 || stride != 2 || p.n_classes != 4) return false;
+  if (Cout <= 32 || Cout > 64 || (long long)p.tiles_n * p.tiles_y * p.tiles_x < 2) return false;
+  tc::Tap taps[tc::MAX_TAPS];
+  int start[3], nt = 0;
+  for (int py = 0; py < 2; ++py) {
+    start[py] = nt;
+    for (int px = 0; px < 2; ++px) {
+      const int c = py * 2 + px;                        // make_plan's class order: py outer, px inner
+      if (p.class_py[c] != py || p.class_px[c] != px) return false;
+      for (int ti = p.class_start[c]; ti < p.class_start[c + 1]; ++ti) {
+        const tc::Tap &a = p.taps[ti];
+        int e = -1;
+        for (int k = start[py]; k < nt; ++k)
+          if (taps[k].dx == a.dx && taps[k].dy == a.dy) e = k;
+        if (e < 0) {
+          if (nt >= tc::MAX_TAPS) return false;
+          e = nt++;
+          taps[e] = tc::Tap{a.dx, a.dy, -1, -1};
+        }
+        if (px == 0) taps[e].widx = a.widx; else taps[e].widx2 = a.widx;
+      }
+    }
+  }
+  start[2] = nt;
+  for (int k = 0; k < nt; ++k) p.taps[k] = taps[k];
+  p.n_classes = 2;
+  for (int c = 0; c < 3; ++c) p.class_start[c] = start[c];
+  p.class_py[0] = 0; p.class_py[1] = 1; p.class_px[0] = p.class_px[1] = 0;
+  p.pair_px = 1; p.n_blocks = 1;
+  BN = 128;
+  return true;
+}
+
 // Debug hook: role timers.  `buf` = device memory for 16 long longs (or nullptr to switch off); every following
 // tc_conv launch makes CTA 0 write, in clocks: [0] TMA producer blocked on a free stage, [1] its total; [2] MMA
 // issuer blocked on a free accumulator, [3] on the operands of a K block, [4] its total; [5] converter warp 4
@@ -751,6 +804,7 @@ extern "C" int unflow_tc_conv(const float *x, int N, int Hin, int Win, int Cin, 
   int BN = 0;
   int rc0 = make_plan(p, BN, N, Hin, Win, Cin, Hout, Wout, Cout, mode, stride, kh, kw, pad_t, pad_l);
   if (rc0) return rc0;
+  pair_px_plan(p, BN, mode, stride, Cout);
   p.out = y; p.out_pitch = y_pitch;
   p.bias = bias; p.slope = slope; p.act = act; p.accumulate = accumulate; p.b_mn = planes_t;
   // K slices (few tiles, long K): partial sums are added into the output, which is zeroed first unless the call
