@@ -110,11 +110,17 @@ struct Cfg {
   static constexpr int B_BYTES = BN / CG * BK * 4;               // this CTA's part of one weight plane
   static constexpr int STAGE_BYTES = (AT ? 1 : 2) * A_BYTES + 2 * B_BYTES;
   static constexpr int B_OFF = (AT ? 1 : 2) * A_BYTES;          // offset of the weight planes inside a stage
-  static constexpr int MAX_STAGES = CG == 2 ? (512 - 2 * BN) / (2 * BK) : (AT ? 4 : 6);
-  static constexpr int STAGES = (200 * 1024 / STAGE_BYTES) < MAX_STAGES ? (200 * 1024 / STAGE_BYTES) : MAX_STAGES;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+  // Two rings: STAGES shared-memory stages (TMA -> converter / MMA) and, with the A operand in tensor memory,
+  // ASLOTS operand slots there (converter -> MMA).  Tensor memory has room for (512 - 2 BN) / 64 slots only (4 at
+  // BN = 128), shared memory for more stages of a CTA pair's 32 KB: the TMA ring is the one that has to cover the
+  // L2 latency, so it runs deeper than the slot ring (role timers with 4 = 4: every role idle ~50 % at 830-900
+  // clocks per K block; tools/tc_conv_check.py --roles).
+  static constexpr int MAX_SLOTS = (512 - 2 * BN) / (2 * BK);
+  static constexpr int STAGES = (200 * 1024 / STAGE_BYTES) < 8 ? (200 * 1024 / STAGE_BYTES) : 8;
+  static constexpr int ASLOTS = !AT ? STAGES : (STAGES < MAX_SLOTS ? STAGES : MAX_SLOTS);
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 512 /*barriers*/;
   static constexpr int ACC_COLS = 2 * BN;                        // two accumulator buffers
-  static constexpr int A_COLS = AT ? STAGES * 2 * BK : 0;        // per stage: 32 columns hi + 32 columns lo
+  static constexpr int A_COLS = AT ? ASLOTS * 2 * BK : 0;        // per slot: 32 columns hi + 32 columns lo
   static constexpr int NEED = ACC_COLS + A_COLS;
   static constexpr int TMEM_COLS = NEED <= 32 ? 32 : NEED <= 64 ? 64 : NEED <= 128 ? 128 : NEED <= 256 ? 256 : 512;
   static_assert(NEED <= 512, "tensor memory has 512 columns");
@@ -177,13 +183,15 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   unsigned char *gbase = smem_raw + (base - s32(smem_raw));
   // stage layout: [A raw (= hi after the split when !AT)] [A lo, only when !AT] [B hi] [B lo]
   const unsigned bars = base + C::STAGES * C::STAGE_BYTES;
-  auto full_raw = [&](int s) { return bars + 8u * s; };
-  auto full_cvt = [&](int s) { return bars + 8u * (C::STAGES + s); };
-  auto empty = [&](int s) { return bars + 8u * (2 * C::STAGES + s); };
-  auto tmem_full = [&](int a) { return bars + 8u * (3 * C::STAGES + a); };
-  auto tmem_empty = [&](int a) { return bars + 8u * (3 * C::STAGES + 2 + a); };
-  const unsigned tmem_slot = bars + 8u * (3 * C::STAGES + 4);
-  volatile unsigned *tmem_slot_ptr = (volatile unsigned *)(gbase + C::STAGES * C::STAGE_BYTES + 8 * (3 * C::STAGES + 4));
+  constexpr int NB0 = 2 * C::STAGES + 2 * C::ASLOTS;               // barriers before the accumulator ones
+  auto full_raw = [&](int s) { return bars + 8u * s; };               // stage s landed (TMA)
+  auto empty = [&](int s) { return bars + 8u * (C::STAGES + s); };    // stage s consumed (MMAs done)
+  auto full_cvt = [&](int a) { return bars + 8u * (2 * C::STAGES + a); };               // operand slot a written
+  auto a_empty = [&](int a) { return bars + 8u * (2 * C::STAGES + C::ASLOTS + a); };    // operand slot a consumed
+  auto tmem_full = [&](int a) { return bars + 8u * (NB0 + a); };
+  auto tmem_empty = [&](int a) { return bars + 8u * (NB0 + 2 + a); };
+  const unsigned tmem_slot = bars + 8u * (NB0 + 4);
+  volatile unsigned *tmem_slot_ptr = (volatile unsigned *)(gbase + C::STAGES * C::STAGE_BYTES + 8 * (NB0 + 4));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = p.tiles_n * p.tiles_y * p.tiles_x;
@@ -197,8 +205,11 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
       mbar_init(full_raw(s), 1);
-      mbar_init(full_cvt(s), 4 * CG);
       mbar_init(empty(s), 1);
+    }
+    for (int a = 0; a < C::ASLOTS; ++a) {
+      mbar_init(full_cvt(a), 4 * CG);
+      mbar_init(a_empty(a), 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tmem_full(a), 1);
@@ -277,8 +288,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | (p.b_mn ? (1u << 16) : 0u) |
                              ((unsigned)(BN >> 3) << 17) | ((unsigned)((CG * BM) >> 4) << 24);
       const unsigned long long kstep = p.b_mn ? 64ull : 2ull;    // 8 contraction elements: 8 rows of 128 B / 32 bytes
-      int s = 0, acc = 0;
-      unsigned ph = 0, aph = 0;
+      int s = 0, acc = 0, sl = 0;
+      unsigned ph = 0, aph = 0, slph = 0;
       long long t_wait_acc = 0, t_wait_ops = 0, t_all = clock64();
       for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
         const int iters = decode_work<CG>(p, tile, rank).iters;
@@ -295,10 +306,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           if (CG == 2) {
             // the converter warps of BOTH CTAs arrive here after their own TMA barrier: activations split and
             // both halves of the weight tile landed
-            mbar_wait_cluster(full_cvt(s), ph);
+            mbar_wait_cluster(full_cvt(sl), slph);
           } else {
             mbar_wait(full_raw(s), ph);        // weights landed (TMA)
-            mbar_wait(full_cvt(s), ph);        // activations split (converter warps)
+            mbar_wait(full_cvt(sl), slph);     // activations split (converter warps)
           }
           t_wait_ops += clock64() - t1;
           tc_fence_after();
@@ -308,7 +319,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                                                  : umma_desc_k128(st + C::B_OFF + C::B_BYTES);
           if (elect_one()) {
           if (CG == 2) {
-            const unsigned ta_hi = tmem_base + (unsigned)(C::ACC_COLS + s * 2 * BK), ta_lo = ta_hi + BK;
+            const unsigned ta_hi = tmem_base + (unsigned)(C::ACC_COLS + sl * 2 * BK), ta_lo = ta_hi + BK;
 #pragma unroll
             for (int k = 0; k < BK / 8; ++k) {
               const unsigned long long adv = kstep * (unsigned long long)k;
@@ -317,7 +328,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
               umma_tf32_ts_pair(d, ta_hi + 8 * k, b_hi + adv, idesc, 1u);
             }
           } else if (AT) {
-            const unsigned ta_hi = tmem_base + (unsigned)(C::ACC_COLS + s * 2 * BK), ta_lo = ta_hi + BK;
+            const unsigned ta_hi = tmem_base + (unsigned)(C::ACC_COLS + sl * 2 * BK), ta_lo = ta_hi + BK;
 #pragma unroll
             for (int k = 0; k < BK / 8; ++k) {          // A: 8 TMEM columns per K step; B: +32 bytes
               const unsigned long long adv = kstep * (unsigned long long)k;
@@ -335,8 +346,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
               umma_tf32(d, a_hi + adva, b_hi + adv, idesc, 1u);
             }
           }
-          // frees the stage when these MMAs have read it (pair: in both CTAs)
+          // frees the stage and the operand slot when these MMAs have read them (pair: in both CTAs)
           if (CG == 2) umma_commit_pair(empty(s)); else umma_commit(empty(s));
+          if (AT) { if (CG == 2) umma_commit_pair(a_empty(sl)); else umma_commit(a_empty(sl)); }
           if (in_chunk == p.chunk - 1 || it == iters - 1) {
             // chunk complete -> epilogue warps (of both CTAs) add it to their registers
             if (CG == 2) umma_commit_pair(tmem_full(acc)); else umma_commit(tmem_full(acc));
@@ -344,6 +356,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           }     // elect_one
           __syncwarp();
           if (++s == C::STAGES) { s = 0; ph ^= 1u; }
+          if (++sl == C::ASLOTS) { sl = 0; slph ^= 1u; }
           if (in_chunk == p.chunk - 1 || it == iters - 1) {
             if (++acc == 2) { acc = 0; aph ^= 1u; }
           }
@@ -354,13 +367,14 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   } else if (warp >= 4 && warp < 8) {
     // ===================== activation split =====================
     const int tid = threadIdx.x - 128;
-    int s = 0;
-    unsigned ph = 0;
+    int s = 0, sl = 0;
+    unsigned ph = 0, slph = 0;
     long long t_wait = 0, t_all = clock64();
     for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
       const int iters = decode_work<CG>(p, tile, rank).iters;
       for (int it = 0; it < iters; ++it) {
         { const long long t0 = clock64(); mbar_wait(full_raw(s), ph); t_wait += clock64() - t0; }
+        if (AT) { mbar_wait(a_empty(sl), slph ^ 1u); tc_fence_after(); }   // the MMAs that read this operand slot last are done
         if (AT) {
           // thread = tile row: read the row's 32 channels (8 x 16 bytes; the 128-byte swizzle stores logical
           // chunk j of row r at chunk j ^ (r & 7) -- a quarter warp hits all 32 banks), split, and store
@@ -378,7 +392,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
               lo[4 * j + e] = __float_as_uint(x4[e] - h);
             }
           }
-          const unsigned ta = tmem_base + ((unsigned)((warp & 3) * 32) << 16) + (unsigned)(C::ACC_COLS + s * 2 * BK);
+          const unsigned ta = tmem_base + ((unsigned)((warp & 3) * 32) << 16) + (unsigned)(C::ACC_COLS + sl * 2 * BK);
           tmem_st32(ta, hi);
           tmem_st32(ta + BK, lo);
           asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
@@ -400,9 +414,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         }
         __syncwarp();
         if (lane == 0) {
-          if (CG == 2) mbar_arrive_cta(full_cvt(s), 0); else mbar_arrive(full_cvt(s));
+          if (CG == 2) mbar_arrive_cta(full_cvt(sl), 0); else mbar_arrive(full_cvt(sl));
         }
         if (++s == C::STAGES) { s = 0; ph ^= 1u; }
+        if (++sl == C::ASLOTS) { sl = 0; slph ^= 1u; }
       }
     }
     if (p.dbg && blockIdx.x == 0 && threadIdx.x == 128) { p.dbg[5] = t_wait; p.dbg[6] = clock64() - t_all; }
