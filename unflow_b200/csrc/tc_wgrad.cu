@@ -71,10 +71,13 @@ struct Cfg {
   static constexpr int B_BYTES = BN / CG * KP * 4;               // this CTA's part of the G tile
   static constexpr int STAGE_BYTES = A_BYTES + 2 * B_BYTES;
   static constexpr int B_OFF = A_BYTES;
-  static constexpr int STAGES = (200 * 1024 / STAGE_BYTES) < 4 ? (200 * 1024 / STAGE_BYTES) : 4;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+  // shared-memory stages (TMA ring) and tensor-memory operand slots for the split P tile (see tc_conv.cu, Cfg)
+  static constexpr int STAGES = (200 * 1024 / STAGE_BYTES) < 8 ? (200 * 1024 / STAGE_BYTES) : 8;
+  static constexpr int MAX_SLOTS = (512 - 2 * BN) / (2 * KP);
+  static constexpr int ASLOTS = STAGES < MAX_SLOTS ? STAGES : MAX_SLOTS;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 512;
   static constexpr int ACC_COLS = 2 * BN;
-  static constexpr int A_COLS = STAGES * 2 * KP;
+  static constexpr int A_COLS = ASLOTS * 2 * KP;
   static constexpr int NEED = ACC_COLS + A_COLS;
   static constexpr int TMEM_COLS = NEED <= 32 ? 32 : NEED <= 64 ? 64 : NEED <= 128 ? 128 : NEED <= 256 ? 256 : 512;
   static_assert(NEED <= 512, "tensor memory has 512 columns");
@@ -115,10 +118,12 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant_
   auto full_raw = [&](int s) { return bars + 8u * s; };
   auto full_cvt = [&](int s) { return bars + 8u * (C::STAGES + s); };
   auto empty = [&](int s) { return bars + 8u * (2 * C::STAGES + s); };
-  auto tmem_full = [&](int a) { return bars + 8u * (3 * C::STAGES + a); };
-  auto tmem_empty = [&](int a) { return bars + 8u * (3 * C::STAGES + 2 + a); };
-  const unsigned tmem_slot = bars + 8u * (3 * C::STAGES + 4);
-  volatile unsigned *tmem_slot_ptr = (volatile unsigned *)(gbase + C::STAGES * C::STAGE_BYTES + 8 * (3 * C::STAGES + 4));
+  constexpr int NB0 = 3 * C::STAGES + C::ASLOTS;
+  auto a_empty = [&](int a) { return bars + 8u * (3 * C::STAGES + a); };     // operand slot a consumed by the MMAs
+  auto tmem_full = [&](int a) { return bars + 8u * (NB0 + a); };
+  auto tmem_empty = [&](int a) { return bars + 8u * (NB0 + 2 + a); };
+  const unsigned tmem_slot = bars + 8u * (NB0 + 4);
+  volatile unsigned *tmem_slot_ptr = (volatile unsigned *)(gbase + C::STAGES * C::STAGE_BYTES + 8 * (NB0 + 4));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_items = p.n_chunks * (CG == 2 ? (p.r_blocks + 1) / 2 : p.r_blocks) * p.c_blocks;
@@ -133,6 +138,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant_
       mbar_init(full_cvt(s), 6 * CG);           // 4 warps (P -> tensor memory) + 2 warps (G in shared memory), per CTA
       mbar_init(empty(s), 1);
     }
+    for (int a = 0; a < C::ASLOTS; ++a) mbar_init(a_empty(a), 1);
     for (int a = 0; a < 2; ++a) {
       mbar_init(tmem_full(a), 1);
       mbar_init(tmem_empty(a), 8 * CG);
@@ -205,7 +211,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant_
       // (A lives in tensor memory: K-major by construction -- lane = row, column = K; B is MN-major, bit 16)
       const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) |
                              ((unsigned)(BN >> 3) << 17) | ((unsigned)((CG * BM) >> 4) << 24);
-      int s = 0, acc = 0;
+      int s = 0, acc = 0, sl = 0;
       unsigned ph = 0, aph = 0;
       for (int item = first_item; item < total_items; item += item_step) {
         const Item w = decode_item<CG>(p, item, rank);
@@ -227,7 +233,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant_
           const unsigned st = base + s * C::STAGE_BYTES;
           const unsigned long long b_hi = umma_desc_mn128(st + C::B_OFF, 4096);
           const unsigned long long b_lo = umma_desc_mn128(st + C::B_OFF + C::B_BYTES, 4096);
-          const unsigned ta_hi = tmem_base + (unsigned)(C::ACC_COLS + s * 2 * KP), ta_lo = ta_hi + KP;
+          const unsigned ta_hi = tmem_base + (unsigned)(C::ACC_COLS + sl * 2 * KP), ta_lo = ta_hi + KP;
           if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < KP / 8; ++k) {            // A: 8 TMEM columns (pixels) per K step; B: 8 rows = 1024 B
@@ -243,12 +249,14 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant_
             }
           }
           if (CG == 2) umma_commit_pair(empty(s)); else umma_commit(empty(s));
+          if (CG == 2) umma_commit_pair(a_empty(sl)); else umma_commit(a_empty(sl));
           if (in_chunk == p.chunk - 1 || it == iters - 1) {
             if (CG == 2) umma_commit_pair(tmem_full(acc)); else umma_commit(tmem_full(acc));
           }
           }     // elect_one
           __syncwarp();
           if (++s == C::STAGES) { s = 0; ph ^= 1u; }
+          if (++sl == C::ASLOTS) sl = 0;
           if (in_chunk == p.chunk - 1 || it == iters - 1) {
             if (++acc == 2) { acc = 0; aph ^= 1u; }
           }
@@ -261,13 +269,15 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant_
     // (The G tile is split by all six converter warps, half here and half in warps 2-3: one warp per scheduler
     // could not keep up with both tiles -- ncu: 45 % of the tensor pipe with the ALU pipe of the converter warps
     // saturated -- and two warps alone cannot split 16 KB per K block in time either.)
-    int s = 0;
-    unsigned ph = 0;
+    int s = 0, sl = 0;
+    unsigned ph = 0, slph = 0;
     for (int item = first_item; item < total_items; item += item_step) {
       const Item w = decode_item<CG>(p, item, rank);
       const int iters = chunk_len(p, w.chunk);
       for (int it = 0; it < iters; ++it) {
         mbar_wait(full_raw(s), ph);
+        mbar_wait(a_empty(sl), slph ^ 1u);       // the MMAs that read this operand slot last are done
+        tc_fence_after();
         const float *grp = reinterpret_cast<const float *>(gbase + s * C::STAGE_BYTES + (warp & 3) * 4096) + lane;
         unsigned hi[KP], lo[KP];
 #pragma unroll
@@ -277,7 +287,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant_
           hi[k] = __float_as_uint(h);
           lo[k] = __float_as_uint(v - h);
         }
-        const unsigned ta = tmem_base + ((unsigned)((warp & 3) * 32) << 16) + (unsigned)(C::ACC_COLS + s * 2 * KP);
+        const unsigned ta = tmem_base + ((unsigned)((warp & 3) * 32) << 16) + (unsigned)(C::ACC_COLS + sl * 2 * KP);
         tmem_st32(ta, hi);
         tmem_st32(ta + KP, lo);
         {                                    // ... and the first half of G (warps 2-3 take the second half)
@@ -301,6 +311,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant_
           if (CG == 2) mbar_arrive_cta(full_cvt(s), 0); else mbar_arrive(full_cvt(s));
         }
         if (++s == C::STAGES) { s = 0; ph ^= 1u; }
+        if (++sl == C::ASLOTS) { sl = 0; slph ^= 1u; }
       }
     }
   } else if (warp == 2 || warp == 3) {
