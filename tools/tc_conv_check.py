@@ -300,6 +300,24 @@ def main():
                 say(case="deconv2 pair=%d pair_px=%d" % (pair, ppx), us=bench(fn))
             lib.unflow_set_int_option(b"tc_pair_px", 1)
         set_pair(1)
+        # the weight-gradient kernel (same timers; [9] = converter blocked on a free operand slot)
+        for pair in (0, 1):
+            set_pair(pair)
+            for (label, N, Cin, Cout, H, W) in [("wgrad conv3_1", B, 473, 256, 48, 160), ("wgrad conv4_1", B, 512, 512, 24, 80)]:
+                x = make_x(N, Cin, H, W, T.round4(Cin), seed=Cin + 1)
+                gy = make_x(N, Cout, H, W, None, seed=Cout + 2)
+                dw = torch.zeros(Cout, Cin, 3, 3, device=dev).contiguous(memory_format=torch.channels_last)
+                fn = lambda: T.wgrad(gy, x, dw, stride=1, kh=3, kw=3, pad_t=1, pad_l=1)
+                for gs in (1, 3):
+                    assert lib.unflow_set_int_option(b"tc_wgrad_gsplit", gs) == 0
+                    fn(); torch.cuda.synchronize()
+                    assert lib.unflow_tc_conv_debug(buf.data_ptr()) == 0
+                    buf.zero_(); fn(); torch.cuda.synchronize(); lib.unflow_tc_conv_debug(None)
+                    v = buf.tolist()
+                    say(case="%s pair=%d gsplit=%d" % (label, pair, gs), us=bench(fn), slot_wait=int(v[9]),
+                        **{n: int(xx) for n, xx in zip(names, v)})
+                lib.unflow_set_int_option(b"tc_wgrad_gsplit", 2)
+        set_pair(1)
         return
     if "--chunk-test" in sys.argv:       # K blocks per tensor-memory accumulation: accuracy and time
         from unflow_b200 import _native

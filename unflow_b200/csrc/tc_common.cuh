@@ -16,6 +16,7 @@ constexpr int BK = 32;           // fp32 elements per K block = 128 bytes = one 
 constexpr int CHUNK = 8;
 constexpr int A_BYTES = BM * BK * 4;   // 16 KB
 extern int g_a_in_tmem;                // tc_conv.cu: A operand of the MMAs in tensor memory (1) or shared memory (0)
+extern long long *g_dbg;               // tc_conv.cu: role-timer buffer (unflow_tc_conv_debug)
 extern int g_chunk;                    // tc_conv.cu: K blocks accumulated in tensor memory between register adds (default CHUNK)
 extern int g_pair;                     // tc_conv.cu: CTA pairs (cta_group::2): 0 never, 1 where the model says so, 2 wherever possible
 

@@ -50,6 +50,8 @@ struct WgradParams {
   int cgroups, vgroups;             // 32-channel groups of G per tap; (tap, group) pairs = "virtual" column groups
   int r_blocks, c_blocks, taps, kw;  // c_blocks: blocks of BN/32 consecutive virtual groups
   int chunk;                        // K blocks per tensor-memory accumulation (tc::g_chunk)
+  long long *dbg;                   // role timers of CTA 0 (unflow_tc_conv_debug), or nullptr
+  int g_first;                      // float4s of the G tile split by warps 4-7 (after their P tile); warps 2-3 take the rest
   int stride, stride_x, pad_t, pad_l;   // stride_x = 1 in the row-window form (x stride inside the tensor map)
   float *dw;
   long long pitch_r, pitch_t;       // dW[r * pitch_r + t * pitch_t + c]
@@ -168,6 +170,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant_
     {
       int s = 0;
       unsigned ph = 0;
+      long long t_wait = 0, t_all = clock64();
       for (int item = first_item; item < total_items; item += item_step) {
         const Item w = decode_item<CG>(p, item, rank);
         int gch[GROUPS], gdx[GROUPS], gdy[GROUPS];           // per column group of this CTA: channel, tap offset
@@ -187,7 +190,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant_
           const int px = (q % p.tiles_x) * p.TW; q /= p.tiles_x;
           const int py = (q % p.tiles_y) * p.TH; q /= p.tiles_y;
           const int pn = q * p.TN;
-          mbar_wait(empty(s), ph ^ 1u);
+          { const long long t0 = clock64(); mbar_wait(empty(s), ph ^ 1u); t_wait += clock64() - t0; }
           const unsigned st = base + s * C::STAGE_BYTES;
           if (elect_one()) {
             mbar_expect_tx(full_raw(s), (unsigned)(A_BYTES + C::B_BYTES));
@@ -203,6 +206,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant_
           if (++s == C::STAGES) { s = 0; ph ^= 1u; }
         }
       }
+      if (p.dbg && blockIdx.x == 0 && lane == 0) { p.dbg[0] = t_wait; p.dbg[1] = clock64() - t_all; }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (whole warp converged, one elected lane issues: tc_common.cuh) ==========
@@ -213,22 +217,27 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant_
                              ((unsigned)(BN >> 3) << 17) | ((unsigned)((CG * BM) >> 4) << 24);
       int s = 0, acc = 0, sl = 0;
       unsigned ph = 0, aph = 0;
+      long long t_wait_acc = 0, t_wait_ops = 0, t_all = clock64();
       for (int item = first_item; item < total_items; item += item_step) {
         const Item w = decode_item<CG>(p, item, rank);
         const int iters = chunk_len(p, w.chunk);
         for (int it = 0; it < iters; ++it) {
           const int in_chunk = it % p.chunk;
           if (in_chunk == 0) {
+            const long long t0 = clock64();
             if (CG == 2) mbar_wait_cluster(tmem_empty(acc), aph ^ 1u); else mbar_wait(tmem_empty(acc), aph ^ 1u);
+            t_wait_acc += clock64() - t0;
             tc_fence_after();
           }
           const unsigned d = tmem_base + (unsigned)(acc * BN);
+          const long long t1 = clock64();
           if (CG == 2) {
             mbar_wait_cluster(full_cvt(s), ph);      // the converter warps of both CTAs, each behind its own TMA barrier
           } else {
             mbar_wait(full_raw(s), ph);
             mbar_wait(full_cvt(s), ph);
           }
+          t_wait_ops += clock64() - t1;
           tc_fence_after();
           const unsigned st = base + s * C::STAGE_BYTES;
           const unsigned long long b_hi = umma_desc_mn128(st + C::B_OFF, 4096);
@@ -262,6 +271,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant_
           }
         }
       }
+      if (p.dbg && blockIdx.x == 0 && lane == 0) { p.dbg[2] = t_wait_acc; p.dbg[3] = t_wait_ops; p.dbg[4] = clock64() - t_all; }
     }
   } else if (warp >= 4 && warp < 8) {
     // ===================== P -> tensor memory =====================
@@ -271,12 +281,13 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant_
     // saturated -- and two warps alone cannot split 16 KB per K block in time either.)
     int s = 0, sl = 0;
     unsigned ph = 0, slph = 0;
+    long long t_wait = 0, t_wait_slot = 0, t_all = clock64();
     for (int item = first_item; item < total_items; item += item_step) {
       const Item w = decode_item<CG>(p, item, rank);
       const int iters = chunk_len(p, w.chunk);
       for (int it = 0; it < iters; ++it) {
-        mbar_wait(full_raw(s), ph);
-        mbar_wait(a_empty(sl), slph ^ 1u);       // the MMAs that read this operand slot last are done
+        { const long long t0 = clock64(); mbar_wait(full_raw(s), ph); t_wait += clock64() - t0; }
+        { const long long t0 = clock64(); mbar_wait(a_empty(sl), slph ^ 1u); t_wait_slot += clock64() - t0; }   // MMAs done with this slot
         tc_fence_after();
         const float *grp = reinterpret_cast<const float *>(gbase + s * C::STAGE_BYTES + (warp & 3) * 4096) + lane;
         unsigned hi[KP], lo[KP];
@@ -294,7 +305,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant_
           float4 *a = reinterpret_cast<float4 *>(gbase + s * C::STAGE_BYTES + C::B_OFF);
           float4 *l = reinterpret_cast<float4 *>(gbase + s * C::STAGE_BYTES + C::B_OFF + C::B_BYTES);
 #pragma unroll
-          for (int i = threadIdx.x - 128; i < C::B_BYTES / 32; i += 128) {
+          for (int i = threadIdx.x - 128; i < p.g_first; i += 128) {
             const float4 v = a[i];
             float4 h, r;
             h.x = tf32_rna_fast(v.x); h.y = tf32_rna_fast(v.y); h.z = tf32_rna_fast(v.z); h.w = tf32_rna_fast(v.w);
@@ -314,6 +325,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant_
         if (++sl == C::ASLOTS) { sl = 0; slph ^= 1u; }
       }
     }
+    if (p.dbg && blockIdx.x == 0 && threadIdx.x == 128) { p.dbg[5] = t_wait; p.dbg[6] = clock64() - t_all; p.dbg[9] = t_wait_slot; }
   } else if (warp == 2 || warp == 3) {
     // ===================== G split in shared memory: hi in place, lo beside it =====================
     const int tid = threadIdx.x - 64;                 // 0..63
@@ -328,7 +340,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant_
         float4 *a = reinterpret_cast<float4 *>(stp + C::B_OFF);
         float4 *l = reinterpret_cast<float4 *>(stp + C::B_OFF + C::B_BYTES);
 #pragma unroll
-        for (int i = C::B_BYTES / 32 + tid; i < C::B_BYTES / 16; i += 64) {
+        for (int i = p.g_first + tid; i < C::B_BYTES / 16; i += 64) {
           const float4 v = a[i];
           float4 h, r;
           h.x = tf32_rna_fast(v.x); h.y = tf32_rna_fast(v.y); h.z = tf32_rna_fast(v.z); h.w = tf32_rna_fast(v.w);
@@ -352,6 +364,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant_
     const int row = q * 32 + lane;
     int acc = 0;
     unsigned aph = 0;
+    long long t_wait = 0, t_all = clock64();
     for (int item = first_item; item < total_items; item += item_step) {
       const Item w = decode_item<CG>(p, item, rank);
       const int iters = chunk_len(p, w.chunk);
@@ -360,7 +373,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant_
 #pragma unroll
       for (int c = 0; c < COLS; ++c) sum[c] = 0.f;
       for (int ck = 0; ck < chunks; ++ck) {
-        mbar_wait(tmem_full(acc), aph);
+        { const long long t0 = clock64(); mbar_wait(tmem_full(acc), aph); t_wait += clock64() - t0; }
         tc_fence_after();
         const unsigned taddr = tmem_base + ((unsigned)(q * 32) << 16) + (unsigned)(acc * BN + half * COLS);
 #pragma unroll
@@ -393,6 +406,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant_
         }
       }
     }
+    if (p.dbg && blockIdx.x == 0 && threadIdx.x == 256) { p.dbg[7] = t_wait; p.dbg[8] = clock64() - t_all; }
   }
   tc_fence_before();
   if (CG == 2) cluster_sync_all(); else __syncthreads();
@@ -404,6 +418,8 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant_
   }
 }
 
+int g_wgrad_gsplit = 2;   // unflow_set_int_option("tc_wgrad_gsplit"): share of the G tile split by warps 4-7: 0 = none, 3 = a quarter, 1 / 2 = half (default)
+
 template <int BN, int CG>
 static int launch_v(const CUtensorMap &mP, const CUtensorMap &mG, const WgradParams &p, cudaStream_t stream) {
   using C = Cfg<BN, CG>;
@@ -414,6 +430,12 @@ static int launch_v(const CUtensorMap &mP, const CUtensorMap &mG, const WgradPar
     attr_set = true;
   }
   const long long total = (long long)p.n_chunks * (CG == 2 ? (p.r_blocks + 1) / 2 : p.r_blocks) * p.c_blocks;
+  // Who splits the G tile?  The role timers (tools/tc_conv_check.py --roles) show the P-converter warps 4-7 busy
+  // 85 % and the MMA issuer waiting 40 % for operands in the pair kernel, so the converter warps are what bounds
+  // it; but the two spare warps cannot take more of the G tile than half (conv3_1, pairs: half 580 us, three
+  // quarters 610 us, all of it 670 us): half / half stays.
+  WgradParams q = p;
+  q.g_first = g_wgrad_gsplit == 0 ? 0 : g_wgrad_gsplit == 3 ? C::B_BYTES / 64 : C::B_BYTES / 32;
   if (CG == 2) {
     const int pairs = total < kNumSMs / 2 ? (int)total : kNumSMs / 2;
     cudaLaunchConfig_t cfg = {};
@@ -422,11 +444,11 @@ static int launch_v(const CUtensorMap &mP, const CUtensorMap &mG, const WgradPar
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, tc_wgrad_kernel<BN, CG>, mP, mG, p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, tc_wgrad_kernel<BN, CG>, mP, mG, q);
     if (e != cudaSuccess) { set_error("tc_wgrad: cluster launch failed: %s", cudaGetErrorString(e)); return UNFLOW_ECUDA; }
   } else {
     const int grid = total < kNumSMs ? (int)total : kNumSMs;
-    tc_wgrad_kernel<BN, CG><<<grid, NTHREADS, C::SMEM_BYTES, stream>>>(mP, mG, p);
+    tc_wgrad_kernel<BN, CG><<<grid, NTHREADS, C::SMEM_BYTES, stream>>>(mP, mG, q);
   }
   count_launch();
   return check_launch("tc_wgrad_kernel");
@@ -461,7 +483,7 @@ static int make_plan(WgradParams &p, int &BN, int N, int Hp, int Wp, int R, int 
   UNFLOW_REQUIRE(N > 0 && Hp > 0 && Wp > 0 && R > 0 && C > 0, "tc_wgrad: bad extents");
   UNFLOW_REQUIRE(stride == 1 || stride == 2, "tc_wgrad: stride must be 1 or 2");
   UNFLOW_REQUIRE(kh > 0 && kw > 0 && kh * kw <= 64, "tc_wgrad: at most 64 taps");
-  p.N = N; p.Hp = Hp; p.Wp = Wp; p.R = R; p.C = C; p.chunk = g_chunk;
+  p.N = N; p.Hp = Hp; p.Wp = Wp; p.R = R; p.C = C; p.chunk = g_chunk; p.dbg = g_dbg;
   p.taps = kh * kw; p.kw = kw; p.stride = p.stride_x = stride; p.pad_t = pad_t; p.pad_l = pad_l;
   choose_box(p);
   p.cgroups = (C + 31) / 32; p.vgroups = p.taps * p.cgroups;
@@ -479,6 +501,7 @@ static int make_plan(WgradParams &p, int &BN, int N, int Hp, int Wp, int R, int 
 }
 
 }  // namespace tcw
+int set_tc_wgrad_gsplit(int v) { if (v < 0 || v > 3) return 0; tcw::g_wgrad_gsplit = v; return 1; }
 }  // namespace unflow
 
 using namespace unflow;
