@@ -319,6 +319,19 @@ def main():
                 lib.unflow_set_int_option(b"tc_wgrad_gsplit", 2)
         set_pair(1)
         return
+    if "--wgrad-trunc" in sys.argv:      # experiment: hi = raw fp32 (truncated by the tensor core), lo = x - trunc(x)
+        from unflow_b200 import _native
+        for tr in (0, 1):
+            assert _native.lib().unflow_set_int_option(b"tc_wgrad_trunc", tr) == 0
+            say(option="tc_wgrad_trunc", value=tr)
+            B = 8
+            case_wgrad("wgrad 3x3 s1 ragged", 2, 70, 50, 13, 21, 3, 1, (1, 1, 1, 1), pitch_x=80)
+            case_wgrad("wgrad conv3_1", B, 473, 256, 48, 160, 3, 1, (1, 1, 1, 1), pitch_x=476, time_it=True)
+            case_wgrad("wgrad conv4_1", B, 512, 512, 24, 80, 3, 1, (1, 1, 1, 1), time_it=True)
+            case_wgrad("wgrad conv2 (5x5 s2)", B, 64, 128, 192, 640, 5, 2, (1, 2, 1, 2), time_it=True)
+            case_wgrad("wgrad deconv2", B, 386, 64, 48, 160, 4, 2, None, pitch_x=388, time_it=True, deconv=True)
+        _native.lib().unflow_set_int_option(b"tc_wgrad_trunc", 0)
+        return
     if "--chunk-test" in sys.argv:       # K blocks per tensor-memory accumulation: accuracy and time
         from unflow_b200 import _native
         for ck in (4, 8, 16, 32):

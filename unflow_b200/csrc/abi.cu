@@ -21,6 +21,7 @@ int set_tc_chunk(int v);        // tc_conv.cu
 int set_tc_ksplit(int v);       // tc_conv.cu
 int set_tc_pair_px(int v);      // tc_conv.cu
 int set_tc_wgrad_gsplit(int v); // tc_wgrad.cu
+int set_tc_wgrad_trunc(int v);  // tc_wgrad.cu
 int set_narrow_fwd_tma(int v);  // narrow_conv.cu
 void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 }  // namespace unflow
@@ -41,6 +42,7 @@ int unflow_set_int_option(const char *name, int value) {
   if (name && !strcmp(name, "tc_ksplit") && unflow::set_tc_ksplit(value)) return UNFLOW_OK;
   if (name && !strcmp(name, "tc_pair_px") && unflow::set_tc_pair_px(value)) return UNFLOW_OK;
   if (name && !strcmp(name, "tc_wgrad_gsplit") && unflow::set_tc_wgrad_gsplit(value)) return UNFLOW_OK;
+  if (name && !strcmp(name, "tc_wgrad_trunc") && unflow::set_tc_wgrad_trunc(value)) return UNFLOW_OK;
   if (name && !strcmp(name, "narrow_fwd_tma") && unflow::set_narrow_fwd_tma(value)) return UNFLOW_OK;
   unflow::set_error("unknown option or value: %s=%d", name ? name : "(null)", value);
   return UNFLOW_EINVAL;

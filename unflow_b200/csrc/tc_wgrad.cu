@@ -51,6 +51,7 @@ struct WgradParams {
   int r_blocks, c_blocks, taps, kw;  // c_blocks: blocks of BN/32 consecutive virtual groups
   int chunk;                        // K blocks per tensor-memory accumulation (tc::g_chunk)
   long long *dbg;                   // role timers of CTA 0 (unflow_tc_conv_debug), or nullptr
+  int trunc;                        // experiment: hi = the raw fp32 (the tensor core drops the low 13 bits itself), lo = x - trunc(x)
   int g_first;                      // float4s of the G tile split by warps 4-7 (after their P tile); warps 2-3 take the rest
   int stride, stride_x, pad_t, pad_l;   // stride_x = 1 in the row-window form (x stride inside the tensor map)
   float *dw;
@@ -294,9 +295,14 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant_
 #pragma unroll
         for (int k = 0; k < KP; ++k) {
           const float v = grp[k * 32];
-          const float h = tf32_rna_fast(v);
-          hi[k] = __float_as_uint(h);
-          lo[k] = __float_as_uint(v - h);
+          if (p.trunc) {
+            hi[k] = __float_as_uint(v);
+            lo[k] = __float_as_uint(v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u));
+          } else {
+            const float h = tf32_rna_fast(v);
+            hi[k] = __float_as_uint(h);
+            lo[k] = __float_as_uint(v - h);
+          }
         }
         const unsigned ta = tmem_base + ((unsigned)((warp & 3) * 32) << 16) + (unsigned)(C::ACC_COLS + sl * 2 * KP);
         tmem_st32(ta, hi);
@@ -308,6 +314,12 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant_
           for (int i = threadIdx.x - 128; i < p.g_first; i += 128) {
             const float4 v = a[i];
             float4 h, r;
+            if (p.trunc) {
+              r.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); r.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+              r.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); r.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+              l[i] = r;
+              continue;
+            }
             h.x = tf32_rna_fast(v.x); h.y = tf32_rna_fast(v.y); h.z = tf32_rna_fast(v.z); h.w = tf32_rna_fast(v.w);
             r.x = v.x - h.x; r.y = v.y - h.y; r.z = v.z - h.z; r.w = v.w - h.w;
             a[i] = h;
@@ -343,6 +355,12 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant_
         for (int i = p.g_first + tid; i < C::B_BYTES / 16; i += 64) {
           const float4 v = a[i];
           float4 h, r;
+          if (p.trunc) {
+            r.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); r.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+            r.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); r.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+            l[i] = r;
+            continue;
+          }
           h.x = tf32_rna_fast(v.x); h.y = tf32_rna_fast(v.y); h.z = tf32_rna_fast(v.z); h.w = tf32_rna_fast(v.w);
           r.x = v.x - h.x; r.y = v.y - h.y; r.z = v.z - h.z; r.w = v.w - h.w;
           a[i] = h;
@@ -418,6 +436,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant_
   }
 }
 
+int g_wgrad_trunc = 0;    // unflow_set_int_option("tc_wgrad_trunc"): experiment, see WgradParams::trunc
 int g_wgrad_gsplit = 2;   // unflow_set_int_option("tc_wgrad_gsplit"): share of the G tile split by warps 4-7: 0 = none, 3 = a quarter, 1 / 2 = half (default)
 
 template <int BN, int CG>
@@ -435,6 +454,7 @@ static int launch_v(const CUtensorMap &mP, const CUtensorMap &mG, const WgradPar
   // it; but the two spare warps cannot take more of the G tile than half (conv3_1, pairs: half 580 us, three
   // quarters 610 us, all of it 670 us): half / half stays.
   WgradParams q = p;
+  q.trunc = g_wgrad_trunc;
   q.g_first = g_wgrad_gsplit == 0 ? 0 : g_wgrad_gsplit == 3 ? C::B_BYTES / 64 : C::B_BYTES / 32;
   if (CG == 2) {
     const int pairs = total < kNumSMs / 2 ? (int)total : kNumSMs / 2;
@@ -501,6 +521,7 @@ static int make_plan(WgradParams &p, int &BN, int N, int Hp, int Wp, int R, int 
 }
 
 }  // namespace tcw
+int set_tc_wgrad_trunc(int v) { if (v != 0 && v != 1) return 0; tcw::g_wgrad_trunc = v; return 1; }
 int set_tc_wgrad_gsplit(int v) { if (v < 0 || v > 3) return 0; tcw::g_wgrad_gsplit = v; return 1; }
 }  // namespace unflow
 
