@@ -93,27 +93,32 @@ def main():
     t = timeit(lambda: torch.autograd.grad(o, (imr, flr), go, retain_graph=True))
     report("image_warp bwd (dflow+dimage) B4 384x1280x3", *t, 4 * Bl * h * w * (3 * 3 + 4))
 
-    # flow heads (csrc/narrow_conv.cu) at the shapes of the B=4 bidirectional step, both loaders
+    # flow heads at the shapes of the B=4 bidirectional step, input = channel slice of a pitch-padded NHWC buffer
+    # (what the decoder's concat buffers are): TMA-staged kernels (csrc/narrow_conv_tma.cu) and the cp.async ones
     from unflow_b200 import _native
     from unflow_b200.e2eflow.core import conv_ops
     for (N, C, hh, ww, tag) in ((8, 194, 96, 320, "flow2"), (8, 386, 48, 160, "flow3")):
-        x = torch.randn(N, C, hh, ww, device="cuda").contiguous(memory_format=torch.channels_last)
+        buf = torch.randn(N, hh, ww, (C + 3) // 4 * 4, device="cuda")
+        x = buf[..., :C].permute(0, 3, 1, 2)
         wgt = (torch.randn(2, C, 3, 3, device="cuda") * 0.05).contiguous(memory_format=torch.channels_last)
         bias = torch.zeros(2, device="cuda")
         g = torch.randn(N, 2, hh, ww, device="cuda").contiguous(memory_format=torch.channels_last)
         nbytes = 4 * N * hh * ww * (C + 2)
         flops = 2 * N * hh * ww * C * 18
-        for loader in (2,):          # the one staging loader left (row-wise cp.async)
+        for tma in (1, 0):
+            assert _native.lib().unflow_set_int_option(b"narrow_fwd_tma", tma) == 0
+            name = "tma" if tma else "cp.async"
             wr = wgt.clone().requires_grad_(True)
             with torch.no_grad():
                 t = timeit(lambda: conv_ops._NarrowConv3x3.apply(x, wgt, bias))
-            report("narrow_conv_fwd %s loader%d" % (tag, loader), *t, nbytes, flops)
+            report("narrow_conv_fwd %s %s" % (tag, name), *t, nbytes, flops)
 
             def fwd_bwd():
                 y = conv_ops._NarrowConv3x3.apply(x, wr, bias)     # x needs no grad: wgrad + bias grad only
                 y.backward(g)
             t = timeit(fwd_bwd)
-            report("narrow_conv fwd+wgrad %s loader%d" % (tag, loader), *t, 2 * nbytes, 2 * flops)
+            report("narrow_conv fwd+wgrad %s %s" % (tag, name), *t, 2 * nbytes, 2 * flops)
+        _native.lib().unflow_set_int_option(b"narrow_fwd_tma", 1)
 
 
 if __name__ == "__main__":
