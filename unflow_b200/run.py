@@ -250,6 +250,13 @@ def main(argv=None):
         if args.ow and os.path.isdir(ckpt_dir):
             shutil.rmtree(ckpt_dir)
         os.makedirs(ckpt_dir, exist_ok=True)
+        # experiment.py (Experiment.__init__): the run's config is kept in log/ex/<name>/config.ini -- where
+        # eval.py (eval_gui.py:97-116) looks for the parameters a checkpoint was trained with
+        if not args.debug and os.path.isfile(args.config):
+            ex_dir = os.path.join(log_dir, 'ex', args.ex)
+            os.makedirs(ex_dir, exist_ok=True)
+            if args.ow or not os.path.isfile(os.path.join(ex_dir, 'config.ini')):
+                shutil.copyfile(args.config, os.path.join(ex_dir, 'config.ini'))
     if world > 1:
         dist.barrier()
 
@@ -305,6 +312,10 @@ def main(argv=None):
                 print("-- eval: i = {}".format(i))
                 for k in sorted(result):
                     print("   {} = {}".format(k, result[k]))
+            if world > 1:
+                # rank 0 alone writes the checkpoint and evaluates: the others wait here instead of inside the
+                # next step's all-reduce (where the wait would run into the NCCL watchdog and count as step time)
+                dist.barrier()
     if batches is not None:
         batches.close()
     if world > 1:
