@@ -276,6 +276,9 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant_
     }
   } else if (warp >= 4 && warp < 8) {
     // ===================== P -> tensor memory =====================
+    // (Tried and removed: software-pipelining this role by one K block -- the next block's 32 values loaded before
+    // the current block's stores / G share / fences are waited for.  conv3_1: 747 instead of 555 us: the arrive of
+    // block i then waits for the TMA of block i + 1, and the MMA issuer starves.)
     // warp = 32-channel group = TMEM lane quarter, lane = channel; column k of the operand = pixel k.
     // (The G tile is split by all six converter warps, half here and half in warps 2-3: one warp per scheduler
     // could not keep up with both tiles -- ncu: 45 % of the tensor pipe with the ALU pipe of the converter warps
