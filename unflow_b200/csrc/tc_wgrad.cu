@@ -38,7 +38,8 @@ namespace tcw {
 
 using namespace unflow::tc;
 
-constexpr int NTHREADS = 512;
+constexpr int NTHREADS = 640;       // 20 warps: 0 TMA, 1 MMA, 2-3 + 16-19 G split, 4-7 P -> tensor memory, 8-15 epilogue
+constexpr int GWARPS = 6;
 constexpr int KP = 32;              // pixels per K block
 
 struct WgradParams {
@@ -138,7 +139,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant_
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
       mbar_init(full_raw(s), 1);
-      mbar_init(full_cvt(s), 6 * CG);           // 4 warps (P -> tensor memory) + 2 warps (G in shared memory), per CTA
+      mbar_init(full_cvt(s), (4 + GWARPS) * CG);   // 4 warps (P -> tensor memory) + 6 warps (G in shared memory), per CTA
       mbar_init(empty(s), 1);
     }
     for (int a = 0; a < C::ASLOTS; ++a) mbar_init(a_empty(a), 1);
@@ -341,9 +342,9 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant_
       }
     }
     if (p.dbg && blockIdx.x == 0 && threadIdx.x == 128) { p.dbg[5] = t_wait; p.dbg[6] = clock64() - t_all; p.dbg[9] = t_wait_slot; }
-  } else if (warp == 2 || warp == 3) {
+  } else if (warp == 2 || warp == 3 || warp >= 16) {
     // ===================== G split in shared memory: hi in place, lo beside it =====================
-    const int tid = threadIdx.x - 64;                 // 0..63
+    const int tid = (warp < 4 ? warp - 2 : warp - 14) * 32 + lane;     // 0..191
     int s = 0;
     unsigned ph = 0;
     for (int item = first_item; item < total_items; item += item_step) {
@@ -355,7 +356,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant_
         float4 *a = reinterpret_cast<float4 *>(stp + C::B_OFF);
         float4 *l = reinterpret_cast<float4 *>(stp + C::B_OFF + C::B_BYTES);
 #pragma unroll
-        for (int i = p.g_first + tid; i < C::B_BYTES / 16; i += 64) {
+        for (int i = p.g_first + tid; i < C::B_BYTES / 16; i += 32 * GWARPS) {
           const float4 v = a[i];
           float4 h, r;
           if (p.trunc) {
@@ -377,7 +378,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant_
         if (++s == C::STAGES) { s = 0; ph ^= 1u; }
       }
     }
-  } else if (warp >= 8) {
+  } else if (warp >= 8 && warp < 16) {
     // ===================== epilogue: fp32 register accumulation, then red.add into dW =====================
     constexpr int COLS = BN / 2;
     const int q = warp & 3;
@@ -458,7 +459,7 @@ static int launch_v(const CUtensorMap &mP, const CUtensorMap &mG, const WgradPar
   // quarters 610 us, all of it 670 us): half / half stays.
   WgradParams q = p;
   q.trunc = g_wgrad_trunc;
-  q.g_first = g_wgrad_gsplit == 0 ? 0 : g_wgrad_gsplit == 3 ? C::B_BYTES / 64 : C::B_BYTES / 32;
+  q.g_first = (g_wgrad_gsplit == 0 || g_wgrad_gsplit == 2) ? 0 : g_wgrad_gsplit == 3 ? C::B_BYTES / 64 : C::B_BYTES / 32;
   if (CG == 2) {
     const int pairs = total < kNumSMs / 2 ? (int)total : kNumSMs / 2;
     cudaLaunchConfig_t cfg = {};
