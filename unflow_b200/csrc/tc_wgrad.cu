@@ -24,7 +24,9 @@
 //   warp 0      TMA: per K block 4 boxes of P (32 px x 32 ch each) and BN/32 boxes of G (element
 //               stride = the conv stride, tap offset in the start coordinate, zero fill outside)
 //   warps 4-7   P tile -> hi / lo in TENSOR MEMORY (lane = channel: the transposing read is free)
-//   warps 2-3   G tile: hi = tf32(v) in place, lo = v - hi beside it (shared memory)
+//   warps 2-3, 16-19   G tile: hi = tf32(v) in place, lo = v - hi beside it (shared memory).  20 warps: with 16
+//               (G shared between warps 2-3 and 4-7) the converter warps were busy 85 % of the time and the MMA
+//               issuer waited 40 % for operands; 24 warps leave 80 registers per thread and spill (slower).
 //   warp 1      tcgen05.mma kind::tf32, A from tensor memory, B MN-major from shared memory:
 //               lo*hi + hi*lo + hi*hi per 8-pixel K step
 //   warps 8-15  every 8 K blocks: tcgen05.ld the TMEM accumulator and add it to fp32 registers (see
