@@ -20,7 +20,7 @@ One JSON line on rank 0:
           the fp32-FMA fraction and the same figures for the other hand-written kernels
   cpu_baseline  (N=1) the CPU oracle (a restatement of the reference -- the reference itself has
           no CPU path for this graph) on a bounded sample, timed on the host cores
-  clocks  nvidia-smi SM clock / throttle reasons sampled during the timed region
+  clocks  nvidia-smi SM clock / throttle reasons sampled (every 100 ms) during the timed region
 Timing: CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks.
 L2: one step streams several GB of activations (>> 126 MB L2), so no explicit flush is needed.
 """
@@ -58,7 +58,10 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons, sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons.  ONE nvidia-smi process per bench run, started before the warm-up
+    and sampling every 100 ms; every line is stamped with the host time it arrived at, and a timed region
+    (bracketed by synchronisations) picks the samples that fall inside it.  (A sampler started at the beginning
+    of a 0.28 s region often delivered its first line after the region had ended: "samples": 0.)"""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -66,12 +69,14 @@ class ClockSampler:
     def __init__(self, gpu_index):
         self.gpu = gpu_index
         self.proc = None
-        self.lines = []
+        self.lines = []          # (arrival time, line)
 
     def start(self):
+        if self.proc is not None:
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -80,19 +85,32 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
-    def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
+    def close(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+            self.proc = None
+
+    def window(self, t0, t1):
+        """Statistics of the samples that arrived in [t0, t1]; if there are none (a very short region), of
+        the samples within 0.3 s around it -- flagged "around_region" (they see the warm-up replays of the same
+        step that precede the region and the legs that follow it)."""
+        if self.proc is None and not self.lines:
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)         # let the sample that covers the end of the region arrive
+        pick = [ln for (t, ln) in self.lines if t0 <= t <= t1 + 0.1]
+        widened = False
+        if not pick:
+            pick = [ln for (t, ln) in self.lines if t0 - 0.3 <= t <= t1 + 0.3]
+            widened = True
         sm, smax, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ln in pick:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 8:
                 continue
@@ -103,9 +121,12 @@ class ClockSampler:
             for n, v in zip(names, f[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
-        return {"sm_mhz": statistics.median(sm) if sm else None,
-                "sm_max_mhz": max(smax) if smax else None, "samples": len(sm),
-                "reasons": sorted(reasons)}
+        out = {"sm_mhz": statistics.median(sm) if sm else None,
+               "sm_max_mhz": max(smax) if smax else None, "samples": len(sm),
+               "reasons": sorted(reasons)}
+        if widened:
+            out["around_region"] = True
+        return out
 
 
 def make_batch(rank, pinned):
@@ -158,23 +179,26 @@ def run_ours(args):
     def resident_step():
         return trainer.step(d_im1, d_im2)
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()          # runs for the whole bench; timed regions pick their samples by time
+
     def timed(fn, steps, hook=False):
         barrier()
-        sampler = ClockSampler(local)
-        if rank == 0:
-            sampler.start()
         _native.reset_launch_count()
         if hook:
             ops.kernel_timer.enable()
         start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.time()
         start.record()
         for _ in range(steps):
             fn()
         end.record()
         barrier()
+        t1 = time.time()
         launches = _native.launch_count()
         ktimes = ops.kernel_timer.collect() if hook else {}
-        clocks = sampler.stop() if rank == 0 else None
+        clocks = sampler.window(t0, t1) if rank == 0 else None
         ms = torch.tensor([start.elapsed_time(end)], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -232,6 +256,7 @@ def run_ours(args):
                       "unit": "frame-pairs/s", "conv_precision": "fp32 (cuDNN, no tensor cores)"}
         conv_ops.set_mode(args.conv)
 
+    sampler.close()
     params_in_sync = None
     if world > 1:
         # every rank must hold bit-identical variables after the timed steps (same all-reduced
