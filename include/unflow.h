@@ -299,7 +299,8 @@ int unflow_conv3x3_narrow_wgrad(const float *x, long long x_pitch, const float *
 int unflow_tc_conv_debug(long long *buf);
 /* unflow_tc_conv_plan (host only, for the CPU tests): the tap / class / tile plan the launcher builds,
  * as integers (layout in csrc/tc_conv.cu); returns the count written, -needed when `cap` is too
- * small, -1 on invalid arguments. */
+ * small, -1 on invalid arguments.  mode | 4: with the two-parity-classes-per-tile rewrite the launcher applies
+ * to transposed layers of 33..64 output channels. */
 int unflow_tc_conv_plan(int N, int Hin, int Win, int Cin, int Hout, int Wout, int Cout, int mode,
                         int stride, int kh, int kw, int pad_t, int pad_l, int *out, int cap);
 int unflow_tc_wsplit(const float *w, float *w_hi, float *w_lo, int taps, int R, int C, long long s_t,

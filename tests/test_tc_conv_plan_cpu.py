@@ -13,8 +13,8 @@ from unflow_b200 import _native
 
 
 def plan(N, Hin, Win, Cin, Hout, Wout, Cout, mode, stride, kh, kw, pt, pl):
-    buf = (ctypes.c_int * 512)()
-    n = _native.lib().unflow_tc_conv_plan(N, Hin, Win, Cin, Hout, Wout, Cout, mode, stride, kh, kw, pt, pl, buf, 512)
+    buf = (ctypes.c_int * 640)()
+    n = _native.lib().unflow_tc_conv_plan(N, Hin, Win, Cin, Hout, Wout, Cout, mode, stride, kh, kw, pt, pl, buf, 640)
     assert n > 0, n
     v = list(buf[:n])
     keys = ["n_classes", "s_in", "s_out", "Hit", "Wit", "TW", "TH", "TN", "tiles_x", "tiles_y", "tiles_n",
@@ -23,6 +23,9 @@ def plan(N, Hin, Win, Cin, Hout, Wout, Cout, mode, stride, kh, kw, pt, pl):
     p["class_start"] = v[15:20]
     p["class_pxy"] = [(v[20 + 2 * i], v[21 + 2 * i]) for i in range(4)]
     p["taps"] = [tuple(v[28 + 3 * i: 31 + 3 * i]) for i in range(p["ntaps"])]
+    tail = v[28 + 3 * p["ntaps"]:]
+    p["pair_px"] = tail[0]
+    p["widx2"] = tail[1:1 + p["ntaps"]]
     return p
 
 
@@ -225,3 +228,76 @@ def test_wgrad_split_k_fills_the_gpu():
     # conv2 (64 input channels, 25 taps): two taps share one 128-wide block instead of half-empty MMAs
     p = wgrad_plan(8, 96, 320, 128, 64, 2, 5, 5, 1, 1)
     assert p["BN"] == 128 and p["cgroups"] == 2 and p["c_blocks"] == 13
+
+
+def execute_pair_px(p, x, w_taps, N, Hout, Wout, Cout):
+    """The two-parity-classes-per-tile form (csrc/tc_conv.cu, pair_px_plan): a class = an output ROW parity, a
+    tile computes 2 * Cout virtual columns -- [0, Cout) the channels of px = 0 with tap widx, [Cout, 2 Cout) those
+    of px = 1 with tap widx2; -1 = that class has no tap for the input offset (zero weights)."""
+    _, Hin, Win, Cin = x.shape
+    out = torch.full((N, Hout, Wout, Cout), float("nan"), dtype=x.dtype)
+    written = torch.zeros((N, Hout, Wout), dtype=torch.int32)
+    TW, TH, TN = p["TW"], p["TH"], p["TN"]
+    assert p["pair_px"] == 1 and p["n_classes"] == 2 and p["n_blocks"] == 1 and p["BN"] == 128 and p["s_out"] == 2
+    for cls in range(2):
+        py = p["class_pxy"][cls][1]
+        lo, hi = p["class_start"][cls], p["class_start"][cls + 1]
+        for tn in range(p["tiles_n"]):
+            for ty in range(p["tiles_y"]):
+                for tx in range(p["tiles_x"]):
+                    n0, iy0, ix0 = tn * TN, ty * TH, tx * TW
+                    acc = torch.zeros((TN, TH, TW, 2 * Cout), dtype=x.dtype)
+                    for ti in range(lo, hi):
+                        dx, dy, widx = p["taps"][ti]
+                        widx2 = p["widx2"][ti]
+                        assert widx >= 0 or widx2 >= 0
+                        box = torch.zeros((TN, TH, TW, Cin), dtype=x.dtype)
+                        for a in range(TN):
+                            for b in range(TH):
+                                for c in range(TW):
+                                    n, yy, xx = n0 + a, iy0 + b + dy, ix0 + c + dx
+                                    if n < N and 0 <= yy < Hin and 0 <= xx < Win:
+                                        box[a, b, c] = x[n, yy, xx]
+                        if widx >= 0:
+                            acc[..., :Cout] += box @ w_taps[widx].t()
+                        if widx2 >= 0:
+                            acc[..., Cout:] += box @ w_taps[widx2].t()
+                    for a in range(TN):
+                        for b in range(TH):
+                            for c in range(TW):
+                                n, iy, ix = n0 + a, iy0 + b, ix0 + c
+                                if n < N and iy < p["Hit"] and ix < p["Wit"]:
+                                    for px in range(2):
+                                        oy, ox = 2 * iy + py, 2 * ix + px
+                                        out[n, oy, ox] = acc[a, b, c, px * Cout:(px + 1) * Cout]
+                                        written[n, oy, ox] += 1
+    assert int(written.min()) == 1 and int(written.max()) == 1
+    return out
+
+
+@pytest.mark.parametrize("N,Cin,H,W,Cout,k,pad,out_hw,units", [(2, 5, 9, 12, 40, 4, 1, None, 12), (2, 3, 8, 12, 64, 5, 1, (16, 24), 15),
+                                                              (2, 4, 8, 12, 33, 3, 0, (16, 24), 6)])
+def test_two_parity_classes_per_tile_plan(N, Cin, H, W, Cout, k, pad, out_hw, units):
+    """Narrow (33..64 channel) transposed layers: the paired plan covers every output exactly once, reproduces
+    conv_transpose2d, and needs `units` (input offset, class pair) blocks per channel block where the plain plan has
+    k * k (tap, class) blocks: k4 s2 12 instead of 16, 5x5 s2 15 instead of 25, 3x3 s2 6 instead of 9 -- each at
+    N = 128, which costs the tensor core the same as the plain plan's N = 64."""
+    g = torch.Generator().manual_seed(k * 5 + Cout)
+    x = torch.randn(N, Cin, H, W, generator=g, dtype=torch.float64)
+    w = torch.randn(Cin, Cout, k, k, generator=g, dtype=torch.float64)
+    Ho, Wo = (H - 1) * 2 - 2 * pad + k, (W - 1) * 2 - 2 * pad + k
+    oph = opw = 0
+    if out_hw:
+        oph, opw = out_hw[0] - Ho, out_hw[1] - Wo
+        Ho, Wo = out_hw
+    ref = F.conv_transpose2d(x, w, stride=2, padding=pad, output_padding=(max(oph, 0), max(opw, 0)))[:, :, :Ho, :Wo]
+    p = plan(N, H, W, Cin, Ho, Wo, Cout, 1 | 4, 2, k, k, pad, pad)
+    assert p["pair_px"] == 1 and p["ntaps"] == units
+    plain = plan(N, H, W, Cin, Ho, Wo, Cout, 1, 2, k, k, pad, pad)
+    assert plain["pair_px"] == 0 and plain["ntaps"] == k * k and plain["BN"] == 64
+    w_taps = w.permute(2, 3, 1, 0).reshape(k * k, Cout, Cin)
+    got = execute_pair_px(p, x.permute(0, 2, 3, 1), w_taps, N, Ho, Wo, Cout)
+    torch.testing.assert_close(got.permute(0, 3, 1, 2), ref, rtol=1e-12, atol=1e-12)
+    # layers it is not meant for keep the plain plan
+    assert plan(N, H, W, Cin, Ho, Wo, 128, 1 | 4, 2, k, k, pad, pad)["pair_px"] == 0
+    assert plan(N, H, W, Cin, Ho, Wo, 16, 1 | 4, 2, k, k, pad, pad)["pair_px"] == 0

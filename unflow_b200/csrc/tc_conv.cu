@@ -739,7 +739,7 @@ static int make_plan(tc::ConvParams &p, int &BN, int N, int Hin, int Win, int Ci
 // {+1,0}; 5x5 s2: {0,-1} and {+1,0,-1}): ONE 128-wide tile computes both -- columns [0,64) = the channels of
 // px = 0, [64,128) = those of px = 1 -- over the union of the offsets; where only one class has a tap for an
 // offset the other half of the weight tile is TMA zero fill.  CTA pairs only: rank r loads the weights of class
-// px = r (its half of B).  K blocks per output tile: k4 s2 6 instead of 8, 5x5 s2 15 instead of 25.
+// px = r (its half of B).  K blocks per channel block over all classes: k4 s2 12 instead of 16, 5x5 s2 15 instead of 25.
 static bool pair_px_plan(tc::ConvParams &p, int &BN, int mode, int stride, int Cout) {
   if (!tc::g_pair_px || !tc::g_pair || !tc::g_a_in_tmem || mode != 1 || stride != 2 || p.n_classes != 4) return false;
   if (Cout <= 32 || Cout > 64 || (long long)p.tiles_n * p.tiles_y * p.tiles_x < 2) return false;
@@ -785,11 +785,16 @@ extern "C" int unflow_tc_conv_debug(long long *buf) { tc::g_dbg = buf; return UN
 //  class_start[5], (class_px, class_py)[4], (dx, dy, widx)[ntaps]]; returns the count written.
 extern "C" int unflow_tc_conv_plan(int N, int Hin, int Win, int Cin, int Hout, int Wout, int Cout, int mode,
                                    int stride, int kh, int kw, int pad_t, int pad_l, int *out, int cap) {
+  // mode | 4: also apply the two-parity-classes-per-tile rewrite the launcher uses for narrow transposed layers
+  // (pair_px_plan); the export then ends with [pair_px, widx2[ntaps]] (the px = 1 class's tap per input offset)
+  const int want_pair = (mode >> 2) & 1;
+  mode &= 3;
   tc::ConvParams p{};
   int BN = 0;
   if (make_plan(p, BN, N, Hin, Win, Cin, Hout, Wout, Cout, mode, stride, kh, kw, pad_t, pad_l)) return -1;
+  if (want_pair) pair_px_plan(p, BN, mode, stride, Cout);
   const int nt = p.class_start[p.n_classes];
-  const int need = 15 + 5 + 8 + 3 * nt;
+  const int need = 15 + 5 + 8 + 3 * nt + 1 + nt;
   if (!out || cap < need) return -need;
   int i = 0;
   const int head[15] = {p.n_classes, p.s_in_y, p.s_out, p.Hit, p.Wit, p.TW, p.TH, p.TN, p.tiles_x, p.tiles_y,
@@ -798,6 +803,8 @@ extern "C" int unflow_tc_conv_plan(int N, int Hin, int Win, int Cin, int Hout, i
   for (int k = 0; k < 5; ++k) out[i++] = p.class_start[k];
   for (int k = 0; k < 4; ++k) { out[i++] = p.class_px[k]; out[i++] = p.class_py[k]; }
   for (int k = 0; k < nt; ++k) { out[i++] = p.taps[k].dx; out[i++] = p.taps[k].dy; out[i++] = p.taps[k].widx; }
+  out[i++] = p.pair_px;
+  for (int k = 0; k < nt; ++k) out[i++] = p.taps[k].widx2;
   return i;
 }
 
