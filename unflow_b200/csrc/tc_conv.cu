@@ -1,5 +1,6 @@
 // tc_conv.cu -- the conv / deconv stacks of FlowNet on the 5th-generation tensor cores:
-// a tcgen05 implicit GEMM with the 3xTF32 operand split done in shared memory.
+// a tcgen05 implicit GEMM with the 3xTF32 operand split done inside the kernel (activations: into tensor
+// memory; weights: hi / lo planes made once per step).
 //
 // Replaces the library convolutions behind slim.conv2d / slim.conv2d_transpose
 // (reference src/e2eflow/core/flownet.py:166-233, _flownet_upconv :89-155) for the forward pass
@@ -17,14 +18,17 @@
 // GEMM view per tile: M = 128 output positions (a TW x TH x TN box of one class), N = BN output
 // channels, K = taps x Cin walked in blocks of 32 channels (one 128-byte swizzle row of fp32).
 //
-// Pipeline (one CTA per SM, persistent over tiles, warp-specialised):
+// Pipeline (one CTA per SM -- or a cluster of two CTAs on the two SMs of a TPC, see Cfg -- persistent over tiles,
+// warp-specialised; the issuing warps run converged and one elect.sync lane issues, see tc_common.cuh):
 //   warp 0     TMA producer: per K block one 4-D box of the ACTIVATIONS as they lie in HBM (fp32,
 //              NHWC, any channel pitch -- e.g. a channel slice of a concat buffer; image borders,
 //              the TF SAME padding and the channel tail are TMA zero fill, stride 2 is the tensor
 //              map's element stride) plus the hi and lo planes of the weights.
-//   warps 4-7  split the activation tile in shared memory: hi = tf32(x) in place, lo = x - hi
-//              into a second buffer (same swizzled layout: the split is element-wise).
-//   warp 1     one thread issues tcgen05.mma kind::tf32, three per K step:
+//   warps 4-7  split the activation tile, thread = tile row: hi = tf32(x), lo = x - hi, both stored to TENSOR
+//              MEMORY (tcgen05.st), the MMAs' A operand.  (Template AT = false keeps the first version: the
+//              split written back to shared memory, A and B both read from there -- bound by shared-memory
+//              bandwidth, profiles/r2_ncu_tc_conv.md.)
+//   warp 1     issues tcgen05.mma kind::tf32, three per K step:
 //              lo*hi' + hi*lo' + hi*hi' accumulate in fp32 in TENSOR MEMORY (double-buffered).
 //   warps 8-15 epilogue: the K loop is cut into CHUNKS of 8 K blocks (tc_common.cuh: CHUNK); the tensor core accumulates one
 //              chunk in tensor memory, these warps read it back (tcgen05.ld) and add it to fp32
@@ -42,7 +46,7 @@
 // per instruction that grows LINEARLY with K (measured on B200, this kernel with one accumulation
 // over all of K and cuDNN's TF32 kernels alike: max error / max|y| = 6.8e-9 * K, i.e. 6e-5 at
 // K = 9216 where an fp32 FMA loop has 2e-5; profiles/r2_tc_conv.md).  Cutting K into chunks of
-// 128 and summing the chunks in fp32 registers (round to nearest) removes that term.
+// 256 and summing the chunks in fp32 registers (round to nearest) leaves 1.8e-6.
 #include <algorithm>
 
 #include "tc_common.cuh"
