@@ -2,13 +2,14 @@
 
 'fp32'    plain cuDNN float32 (what the reference's slim.conv2d computes, flownet.py:174-233);
           no tensor cores.
-'3xtf32'  the same contraction on the tensor cores at fp32-level accuracy: every operand is split
-          x = hi + lo (hi = TF32-rounded, lo = exact residual, csrc/split.cu) and
-          hi*hi' + hi*lo' + lo*hi' is evaluated by ONE cuDNN TF32 convolution whose contraction
-          dimension carries the three products side by side (X' = [hi,hi,lo], W' = [hi',lo',hi']):
-          fp32 accumulation inside the MMA, one output write, no extra adds.  Forward, dgrad and
-          wgrad all use the same trick (wgrad concatenates along the batch).  Measured against the
-          fp32 oracle it meets the same 1e-4 flow tolerance as the plain fp32 path.
+'3xtf32'  the same contraction on the tensor cores at fp32-level accuracy (the default of bench.py and the
+          trainer): every operand is split x = hi + lo (hi = TF32-rounded, lo = exact residual) and
+          lo*hi' + hi*lo' + hi*hi' is accumulated by the hand-written tcgen05 kernels (csrc/tc_conv.cu: forward
+          and input gradient, csrc/tc_wgrad.cu: weight gradient, csrc/narrow_conv*.cu: the 2-channel flow
+          heads in exact fp32) with the K loop cut into chunks that are summed in fp32 registers: 1.8e-6 of
+          max|y| against float64 per layer, and the same 1e-4 flow tolerance against the fp32 oracle as the
+          plain fp32 path.  Layers these kernels do not serve (tensors that are not NHWC / 16-byte aligned) fall
+          back to cuDNN TF32 convolutions fed the split operands (csrc/split.cu, the round-1 path).
 'tf32'    single-pass TF32 (reduced precision; never used for parity or the headline number).
 """
 import torch
