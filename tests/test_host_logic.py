@@ -216,3 +216,27 @@ manual_decay_lrs = 0.5e-5,0.25e-5
     (tmp_path / "model.ckpt-5000.pt").write_bytes(b"")
     (tmp_path / "model.ckpt-15000.pt").write_bytes(b"")
     assert R.latest_checkpoint(str(tmp_path))[0] == 15000
+
+
+def test_l2_mask_bytes_for_the_adam_kernel():
+    """core/train.py: one bit per parameter marks the `weights` variables (slim.l2_regularizer, reference
+    flownet.py:176) for the fused Adam kernel: bit k of byte i = element 4 * i + k of the flat buffer."""
+    from unflow_b200.e2eflow.core.train import l2_mask_bytes
+    # weights [0,5), biases [5,7), weights [7,10), padding [10,12)
+    isw, packed = l2_mask_bytes(12, [0, 5, 7], [5, 2, 3], [True, False, True])
+    assert isw.tolist() == [1, 1, 1, 1, 1, 0, 0, 1, 1, 1, 0, 0]
+    assert packed.tolist() == [0b1111, 0b1001, 0b0011] and packed.dtype == torch.uint8
+    for i in range(12):
+        assert (int(packed[i // 4]) >> (i % 4)) & 1 == int(isw[i])
+
+
+def test_nhwc_geometry_of_channel_and_batch_slices():
+    """ops._nhwc_geometry: (batch stride, pixel pitch) of NCHW-shaped tensors with NHWC memory -- dense, a channel
+    slice of a pitch-padded concat buffer, a batch slice; None for NCHW memory."""
+    from unflow_b200.e2eflow.ops import _nhwc_geometry
+    buf = torch.empty(4, 5, 6, 12)
+    assert _nhwc_geometry(buf.permute(0, 3, 1, 2)) == (360, 12)
+    assert _nhwc_geometry(buf[..., 2:9].permute(0, 3, 1, 2)) == (360, 12)
+    assert _nhwc_geometry(buf[1:3, :, :, :8].permute(0, 3, 1, 2)) == (360, 12)
+    assert _nhwc_geometry(torch.empty(2, 8, 5, 6)) is None
+    assert _nhwc_geometry(torch.empty(2, 8, 5, 6).contiguous(memory_format=torch.channels_last)) == (240, 8)

@@ -51,6 +51,17 @@ def learning_rate_at(decay_iters, params):
     return lr
 
 
+def l2_mask_bytes(n, offsets, numels, regularised):
+    """Mask of the regularised elements of the flat parameter buffer in the form csrc/adam.cu reads:
+    (per-element uint8 flags, one byte per float4 with bit k = element 4 * i + k).  ``n`` is a multiple of 4."""
+    isw = torch.zeros(n, dtype=torch.uint8)
+    for off, k, reg in zip(offsets, numels, regularised):
+        if reg:
+            isw[off:off + k] = 1
+    q = isw.view(-1, 4)
+    return isw, (q[:, 0] | (q[:, 1] << 1) | (q[:, 2] << 2) | (q[:, 3] << 3)).contiguous()
+
+
 class Trainer:
     def __init__(self, params, normalization, device, variables=None, seed=1234,
                  loss_fn=unsupervised_loss, process_group=None, augment=False):
@@ -102,12 +113,9 @@ class Trainer:
         self.l2_mask = None
         self.l2_scale = float(self.variables.L2_SCALE)
         if self.device.type == 'cuda' and __import__('os').environ.get('UNFLOW_L2_IN_ADAM', '1') != '0':
-            isw = torch.zeros(self.flat_param.numel(), dtype=torch.uint8)
-            for off, p, name in zip(self._offsets, self.trainable, self.trainable_names):
-                if name.endswith('/weights'):
-                    isw[off:off + p.numel()] = 1
-            q = isw.view(-1, 4)
-            self.l2_mask = (q[:, 0] | (q[:, 1] << 1) | (q[:, 2] << 2) | (q[:, 3] << 3)).contiguous().to(self.device)
+            isw, packed = l2_mask_bytes(self.flat_param.numel(), self._offsets, [p.numel() for p in self.trainable],
+                                        [name.endswith('/weights') for name in self.trainable_names])
+            self.l2_mask = packed.to(self.device)
             self._l2_elements = isw.to(self.device)
             self.variables.l2_in_optimizer = True
 
